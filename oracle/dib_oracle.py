@@ -1,0 +1,456 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (numpy) restatement of the reference's Distributed-IB hot path.
+
+PARITY STATUS: "parity unpinned" against TensorFlow itself.  The reference has no tests and
+TensorFlow/Keras (unpinned 2.x, third-party, absent from /root/reference and from this image)
+cannot be run here.  This oracle is pinned instead by
+  (i)  the closed-form known answers derivable from the reference's own formulas
+       (beta schedule, KL, Bhattacharyya, PE layout, circuit truth table),
+  (ii) golden vectors produced by executing the reference's OWN model code
+       (/root/reference/models.py ``DistributedIBNet.call``, ``InfoBottleneckAnnealingCallback``,
+       /root/reference/utils.py ``bhattacharyya_dist_mat``) on a numpy stand-in for the ``tf``
+       namespace -- tests/golden/make_golden.py, fixtures committed under tests/golden/.
+Keras behaviours that live in the third-party dependency are restated from its published
+semantics and each is marked [KERAS] below.
+
+Each function cites the reference lines it follows (paths relative to /root/reference).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module;
+the product path (dib_b200) never does.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+LOSS_BCE_LOGITS = "bce_logits"          # tf.keras.losses.BinaryCrossentropy(from_logits=True)  data.py:65
+LOSS_SPARSE_CE_LOGITS = "sparse_ce_logits"  # SparseCategoricalCrossentropy(from_logits=True)   data.py:343
+LOSS_MSE = "mse"                        # regression targets (data.py:129 implies it)
+
+
+# ----------------------------------------------------------------------------------------------
+# activations ([KERAS] tf.keras.activations.get(name)); derivatives are written in terms of the
+# OUTPUT h = act(z) because that is what the CUDA backward has at hand.
+# ----------------------------------------------------------------------------------------------
+def act_fwd(name, z, alpha=0.2):
+    if name in (None, "linear"):
+        return z
+    if name == "relu":
+        return np.maximum(z, 0)
+    if name == "tanh":
+        return np.tanh(z)
+    if name == "leaky_relu":
+        return np.where(z > 0, z, alpha * z)
+    if name == "sigmoid":
+        return 1.0 / (1.0 + np.exp(-z))
+    if name == "elu":
+        return np.where(z > 0, z, np.expm1(np.minimum(z, 0)))
+    raise ValueError(f"unknown activation {name!r}")
+
+
+def act_grad_from_output(name, h, alpha=0.2):
+    if name in (None, "linear"):
+        return np.ones_like(h)
+    if name == "relu":
+        return (h > 0).astype(h.dtype)
+    if name == "tanh":
+        return 1.0 - h * h
+    if name == "leaky_relu":
+        return np.where(h > 0, 1.0, alpha).astype(h.dtype)
+    if name == "sigmoid":
+        return h * (1.0 - h)
+    if name == "elu":
+        return np.where(h > 0, 1.0, h + 1.0).astype(h.dtype)
+    raise ValueError(f"unknown activation {name!r}")
+
+
+# ----------------------------------------------------------------------------------------------
+# model description + parameters
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class DIBConfig:
+    """Constructor arguments of DistributedIBNet (models.py:56-66; dropout-free)."""
+    feature_dimensionalities: Sequence[int]
+    feature_encoder_architecture: Sequence[int]
+    integration_network_architecture: Sequence[int]
+    output_dimensionality: int
+    use_positional_encoding: bool = True
+    number_positional_encoding_frequencies: int = 5
+    activation_fn: Optional[str] = "relu"
+    feature_embedding_dimension: int = 32
+    output_activation_fn: Optional[str] = None
+    leaky_alpha: float = 0.2
+
+    @property
+    def number_features(self):
+        return len(self.feature_dimensionalities)
+
+    @property
+    def frequencies(self):
+        # models.py:70 -- 2**np.arange(1, n): n-1 sinusoid blocks (off-by-one vs the docstring)
+        return [2 ** k for k in range(1, self.number_positional_encoding_frequencies)]
+
+    def encoder_input_width(self, i):
+        d = self.feature_dimensionalities[i]
+        return d * (1 + len(self.frequencies)) if self.use_positional_encoding else d
+
+    def encoder_layer_dims(self, i):
+        dims = [self.encoder_input_width(i)] + list(self.feature_encoder_architecture)
+        dims.append(2 * self.feature_embedding_dimension)           # models.py:77
+        return dims
+
+    def integration_layer_dims(self):
+        return ([self.number_features * self.feature_embedding_dimension]  # models.py:81
+                + list(self.integration_network_architecture) + [self.output_dimensionality])
+
+    def param_shapes(self):
+        """Flat order: feature 0 (W1,b1,W2,b2,...), feature 1 ..., integration (W,b)...  Kernels are
+        Keras-oriented [in, out] (tf.keras.layers.Dense)."""
+        shapes = []
+        for i in range(self.number_features):
+            d = self.encoder_layer_dims(i)
+            for k in range(len(d) - 1):
+                shapes += [(d[k], d[k + 1]), (d[k + 1],)]
+        d = self.integration_layer_dims()
+        for k in range(len(d) - 1):
+            shapes += [(d[k], d[k + 1]), (d[k + 1],)]
+        return shapes
+
+    def param_count(self):
+        return int(sum(int(np.prod(s)) for s in self.param_shapes()))
+
+
+def glorot_uniform_params(cfg: DIBConfig, rng: np.random.Generator, dtype=np.float32) -> np.ndarray:
+    """[KERAS] Dense default init: kernel glorot_uniform (limit sqrt(6/(fan_in+fan_out))), bias zeros.
+    The RNG stream is ours (numpy Generator); Keras' own stream is irreproducible without TF."""
+    out = []
+    for s in cfg.param_shapes():
+        if len(s) == 2:
+            lim = math.sqrt(6.0 / (s[0] + s[1]))
+            out.append(rng.uniform(-lim, lim, size=s).astype(dtype).ravel())
+        else:
+            out.append(np.zeros(s, dtype=dtype))
+    return np.concatenate(out)
+
+
+def unflatten(cfg: DIBConfig, flat: np.ndarray):
+    """-> (encoders: list over features of [(W,b),...], integration: [(W,b),...])"""
+    views, off = [], 0
+    for s in cfg.param_shapes():
+        n = int(np.prod(s))
+        views.append(flat[off:off + n].reshape(s))
+        off += n
+    assert off == flat.size
+    it = iter(views)
+    n_enc_layers = len(cfg.feature_encoder_architecture) + 1
+    encoders = [[(next(it), next(it)) for _ in range(n_enc_layers)] for _ in range(cfg.number_features)]
+    n_int_layers = len(cfg.integration_network_architecture) + 1
+    integration = [(next(it), next(it)) for _ in range(n_int_layers)]
+    return encoders, integration
+
+
+# ----------------------------------------------------------------------------------------------
+# forward pieces
+# ----------------------------------------------------------------------------------------------
+def positional_encoding(x, frequencies):
+    """models.py:22-23: concat([x] + [sin(f*x) for f in frequencies], -1)  (block-major)."""
+    return np.concatenate([x] + [np.sin(f * x) for f in frequencies], axis=-1)
+
+
+def split_features(cfg: DIBConfig, x):
+    """models.py:101: tf.split(inputs, feature_dimensionalities, axis=-1)."""
+    offs = np.cumsum([0] + list(cfg.feature_dimensionalities))
+    assert x.shape[-1] == offs[-1]                                   # models.py:89
+    return [x[:, offs[i]:offs[i + 1]] for i in range(cfg.number_features)]
+
+
+def encoder_forward(cfg: DIBConfig, layers, x_i, keep=False):
+    """models.py:72-78 Sequential: [PE] -> Dense(h,act)... -> Dense(2E) (linear).  a15 contract."""
+    h = positional_encoding(x_i, cfg.frequencies) if cfg.use_positional_encoding else x_i
+    acts = [h]
+    for k, (W, b) in enumerate(layers):
+        z = h @ W + b
+        h = act_fwd(cfg.activation_fn, z, cfg.leaky_alpha) if k < len(layers) - 1 else z
+        acts.append(h)
+    return (h, acts) if keep else h
+
+
+def task_loss_per_sample(loss, pred, y):
+    """[KERAS] per-sample loss value; the compiled loss is its mean over the batch."""
+    if loss == LOSS_BCE_LOGITS:
+        yy = y.reshape(pred.shape).astype(pred.dtype)
+        l = np.maximum(pred, 0) - pred * yy + np.log1p(np.exp(-np.abs(pred)))
+        return l.mean(axis=-1)
+    if loss == LOSS_SPARSE_CE_LOGITS:
+        m = pred.max(axis=-1, keepdims=True)
+        lse = (m + np.log(np.exp(pred - m).sum(axis=-1, keepdims=True)))[:, 0]
+        return lse - pred[np.arange(pred.shape[0]), y.astype(np.int64).ravel()]
+    if loss == LOSS_MSE:
+        yy = y.reshape(pred.shape).astype(pred.dtype)
+        return ((pred - yy) ** 2).mean(axis=-1)
+    raise ValueError(loss)
+
+
+def task_loss_grad(loss, pred, y):
+    """d(sum_b per-sample loss)/d pred  (caller scales by 1/B)."""
+    if loss == LOSS_BCE_LOGITS:
+        yy = y.reshape(pred.shape).astype(pred.dtype)
+        return (1.0 / (1.0 + np.exp(-pred)) - yy) / pred.shape[-1]
+    if loss == LOSS_SPARSE_CE_LOGITS:
+        m = pred.max(axis=-1, keepdims=True)
+        p = np.exp(pred - m)
+        p /= p.sum(axis=-1, keepdims=True)
+        p[np.arange(pred.shape[0]), y.astype(np.int64).ravel()] -= 1.0
+        return p
+    if loss == LOSS_MSE:
+        yy = y.reshape(pred.shape).astype(pred.dtype)
+        return 2.0 * (pred - yy) / pred.shape[-1]
+    raise ValueError(loss)
+
+
+def accuracy_count(loss, pred, y):
+    """[KERAS] metrics=['accuracy'] resolution: binary_accuracy (threshold 0.5 applied to the RAW
+    model output, logits included) for a BCE loss; sparse_categorical_accuracy for sparse CE.
+    Returns the SUM over the batch of per-sample accuracies."""
+    if loss == LOSS_SPARSE_CE_LOGITS:
+        return float((pred.argmax(axis=-1) == y.astype(np.int64).ravel()).sum())
+    yy = y.reshape(pred.shape)
+    return float(((pred > 0.5).astype(np.float64) == yy).mean(axis=-1).sum())
+
+
+@dataclass
+class ForwardResult:
+    pred: np.ndarray
+    emb: np.ndarray               # [B, F*E] concat of u_i (models.py:122)
+    kl_per_feature: np.ndarray    # [F], mean over batch (models.py:111-112), nats
+    task_loss: float              # mean over batch
+    loss: float                   # task + beta*sum KL (models.py:118 + compiled loss)
+    acc_sum: float
+    cache: dict = field(default_factory=dict)
+
+
+def forward(cfg: DIBConfig, flat_params, x, eps, beta, y=None, loss=None, keep=False, dtype=np.float64):
+    """models.py:96-123 with eps explicit: u = mu + exp(logvar/2)*eps  (== tf.random.normal(mean=mu,
+    stddev=exp(logvar/2)), models.py:108).  eps: [B, F, E]."""
+    p = np.asarray(flat_params, dtype=dtype)
+    x = np.asarray(x, dtype=dtype)
+    eps = np.asarray(eps, dtype=dtype)
+    encoders, integration = unflatten(cfg, p)
+    E = cfg.feature_embedding_dimension
+    xs = split_features(cfg, x)
+    embs, kls, enc_cache = [], [], []
+    for i in range(cfg.number_features):
+        o, acts = encoder_forward(cfg, encoders[i], xs[i], keep=True)
+        mu, lv = o[:, :E], o[:, E:]                                   # models.py:106 tf.split(.,2,-1)
+        u = mu + np.exp(lv / 2.0) * eps[:, i, :]                      # models.py:108
+        kl = (0.5 * (mu ** 2 + np.exp(lv) - lv - 1.0)).sum(axis=-1).mean()   # models.py:111-112
+        embs.append(u)
+        kls.append(kl)
+        enc_cache.append((acts, mu, lv))
+    emb = np.concatenate(embs, axis=-1)                               # models.py:122
+    h = emb
+    int_acts = [h]
+    for k, (W, b) in enumerate(integration):
+        z = h @ W + b
+        if k < len(integration) - 1:
+            h = act_fwd(cfg.activation_fn, z, cfg.leaky_alpha)
+        else:
+            h = act_fwd(cfg.output_activation_fn, z, cfg.leaky_alpha)  # models.py:83
+        int_acts.append(h)
+    pred = h
+    kls = np.asarray(kls, dtype=dtype)
+    res = ForwardResult(pred=pred, emb=emb, kl_per_feature=kls, task_loss=float("nan"),
+                        loss=float("nan"), acc_sum=float("nan"))
+    if y is not None:
+        res.task_loss = float(task_loss_per_sample(loss, pred, y).mean())
+        res.loss = res.task_loss + float(beta) * float(kls.sum())     # models.py:118
+        res.acc_sum = accuracy_count(loss, pred, y)
+    if keep:
+        res.cache = dict(enc=enc_cache, int_acts=int_acts, encoders=encoders, integration=integration)
+    return res
+
+
+def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.float64, batch_for_mean=None):
+    """Reverse mode through forward() (what GradientTape does inside Keras' train_step).
+    Returns (flat grads of mean-loss, ForwardResult).  ``batch_for_mean`` lets a shard of a larger
+    global batch produce its additive share (grads scale 1/B_global)."""
+    fr = forward(cfg, flat_params, x, eps, beta, y=y, loss=loss, keep=True, dtype=dtype)
+    B = x.shape[0] if batch_for_mean is None else batch_for_mean
+    E = cfg.feature_embedding_dimension
+    c = fr.cache
+    eps = np.asarray(eps, dtype=dtype)
+    # integration network backward
+    int_acts, integration = c["int_acts"], c["integration"]
+    dz = task_loss_grad(loss, fr.pred, y) / B
+    dz = dz * act_grad_from_output(cfg.output_activation_fn, int_acts[-1], cfg.leaky_alpha)
+    int_grads = [None] * len(integration)
+    for k in reversed(range(len(integration))):
+        W, _ = integration[k]
+        int_grads[k] = (int_acts[k].T @ dz, dz.sum(axis=0))
+        dh = dz @ W.T
+        if k > 0:
+            dz = dh * act_grad_from_output(cfg.activation_fn, int_acts[k], cfg.leaky_alpha)
+    d_emb = dh
+    enc_grads = []
+    for i in range(cfg.number_features):
+        acts, mu, lv = c["enc"][i]
+        layers = c["encoders"][i]
+        du = d_emb[:, i * E:(i + 1) * E]
+        sig = np.exp(lv / 2.0)
+        dmu = du + beta * mu / B
+        dlv = du * eps[:, i, :] * 0.5 * sig + beta * 0.5 * (np.exp(lv) - 1.0) / B
+        dz = np.concatenate([dmu, dlv], axis=-1)
+        g = [None] * len(layers)
+        for k in reversed(range(len(layers))):
+            W, _ = layers[k]
+            g[k] = (acts[k].T @ dz, dz.sum(axis=0))
+            if k > 0:
+                dz = (dz @ W.T) * act_grad_from_output(cfg.activation_fn, acts[k], cfg.leaky_alpha)
+        enc_grads.append(g)
+    flat = []
+    for g in enc_grads:
+        for gw, gb in g:
+            flat += [gw.ravel(), gb.ravel()]
+    for gw, gb in int_grads:
+        flat += [gw.ravel(), gb.ravel()]
+    return np.concatenate(flat), fr
+
+
+# ----------------------------------------------------------------------------------------------
+# optimizer / schedule / fit
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class AdamState:
+    m: np.ndarray
+    v: np.ndarray
+    t: int = 0
+
+
+def adam_step(params, grads, st: AdamState, lr, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+    """[KERAS] tf.keras.optimizers.Adam (non-amsgrad) dense update:
+        t += 1; lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; w -= lr_t * m / (sqrt(v) + eps)
+    (epsilon OUTSIDE the bias correction, default 1e-7; lr from train.py:129 / nb-radial Adam(lr))."""
+    st.t += 1
+    dt = params.dtype.type
+    lr_t = dt(lr) * dt(math.sqrt(1.0 - beta_2 ** st.t)) / dt(1.0 - beta_1 ** st.t)
+    st.m += (grads - st.m) * dt(1.0 - beta_1)
+    st.v += (grads * grads - st.v) * dt(1.0 - beta_2)
+    params -= lr_t * st.m / (np.sqrt(st.v) + dt(epsilon))
+    return params
+
+
+def beta_schedule(epoch, beta_start, beta_end, number_pretraining_epochs, number_annealing_epochs):
+    """models.py:147-149, evaluated in float32 like the TF ops there."""
+    f = np.float32
+    frac = f(max(epoch - number_pretraining_epochs, 0)) / f(number_annealing_epochs)
+    return f(np.exp(np.log(f(beta_start)) + frac * (np.log(f(beta_end)) - np.log(f(beta_start)))))
+
+
+def fit(cfg: DIBConfig, flat_params, x, y, *, loss, epochs, batch_size, lr,
+        eps_fn: Callable[[int, np.ndarray], np.ndarray],
+        perm_fn: Optional[Callable[[int, int], np.ndarray]] = None,
+        beta_fn: Optional[Callable[[int], float]] = None,
+        validation_data=None, dtype=np.float64, adam_kwargs=None):
+    """[KERAS] Model.fit epoch mechanics around the reference's call() (train.py:157-166):
+      * per epoch: on_epoch_begin sets beta (models.py:147); indices shuffled (perm_fn(epoch, N));
+        consecutive batches incl. a short last one;
+      * history['loss'] = sample-weighted running mean of (task + beta*sumKL); history['accuracy']
+        = sample-weighted mean; history['KL{i}'] and ['beta'] = UNWEIGHTED mean over batches
+        (add_metric -> Mean with weight 1, models.py:115,121);
+      * validation after every epoch with the same call() -- noise still sampled (train.py:264-265)
+        -- in batches of batch_size, giving val_* twins.
+    eps_fn(step, global_sample_ids) -> eps [n, F, E]; step counts optimizer steps from 0 for
+    training batches; validation passes use step = 2**31 + epoch.
+    """
+    p = np.array(flat_params, dtype=dtype, copy=True)
+    st = AdamState(np.zeros_like(p), np.zeros_like(p))
+    N = x.shape[0]
+    F = cfg.number_features
+    hist = {k: [] for k in ["loss", "accuracy", "beta"] + [f"KL{i}" for i in range(F)]}
+    if validation_data is not None:
+        for k in list(hist):
+            hist["val_" + k] = []
+    step = 0
+    beta = 1.0                                                         # models.py:86
+    adam_kwargs = adam_kwargs or {}
+    for epoch in range(epochs):
+        if beta_fn is not None:
+            beta = float(beta_fn(epoch))
+        perm = perm_fn(epoch, N) if perm_fn is not None else np.arange(N)
+        sums = dict(loss=0.0, acc=0.0, n=0, kl=np.zeros(F), nb=0)
+        for b0 in range(0, N, batch_size):
+            idx = perm[b0:b0 + batch_size]
+            eps = eps_fn(step, idx)
+            g, fr = train_grads(cfg, p, x[idx], y[idx], eps, beta, loss, dtype=dtype)
+            adam_step(p, g.astype(dtype), st, lr, **adam_kwargs)
+            n = len(idx)
+            sums["loss"] += fr.loss * n
+            sums["acc"] += fr.acc_sum
+            sums["n"] += n
+            sums["kl"] += fr.kl_per_feature
+            sums["nb"] += 1
+            step += 1
+        hist["loss"].append(sums["loss"] / sums["n"])
+        hist["accuracy"].append(sums["acc"] / sums["n"])
+        hist["beta"].append(beta)
+        for i in range(F):
+            hist[f"KL{i}"].append(sums["kl"][i] / sums["nb"])
+        if validation_data is not None:
+            xv, yv = validation_data
+            vs = dict(loss=0.0, acc=0.0, n=0, kl=np.zeros(F), nb=0)
+            for b0 in range(0, xv.shape[0], batch_size):
+                idx = np.arange(b0, min(b0 + batch_size, xv.shape[0]))
+                eps = eps_fn(2 ** 31 + epoch, idx)
+                fr = forward(cfg, p, xv[idx], eps, beta, y=yv[idx], loss=loss, dtype=dtype)
+                vs["loss"] += fr.loss * len(idx)
+                vs["acc"] += fr.acc_sum
+                vs["n"] += len(idx)
+                vs["kl"] += fr.kl_per_feature
+                vs["nb"] += 1
+            hist["val_loss"].append(vs["loss"] / vs["n"])
+            hist["val_accuracy"].append(vs["acc"] / vs["n"])
+            hist["val_beta"].append(beta)
+            for i in range(F):
+                hist[f"val_KL{i}"].append(vs["kl"][i] / vs["nb"])
+    return p, hist
+
+
+# ----------------------------------------------------------------------------------------------
+# compression matrices (a14)
+# ----------------------------------------------------------------------------------------------
+def bhattacharyya_dist_mat(mus1, logvars1, mus2, logvars2):
+    """utils.py:177-212 in its O(N*M*E) closed form (the reference materialises N*M*E*E diagonals):
+       D = 1/8 sum_e (mu1-mu2)^2/sbar + 1/2 [ sum_e ln sbar - 1/2 (sum lv1 + sum lv2) ],
+       sbar = (exp(lv1)+exp(lv2))/2."""
+    mus1, logvars1, mus2, logvars2 = [np.asarray(a, dtype=np.float64) for a in (mus1, logvars1, mus2, logvars2)]
+    d = mus1[:, None, :] - mus2[None, :, :]
+    sbar = 0.5 * (np.exp(logvars1)[:, None, :] + np.exp(logvars2)[None, :, :])
+    term1 = 0.125 * (d * d / sbar).sum(-1)
+    term2 = 0.5 * (np.log(sbar).sum(-1) - 0.5 * (logvars1.sum(-1)[:, None] + logvars2.sum(-1)[None, :]))
+    return term1 + term2
+
+
+def compression_matrix(cfg: DIBConfig, flat_params, feature_ind, x_rows, dtype=np.float64):
+    """visualization.py:31-34: encoder forward (no noise) -> Bhattacharyya -> exp(-D)."""
+    encoders, _ = unflatten(cfg, np.asarray(flat_params, dtype=dtype))
+    o = encoder_forward(cfg, encoders[feature_ind], np.asarray(x_rows, dtype=dtype))
+    E = cfg.feature_embedding_dimension
+    mu, lv = o[:, :E], o[:, E:]
+    return np.exp(-bhattacharyya_dist_mat(mu, lv, mu, lv))
+
+
+# ----------------------------------------------------------------------------------------------
+# fixture: the paper's Boolean circuit (data.py:21-57) -- deterministic known answer
+# ----------------------------------------------------------------------------------------------
+def boolean_circuit_truth_table():
+    spec = [[1, 0, 1], [2, 8, 7], [0, 4, 3], [1, 11, 5], [2, 6, 12], [2, 13, 9], [1, 14, 10],
+            [0, 15, 2], [0, 17, 16]]                                   # data.py:40
+    gates = [np.logical_and, np.logical_or, np.logical_xor]            # data.py:25
+    grids = np.meshgrid(*[[0, 1]] * 10)                                # data.py:50-52
+    tt = np.stack(grids, -1).reshape(-1, 10)
+    for g, a, b in spec:
+        tt = np.concatenate([tt, gates[g](tt[:, a], tt[:, b]).astype(np.int32)[:, None]], -1)
+    x = 2 * tt[:, :10] - 1                                             # data.py:56
+    y = tt[:, -1]
+    return x.astype(np.float32), y.astype(np.float32)

@@ -1,0 +1,176 @@
+"""CPU: the oracle against (i) golden vectors produced by the reference's own code (tests/golden/
+make_golden.py), (ii) the closed-form known answers of SURVEY.md section 4, (iii) itself (finite differences,
+torch-autograd twin, data-parallel shard additivity)."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dib_oracle as O
+from oracle import philox
+
+CASES = ["c0_small", "pendulum_like", "radial_like", "odd_shapes"]
+
+
+def load_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"ref_forward_{name}.npz"))
+    cfg = O.DIBConfig(**ast.literal_eval(str(z["cfg"])))
+    return cfg, z
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_code(golden_dir, name):
+    cfg, z = load_case(golden_dir, name)
+    fr = O.forward(cfg, z["params"], z["x"], z["eps"], float(z["beta"]))
+    np.testing.assert_allclose(fr.pred, z["pred"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(fr.kl_per_feature, z["kl"], rtol=1e-12)
+    np.testing.assert_allclose(float(z["beta"]) * fr.kl_per_feature.sum(), z["ib_loss"], rtol=1e-12)
+    encs, _ = O.unflatten(cfg, z["params"].astype(np.float64))
+    xs = O.split_features(cfg, z["x"].astype(np.float64))
+    for i in range(cfg.number_features):
+        np.testing.assert_allclose(O.encoder_forward(cfg, encs[i], xs[i]), z[f"enc{i}"], rtol=1e-12, atol=1e-12)
+
+
+def test_beta_schedule_golden_and_kat(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_beta_schedule.npz"))
+    for tag in ["train_py_defaults", "nb_radial", "bench"]:
+        b0, b1, npre, nann = z[tag + "_args"]
+        got = [O.beta_schedule(int(e), b0, b1, int(npre), int(nann)) for e in z[tag + "_epochs"]]
+        np.testing.assert_array_equal(np.array(got, dtype=np.float32), z[tag + "_beta"])
+    # SURVEY.md section 4 KAT values (evaluated from models.py:147-149)
+    f = lambda e: O.beta_schedule(e, 1e-4, 3.0, 1000, 10000)
+    assert f(0) == f(1000) == np.float32(9.999999e-05)
+    np.testing.assert_allclose(f(1001), 1.0010313e-04, rtol=2e-7)
+    np.testing.assert_allclose(f(6000), 1.7320503e-02, rtol=2e-6)
+    np.testing.assert_allclose(f(10999), 2.9969075, rtol=2e-6)
+    np.testing.assert_allclose(O.beta_schedule(249, 1e-6, 1.0, 0, 250), 0.94623667, rtol=2e-6)
+
+
+def test_kl_closed_form_kat():
+    mu = np.array([[1., -2.], [0., .5]])
+    lv = np.array([[0., np.log(4.)], [-1., 1.]])
+    per_row = (0.5 * (mu ** 2 + np.exp(lv) - lv - 1)).sum(-1)
+    np.testing.assert_allclose(per_row, [3.30685282, 0.66808063], rtol=1e-8)
+    np.testing.assert_allclose(per_row.mean(), 1.98746673, rtol=1e-8)
+
+
+def test_bhattacharyya_golden_and_kat(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_bhattacharyya.npz"))
+    np.testing.assert_allclose(O.bhattacharyya_dist_mat(z["mu"], z["lv"], z["mu"], z["lv"]), z["D"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(O.bhattacharyya_dist_mat(z["mu3"], z["lv3"], z["mu4"], z["lv4"]), z["D34"], rtol=1e-9, atol=1e-10)
+    D2 = O.bhattacharyya_dist_mat(z["mu2"], z["lv2"], z["mu2"], z["lv2"])
+    np.testing.assert_allclose(D2[0, 1], 0.48466528, rtol=1e-7)
+    np.testing.assert_allclose(np.exp(-D2[0, 1]), 0.61590331, rtol=1e-7)
+    np.testing.assert_allclose(np.diag(D2), 0, atol=1e-12)
+
+
+def test_positional_encoding_layout():
+    cfg = O.DIBConfig([2], [4], [4], 1)
+    assert cfg.frequencies == [2, 4, 8, 16]
+    x = np.array([[0.1, -0.3]])
+    pe = O.positional_encoding(x, cfg.frequencies)
+    assert pe.shape == (1, 10)
+    np.testing.assert_allclose(pe[0], [0.1, -0.3, np.sin(.2), np.sin(-.6), np.sin(.4), np.sin(-1.2),
+                                       np.sin(.8), np.sin(-2.4), np.sin(1.6), np.sin(-4.8)])
+
+
+def test_boolean_circuit_truth_table_kat():
+    x, y = O.boolean_circuit_truth_table()
+    assert x.shape == (1024, 10) and set(np.unique(x)) == {-1.0, 1.0}
+    assert y.sum() == 224
+    p = y.mean()
+    H = -(p * np.log2(p) + (1 - p) * np.log2(1 - p))
+    np.testing.assert_allclose(H, 0.757878, atol=1e-6)
+    # single-input mutual informations (bits), SURVEY.md section 4
+    mi = []
+    for j in range(10):
+        m = 0.0
+        for xv in (-1, 1):
+            for yv in (0, 1):
+                pxy = np.mean((x[:, j] == xv) & (y == yv))
+                if pxy > 0:
+                    m += pxy * np.log2(pxy / (np.mean(x[:, j] == xv) * np.mean(y == yv)))
+        mi.append(m)
+    np.testing.assert_allclose(mi, [0.0041, 0.0041, 0.2635, 0, 0, 0, 0.0010, 0, 0, 0.0524], atol=6e-5)
+
+
+def test_param_count_c0():
+    cfg = O.DIBConfig([1] * 16, [128, 128], [256, 256], 1)
+    assert cfg.param_count() == 605953
+    cfg = O.DIBConfig([1] * 100, [128, 128], [256] * 3, 1, use_positional_encoding=False)
+    assert cfg.param_count() == 3453697         # nb-radial shape, SURVEY.md section 8(d)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10
+    r = philox.philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    r = philox.philox4x32_10(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)
+    assert [int(v) for v in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = philox.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
+    assert [int(v) for v in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_normal_moments_and_sharding():
+    ids = np.arange(4096)
+    e = philox.normal_noise(7, 3, ids, 4, 32)
+    assert e.shape == (4096, 4, 32)
+    assert abs(e.mean()) < 0.01 and abs(e.std() - 1) < 0.01
+    # indexed by GLOBAL sample id: a shard sees exactly its rows
+    e2 = philox.normal_noise(7, 3, ids[1000:1100], 4, 32)
+    np.testing.assert_array_equal(e[1000:1100], e2)
+    assert not np.allclose(e, philox.normal_noise(7, 4, ids, 4, 32))
+
+
+@pytest.mark.parametrize("loss,out,act", [(O.LOSS_BCE_LOGITS, 1, "relu"), (O.LOSS_MSE, 3, "tanh"),
+                                          (O.LOSS_SPARSE_CE_LOGITS, 4, "leaky_relu")])
+def test_gradients_finite_difference(loss, out, act):
+    rng = np.random.default_rng(0)
+    cfg = O.DIBConfig([1, 2, 1], [8, 6], [10], out, activation_fn=act, feature_embedding_dimension=3,
+                      number_positional_encoding_frequencies=3)
+    p = O.glorot_uniform_params(cfg, rng, dtype=np.float64)
+    p += 0.1 * rng.standard_normal(p.size)
+    B = 5
+    x = rng.standard_normal((B, 4))
+    eps = rng.standard_normal((B, 3, 3))
+    y = rng.integers(0, out, size=B).astype(np.float64) if loss == O.LOSS_SPARSE_CE_LOGITS else \
+        (rng.integers(0, 2, size=(B, out)).astype(np.float64) if loss == O.LOSS_BCE_LOGITS else rng.standard_normal((B, out)))
+    beta = 0.37
+    g, fr = O.train_grads(cfg, p, x, y, eps, beta, loss)
+    idx = rng.choice(p.size, size=40, replace=False)
+    for j in idx:
+        d = np.zeros_like(p)
+        d[j] = 1e-6
+        lp = O.forward(cfg, p + d, x, eps, beta, y=y, loss=loss).loss
+        lm = O.forward(cfg, p - d, x, eps, beta, y=y, loss=loss).loss
+        np.testing.assert_allclose(g[j], (lp - lm) / 2e-6, rtol=2e-4, atol=1e-8)
+
+
+def test_data_parallel_shards_are_additive():
+    rng = np.random.default_rng(1)
+    cfg = O.DIBConfig([1] * 3, [8], [8], 1, feature_embedding_dimension=4)
+    p = O.glorot_uniform_params(cfg, rng, dtype=np.float64)
+    B = 12
+    x, y = rng.standard_normal((B, 3)), rng.integers(0, 2, size=B).astype(np.float64)
+    eps = rng.standard_normal((B, 3, 4))
+    g, _ = O.train_grads(cfg, p, x, y, eps, 0.2, O.LOSS_BCE_LOGITS)
+    parts = [O.train_grads(cfg, p, x[s], y[s], eps[s], 0.2, O.LOSS_BCE_LOGITS, batch_for_mean=B)[0]
+             for s in (slice(0, 6), slice(6, 12))]
+    np.testing.assert_allclose(parts[0] + parts[1], g, rtol=1e-10, atol=1e-14)
+
+
+def test_fit_history_keys_and_learning():
+    x, y = O.boolean_circuit_truth_table()
+    cfg = O.DIBConfig([1] * 10, [16], [32], 1, feature_embedding_dimension=4)
+    rng = np.random.default_rng(2)
+    p0 = O.glorot_uniform_params(cfg, rng)
+    eps_fn = lambda step, ids: philox.normal_noise(5, step, ids, 10, 4, dtype=np.float64)
+    perm_fn = lambda e, n: np.random.default_rng(100 + e).permutation(n)
+    _, h = O.fit(cfg, p0, x.astype(np.float64), y.astype(np.float64), loss=O.LOSS_BCE_LOGITS, epochs=3,
+                 batch_size=100, lr=3e-3, eps_fn=eps_fn, perm_fn=perm_fn,
+                 beta_fn=lambda e: O.beta_schedule(e, 1e-4, 1e-2, 1, 2), validation_data=(x.astype(np.float64), y.astype(np.float64)))
+    for k in ["loss", "accuracy", "beta", "val_loss", "val_accuracy"] + [f"KL{i}" for i in range(10)] + [f"val_KL{i}" for i in range(10)]:
+        assert len(h[k]) == 3
+    assert h["loss"][-1] < h["loss"][0]
+    assert h["beta"][0] == h["beta"][1] == float(np.float32(9.999999e-05))
