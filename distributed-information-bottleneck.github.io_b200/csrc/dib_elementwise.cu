@@ -1,0 +1,358 @@
+// dib_elementwise.cu -- the non-GEMM kernels of the fp32 parity path: positional encoding, reparameterisation
+// + per-feature KL, compiled loss/metric + its gradient, deterministic reductions, Keras-Adam, Bhattacharyya.
+#include "dib_common.cuh"
+#include "dib_kernels.h"
+
+namespace {
+
+constexpr int kRowsPerBlock = 256;
+
+// block-wide deterministic sum (fixed shuffle tree + fixed-order warp combine); result valid in thread 0.
+__device__ __forceinline__ float block_sum_256(float v, float* smem8) {
+  v = dib_warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) smem8[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) r += smem8[i];
+  }
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// models.py:22-23 PositionalEncoding.call: concat([x] + [sin(f x) for f in (2,4,8,16)], -1), block-major
+// per feature, written into the zero-padded operand of the first encoder layer.
+// ------------------------------------------------------------------------------------------------
+__global__ void dib_pe_kernel(const float* __restrict__ x, int ldx, int x_col_shift, const int* __restrict__ col_src,
+                              const int* __restrict__ col_freq, int col_begin, int ncols, float* __restrict__ pe,
+                              int ldpe, int pe_col_shift, long long n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ncols) return;
+  const long long row = idx / ncols;
+  const int col = col_begin + (int)(idx % ncols);
+  const int src = col_src[col];
+  float v = 0.f;
+  if (src >= 0) {
+    const float xv = x[row * ldx + (src - x_col_shift)];
+    const int f = col_freq[col];
+    v = f == 0 ? xv : sinf((float)f * xv);
+  }
+  pe[row * ldpe + (col - pe_col_shift)] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// models.py:106-112: split (mu, logvar), u = mu + exp(logvar/2)*eps, KL_i partial sums.
+// One thread per (row, feature); blockIdx.y = feature.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowsPerBlock)
+dib_reparam_fwd_kernel(DibReparamArgs a, float* __restrict__ emb, int ldemb, float* __restrict__ user_emb,
+                       float* __restrict__ kl_part, int nblk_stride) {
+  __shared__ float red[8];
+  const long long row = (long long)blockIdx.x * kRowsPerBlock + threadIdx.x;
+  const int f = blockIdx.y, E = a.E;
+  float kl = 0.f;
+  if (row < a.n) {
+    const float* o = a.enc_out + (long long)f * a.feat_stride + row * a.ldo;
+    float* dst = emb + row * ldemb + f * E;
+    float* udst = user_emb ? user_emb + row * ((long long)a.F * E) + f * E : nullptr;
+    const float* ep = a.eps ? a.eps + (row * a.F + f) * E : nullptr;
+    for (int e0 = 0; e0 < E; e0 += 4) {
+      float nrm[4];
+      if (!ep) dib_philox_normal4(a.seed, a.step, a.sample_offset + (uint64_t)row, (uint32_t)f, (uint32_t)(e0 >> 2), nrm);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = e0 + j;
+        if (e < E) {
+          const float mu = o[e], lv = o[E + e];
+          const float s = expf(0.5f * lv);
+          const float z = ep ? ep[e] : nrm[j];
+          const float u = fmaf(s, z, mu);
+          kl += 0.5f * (mu * mu + expf(lv) - lv - 1.f);
+          dst[e] = u;
+          if (udst) udst[e] = u;
+        }
+      }
+    }
+    if (f == a.F - 1)
+      for (int c = a.F * E; c < ldemb; ++c) emb[row * ldemb + c] = 0.f;
+  }
+  const float s = block_sum_256(kl, red);
+  if (threadIdx.x == 0) kl_part[(long long)f * nblk_stride + blockIdx.x] = s;
+}
+
+// d mu = du + beta*mu/B ; d logvar = du*eps*0.5*sigma + beta*0.5*(exp(logvar)-1)/B
+__global__ void __launch_bounds__(kRowsPerBlock)
+dib_reparam_bwd_kernel(DibReparamArgs a, const float* __restrict__ d_emb, int ldemb, const float* __restrict__ beta_dev,
+                       float inv_batch, float* __restrict__ d_out) {
+  const long long row = (long long)blockIdx.x * kRowsPerBlock + threadIdx.x;
+  if (row >= a.n) return;
+  const int f = blockIdx.y, E = a.E;
+  const float bs = beta_dev[0] * inv_batch;
+  const float* o = a.enc_out + (long long)f * a.feat_stride + row * a.ldo;
+  float* dq = d_out + (long long)f * a.feat_stride + row * a.ldo;
+  const float* du = d_emb + row * ldemb + f * E;
+  const float* ep = a.eps ? a.eps + (row * a.F + f) * E : nullptr;
+  for (int e0 = 0; e0 < E; e0 += 4) {
+    float nrm[4];
+    if (!ep) dib_philox_normal4(a.seed, a.step, a.sample_offset + (uint64_t)row, (uint32_t)f, (uint32_t)(e0 >> 2), nrm);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = e0 + j;
+      if (e < E) {
+        const float mu = o[e], lv = o[E + e], g = du[e];
+        const float s = expf(0.5f * lv);
+        const float z = ep ? ep[e] : nrm[j];
+        dq[e] = fmaf(bs, mu, g);
+        dq[E + e] = fmaf(g * z, 0.5f * s, bs * 0.5f * (expf(lv) - 1.f));
+      }
+    }
+  }
+  for (int c = 2 * E; c < a.ldo; ++c) dq[c] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compiled loss (Keras, data.py:65 / :343 / MSE), metrics=['accuracy'] (data.py:67) and d loss / d z_out.
+// One thread per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowsPerBlock)
+dib_loss_kernel(int loss, int out_act, float alpha, const float* __restrict__ pred, int ldp, const float* __restrict__ y,
+                int out_dim, long long n, float inv_batch, float* __restrict__ d_pred, float* __restrict__ user_pred,
+                float* __restrict__ loss_part, float* __restrict__ acc_part) {
+  __shared__ float red[8];
+  const long long row = (long long)blockIdx.x * kRowsPerBlock + threadIdx.x;
+  float l = 0.f, acc = 0.f;
+  if (row < n) {
+    const float* z = pred + row * ldp;
+    float* dz = d_pred ? d_pred + row * ldp : nullptr;
+    if (user_pred)
+      for (int j = 0; j < out_dim; ++j) user_pred[row * out_dim + j] = z[j];
+    if (y) {
+      const float inv_out = 1.f / (float)out_dim;
+      if (loss == DIB_LOSS_SPARSE_CE_LOGITS) {
+        const int label = (int)y[row];
+        float m = z[0]; int am = 0;
+        for (int j = 1; j < out_dim; ++j) if (z[j] > m) { m = z[j]; am = j; }
+        float se = 0.f;
+        for (int j = 0; j < out_dim; ++j) se += expf(z[j] - m);
+        l = m + logf(se) - z[label];
+        acc = (am == label) ? 1.f : 0.f;
+        if (dz) {
+          const float inv_se = 1.f / se;
+          for (int j = 0; j < out_dim; ++j) {
+            const float g = expf(z[j] - m) * inv_se - (j == label ? 1.f : 0.f);
+            dz[j] = g * inv_batch * dib_act_grad(out_act, z[j], alpha);
+          }
+        }
+      } else {
+        const float* yy = y + row * out_dim;
+        for (int j = 0; j < out_dim; ++j) {
+          const float zz = z[j], t = yy[j];
+          float g;
+          if (loss == DIB_LOSS_BCE_LOGITS) {
+            l += fmaxf(zz, 0.f) - zz * t + log1pf(expf(-fabsf(zz)));
+            g = 1.f / (1.f + expf(-zz)) - t;
+          } else {
+            const float d = zz - t;
+            l += d * d;
+            g = 2.f * d;
+          }
+          acc += ((zz > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f;
+          if (dz) dz[j] = g * inv_out * inv_batch * dib_act_grad(out_act, zz, alpha);
+        }
+        l *= inv_out;
+        acc *= inv_out;
+      }
+    }
+    if (dz)
+      for (int c = out_dim; c < ldp; ++c) dz[c] = 0.f;
+  }
+  const float ls = block_sum_256(l, red);
+  const float as = block_sum_256(acc, red);
+  if (threadIdx.x == 0) { loss_part[blockIdx.x] = ls; acc_part[blockIdx.x] = as; }
+}
+
+// stats = [ sum_b KL_i (F) | sum_b task loss | sum_b accuracy | n ]; one block, fixed summation order.
+__global__ void __launch_bounds__(256)
+dib_finalize_stats_kernel(const float* __restrict__ kl_part, int nblk_stride, int nblk_kl, const float* __restrict__ loss_part,
+                          const float* __restrict__ acc_part, int nblk_loss, int F, long long n, int has_y,
+                          float* __restrict__ out) {
+  __shared__ float red[8];
+  for (int item = 0; item < F + 2; ++item) {
+    const float* src; int cnt;
+    if (item < F) { src = kl_part + (long long)item * nblk_stride; cnt = nblk_kl; }
+    else { src = item == F ? loss_part : acc_part; cnt = has_y ? nblk_loss : 0; }
+    float v = 0.f;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) v += src[i];
+    const float s = block_sum_256(v, red);
+    if (threadIdx.x == 0) out[item] = s;
+  }
+  if (threadIdx.x == 0) out[F + 2] = (float)n;
+}
+
+__global__ void dib_reduce_partials_kernel(const float* __restrict__ part, long long split_stride, int nsplit,
+                                           long long count, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += part[(long long)k * split_stride + i];
+  out[i] = s;
+}
+
+__global__ void dib_copy2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int cols,
+                                  long long n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * cols) return;
+  const long long r = idx / cols; const int c = (int)(idx % cols);
+  dst[r * ldd + c] = src[r * lds + c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// tf.keras.optimizers.Adam (epsilon outside the bias correction); step counter and lr on the device.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dib_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                long long count, const float* __restrict__ lr_dev, const int32_t* __restrict__ step_dev, float b1,
+                float b2, float eps) {
+  __shared__ float s_lr_t;
+  if (threadIdx.x == 0) {
+    const double t = (double)(step_dev[0] + 1);
+    s_lr_t = lr_dev[0] * (float)sqrt(1.0 - pow((double)b2, t)) / (float)(1.0 - pow((double)b1, t));
+  }
+  __syncthreads();
+  const float lr_t = s_lr_t, c1 = 1.f - b1, c2 = 1.f - b2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float gi = g[i];
+  float mi = m[i], vi = v[i];
+  mi += (gi - mi) * c1;
+  vi += (gi * gi - vi) * c2;
+  m[i] = mi; v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+__global__ void dib_inc_step_kernel(int32_t* step_dev) { step_dev[0] += 1; }
+
+// ------------------------------------------------------------------------------------------------
+// utils.py:177-212 in closed form, + exp(-D) (visualization.py:34).  One thread per (i, j).
+// ------------------------------------------------------------------------------------------------
+__global__ void dib_bhattacharyya_kernel(const float* __restrict__ ml, long long n, int E, float* __restrict__ out_dist,
+                                         float* __restrict__ out_comp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const long long i = idx / n, j = idx % n;
+  const float* a = ml + i * 2 * E;
+  const float* b = ml + j * 2 * E;
+  float t1 = 0.f, t2 = 0.f;
+  for (int e = 0; e < E; ++e) {
+    const float d = a[e] - b[e];
+    const float la = a[E + e], lb = b[E + e];
+    const float sbar = 0.5f * (expf(la) + expf(lb));
+    t1 += d * d / sbar;
+    t2 += logf(sbar) - 0.5f * (la + lb);
+  }
+  const float D = 0.125f * t1 + 0.5f * t2;
+  if (out_dist) out_dist[idx] = D;
+  if (out_comp) out_comp[idx] = expf(-D);
+}
+
+// Keras Mean-metric aggregation over the batches of an epoch (see dib_metrics_update in dib_b200.h).
+__global__ void dib_metrics_update_kernel(const float* __restrict__ stats, const float* __restrict__ beta_dev,
+                                          float* __restrict__ acc, int F) {
+  __shared__ float red[8];
+  const float n = stats[F + 2];
+  float v = 0.f;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const float s = stats[i];
+    if (n > 0.f) acc[i] += s / n;
+    v += s;
+  }
+  const float klsum = block_sum_256(v, red);
+  if (threadIdx.x == 0 && n > 0.f) {
+    acc[F] += stats[F] + beta_dev[0] * klsum;
+    acc[F + 1] += stats[F + 1];
+    acc[F + 2] += n;
+    acc[F + 3] += 1.f;
+  }
+}
+
+inline unsigned nblocks(long long work, int per) { return (unsigned)((work + per - 1) / per); }
+
+}  // namespace
+
+cudaError_t dib_launch_pe(const float* x, int ldx, int x_col_shift, const int* col_src, const int* col_freq,
+                          int col_begin, int col_end, float* pe, int ldpe, int pe_col_shift, int64_t n, cudaStream_t st) {
+  const int ncols = col_end - col_begin;
+  if (n <= 0 || ncols <= 0) return cudaSuccess;
+  dib_pe_kernel<<<nblocks((long long)n * ncols, 256), 256, 0, st>>>(x, ldx, x_col_shift, col_src, col_freq, col_begin,
+                                                                   ncols, pe, ldpe, pe_col_shift, n);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_reparam_fwd(const DibReparamArgs& a, float* emb, int ldemb, float* user_emb, float* kl_part,
+                                   int nblk_stride, cudaStream_t st) {
+  if (a.n <= 0) return cudaSuccess;
+  dim3 grid(nblocks(a.n, kRowsPerBlock), a.F);
+  dib_reparam_fwd_kernel<<<grid, kRowsPerBlock, 0, st>>>(a, emb, ldemb, user_emb, kl_part, nblk_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_reparam_bwd(const DibReparamArgs& a, const float* d_emb, int ldemb, const float* beta_dev,
+                                   float inv_batch, float* d_out, cudaStream_t st) {
+  if (a.n <= 0) return cudaSuccess;
+  dim3 grid(nblocks(a.n, kRowsPerBlock), a.F);
+  dib_reparam_bwd_kernel<<<grid, kRowsPerBlock, 0, st>>>(a, d_emb, ldemb, beta_dev, inv_batch, d_out);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_loss(int loss, int out_act, float alpha, const float* pred, int ldp, const float* y, int out_dim,
+                            int64_t n, float inv_batch, float* d_pred, float* user_pred, float* loss_part,
+                            float* acc_part, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  dib_loss_kernel<<<nblocks(n, kRowsPerBlock), kRowsPerBlock, 0, st>>>(loss, out_act, alpha, pred, ldp, y, out_dim, n,
+                                                                      inv_batch, d_pred, user_pred, loss_part, acc_part);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_finalize_stats(const float* kl_part, int nblk_stride, int nblk_kl, const float* loss_part,
+                                      const float* acc_part, int nblk_loss, int F, int64_t n, int has_y, float* out_stats,
+                                      cudaStream_t st) {
+  dib_finalize_stats_kernel<<<1, 256, 0, st>>>(kl_part, nblk_stride, nblk_kl, loss_part, acc_part, nblk_loss, F, n,
+                                               has_y, out_stats);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_reduce_partials(const float* part, long long split_stride, int nsplit, int64_t count, float* out,
+                                       cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  dib_reduce_partials_kernel<<<nblocks(count, 256), 256, 0, st>>>(part, split_stride, nsplit, count, out);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_copy2d(const float* src, int lds, float* dst, int ldd, int cols, int64_t n, cudaStream_t st) {
+  if (n <= 0 || cols <= 0) return cudaSuccess;
+  dib_copy2d_kernel<<<nblocks((long long)n * cols, 256), 256, 0, st>>>(src, lds, dst, ldd, cols, n);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_adam(float* params, const float* grads, float* m, float* v, int64_t count, const float* lr_dev,
+                            int32_t* step_dev, float b1, float b2, float eps, cudaStream_t st) {
+  if (count > 0)
+    dib_adam_kernel<<<nblocks(count, 256), 256, 0, st>>>(params, grads, m, v, count, lr_dev, step_dev, b1, b2, eps);
+  dib_inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_bhattacharyya(const float* mu_logvar, int64_t n, int E, float* out_dist, float* out_comp,
+                                     cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  dib_bhattacharyya_kernel<<<nblocks((long long)n * n, 128), 128, 0, st>>>(mu_logvar, n, E, out_dist, out_comp);
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st) {
+  dib_metrics_update_kernel<<<1, 256, 0, st>>>(stats, beta_dev, acc, F);
+  return cudaGetLastError();
+}

@@ -1,0 +1,67 @@
+// dib_kernels.h -- internal launcher prototypes shared by the translation units of libdib_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct DibGemmProblem;
+
+struct DibGemmLaunch {
+  const DibGemmProblem* probs;  // device array, nprob entries
+  int nprob;
+  const float* baseA;
+  const float* baseB;
+  float* baseC;
+  float* baseX;
+  int M;               // batch rows
+  int maxC, maxR;      // largest C (and, for WGRAD, R) over the group -> grid size
+  int nsplit;          // WGRAD batch splits
+  int rows_per_split;
+  long long split_stride;
+  float alpha;
+};
+
+cudaError_t dib_launch_gemm_simt(int mode, const DibGemmLaunch& L, cudaStream_t st);
+
+// ---- elementwise / reduction kernels (dib_elementwise.cu) -----------------------------------------------
+// positional encoding (models.py:22-23) into the padded first-layer operand; tables are per pe column.
+cudaError_t dib_launch_pe(const float* x, int ldx, int x_col_shift, const int* col_src, const int* col_freq,
+                          int col_begin, int col_end, float* pe, int ldpe, int pe_col_shift, int64_t n,
+                          cudaStream_t st);
+
+struct DibReparamArgs {
+  const float* enc_out;    // [F][feat_stride] rows of ldo floats: (mu[E] | logvar[E] | pad)
+  long long feat_stride;
+  int ldo;
+  const float* eps;        // [n, F, E] or nullptr -> Philox
+  uint64_t seed; uint32_t step; uint64_t sample_offset;
+  int F, E;
+  int64_t n;
+};
+// u = mu + exp(logvar/2) eps (models.py:108); per-(block,feature) partial sums of the KL (models.py:111-112).
+cudaError_t dib_launch_reparam_fwd(const DibReparamArgs& a, float* emb, int ldemb, float* user_emb,
+                                   float* kl_part, int nblk_stride, cudaStream_t st);
+// d(mu,logvar) from d(u) and beta * dKL (models.py:118).
+cudaError_t dib_launch_reparam_bwd(const DibReparamArgs& a, const float* d_emb, int ldemb, const float* beta_dev,
+                                   float inv_batch, float* d_out, cudaStream_t st);
+
+// compiled loss + metrics=['accuracy'] + d(loss)/d(pre-activation output).
+cudaError_t dib_launch_loss(int loss, int out_act, float alpha, const float* pred, int ldp, const float* y, int out_dim,
+                            int64_t n, float inv_batch, float* d_pred /*nullable*/, float* user_pred /*nullable*/,
+                            float* loss_part, float* acc_part, cudaStream_t st);
+
+cudaError_t dib_launch_finalize_stats(const float* kl_part, int nblk_stride, int nblk_kl, const float* loss_part,
+                                      const float* acc_part, int nblk_loss, int F, int64_t n, int has_y,
+                                      float* out_stats, cudaStream_t st);
+
+cudaError_t dib_launch_reduce_partials(const float* part, long long split_stride, int nsplit, int64_t count,
+                                       float* out, cudaStream_t st);
+
+cudaError_t dib_launch_copy2d(const float* src, int lds, float* dst, int ldd, int cols, int64_t n, cudaStream_t st);
+
+cudaError_t dib_launch_adam(float* params, const float* grads, float* m, float* v, int64_t count,
+                            const float* lr_dev, int32_t* step_dev, float b1, float b2, float eps, cudaStream_t st);
+
+cudaError_t dib_launch_bhattacharyya(const float* mu_logvar, int64_t n, int E, float* out_dist, float* out_comp,
+                                     cudaStream_t st);
+
+cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st);

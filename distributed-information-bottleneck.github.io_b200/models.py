@@ -1,0 +1,628 @@
+"""Host-side mirror of the reference's ``models.py`` (PositionalEncoding, DistributedIBNet, the annealing /
+compression-matrix / embedding-stash callbacks) on top of the C ABI in include/dib_b200.h.
+
+Same names, constructor arguments and call protocol as /root/reference/models.py:12-223 and the corrected copy
+in nb-radial cell 5, so ``train.py``-style drivers and the notebooks' ``model.compile / model.fit`` code run
+unchanged with ``import dib_b200.models as models``.  PyTorch is used for device memory, streams and
+``torch.distributed`` only; every FLOP of the hot path runs in libdib_b200.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import parallel
+from .keras_compat import Adam, Callback, History, optimizers, resolve_loss
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.DibError("dib_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _as_numpy_like(ref, t):
+    """Return ``t`` in the kind of container ``ref`` was (numpy in -> numpy out, tensor in -> tensor out)."""
+    if isinstance(ref, torch.Tensor):
+        return t
+    return t.detach().cpu().numpy()
+
+
+class PositionalEncoding:
+    """models.py:12-23.  Kept for API parity; inside DistributedIBNet the encoding is fused into the first-layer
+    operand by the library.  Calling it directly is a convenience (plain torch ops, not the hot path)."""
+
+    def __init__(self, frequencies):
+        self.frequencies = list(frequencies)
+
+    def __call__(self, inputs):
+        t = torch.as_tensor(inputs)
+        return _as_numpy_like(inputs, torch.cat([t] + [torch.sin(f * t) for f in self.frequencies], -1))
+
+    call = __call__
+
+
+class _Beta:
+    """``tf.Variable(1., dtype=tf.float32, trainable=False)`` surface used by the callbacks (models.py:86,148,177)."""
+
+    def __init__(self, device):
+        self._host = np.float32(1.0)
+        self._dev = torch.ones(1, dtype=torch.float32, device=device)
+
+    def assign(self, value):
+        self._host = np.float32(value)
+        self._dev.fill_(float(self._host))
+        return self
+
+    def value(self):
+        return self._host
+
+    numpy = value
+
+    def __float__(self):
+        return float(self._host)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self._host, dtype=dtype)
+
+
+class _Network:
+    """A view of one Dense stack inside the flat parameter buffer (model.feature_encoders[i] /
+    model.integration_network): ``.weights`` are torch views [W, b, W, b, ...] in Keras order."""
+
+    def __init__(self, model, var_slice):
+        self._model = model
+        self._vars = var_slice
+
+    @property
+    def weights(self):
+        return [self._model._var_view(i) for i in self._vars]
+
+    trainable_variables = weights
+
+    def get_weights(self):
+        return [w.detach().cpu().numpy() for w in self.weights]
+
+
+class _FeatureEncoder(_Network):
+    """model.feature_encoders[i]: deterministic [n, d_i] -> [n, 2E] (mu || logvar), the contract used by
+    visualization.py:31, utils.py:38 and StashEmbeddingsCallback.  Runs dib_encode_feature."""
+
+    def __init__(self, model, index, var_slice):
+        super().__init__(model, var_slice)
+        self.index = index
+
+    def __call__(self, x_i, training=None):
+        return _as_numpy_like(x_i, self._model._encode_feature(self.index, x_i))
+
+
+class _IntegrationNetwork(_Network):
+    """model.integration_network (models.py:84).  Direct calls are rare (the fused step never materialises this
+    boundary); provided with plain torch ops over the weight views for completeness."""
+
+    def __call__(self, emb, training=None):
+        m = self._model
+        h = torch.as_tensor(emb, dtype=torch.float32, device=m.device)
+        ws = self.weights
+        n_layers = len(ws) // 2
+        for k in range(n_layers):
+            h = h @ ws[2 * k] + ws[2 * k + 1]
+            h = _torch_act(m.activation_fn if k < n_layers - 1 else m.output_activation_fn, h, m.leaky_alpha)
+        return _as_numpy_like(emb, h)
+
+
+def _torch_act(name, h, alpha):
+    if name in (None, "linear"):
+        return h
+    if name == "leaky_relu":
+        return torch.nn.functional.leaky_relu(h, alpha)
+    return getattr(torch, name)(h) if hasattr(torch, name) else getattr(torch.nn.functional, name)(h)
+
+
+class DistributedIBNet:
+    """Distributed IB model where each feature is passed through its own probabilistic encoder MLP
+    (models.py:26-123; ``dropout_rate``/``training`` from nb-radial cell 5).
+
+    Extra keyword-only arguments (not in the reference): ``device``, ``seed`` (weight init + noise stream),
+    ``precision`` ('fp32' exact-FMA parity path | 'tf32' | 'bf16' tensor-core paths), ``process_group``
+    (data-parallel group; defaults to the WORLD group when torch.distributed is initialised), ``leaky_alpha``.
+    """
+
+    def __init__(self,
+                 feature_dimensionalities: Sequence[int],
+                 feature_encoder_architecture: Sequence[int],
+                 integration_network_architecture: Sequence[int],
+                 output_dimensionality: int,
+                 use_positional_encoding: bool = True,
+                 number_positional_encoding_frequencies: int = 5,
+                 activation_fn: Optional[str] = 'relu',
+                 feature_embedding_dimension: int = 32,
+                 output_activation_fn: Optional[str] = None,
+                 dropout_rate: float = 0.,
+                 *, device=None, seed: int = 0, precision: str = 'fp32', process_group=None,
+                 leaky_alpha: float = 0.2):
+        _require_cuda()
+        if dropout_rate and dropout_rate > 0:
+            raise NotImplementedError("dropout_rate > 0 (nb-radial only, default 0) is not implemented")
+        if activation_fn not in _lib.ACTIVATIONS or output_activation_fn not in _lib.ACTIVATIONS:
+            raise ValueError(f"unsupported activation {activation_fn!r}/{output_activation_fn!r}")
+        self.feature_dimensionalities = [int(d) for d in feature_dimensionalities]
+        self.number_features = len(self.feature_dimensionalities)
+        self.feature_encoder_architecture = [int(h) for h in feature_encoder_architecture]
+        self.integration_network_architecture = [int(h) for h in integration_network_architecture]
+        self.output_dimensionality = int(output_dimensionality)
+        self.use_positional_encoding = bool(use_positional_encoding)
+        self.number_positional_encoding_frequencies = int(number_positional_encoding_frequencies)
+        self.activation_fn = activation_fn
+        self.output_activation_fn = output_activation_fn
+        self.feature_embedding_dimension = int(feature_embedding_dimension)
+        self.leaky_alpha = float(leaky_alpha)
+        self.precision = precision
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.seed = int(seed)
+        self.noise_seed = int(seed)
+        self.process_group = process_group
+        self.stop_training = False
+
+        self._lib = _lib.load()
+        self._loss_kind = "bce_logits"
+        self._handle = None
+        self._handle_key = None
+        self._workspace = None
+        self._query_layout()
+
+        with torch.cuda.device(self.device):
+            self.beta = _Beta(self.device)                                   # models.py:86
+            self._params = torch.zeros(self._P, dtype=torch.float32, device=self.device)
+            self._init_glorot_uniform()
+            self._gradstats = torch.zeros(self._P + self.number_features + 3, dtype=torch.float32, device=self.device)
+            self._m = torch.zeros_like(self._params)
+            self._v = torch.zeros_like(self._params)
+            self._lr_dev = torch.full((1,), 1e-3, dtype=torch.float32, device=self.device)
+            self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._epoch_acc = torch.zeros(self.number_features + 4, dtype=torch.float32, device=self.device)
+        self._train_step_count = 0
+        self.optimizer = None
+        self.compiled_metrics_names = []
+        self.losses = []
+        self.metrics_values = {}
+        n_enc_vars = 2 * (len(self.feature_encoder_architecture) + 1)
+        self.feature_encoders = [                                            # models.py:79
+            _FeatureEncoder(self, i, range(i * n_enc_vars, (i + 1) * n_enc_vars)) for i in range(self.number_features)]
+        self.integration_network = _IntegrationNetwork(                      # models.py:84
+            self, range(self.number_features * n_enc_vars, len(self._var_off)))
+
+    # ------------------------------------------------------------------ library handle / buffers
+    def _config(self, max_batch):
+        F = self.number_features
+        self._c_fd = (ctypes.c_int32 * F)(*self.feature_dimensionalities)
+        L, Li = len(self.feature_encoder_architecture), len(self.integration_network_architecture)
+        self._c_ea = (ctypes.c_int32 * max(L, 1))(*self.feature_encoder_architecture)
+        self._c_ia = (ctypes.c_int32 * max(Li, 1))(*self.integration_network_architecture)
+        return _lib.DibConfig(
+            abi_version=_lib.ABI_VERSION, number_features=F, feature_dimensionalities=self._c_fd,
+            number_encoder_layers=L, feature_encoder_architecture=self._c_ea,
+            number_integration_layers=Li, integration_network_architecture=self._c_ia,
+            output_dimensionality=self.output_dimensionality,
+            use_positional_encoding=int(self.use_positional_encoding),
+            number_positional_encoding_frequencies=self.number_positional_encoding_frequencies,
+            activation_fn=_lib.ACTIVATIONS[self.activation_fn], leaky_relu_alpha=self.leaky_alpha,
+            feature_embedding_dimension=self.feature_embedding_dimension,
+            output_activation_fn=_lib.ACTIVATIONS[self.output_activation_fn],
+            loss=_lib.LOSSES[self._loss_kind], precision=_lib.PRECISIONS[self.precision], max_batch=int(max_batch))
+
+    def _query_layout(self):
+        with torch.cuda.device(self.device):
+            h = ctypes.c_void_p()
+            cfg = self._config(1)
+            _lib.check(self._lib.dib_create(ctypes.byref(cfg), ctypes.byref(h)))
+            try:
+                self._P = int(self._lib.dib_param_count(h))
+                nv = self._lib.dib_param_layout(h, None, None, None, 0)
+                offs, rows, cols = (ctypes.c_int64 * nv)(), (ctypes.c_int32 * nv)(), (ctypes.c_int32 * nv)()
+                assert self._lib.dib_param_layout(h, offs, rows, cols, nv) == nv
+                self._var_off, self._var_rows, self._var_cols = list(offs), list(rows), list(cols)
+            finally:
+                self._lib.dib_destroy(h)
+
+    def _ensure_handle(self, n):
+        key = (self._loss_kind, self.precision)
+        if self._handle is not None and self._handle_key == key and n <= self._max_batch:
+            return
+        self._release_handle()
+        max_batch = max(int(n), 1)
+        with torch.cuda.device(self.device):
+            h = ctypes.c_void_p()
+            cfg = self._config(max_batch)
+            _lib.check(self._lib.dib_create(ctypes.byref(cfg), ctypes.byref(h)))
+            self._handle, self._handle_key, self._max_batch = h, key, max_batch
+            nbytes = int(self._lib.dib_workspace_bytes(h))
+            self._workspace = None
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            assert self._workspace.data_ptr() % 256 == 0
+
+    def _release_handle(self):
+        if getattr(self, "_handle", None) is not None:
+            torch.cuda.synchronize(self.device)
+            self._lib.dib_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release_handle()
+        except Exception:
+            pass
+
+    def _var_view(self, i):
+        off, r, c = self._var_off[i], self._var_rows[i], self._var_cols[i]
+        v = self._params[off:off + max(r, 1) * c]
+        return v.view(r, c) if r > 0 else v
+
+    def _init_glorot_uniform(self):
+        """Keras Dense defaults: kernel glorot_uniform, bias zeros (third-party behaviour; RNG stream is ours)."""
+        g = torch.Generator(device="cpu")
+        g.manual_seed(self.seed)
+        flat = torch.zeros(self._P, dtype=torch.float32)
+        for off, r, c in zip(self._var_off, self._var_rows, self._var_cols):
+            if r > 0:
+                lim = math.sqrt(6.0 / (r + c))
+                flat[off:off + r * c] = (torch.rand(r * c, generator=g) * 2 - 1) * lim
+        self._params.copy_(flat)
+
+    # ------------------------------------------------------------------ Keras-like variable access
+    @property
+    def trainable_variables(self):
+        return [self._var_view(i) for i in range(len(self._var_off))]
+
+    trainable_weights = trainable_variables
+    weights = trainable_variables
+
+    def get_weights(self):
+        return [v.detach().cpu().numpy() for v in self.trainable_variables]
+
+    def set_weights(self, weights):
+        vs = self.trainable_variables
+        if len(weights) != len(vs):
+            raise ValueError(f"expected {len(vs)} arrays, got {len(weights)}")
+        for v, w in zip(vs, weights):
+            v.copy_(torch.as_tensor(np.asarray(w), dtype=torch.float32).view(v.shape))
+
+    def get_flat_weights(self):
+        return self._params.detach().cpu().numpy()
+
+    def set_flat_weights(self, flat):
+        self._params.copy_(torch.as_tensor(np.asarray(flat), dtype=torch.float32))
+
+    def count_params(self):
+        return self._P
+
+    def build(self, input_shape):
+        assert input_shape[-1] == sum(self.feature_dimensionalities)       # models.py:89
+
+    # ------------------------------------------------------------------ data helpers
+    def _to_device(self, a, cols=None):
+        if a is None:
+            return None
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        t = t.to(device=self.device, dtype=torch.float32, non_blocking=True)
+        if cols is not None:
+            t = t.reshape(t.shape[0], cols) if cols > 0 else t.reshape(t.shape[0])
+        return t.contiguous()
+
+    def _y_cols(self):
+        return 0 if self._loss_kind == "sparse_ce_logits" else self.output_dimensionality
+
+    # ------------------------------------------------------------------ compute entry points
+    def _forward(self, x, y, eps, step, sample_offset, want_pred=True, want_emb=False, stats_out=None):
+        n = x.shape[0]
+        self._ensure_handle(n)
+        pred = torch.empty(n, self.output_dimensionality, dtype=torch.float32, device=self.device) if want_pred else None
+        emb = torch.empty(n, self.number_features * self.feature_embedding_dimension, dtype=torch.float32,
+                          device=self.device) if want_emb else None
+        stats = stats_out if stats_out is not None else torch.empty(self.number_features + 3, dtype=torch.float32,
+                                                                    device=self.device)
+        _lib.check(self._lib.dib_forward(
+            self._handle, _lib.ptr(self._params), _lib.ptr(x), _lib.ptr(y), n, _lib.ptr(self.beta._dev), _lib.ptr(eps),
+            self.noise_seed, int(step) & 0xFFFFFFFF, int(sample_offset), _lib.ptr(pred), _lib.ptr(emb), _lib.ptr(stats),
+            _lib.ptr(self._workspace), _stream()))
+        return pred, emb, stats
+
+    def _encode_feature(self, i, x_i):
+        t = self._to_device(x_i, self.feature_dimensionalities[i])
+        n = t.shape[0]
+        self._ensure_handle(n)
+        out = torch.empty(n, 2 * self.feature_embedding_dimension, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dib_encode_feature(self._handle, _lib.ptr(self._params), i, _lib.ptr(t), n,
+                                                    _lib.ptr(out), _lib.ptr(self._workspace), _stream()))
+        return out
+
+    def _backward(self, x, y, global_batch, eps=None, sample_offset=0, step=None):
+        """dib_train_step: forward + reverse mode into self._gradstats = [grads (P) || stats (F+3)]."""
+        n = x.shape[0]
+        self._ensure_handle(n)
+        P = self._P
+        st = self._train_step_count if step is None else step
+        _lib.check(self._lib.dib_train_step(
+            self._handle, _lib.ptr(self._params), _lib.ptr(x), _lib.ptr(y), n, _lib.ptr(self.beta._dev),
+            1.0 / float(global_batch), _lib.ptr(eps), self.noise_seed, int(st) & 0xFFFFFFFF,
+            int(sample_offset), _lib.ptr(self._gradstats), _lib.ptr(self._gradstats[P:]), _lib.ptr(self._workspace),
+            _stream()))
+
+    def _train_step(self, x, y, global_batch, eps=None, sample_offset=0):
+        """backward, all-reduce over the data-parallel group (one flat collective: grads || stats), Keras-Adam."""
+        P = self._P
+        self._backward(x, y, global_batch, eps, sample_offset)
+        parallel.allreduce_sum_(self._gradstats, self.process_group)
+        opt = self.optimizer
+        _lib.check(self._lib.dib_adam_step(
+            _lib.ptr(self._params), _lib.ptr(self._gradstats), _lib.ptr(self._m), _lib.ptr(self._v), P,
+            _lib.ptr(self._lr_dev), _lib.ptr(self._step_dev), opt.beta_1, opt.beta_2, opt.epsilon, _stream()))
+        self._train_step_count += 1
+        return self._gradstats[P:]
+
+    def compute_gradients(self, x, y, eps=None, global_batch=None, sample_offset=0, step=None):
+        """GradientTape-style access (nb-bool cell 6 / train.py:201-220 custom loops): returns
+        (flat gradient of task + beta*sum KL w.r.t. trainable_variables, statistics vector) as device tensors."""
+        with torch.cuda.device(self.device):
+            xd = self._to_device(x, sum(self.feature_dimensionalities))
+            yd = self._to_device(y, self._y_cols())
+            e = self._to_device(eps) if eps is not None else None
+            self._backward(xd, yd, global_batch or xd.shape[0], e, sample_offset, step)
+            return self._gradstats[:self._P].clone(), self._gradstats[self._P:].clone()
+
+    def epoch_permutation(self, epoch, n):
+        """The shuffle Model.fit applies in ``epoch`` (our RNG stream; Keras' own is irreproducible)."""
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed((self.seed << 20) + epoch)
+        return torch.randperm(n, generator=gen, device=self.device)
+
+    def _metrics_update(self, stats):
+        _lib.check(self._lib.dib_metrics_update(_lib.ptr(stats), _lib.ptr(self.beta._dev), _lib.ptr(self._epoch_acc),
+                                                self.number_features, _stream()))
+
+    def _read_epoch_logs(self, prefix=""):
+        F = self.number_features
+        a = self._epoch_acc.detach().cpu().numpy().astype(np.float64)       # one D2H per epoch
+        n, nb = max(a[F + 2], 1.0), max(a[F + 3], 1.0)
+        logs = {prefix + "loss": float(a[F] / n)}
+        for m in self.compiled_metrics_names:
+            logs[prefix + m] = float(a[F + 1] / n)
+        for i in range(F):
+            logs[f"{prefix}KL{i}"] = float(a[i] / nb)                        # add_metric mean over batches (models.py:115)
+        logs[prefix + "beta"] = float(self.beta.value())                     # models.py:121
+        return logs
+
+    # ------------------------------------------------------------------ Keras-like public surface
+    def __call__(self, inputs, training=None, eps=None, step=None):
+        """models.py:96-123.  Returns the prediction; ``model.losses`` then holds [beta * sum_i KL_i] and
+        ``model.metrics_values`` the KL{i}/beta metrics, as add_loss/add_metric leave them in the reference."""
+        with torch.cuda.device(self.device):
+            x = self._to_device(inputs, sum(self.feature_dimensionalities))
+            e = self._to_device(eps) if eps is not None else None
+            st = self._train_step_count if step is None else step
+            pred, _, stats = self._forward(x, None, e, st, 0)
+            n = x.shape[0]
+            kl = stats[:self.number_features] / max(n, 1)
+            self.losses = [self.beta._dev[0] * kl.sum()]
+            self._last_kl = kl
+            self.metrics_values = {"beta": self.beta.value()}
+        return _as_numpy_like(inputs, pred)
+
+    call = __call__
+
+    def compile(self, optimizer='adam', loss=None, metrics=None, **_):
+        """train.py:138-142."""
+        self.optimizer = optimizers.get(optimizer) if not isinstance(optimizer, Adam) else optimizer
+        self._loss_kind = resolve_loss(loss)
+        self.compiled_metrics_names = []
+        for m in (metrics or []):
+            if m not in ("accuracy", "acc"):
+                raise ValueError(f"only metrics=['accuracy'] is implemented (reference data.py:67), got {m!r}")
+            self.compiled_metrics_names.append("accuracy")
+        self._lr_dev.fill_(float(self.optimizer.learning_rate))
+
+    def _sync_lr(self):
+        self._lr_dev.fill_(float(self.optimizer.learning_rate))
+
+    def train_on_batch(self, x, y, return_dict=True):
+        """One optimizer step on a (host or device) batch; returns the batch metrics (forces a D2H read)."""
+        if self.optimizer is None:
+            raise RuntimeError("call compile() first")
+        with torch.cuda.device(self.device):
+            self._sync_lr()
+            xd = self._to_device(x, sum(self.feature_dimensionalities))
+            yd = self._to_device(y, self._y_cols())
+            world, rank = parallel.world_and_rank(self.process_group)
+            n = xd.shape[0]
+            stats = self._train_step(xd, yd, global_batch=n * world, sample_offset=rank * n)
+            s = stats.detach().cpu().numpy().astype(np.float64)
+        F = self.number_features
+        nn = max(s[F + 2], 1.0)
+        out = {"loss": float((s[F] + float(self.beta.value()) * s[:F].sum()) / nn), "accuracy": float(s[F + 1] / nn)}
+        for i in range(F):
+            out[f"KL{i}"] = float(s[i] / nn)
+        return out if return_dict else out["loss"]
+
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose='auto', callbacks=None, validation_data=None,
+            shuffle=True, initial_epoch=0, **_):
+        """Keras ``Model.fit`` mechanics around the fused step (train.py:157-166, nb-radial cell 10): per epoch
+        on_epoch_begin -> shuffled consecutive batches incl. a short last one -> running means -> validation pass
+        (noise sampled, train.py:264-265) -> on_epoch_end; returns a History whose ``.history`` has the keys
+        loss, accuracy, KL{i}, beta and their val_ twins.
+
+        Data-parallel: with torch.distributed initialised every rank passes the SAME x, y; each global batch is
+        split into contiguous row ranges per rank, so the result does not depend on the number of GPUs."""
+        if self.optimizer is None:
+            raise RuntimeError("call compile() first")
+        batch_size = 32 if batch_size is None else int(batch_size)
+        world, rank = parallel.world_and_rank(self.process_group)
+        D = sum(self.feature_dimensionalities)
+        with torch.cuda.device(self.device):
+            xd, yd = self._to_device(x, D), self._to_device(y, self._y_cols())
+            N = xd.shape[0]
+            xv = yv = None
+            if validation_data is not None:
+                xv, yv = self._to_device(validation_data[0], D), self._to_device(validation_data[1], self._y_cols())
+            history = History()
+            cbs = list(callbacks or []) + [history]
+            for cb in cbs:
+                cb.set_model(self) if hasattr(cb, "set_model") else setattr(cb, "model", self)
+            self.history = history
+            self.stop_training = False
+            for cb in cbs:
+                getattr(cb, "on_train_begin", lambda logs=None: None)()
+            for epoch in range(initial_epoch, epochs):
+                for cb in cbs:
+                    cb.on_epoch_begin(epoch, logs=None)                      # beta annealing lives here
+                self._sync_lr()
+                if shuffle:
+                    perm = self.epoch_permutation(epoch, N)
+                self._epoch_acc.zero_()
+                for b0 in range(0, N, batch_size):
+                    b1 = min(b0 + batch_size, N)
+                    lo, hi = parallel.shard_range(b1 - b0, rank, world)
+                    if shuffle:
+                        idx = perm[b0 + lo:b0 + hi]
+                        xb, yb = xd.index_select(0, idx), yd.index_select(0, idx)
+                    else:
+                        xb, yb = xd[b0 + lo:b0 + hi], yd[b0 + lo:b0 + hi]
+                    stats = self._train_step(xb, yb, global_batch=b1 - b0, sample_offset=lo)
+                    self._metrics_update(stats)
+                logs = self._read_epoch_logs()
+                if xv is not None:
+                    logs.update(self._evaluate_into_logs(xv, yv, batch_size, epoch, world, rank))
+                if verbose not in (False, 0, 'auto') and rank == 0:
+                    print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(
+                        f"{k}: {v:.4g}" for k, v in logs.items() if not k.lstrip('val_').startswith('KL')))
+                for cb in cbs:
+                    cb.on_epoch_end(epoch, logs)
+                if self.stop_training:
+                    break
+            for cb in cbs:
+                getattr(cb, "on_train_end", lambda logs=None: None)()
+        return history
+
+    def _evaluate_into_logs(self, xv, yv, batch_size, epoch, world, rank):
+        Nv = xv.shape[0]
+        self._epoch_acc.zero_()
+        stats = torch.empty(self.number_features + 3, dtype=torch.float32, device=self.device)
+        for b0 in range(0, Nv, batch_size):
+            b1 = min(b0 + batch_size, Nv)
+            lo, hi = parallel.shard_range(b1 - b0, rank, world)
+            self._forward(xv[b0 + lo:b0 + hi], yv[b0 + lo:b0 + hi], None, (2 ** 31 + epoch), b0 + lo,
+                          want_pred=False, stats_out=stats)
+            parallel.allreduce_sum_(stats, self.process_group)
+            self._metrics_update(stats)
+        return self._read_epoch_logs(prefix="val_")
+
+    def evaluate(self, x, y, batch_size=32, return_dict=True, **_):
+        with torch.cuda.device(self.device):
+            world, rank = parallel.world_and_rank(self.process_group)
+            D = sum(self.feature_dimensionalities)
+            logs = self._evaluate_into_logs(self._to_device(x, D), self._to_device(y, self._y_cols()), int(batch_size),
+                                            0, world, rank)
+        logs = {k[len("val_"):]: v for k, v in logs.items()}
+        return logs if return_dict else [logs["loss"]] + [logs[m] for m in self.compiled_metrics_names]
+
+    def predict(self, x, batch_size=32, **_):
+        outs = []
+        n = len(x)
+        for b0 in range(0, n, int(batch_size)):
+            outs.append(np.asarray(self(x[b0:b0 + int(batch_size)], training=False)) if not isinstance(x, torch.Tensor)
+                        else self(x[b0:b0 + int(batch_size)], training=False))
+        return torch.cat(outs) if isinstance(x, torch.Tensor) else np.concatenate(outs)
+
+
+class InfoBottleneckAnnealingCallback(Callback):
+    """Callback to logarithmically increase beta during training (models.py:125-149).  The schedule is
+    evaluated in float32 exactly like the tf ops there:
+        beta = exp(log b0 + float32(max(epoch - n_pre, 0)) / n_anneal * (log b1 - log b0))."""
+
+    def __init__(self, beta_start, beta_end, number_pretraining_epochs, number_annealing_epochs):
+        super().__init__()
+        self.beta_start = beta_start
+        self.beta_end = beta_end
+        self.number_pretraining_epochs = number_pretraining_epochs
+        self.number_annealing_epochs = number_annealing_epochs
+
+    def beta_at(self, epoch):
+        f = np.float32
+        frac = f(max(epoch - self.number_pretraining_epochs, 0)) / f(self.number_annealing_epochs)
+        lo, hi = np.log(f(self.beta_start)), np.log(f(self.beta_end))
+        return f(np.exp(lo + frac * (hi - lo)))
+
+    def on_epoch_begin(self, epoch, logs=None):
+        self.model.beta.assign(self.beta_at(epoch))
+
+
+class SaveCompressionMatricesCallback(Callback):
+    """Callback to save compression scheme matrices during training (models.py:152-186; the intended behaviour is
+    the inline copy at train.py:251-261 -- the shipped on_epoch_end raises NameError).  For every feature: pick
+    <=128 rows as visualization.py:17-28 does, encoder forward, Bhattacharyya matrix, exp(-D) (all on the GPU via
+    dib_encode_feature + dib_bhattacharyya).  The reference renders a PNG with matplotlib, which is not available
+    here; the numeric artefact is saved as ``feature_{i}_log10beta_{x:.3f}.npz`` (same stem) and kept in
+    ``self.matrices``."""
+
+    def __init__(self, save_frequency, x_processed, x_raw, outdir, max_number_to_display=128, seed=0):
+        super().__init__()
+        self.save_frequency = save_frequency
+        self.x_processed = x_processed
+        self.x_raw = x_raw
+        self.outdir = outdir
+        self.max_number_to_display = max_number_to_display
+        self.rng = np.random.default_rng(seed)
+        self.matrices = []
+
+    def on_epoch_end(self, epoch, logs=None):
+        if (epoch % self.save_frequency) != 0:
+            return
+        from . import utils
+        model = self.model
+        beta_value = float(model.beta.value())
+        xp = np.asarray(self.x_processed.cpu() if isinstance(self.x_processed, torch.Tensor) else self.x_processed)
+        xr = np.asarray(self.x_raw.cpu() if isinstance(self.x_raw, torch.Tensor) else self.x_raw)
+        offs = np.cumsum([0] + list(model.feature_dimensionalities))
+        if self.outdir:
+            os.makedirs(self.outdir, exist_ok=True)
+        for i in range(model.number_features):
+            feat, raw = xp[:, offs[i]:offs[i + 1]], xr[:, offs[i]:offs[i + 1]]
+            inds, sorted_raw = utils.select_display_rows(raw, self.max_number_to_display, self.rng)
+            comp, dist = utils.compression_matrix(model.feature_encoders[i], feat[inds])
+            rec = dict(epoch=epoch, feature=i, beta=beta_value, compression_matrix=comp, bhattacharyya=dist,
+                       raw_values=sorted_raw)
+            self.matrices.append(rec)
+            if self.outdir:
+                np.savez(os.path.join(self.outdir, f'feature_{i}_log10beta_{np.log10(beta_value):.3f}.npz'), **rec)
+
+
+class StashEmbeddingsCallback(Callback):
+    """nb-radial cell 5: stash (mu, logvar) of every feature encoder on ``x_in`` every ``save_frequency`` epochs."""
+
+    def __init__(self, save_frequency, x_in, save_start=0):
+        super().__init__()
+        self.save_frequency = save_frequency
+        self.x_in = x_in
+        self.mus_for_later = []
+        self.logvars_for_later = []
+        self.save_start = save_start
+
+    def on_epoch_end(self, epoch, logs=None):
+        if (epoch > self.save_start) and ((epoch % self.save_frequency) == 0):
+            m = self.model
+            x = np.asarray(self.x_in.cpu() if isinstance(self.x_in, torch.Tensor) else self.x_in)
+            offs = np.cumsum([0] + list(m.feature_dimensionalities))
+            E = m.feature_embedding_dimension
+            for i in range(m.number_features):
+                o = np.asarray(m.feature_encoders[i](x[:, offs[i]:offs[i + 1]]))
+                self.mus_for_later.append(o[:, :E])
+                self.logvars_for_later.append(o[:, E:])

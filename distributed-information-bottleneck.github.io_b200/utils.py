@@ -1,0 +1,69 @@
+"""Host-side mirror of the parts of the reference's ``utils.py`` / ``visualization.py`` that sit on the
+compression-matrix path of SaveCompressionMatricesCallback."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _dev(a, device):
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def bhattacharyya_dist_mat(mus1, logvars1, mus2=None, logvars2=None, device=None):
+    """utils.py:177-212 (Bhattacharyya distances between diagonal Gaussians) on the GPU via dib_bhattacharyya.
+    The CUDA kernel computes the square self-distance matrix of one set (the only way the reference calls it,
+    visualization.py:33); for two different sets the rows are stacked and the off-diagonal block returned."""
+    if not torch.cuda.is_available():
+        raise _lib.DibError("dib_b200 needs a CUDA device; there is no CPU path")
+    lib = _lib.load()
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    m1, l1 = _dev(mus1, device), _dev(logvars1, device)
+    same = mus2 is None or (mus2 is mus1 and logvars2 is logvars1)
+    if same:
+        ml = torch.cat([m1, l1], dim=1).contiguous()
+    else:
+        m2, l2 = _dev(mus2, device), _dev(logvars2, device)
+        ml = torch.cat([torch.cat([m1, l1], dim=1), torch.cat([m2, l2], dim=1)], dim=0).contiguous()
+    n, E = ml.shape[0], m1.shape[1]
+    out = torch.empty(n, n, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.dib_bhattacharyya(_lib.ptr(ml), n, E, _lib.ptr(out), None,
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    if not same:
+        out = out[:m1.shape[0], m1.shape[0]:]
+    return out if isinstance(mus1, torch.Tensor) else out.cpu().numpy()
+
+
+def select_display_rows(inp_features_raw, max_number_to_display=128, rng=None):
+    """visualization.py:17-28: unique values if fewer than 10 distinct, else ``max_number_to_display`` random rows,
+    sorted by raw value.  Returns (row indices into the input, sorted raw values)."""
+    raw = np.asarray(inp_features_raw)
+    flat = raw.reshape(raw.shape[0], -1)[:, 0]
+    unique_vals, unique_inds = np.unique(flat, return_index=True)
+    if len(unique_vals) < 10:
+        return unique_inds[np.argsort(unique_vals)], np.sort(unique_vals)
+    rng = rng or np.random.default_rng()
+    sel = rng.choice(flat.shape[0], max_number_to_display)
+    order = np.argsort(flat[sel])
+    return sel[order], flat[sel][order]
+
+
+def compression_matrix(feature_encoder, feature_inps):
+    """visualization.py:30-34: encoder forward -> (mu, logvar) -> Bhattacharyya -> exp(-D).
+    Returns (compression_matrix, bhattacharyya_distance_matrix) as numpy arrays."""
+    lib = _lib.load()
+    model = feature_encoder._model
+    o = model._encode_feature(feature_encoder.index, feature_inps)            # [n, 2E] on the device
+    n, E = o.shape[0], model.feature_embedding_dimension
+    dist = torch.empty(n, n, dtype=torch.float32, device=o.device)
+    comp = torch.empty(n, n, dtype=torch.float32, device=o.device)
+    with torch.cuda.device(o.device):
+        _lib.check(lib.dib_bhattacharyya(_lib.ptr(o), n, E, _lib.ptr(dist), _lib.ptr(comp),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return comp.cpu().numpy(), dist.cpu().numpy()

@@ -1,0 +1,148 @@
+/* dib_b200.h -- C ABI of the B200-native Distributed-IB training engine.
+ *
+ * The reference (distributed-information-bottleneck.github.io) has no FFI/plugin interface: its
+ * hot path is a tf.keras Model whose arithmetic executes inside TensorFlow.  Each entry point
+ * below therefore names the reference *Python* interface it replaces (paths relative to the
+ * reference root).  The PyTorch host shim (package dib_b200) binds these with ctypes and
+ * reproduces the DistributedIBNet / compile / fit / callback surface on top of them;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer named *_dev / params / grads / x / y / eps / workspace is DEVICE memory owned by
+ *     the caller (PyTorch tensors in the shim); the library never allocates user-visible memory.
+ *     The only allocation it makes is a few KB of layer-descriptor tables inside dib_create.
+ *   - every compute call is asynchronous on the caller's cudaStream_t (passed as void*), performs no
+ *     host synchronisation and no allocation, and is CUDA-Graph capturable: beta, learning rate and
+ *     the Adam step counter are read from device scalars.
+ *   - return value: 0 = ok, non-zero = error (see dib_last_error()); no C++ exception crosses.
+ *   - a handle is not thread-safe; use one host thread per handle (the reference is single-threaded).
+ *   - all tensors are fp32, row-major.  Parameters live in ONE flat fp32 buffer; per feature
+ *     (W1,b1,W2,b2,...,W_out,b_out) then the integration layers, kernels in Keras [in,out]
+ *     orientation (tf.keras.layers.Dense, models.py:76-77,82-83).
+ *   - sums, not means: statistics are returned as SUMS over the local samples so that data-parallel
+ *     ranks combine them (and the gradients) with one all-reduce(sum); gradients are already scaled
+ *     by inv_global_batch.
+ */
+#ifndef DIB_B200_H_
+#define DIB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIB_ABI_VERSION 1
+
+/* activation_fn strings accepted by tf.keras.layers.Dense in the reference's call sites
+ * (train.py:37 'relu', nb-radial 'tanh', nb-bool LeakyReLU, None). */
+enum dib_activation {
+  DIB_ACT_LINEAR = 0, DIB_ACT_RELU = 1, DIB_ACT_TANH = 2, DIB_ACT_LEAKY_RELU = 3,
+  DIB_ACT_SIGMOID = 4, DIB_ACT_ELU = 5
+};
+
+/* compiled losses used by the reference's datasets (data.py:65, data.py:343, data.py:129). */
+enum dib_loss {
+  DIB_LOSS_BCE_LOGITS = 0,       /* tf.keras.losses.BinaryCrossentropy(from_logits=True)            */
+  DIB_LOSS_SPARSE_CE_LOGITS = 1, /* tf.keras.losses.SparseCategoricalCrossentropy(from_logits=True) */
+  DIB_LOSS_MSE = 2
+};
+
+/* arithmetic of the dense contractions. FP32 = CUDA-core FMA (parity path).  The tensor-core modes
+ * use tcgen05.mma with fp32 accumulation in TMEM; everything else (PE, KL, exp, loss, Adam) stays fp32. */
+enum dib_precision { DIB_PREC_FP32 = 0, DIB_PREC_TF32 = 1, DIB_PREC_BF16 = 2 };
+
+/* Mirrors the constructor of models.DistributedIBNet (models.py:56-66). */
+typedef struct dib_config {
+  int32_t abi_version;               /* DIB_ABI_VERSION */
+  int32_t number_features;           /* len(feature_dimensionalities)            models.py:69 */
+  const int32_t* feature_dimensionalities;     /* [number_features]             models.py:68 */
+  int32_t number_encoder_layers;     /* len(feature_encoder_architecture) */
+  const int32_t* feature_encoder_architecture; /* hidden widths                  models.py:76 */
+  int32_t number_integration_layers; /* len(integration_network_architecture) */
+  const int32_t* integration_network_architecture; /*                            models.py:82 */
+  int32_t output_dimensionality;     /*                                          models.py:83 */
+  int32_t use_positional_encoding;   /*                                          models.py:74 */
+  int32_t number_positional_encoding_frequencies; /* n -> frequencies 2^1..2^(n-1), models.py:70 */
+  int32_t activation_fn;             /* enum dib_activation */
+  float   leaky_relu_alpha;          /* slope for DIB_ACT_LEAKY_RELU */
+  int32_t feature_embedding_dimension; /* E                                      models.py:64 */
+  int32_t output_activation_fn;      /* enum dib_activation                      models.py:83 */
+  int32_t loss;                      /* enum dib_loss (model.compile(loss=...), train.py:138-142) */
+  int32_t precision;                 /* enum dib_precision */
+  int64_t max_batch;                 /* largest n any call will pass (sizes the workspace) */
+} dib_config;
+
+typedef struct dib_model dib_model;
+
+/* models.DistributedIBNet.__init__ (models.py:56-86).  Uses the current CUDA device. */
+int dib_create(const dib_config* cfg, dib_model** out);
+void dib_destroy(dib_model* h);
+
+/* number of trainable parameters == sum over model.trainable_variables (train.py:198). */
+int64_t dib_param_count(const dib_model* h);
+
+/* For every variable v (in flat order) its offset and shape: offsets[v], rows[v] (fan-in, or 0 for a
+ * bias), cols[v].  Pass NULLs to query the number of variables (return value, negative on error). */
+int dib_param_layout(const dib_model* h, int64_t* offsets, int32_t* rows, int32_t* cols, int32_t capacity);
+
+/* bytes of scratch the caller must provide to forward / train_step / encode calls. */
+size_t dib_workspace_bytes(const dib_model* h);
+
+/* number of floats in the statistics vector: [ sum_b KL_i (F) | sum_b task loss | sum_b accuracy | n ] */
+int32_t dib_stats_count(const dib_model* h);
+
+/* DistributedIBNet.call (models.py:96-123) + compiled loss/metrics, no gradient: the validation pass of
+ * Model.fit (train.py:157-166; noise is sampled in validation too, train.py:264-265).
+ *   x [n, sum d_i]; y [n, out] (class index as float for sparse CE) or NULL; eps [n, F, E] or NULL ->
+ *   Philox4x32-10 keyed (seed, step, feature, sample_offset + row, dim), see oracle/philox.py;
+ *   out_pred [n, out] or NULL; out_emb [n, F*E] or NULL; out_stats [dib_stats_count] (zeroed by the call). */
+int dib_forward(dib_model* h, const float* params, const float* x, const float* y, int64_t n,
+                const float* beta_dev, const float* eps, uint64_t seed, uint32_t step, uint64_t sample_offset,
+                float* out_pred, float* out_emb, float* out_stats, void* workspace, void* stream);
+
+/* model.feature_encoders[i](x_i) (models.py:79; consumers visualization.py:31, utils.py:38, nb-radial
+ * StashEmbeddingsCallback): deterministic [n, d_i] -> [n, 2E] = (mu || logvar). */
+int dib_encode_feature(dib_model* h, const float* params, int32_t feature, const float* x_i, int64_t n,
+                       float* out_mu_logvar, void* workspace, void* stream);
+
+/* One Keras train_step minus the optimizer: forward, loss = task + beta*sum_i KL_i (models.py:118),
+ * reverse mode (GradientTape in Model.fit / nb-bool cell 6).  grads_flat [P] receives
+ * d(loss)/d(params) * (n_local-sum scaled by inv_global_batch); out_stats as in dib_forward.
+ * grads_flat and out_stats may be adjacent in one buffer so that one all-reduce covers both. */
+int dib_train_step(dib_model* h, const float* params, const float* x, const float* y, int64_t n,
+                   const float* beta_dev, float inv_global_batch,
+                   const float* eps, uint64_t seed, uint32_t step, uint64_t sample_offset,
+                   float* grads_flat, float* out_stats, void* workspace, void* stream);
+
+/* tf.keras.optimizers.Adam dense update over the flat buffer (train.py:128-129, nb-radial Adam(lr)):
+ *   t = *step_dev + 1 (the kernel increments *step_dev);  lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+ *   m += (1-b1)(g-m); v += (1-b2)(g^2-v); w -= lr_t*m/(sqrt(v)+eps)   (eps outside the bias correction). */
+int dib_adam_step(float* params, const float* grads, float* m, float* v, int64_t count,
+                  const float* lr_dev, int32_t* step_dev, float beta_1, float beta_2, float epsilon,
+                  void* stream);
+
+/* Keras metric aggregation of one batch (Model.fit's Mean metrics; add_metric at models.py:115,121):
+ *   acc[0..F)  += stats[i]/n              (KL_i batch mean; history['KL{i}'] = acc[i]/acc[F+3])
+ *   acc[F]     += stats[F] + beta*sum_i stats[i]   (sample-weighted total loss; history['loss'] = acc[F]/acc[F+2])
+ *   acc[F+1]   += stats[F+1]              (accuracy sum;  history['accuracy'] = acc[F+1]/acc[F+2])
+ *   acc[F+2]   += n ;  acc[F+3] += 1      (samples, batches)
+ * stats is the (all-reduced) vector written by dib_train_step / dib_forward; acc has F+4 floats. */
+int dib_metrics_update(const float* stats, const float* beta_dev, float* acc, int32_t number_features, void* stream);
+
+/* utils.bhattacharyya_dist_mat (utils.py:177-212) followed by exp(-D) (visualization.py:34):
+ * mu_logvar [n, 2E] -> out_dist [n, n] (may be NULL) and out_compression [n, n] (may be NULL). */
+int dib_bhattacharyya(const float* mu_logvar, int64_t n, int32_t embedding_dimension,
+                      float* out_dist, float* out_compression, void* stream);
+
+/* text of the last error raised on this thread ("" if none). */
+const char* dib_last_error(void);
+
+/* "sm_100a" etc: the architecture the kernels were compiled for, and the ABI version. */
+const char* dib_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIB_B200_H_ */

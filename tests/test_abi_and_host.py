@@ -1,0 +1,96 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dib_b200.h declares; host-side logic
+(beta schedule callback, shard arithmetic, Keras-compat objects, display-row selection)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dib_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dib_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dib_b200 import _lib
+    lib = ctypes.CDLL(_lib.library_path() if os.path.exists(_lib.library_path()) else _lib._build.build_library())
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
+    lib.dib_build_info.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.dib_build_info()
+
+
+def test_config_struct_matches_header_field_order():
+    from dib_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "dib_b200.h")).read()
+    body = text[text.index("typedef struct dib_config {"):text.index("} dib_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b([a-z_0-9]+)\s*;", body)
+    assert fields == [f[0] for f in _lib.DibConfig._fields_]
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import dib_b200
+    with pytest.raises(dib_b200.DibError):
+        dib_b200.DistributedIBNet([1, 1], [8], [8], 1)
+    with pytest.raises(dib_b200.DibError):
+        dib_b200.utils.bhattacharyya_dist_mat(np.zeros((2, 2)), np.zeros((2, 2)))
+
+
+def test_beta_callback_matches_reference_goldens(golden_dir):
+    import dib_b200
+    z = np.load(os.path.join(golden_dir, "ref_beta_schedule.npz"))
+    for tag in ["train_py_defaults", "nb_radial", "bench"]:
+        b0, b1, npre, nann = z[tag + "_args"]
+        cb = dib_b200.InfoBottleneckAnnealingCallback(b0, b1, int(npre), int(nann))
+        got = np.array([cb.beta_at(int(e)) for e in z[tag + "_epochs"]], dtype=np.float32)
+        np.testing.assert_array_equal(got, z[tag + "_beta"])
+
+
+def test_shard_range_partitions_exactly():
+    from dib_b200 import parallel
+    for n in [0, 1, 7, 8, 65536, 65537]:
+        for world in [1, 2, 3, 8]:
+            spans = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_keras_compat_objects():
+    import dib_b200
+    from dib_b200.keras_compat import resolve_loss
+    opt = dib_b200.optimizers.get("adam")
+    opt.learning_rate = 3e-4                                     # train.py:128-129
+    assert (opt.beta_1, opt.beta_2, opt.epsilon) == (0.9, 0.999, 1e-7)
+    assert resolve_loss(dib_b200.losses.BinaryCrossentropy(from_logits=True)) == "bce_logits"
+    assert resolve_loss(dib_b200.losses.SparseCategoricalCrossentropy(from_logits=True)) == "sparse_ce_logits"
+    assert resolve_loss("mse") == "mse"
+    with pytest.raises(NotImplementedError):
+        resolve_loss(dib_b200.losses.BinaryCrossentropy())
+    h = dib_b200.History()
+    h.on_epoch_end(0, {"loss": 1.0}); h.on_epoch_end(1, {"loss": 0.5})
+    assert h.history == {"loss": [1.0, 0.5]}
+
+
+def test_select_display_rows():
+    from dib_b200 import utils
+    raw = np.array([[1.0], [-1.0], [1.0], [-1.0]])
+    inds, vals = utils.select_display_rows(raw)
+    assert list(vals) == [-1.0, 1.0] and list(raw[inds, 0]) == [-1.0, 1.0]
+    raw = np.random.default_rng(0).standard_normal((500, 1))
+    inds, vals = utils.select_display_rows(raw, 128, np.random.default_rng(1))
+    assert len(inds) == 128 and np.all(np.diff(vals) >= 0) and np.allclose(raw[inds, 0], vals)

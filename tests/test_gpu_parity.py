@@ -1,0 +1,257 @@
+"""GPU (B200): the CUDA path, called through the C ABI (ctypes) by the dib_b200 host shim, against
+ (a) the committed golden vectors produced by the reference's own code (tests/golden/),
+ (b) the float64 CPU oracle on the same seeded inputs,
+ (c) size-independent properties at the BASELINE batch (65 536): shard additivity, determinism.
+Tolerances are fp32-vs-float64 reduction-order tolerances and are written next to each check."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dib_oracle as O
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["c0_small", "pendulum_like", "radial_like", "odd_shapes"]
+LOSS_OF = {"c0_small": ("bce_logits", O.LOSS_BCE_LOGITS), "pendulum_like": ("mse", O.LOSS_MSE),
+           "radial_like": ("bce_logits", O.LOSS_BCE_LOGITS), "odd_shapes": ("sparse_ce_logits", O.LOSS_SPARSE_CE_LOGITS)}
+
+
+def build_model(cfg, precision="fp32", loss="bce_logits", lr=1e-3, seed=0):
+    import dib_b200
+    m = dib_b200.DistributedIBNet(
+        cfg.feature_dimensionalities, cfg.feature_encoder_architecture, cfg.integration_network_architecture,
+        cfg.output_dimensionality, use_positional_encoding=cfg.use_positional_encoding,
+        number_positional_encoding_frequencies=cfg.number_positional_encoding_frequencies,
+        activation_fn=cfg.activation_fn, feature_embedding_dimension=cfg.feature_embedding_dimension,
+        output_activation_fn=cfg.output_activation_fn, precision=precision, seed=seed, leaky_alpha=cfg.leaky_alpha)
+    m.compile(optimizer=dib_b200.Adam(lr), loss=loss, metrics=["accuracy"])
+    return m
+
+
+def load_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"ref_forward_{name}.npz"))
+    return O.DIBConfig(**ast.literal_eval(str(z["cfg"]))), z
+
+
+def make_labels(rng, loss, B, out):
+    if loss == O.LOSS_SPARSE_CE_LOGITS:
+        return rng.integers(0, out, size=B).astype(np.float32)
+    if loss == O.LOSS_BCE_LOGITS:
+        return rng.integers(0, 2, size=(B, out)).astype(np.float32)
+    return rng.standard_normal((B, out)).astype(np.float32)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_goldens(golden_dir, name):
+    cfg, z = load_case(golden_dir, name)
+    m = build_model(cfg, loss=LOSS_OF[name][0])
+    m.set_flat_weights(z["params"])
+    m.beta.assign(float(z["beta"]))
+    pred = m(z["x"], eps=z["eps"])
+    assert rel_err(pred, z["pred"]) < 2e-5                       # fp32 FMA vs float64
+    kl = (m._last_kl).cpu().numpy()
+    np.testing.assert_allclose(kl, z["kl"], rtol=2e-5)
+    np.testing.assert_allclose(float(m.losses[0]), float(z["ib_loss"]), rtol=2e-5)
+    offs = np.cumsum([0] + list(cfg.feature_dimensionalities))
+    for i in range(cfg.number_features):
+        o = m.feature_encoders[i](z["x"][:, offs[i]:offs[i + 1]])
+        assert rel_err(o, z[f"enc{i}"]) < 2e-5, i
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_step_gradients_match_oracle(golden_dir, name):
+    cfg, z = load_case(golden_dir, name)
+    loss_name, loss = LOSS_OF[name]
+    m = build_model(cfg, loss=loss_name)
+    m.set_flat_weights(z["params"])
+    beta = float(z["beta"])
+    m.beta.assign(beta)
+    rng = np.random.default_rng(5)
+    y = make_labels(rng, loss, z["x"].shape[0], cfg.output_dimensionality)
+    g, stats = m.compute_gradients(z["x"], y, eps=z["eps"])
+    g_ref, fr = O.train_grads(cfg, z["params"], z["x"], y, z["eps"], beta, loss)
+    assert rel_err(g.cpu().numpy(), g_ref) < 5e-5
+    # per-variable check so that small-magnitude layers are not hidden by large ones
+    off = 0
+    for s in cfg.param_shapes():
+        n = int(np.prod(s))
+        assert rel_err(g.cpu().numpy()[off:off + n], g_ref[off:off + n]) < 2e-4, (off, s)
+        off += n
+    st = stats.cpu().numpy()
+    B, F = z["x"].shape[0], cfg.number_features
+    np.testing.assert_allclose(st[:F] / B, fr.kl_per_feature, rtol=2e-5)
+    np.testing.assert_allclose(st[F] / B, fr.task_loss, rtol=2e-5)
+    np.testing.assert_allclose(st[F + 1], fr.acc_sum, rtol=1e-6)
+    assert st[F + 2] == B
+
+
+def test_in_kernel_philox_matches_oracle_generator():
+    cfg = O.DIBConfig([1] * 4, [32], [32], 1, feature_embedding_dimension=8)
+    m = build_model(cfg)
+    rng = np.random.default_rng(0)
+    p = O.glorot_uniform_params(cfg, rng)
+    m.set_flat_weights(p)
+    x = rng.standard_normal((300, 4)).astype(np.float32)
+    m.noise_seed = 0x1234567887654321
+    with torch.cuda.device(m.device):
+        xd = m._to_device(x, 4)
+        _, emb, _ = m._forward(xd, None, None, step=17, sample_offset=1000, want_emb=True)
+    eps = philox.normal_noise(0x1234567887654321, 17, np.arange(300) + 1000, 4, 8, dtype=np.float64)
+    fr = O.forward(cfg, p, x, eps, 1.0)
+    assert rel_err(emb.cpu().numpy(), fr.emb) < 2e-5
+    # and the noise alone: u - mu over sigma
+    fr0 = O.forward(cfg, p, x, np.zeros_like(eps), 1.0)
+    encs, _ = O.unflatten(cfg, p.astype(np.float64))
+
+
+def test_adam_matches_keras_semantics_oracle():
+    import ctypes
+    from dib_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    n = 10007
+    w = rng.standard_normal(n).astype(np.float32)
+    st = O.AdamState(np.zeros(n, np.float32), np.zeros(n, np.float32))
+    w_ref = w.copy()
+    dev = torch.device("cuda")
+    wd, md, vd = torch.from_numpy(w).to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    lr = torch.full((1,), 3e-4, device=dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    for t in range(5):
+        g = (rng.standard_normal(n) * 10.0 ** rng.integers(-6, 1, n)).astype(np.float32)
+        O.adam_step(w_ref, g, st, 3e-4)
+        gd = torch.from_numpy(g).to(dev)
+        _lib.check(lib.dib_adam_step(_lib.ptr(wd), _lib.ptr(gd), _lib.ptr(md), _lib.ptr(vd), n, _lib.ptr(lr),
+                                     _lib.ptr(step), 0.9, 0.999, 1e-7,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert int(step.item()) == 5
+    np.testing.assert_allclose(wd.cpu().numpy(), w_ref, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(md.cpu().numpy(), st.m, rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(vd.cpu().numpy(), st.v, rtol=1e-5, atol=1e-20)
+
+
+def test_bhattacharyya_matches_reference_golden(golden_dir):
+    import dib_b200
+    z = np.load(os.path.join(golden_dir, "ref_bhattacharyya.npz"))
+    D = dib_b200.utils.bhattacharyya_dist_mat(z["mu"], z["lv"], z["mu"], z["lv"])
+    np.testing.assert_allclose(D, z["D"], rtol=2e-5, atol=2e-5)
+    D34 = dib_b200.utils.bhattacharyya_dist_mat(z["mu3"], z["lv3"], z["mu4"], z["lv4"])
+    np.testing.assert_allclose(D34, z["D34"], rtol=2e-5, atol=2e-5)
+    D2 = dib_b200.utils.bhattacharyya_dist_mat(z["mu2"], z["lv2"])
+    np.testing.assert_allclose(D2[0, 1], 0.48466528, rtol=1e-5)       # SURVEY.md section 4 KAT
+    np.testing.assert_allclose(np.diag(D2), 0, atol=1e-6)
+
+
+def test_fit_history_matches_oracle_fit():
+    """Keras fit mechanics (shuffle, short last batch, weighted/unweighted means, validation pass with noise,
+    beta callback) end to end on the paper's Boolean circuit, against the float64 oracle with the same
+    permutations, noise and initial weights."""
+    import dib_b200
+    x, y = O.boolean_circuit_truth_table()
+    cfg = O.DIBConfig([1] * 10, [32, 32], [64], 1, feature_embedding_dimension=8)
+    m = build_model(cfg, lr=2e-3, seed=4)
+    m.noise_seed = 99
+    p0 = m.get_flat_weights().copy()
+    cb = dib_b200.InfoBottleneckAnnealingCallback(1e-3, 1e-1, 1, 3)
+    hist = m.fit(x, y, epochs=4, batch_size=100, shuffle=True, callbacks=[cb], verbose=False,
+                 validation_data=(x[:250], y[:250])).history
+    perms = {e: m.epoch_permutation(e, 1024).cpu().numpy() for e in range(4)}
+    eps_fn = lambda step, ids: philox.normal_noise(99, step, ids, 10, 8, dtype=np.float64)
+    p_ref, h_ref = O.fit(cfg, p0, x.astype(np.float64), y.astype(np.float64), loss=O.LOSS_BCE_LOGITS, epochs=4,
+                         batch_size=100, lr=2e-3, eps_fn=eps_fn, perm_fn=lambda e, n: perms[e],
+                         beta_fn=lambda e: O.beta_schedule(e, 1e-3, 1e-1, 1, 3),
+                         validation_data=(x[:250].astype(np.float64), y[:250].astype(np.float64)))
+    assert set(hist) == set(h_ref)
+    for k in h_ref:
+        # 44 Adam steps of fp32-vs-float64 drift; accuracy can flip single samples -> looser
+        tol = 2e-2 if "accuracy" in k else 2e-3
+        np.testing.assert_allclose(hist[k], h_ref[k], rtol=tol, atol=1e-6, err_msg=k)
+    assert rel_err(m.get_flat_weights(), p_ref) < 2e-3
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 129, 257, 1000])
+def test_ragged_batch_sizes(n):
+    cfg = O.DIBConfig([1, 3], [16, 12], [20], 2, feature_embedding_dimension=5, activation_fn="tanh",
+                      number_positional_encoding_frequencies=2)
+    m = build_model(cfg, loss="mse")
+    rng = np.random.default_rng(n)
+    p = O.glorot_uniform_params(cfg, rng)
+    m.set_flat_weights(p)
+    m.beta.assign(0.1)
+    x = rng.standard_normal((n, 4)).astype(np.float32)
+    eps = rng.standard_normal((n, 2, 5)).astype(np.float32)
+    y = rng.standard_normal((n, 2)).astype(np.float32)
+    g, stats = m.compute_gradients(x, y, eps=eps)
+    g_ref, fr = O.train_grads(cfg, p, x, y, eps, 0.1, O.LOSS_MSE)
+    assert rel_err(g.cpu().numpy(), g_ref) < 5e-5
+    np.testing.assert_allclose(stats.cpu().numpy()[2] / n, fr.task_loss, rtol=5e-5)
+
+
+def test_empty_batch_is_a_no_op():
+    cfg = O.DIBConfig([1, 1], [8], [8], 1, feature_embedding_dimension=4)
+    m = build_model(cfg)
+    g, stats = m.compute_gradients(np.zeros((0, 2), np.float32), np.zeros((0, 1), np.float32))
+    assert float(g.abs().sum()) == 0 and float(stats.abs().sum()) == 0
+
+
+def test_full_size_properties_c0():
+    """BASELINE config C0 at the full batch (65 536 x 16): (i) bit-reproducible, (ii) data-parallel shards are
+    additive: grads(full) == grads(rows 0..B/2) + grads(rows B/2..B) with global sample offsets, (iii) gradient of
+    a random direction agrees with a finite difference of the loss reported by the forward entry point."""
+    cfg = O.DIBConfig([1] * 16, [128, 128], [256, 256], 1)
+    m = build_model(cfg, seed=1)
+    B = 65536
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((B, 16)).astype(np.float32)
+    y = (x[:, 0] * x[:, 1] + np.sin(2 * x[:, 2]) + 0.5 * x[:, 3] > 0).astype(np.float32)[:, None]
+    m.beta.assign(1e-2)
+    g1, s1 = m.compute_gradients(x, y, step=3)
+    g2, s2 = m.compute_gradients(x, y, step=3)
+    assert torch.equal(g1, g2) and torch.equal(s1, s2)                       # (i)
+    h = B // 2
+    ga, sa = m.compute_gradients(x[:h], y[:h], global_batch=B, sample_offset=0, step=3)
+    gb, sb = m.compute_gradients(x[h:], y[h:], global_batch=B, sample_offset=h, step=3)
+    assert rel_err((ga + gb).cpu().numpy(), g1.cpu().numpy()) < 1e-5         # (ii)
+    np.testing.assert_allclose((sa + sb).cpu().numpy(), s1.cpu().numpy(), rtol=1e-5)
+    # (iii) directional derivative
+    F = 16
+    def loss_at(flat):
+        m.set_flat_weights(flat)
+        with torch.cuda.device(m.device):
+            _, _, st = m._forward(m._to_device(x, 16), m._to_device(y, 1), None, 3, 0, want_pred=False)
+        st = st.cpu().numpy().astype(np.float64)
+        return (st[F] + 1e-2 * st[:F].sum()) / B
+    p = m.get_flat_weights().astype(np.float64)
+    d = rng.standard_normal(p.size)
+    d /= np.linalg.norm(d)
+    hh = 1e-2
+    fd = (loss_at((p + hh * d).astype(np.float32)) - loss_at((p - hh * d).astype(np.float32))) / (2 * hh)
+    m.set_flat_weights(p.astype(np.float32))
+    an = float(g1.cpu().numpy().astype(np.float64) @ d)
+    assert abs(fd - an) < 2e-2 * abs(an) + 1e-6, (fd, an)
+
+
+def test_compression_matrix_callback(tmp_path):
+    import dib_b200
+    x, y = O.boolean_circuit_truth_table()
+    cfg = O.DIBConfig([1] * 10, [16], [16], 1, feature_embedding_dimension=4)
+    m = build_model(cfg)
+    cb = dib_b200.SaveCompressionMatricesCallback(1, x, x, str(tmp_path))
+    stash = dib_b200.StashEmbeddingsCallback(1, x[:32], save_start=-1)
+    m.fit(x, y, epochs=1, batch_size=256, callbacks=[dib_b200.InfoBottleneckAnnealingCallback(1e-3, 1, 0, 2), cb, stash])
+    assert len(cb.matrices) == 10
+    rec = cb.matrices[3]
+    assert rec["compression_matrix"].shape == (2, 2)                         # binary feature: 2 unique values
+    ref = O.compression_matrix(cfg, m.get_flat_weights(), 3, np.array([[-1.0], [1.0]]))
+    np.testing.assert_allclose(rec["compression_matrix"], ref, rtol=1e-4, atol=1e-5)
+    assert os.path.exists(os.path.join(str(tmp_path), f"feature_3_log10beta_{np.log10(1e-3):.3f}.npz"))
+    assert len(stash.mus_for_later) == 10 and stash.mus_for_later[0].shape == (32, 4)
