@@ -1,5 +1,6 @@
 // dib_api.cu -- the C ABI declared in include/dib_b200.h: model description, workspace plan, and the
 // orchestration of one forward / train step as a fixed sequence of asynchronous launches on the caller's stream.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -12,6 +13,7 @@
 namespace {
 
 thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};
 
 int fail(const std::string& msg) {
   g_last_error = msg;
@@ -64,6 +66,10 @@ struct dib_model {
   std::vector<int> enc_fwd, enc_dgrad, enc_wgrad;  // start index into d_probs per layer j
   std::vector<int> int_fwd, int_dgrad, int_wgrad;
   std::vector<int> enc_maxK;                        // max over features of fan-in of layer j
+  // optional per-launch-group timing with CUDA events on the caller's stream (dib_profile_*)
+  bool profiling = false;
+  struct ProfRec { std::string label; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
 };
 
 namespace {
@@ -217,6 +223,20 @@ struct Ctx {
   int n;
 };
 
+void prof_begin(const Ctx& c, const char* label, int j = -1) {
+  if (!c.h->profiling) return;
+  dib_model::ProfRec r;
+  r.label = label;
+  if (j >= 0) r.label += std::to_string(j);
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, c.st);
+  c.h->prof.push_back(r);
+}
+void prof_end(const Ctx& c) {
+  if (!c.h->profiling) return;
+  cudaEventRecord(c.h->prof.back().b, c.st);
+}
+
 int gemm(const Ctx& c, int mode, int first, int nprob, int maxC, int maxR, int nsplit, int rps) {
   DibGemmLaunch L;
   L.probs = c.h->d_probs + first;
@@ -249,29 +269,72 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
                 uint64_t sample_offset, float inv_batch, bool training, float* user_pred, float* user_emb,
                 float* out_stats) {
   dib_model* h = c.h;
+  prof_begin(c, "pe");
   DIB_CUDA_OK(dib_launch_pe(x, h->D, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, c.n, c.st));
-  for (int j = 0; j <= h->L; ++j)
+  prof_end(c);
+  for (int j = 0; j <= h->L; ++j) {
+    prof_begin(c, "enc_fwd_l", j);
     if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j], h->F, enc_fan_out(h, j), 0, 1, 0)) return 1;
+    prof_end(c);
+  }
   DibReparamArgs ra;
   ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
   ra.eps = eps; ra.seed = seed; ra.step = step; ra.sample_offset = sample_offset;
   ra.F = h->F; ra.E = h->E; ra.n = c.n;
+  prof_begin(c, "reparam_kl_fwd");
   DIB_CUDA_OK(dib_launch_reparam_fwd(ra, c.ws + h->emb.off, h->emb.ld, user_emb, c.ws + h->kl_part_off, h->nblk_max, c.st));
-  for (int j = 0; j <= h->Li; ++j)
+  prof_end(c);
+  for (int j = 0; j <= h->Li; ++j) {
+    prof_begin(c, "int_fwd_l", j);
     if (gemm(c, DIB_GEMM_FWD, h->int_fwd[j], 1, int_fan_out(h, j), 0, 1, 0)) return 1;
+    prof_end(c);
+  }
+  prof_begin(c, "loss_stats");
   DIB_CUDA_OK(dib_launch_loss(h->loss, h->out_act, h->alpha, c.ws + h->pred.off, h->pred.ld, y, h->out, c.n, inv_batch,
                               training ? c.ws + h->d_pred.off : nullptr, user_pred, c.ws + h->loss_part_off,
                               c.ws + h->acc_part_off, c.st));
   const int nblk = (int)DIB_CEIL_DIV((long long)c.n, (long long)kRowsPerBlock);
   DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->nblk_max, nblk, c.ws + h->loss_part_off,
                                         c.ws + h->acc_part_off, nblk, h->F, c.n, y != nullptr, out_stats, c.st));
+  prof_end(c);
   return 0;
 }
 
 }  // namespace
 
 // =================================================================================================
+void dib_note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
 extern "C" {
+
+uint64_t dib_launch_count(void) { return g_launches.load(); }
+
+int dib_profile_enable(dib_model* h, int32_t on) {
+  if (!h) return fail("null model handle");
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
+  h->profiling = on != 0;
+  return 0;
+}
+
+int32_t dib_profile_read(dib_model* h, char* labels, size_t labels_bytes, float* ms, int32_t capacity) {
+  if (!h) { fail("null model handle"); return -1; }
+  std::string all;
+  int32_t n = 0;
+  for (auto& r : h->prof) {
+    if (n >= capacity) break;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) { fail("dib_profile_read: event sync failed"); return -1; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[n++] = t;
+    all += r.label; all += '\n';
+  }
+  if (labels && labels_bytes) {
+    const size_t k = all.size() < labels_bytes - 1 ? all.size() : labels_bytes - 1;
+    memcpy(labels, all.data(), k); labels[k] = 0;
+  }
+  return n;
+}
 
 const char* dib_last_error(void) { return g_last_error.c_str(); }
 
@@ -362,6 +425,7 @@ void dib_destroy(dib_model* h) {
   if (h->d_probs) cudaFree(h->d_probs);
   if (h->d_col_src) cudaFree(h->d_col_src);
   if (h->d_col_freq) cudaFree(h->d_col_freq);
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
 }
 
@@ -429,20 +493,34 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
 
   // integration network backward (GradientTape through models.py:122)
   for (int j = h->Li; j >= 0; --j) {
+    prof_begin(c, "int_wgrad_l", j);
     if (gemm(c, DIB_GEMM_WGRAD, h->int_wgrad[j], 1, int_fan_out(h, j), int_fan_in(h, j), nsplit, (int)rps)) return 1;
+    prof_end(c);
+    prof_begin(c, "int_dgrad_l", j);
     if (gemm(c, DIB_GEMM_DGRAD, h->int_dgrad[j], 1, int_fan_in(h, j), 0, 1, 0)) return 1;
+    prof_end(c);
   }
   DibReparamArgs ra;
   ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
   ra.eps = eps; ra.seed = seed; ra.step = step; ra.sample_offset = sample_offset;
   ra.F = h->F; ra.E = h->E; ra.n = n;
+  prof_begin(c, "reparam_kl_bwd");
   DIB_CUDA_OK(dib_launch_reparam_bwd(ra, c.ws + h->d_emb.off, h->d_emb.ld, beta_dev, inv_global_batch,
                                      c.ws + h->d_out.off, c.st));
+  prof_end(c);
   for (int j = h->L; j >= 0; --j) {
+    prof_begin(c, "enc_wgrad_l", j);
     if (gemm(c, DIB_GEMM_WGRAD, h->enc_wgrad[j], h->F, enc_fan_out(h, j), h->enc_maxK[j], nsplit, (int)rps)) return 1;
-    if (j >= 1 && gemm(c, DIB_GEMM_DGRAD, h->enc_dgrad[j], h->F, h->enc_arch[j - 1], 0, 1, 0)) return 1;
+    prof_end(c);
+    if (j >= 1) {
+      prof_begin(c, "enc_dgrad_l", j);
+      if (gemm(c, DIB_GEMM_DGRAD, h->enc_dgrad[j], h->F, h->enc_arch[j - 1], 0, 1, 0)) return 1;
+      prof_end(c);
+    }
   }
+  prof_begin(c, "wgrad_split_reduce");
   DIB_CUDA_OK(dib_launch_reduce_partials(c.ws + h->part_off, h->Pp, nsplit, h->P, grads_flat, c.st));
+  prof_end(c);
   return 0;
 }
 

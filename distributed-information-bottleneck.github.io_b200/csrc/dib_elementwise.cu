@@ -288,6 +288,7 @@ cudaError_t dib_launch_pe(const float* x, int ldx, int x_col_shift, const int* c
   if (n <= 0 || ncols <= 0) return cudaSuccess;
   dib_pe_kernel<<<nblocks((long long)n * ncols, 256), 256, 0, st>>>(x, ldx, x_col_shift, col_src, col_freq, col_begin,
                                                                    ncols, pe, ldpe, pe_col_shift, n);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
@@ -296,6 +297,7 @@ cudaError_t dib_launch_reparam_fwd(const DibReparamArgs& a, float* emb, int ldem
   if (a.n <= 0) return cudaSuccess;
   dim3 grid(nblocks(a.n, kRowsPerBlock), a.F);
   dib_reparam_fwd_kernel<<<grid, kRowsPerBlock, 0, st>>>(a, emb, ldemb, user_emb, kl_part, nblk_stride);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
@@ -304,6 +306,7 @@ cudaError_t dib_launch_reparam_bwd(const DibReparamArgs& a, const float* d_emb, 
   if (a.n <= 0) return cudaSuccess;
   dim3 grid(nblocks(a.n, kRowsPerBlock), a.F);
   dib_reparam_bwd_kernel<<<grid, kRowsPerBlock, 0, st>>>(a, d_emb, ldemb, beta_dev, inv_batch, d_out);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
@@ -313,6 +316,7 @@ cudaError_t dib_launch_loss(int loss, int out_act, float alpha, const float* pre
   if (n <= 0) return cudaSuccess;
   dib_loss_kernel<<<nblocks(n, kRowsPerBlock), kRowsPerBlock, 0, st>>>(loss, out_act, alpha, pred, ldp, y, out_dim, n,
                                                                       inv_batch, d_pred, user_pred, loss_part, acc_part);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
@@ -321,6 +325,7 @@ cudaError_t dib_launch_finalize_stats(const float* kl_part, int nblk_stride, int
                                       cudaStream_t st) {
   dib_finalize_stats_kernel<<<1, 256, 0, st>>>(kl_part, nblk_stride, nblk_kl, loss_part, acc_part, nblk_loss, F, n,
                                                has_y, out_stats);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
@@ -328,12 +333,14 @@ cudaError_t dib_launch_reduce_partials(const float* part, long long split_stride
                                        cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   dib_reduce_partials_kernel<<<nblocks(count, 256), 256, 0, st>>>(part, split_stride, nsplit, count, out);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
 cudaError_t dib_launch_copy2d(const float* src, int lds, float* dst, int ldd, int cols, int64_t n, cudaStream_t st) {
   if (n <= 0 || cols <= 0) return cudaSuccess;
   dib_copy2d_kernel<<<nblocks((long long)n * cols, 256), 256, 0, st>>>(src, lds, dst, ldd, cols, n);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
@@ -341,7 +348,9 @@ cudaError_t dib_launch_adam(float* params, const float* grads, float* m, float* 
                             int32_t* step_dev, float b1, float b2, float eps, cudaStream_t st) {
   if (count > 0)
     dib_adam_kernel<<<nblocks(count, 256), 256, 0, st>>>(params, grads, m, v, count, lr_dev, step_dev, b1, b2, eps);
+  dib_note_launch();
   dib_inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
@@ -349,10 +358,12 @@ cudaError_t dib_launch_bhattacharyya(const float* mu_logvar, int64_t n, int E, f
                                      cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   dib_bhattacharyya_kernel<<<nblocks((long long)n * n, 128), 128, 0, st>>>(mu_logvar, n, E, out_dist, out_comp);
+  dib_note_launch();
   return cudaGetLastError();
 }
 
 cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st) {
   dib_metrics_update_kernel<<<1, 256, 0, st>>>(stats, beta_dev, acc, F);
+  dib_note_launch();
   return cudaGetLastError();
 }

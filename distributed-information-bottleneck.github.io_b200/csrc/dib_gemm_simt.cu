@@ -251,6 +251,7 @@ cudaError_t launch_cfg(const DibGemmLaunch& L, cudaStream_t st) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
   dib_gemm_simt_kernel<MODE, BR, BC, BT, TM, TN><<<grid, NT, 0, st>>>(
       L.probs, L.baseA, L.baseB, L.baseC, L.baseX, L.M, L.nsplit, L.rows_per_split, L.split_stride, L.alpha);
+  dib_note_launch();
   return cudaGetLastError();
 }
 

@@ -5,6 +5,9 @@
 
 struct DibGemmProblem;
 
+// number of kernels launched by this library in this process (bench.py reports it as gpu_launches)
+void dib_note_launch(int n = 1);
+
 struct DibGemmLaunch {
   const DibGemmProblem* probs;  // device array, nprob entries
   int nprob;

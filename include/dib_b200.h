@@ -136,6 +136,15 @@ int dib_metrics_update(const float* stats, const float* beta_dev, float* acc, in
 int dib_bhattacharyya(const float* mu_logvar, int64_t n, int32_t embedding_dimension,
                       float* out_dist, float* out_compression, void* stream);
 
+/* ---- observability (no reference counterpart) ---------------------------------------------------------
+ * dib_launch_count: kernels launched by this library in this process.
+ * dib_profile_enable(h,1): bracket every launch group of subsequent forward/train_step calls with CUDA events
+ * recorded on the caller's stream; dib_profile_read waits for them and returns up to `capacity` durations (ms)
+ * with '\n'-separated labels; dib_profile_enable(h,0) turns it off and frees the events. */
+uint64_t dib_launch_count(void);
+int dib_profile_enable(dib_model* h, int32_t on);
+int32_t dib_profile_read(dib_model* h, char* labels, size_t labels_bytes, float* ms, int32_t capacity);
+
 /* text of the last error raised on this thread ("" if none). */
 const char* dib_last_error(void);
 

@@ -1,6 +1,10 @@
 import os
 import sys
 
+# the float64 oracle does many small matmuls: a 128-thread BLAS pool on the GPU box makes them crawl
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "8")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -32,3 +36,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _limit_blas_threads():
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=8):
+            yield
+    except ImportError:  # pragma: no cover
+        yield

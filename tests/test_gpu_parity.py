@@ -135,7 +135,8 @@ def test_adam_matches_keras_semantics_oracle():
                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     assert int(step.item()) == 5
     np.testing.assert_allclose(wd.cpu().numpy(), w_ref, rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(md.cpu().numpy(), st.m, rtol=1e-5, atol=1e-12)
+    # m is a sum of terms of mixed sign: compare against its scale (cancellation leaves ~1 ulp of the largest term)
+    np.testing.assert_allclose(md.cpu().numpy(), st.m, rtol=1e-5, atol=1e-6 * np.abs(st.m).max())
     np.testing.assert_allclose(vd.cpu().numpy(), st.v, rtol=1e-5, atol=1e-20)
 
 

@@ -174,3 +174,23 @@ def test_fit_history_keys_and_learning():
         assert len(h[k]) == 3
     assert h["loss"][-1] < h["loss"][0]
     assert h["beta"][0] == h["beta"][1] == float(np.float32(9.999999e-05))
+
+
+def test_numpy_backward_matches_torch_autograd_twin():
+    import torch
+    from oracle.torch_twin import TwinDIB
+    rng = np.random.default_rng(7)
+    cfg = O.DIBConfig([1, 2, 1, 1], [16, 16], [24, 24], 1, feature_embedding_dimension=6)
+    p = O.glorot_uniform_params(cfg, rng, dtype=np.float64) + 0.05 * rng.standard_normal(cfg.param_count())
+    B = 33
+    x, eps = rng.standard_normal((B, 5)), rng.standard_normal((B, 4, 6))
+    y = rng.integers(0, 2, size=(B, 1)).astype(np.float64)
+    g, fr = O.train_grads(cfg, p, x, y, eps, 0.3, O.LOSS_BCE_LOGITS)
+    twin = TwinDIB(cfg, p).double()
+    twin.load_flat(p)
+    twin.beta = 0.3
+    total, task, kls, pred = twin.loss(torch.from_numpy(x), torch.from_numpy(y), O.LOSS_BCE_LOGITS, torch.from_numpy(eps))
+    total.backward()
+    np.testing.assert_allclose(twin.flat_grads().numpy(), g, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(float(total), fr.loss, rtol=1e-12)
+    np.testing.assert_allclose(kls.detach().numpy(), fr.kl_per_feature, rtol=1e-12)
