@@ -61,6 +61,7 @@ struct dib_model {
   int nblk_max = 0;
   // device tables
   DibGemmProblem* d_probs = nullptr;
+  std::vector<DibGemmProblem> h_probs;
   int* d_col_src = nullptr;
   int* d_col_freq = nullptr;
   std::vector<int> enc_fwd, enc_dgrad, enc_wgrad;  // start index into d_probs per layer j
@@ -251,6 +252,10 @@ int gemm(const Ctx& c, int mode, int first, int nprob, int maxC, int maxR, int n
     case DIB_GEMM_DGRAD: L.baseA = c.ws; L.baseB = c.params; L.baseC = c.ws; L.baseX = c.ws; break;
     default: L.baseA = c.ws; L.baseB = c.ws; L.baseC = part; L.baseX = part; break;
   }
+  if (c.h->precision == DIB_PREC_TF32 && dib_gemm_tc_eligible(mode, c.h->h_probs.data() + first, nprob, c.params)) {
+    DIB_CUDA_OK(dib_launch_gemm_tc(mode, L, c.h->h_probs.data() + first, c.st));
+    return 0;
+  }
   DIB_CUDA_OK(dib_launch_gemm_simt(mode, L, c.st));
   return 0;
 }
@@ -338,7 +343,7 @@ int32_t dib_profile_read(dib_model* h, char* labels, size_t labels_bytes, float*
 
 const char* dib_last_error(void) { return g_last_error.c_str(); }
 
-const char* dib_build_info(void) { return "dib_b200 abi=1 arch=sm_100a paths=fp32-simt"; }
+const char* dib_build_info(void) { return "dib_b200 abi=1 arch=sm_100a paths=fp32-simt,tf32-tcgen05"; }
 
 int dib_create(const dib_config* cfg, dib_model** out) {
   if (!cfg || !out) return fail("dib_create: null argument");
@@ -348,7 +353,8 @@ int dib_create(const dib_config* cfg, dib_model** out) {
       cfg->max_batch < 1 || cfg->number_encoder_layers < 0 || cfg->number_integration_layers < 0)
     return fail("dib_create: invalid sizes");
   if (cfg->max_batch > 0x7fffffffll) return fail("dib_create: max_batch too large");
-  if (cfg->precision != DIB_PREC_FP32) return fail("dib_create: only DIB_PREC_FP32 is built into this library");
+  if (cfg->precision != DIB_PREC_FP32 && cfg->precision != DIB_PREC_TF32)
+    return fail("dib_create: precision must be DIB_PREC_FP32 or DIB_PREC_TF32 in this build");
   if (cfg->activation_fn < 0 || cfg->activation_fn > DIB_ACT_ELU || cfg->output_activation_fn < 0 ||
       cfg->output_activation_fn > DIB_ACT_ELU)
     return fail("dib_create: unknown activation");
@@ -405,6 +411,7 @@ int dib_create(const dib_config* cfg, dib_model** out) {
 
   std::vector<DibGemmProblem> probs;
   build_problems(h, probs);
+  h->h_probs = probs;
   cudaError_t e = cudaMalloc(&h->d_probs, probs.size() * sizeof(DibGemmProblem));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_col_src, col_src.size() * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_col_freq, col_freq.size() * sizeof(int));

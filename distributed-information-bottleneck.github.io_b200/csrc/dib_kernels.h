@@ -25,6 +25,10 @@ struct DibGemmLaunch {
 
 cudaError_t dib_launch_gemm_simt(int mode, const DibGemmLaunch& L, cudaStream_t st);
 
+// TF32 tcgen05 path (dib_gemm_tc.cu); `hp` = host copies of the group's problem descriptors
+bool dib_gemm_tc_eligible(int mode, const DibGemmProblem* hp, int nprob, const float* params_base_hint);
+cudaError_t dib_launch_gemm_tc(int mode, const DibGemmLaunch& L, const DibGemmProblem* hp, cudaStream_t st);
+
 // ---- elementwise / reduction kernels (dib_elementwise.cu) -----------------------------------------------
 // positional encoding (models.py:22-23) into the padded first-layer operand; tables are per pe column.
 cudaError_t dib_launch_pe(const float* x, int ldx, int x_col_shift, const int* col_src, const int* col_freq,
