@@ -55,6 +55,9 @@ SIGNATURES = {
     "dib_launch_count": (c_uint64, []),
     "dib_profile_enable": (c_int32, [c_void_p, c_int32]),
     "dib_profile_read": (c_int32, [c_void_p, c_char_p, c_size_t, POINTER(c_float), c_int32]),
+    "dib_debug_gemm_tc": (c_int32, [c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32,
+                                    c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int32,
+                                    c_void_p]),
     "dib_last_error": (c_char_p, []),
     "dib_build_info": (c_char_p, []),
 }

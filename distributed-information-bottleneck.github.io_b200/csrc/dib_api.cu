@@ -341,6 +341,32 @@ int32_t dib_profile_read(dib_model* h, char* labels, size_t labels_bytes, float*
   return n;
 }
 
+// single-problem GEMM through the tensor-core kernel (bring-up / unit tests): see DibGemmProblem for the modes
+int dib_debug_gemm_tc(int32_t mode, const float* A, int32_t lda, const float* B, int32_t ldb, float* Cout, int32_t ldc,
+                      float* X, int32_t ldx, int32_t M, int32_t T, int32_t Ccols, int32_t R, int32_t act,
+                      int32_t nsplit, int32_t rows_per_split, int64_t split_stride, int32_t use_simt, void* stream) {
+  DibGemmProblem p;
+  memset(&p, 0, sizeof(p));
+  p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldx = ldx; p.T = T; p.C = Ccols; p.R = R; p.act = act;
+  p.x_off = 0;
+  DibGemmProblem* dp = nullptr;
+  DIB_CUDA_OK(cudaMalloc(&dp, sizeof(p)));
+  DIB_CUDA_OK(cudaMemcpy(dp, &p, sizeof(p), cudaMemcpyHostToDevice));
+  DibGemmLaunch L;
+  L.probs = dp; L.nprob = 1; L.baseA = A; L.baseB = B; L.baseC = Cout; L.baseX = X; L.M = M;
+  L.maxC = Ccols; L.maxR = R; L.nsplit = nsplit < 1 ? 1 : nsplit; L.rows_per_split = rows_per_split;
+  L.split_stride = split_stride; L.alpha = 0.2f;
+  cudaError_t e;
+  if (use_simt) e = dib_launch_gemm_simt(mode, L, static_cast<cudaStream_t>(stream));
+  else if (!dib_gemm_tc_eligible(mode, &p, 1, nullptr)) { cudaFree(dp); return fail("dib_debug_gemm_tc: not eligible"); }
+  else e = dib_launch_gemm_tc(mode, L, &p, static_cast<cudaStream_t>(stream));
+  cudaError_t e2 = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  cudaFree(dp);
+  if (e != cudaSuccess) return fail(std::string("launch: ") + cudaGetErrorString(e));
+  if (e2 != cudaSuccess) return fail(std::string("sync: ") + cudaGetErrorString(e2));
+  return 0;
+}
+
 const char* dib_last_error(void) { return g_last_error.c_str(); }
 
 const char* dib_build_info(void) { return "dib_b200 abi=1 arch=sm_100a paths=fp32-simt,tf32-tcgen05"; }

@@ -6,6 +6,7 @@
 //
 // Canonical form Out[R x C] = sum_t Aop[R x T] * Bop[T x C]; operand majors per mode
 //   FWD    A = h[M x K]   K-major | B = W[K x N]        MN-major      (reduction over fan-in)
+//   (K-major tiles: SWIZZLE_128B; MN-major fp32 tiles: SWIZZLE_128B with 32-byte atoms, see dib_sm100.cuh)
 //   DGRAD  A = dz[M x N]  K-major | B = W[K x N] as [k][n] K-major    (reduction over fan-out)
 //   WGRAD  A = h[m][k]   MN-major | B = dz[m][n]        MN-major      (reduction over a batch slice)
 // CTA tile 128 x BN (BN = 64 | 128), K step 32 fp32 (= one 128-byte swizzle span) per pipeline stage.
@@ -118,9 +119,9 @@ dib_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
         for (int kk = 0; kk < kBK / 8; ++kk) {          // UMMA K = 8 for tf32 (32 bytes)
           // K-major: advance 32 B inside the 128 B swizzle span; MN-major: advance 8 k-rows (1024 B)
-          const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + kk * 1024, kBK * 128, 1024)
+          const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + kk * 1024, kBK * 128, 512, kLayoutSw128Base32)
                                       : umma_smem_desc(a_addr + kk * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + kk * 1024, kBK * 128, 1024)
+          const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + kk * 1024, kBK * 128, 512, kLayoutSw128Base32)
                                       : umma_smem_desc(b_addr + kk * 32, 16, 1024);
           umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
         }
@@ -140,10 +141,10 @@ dib_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         mbar_wait(full_bar(s), ph);
         if (et < BN) {
           const uint8_t* bt = smem_gen + s * L::kStageBytes + kABytes + (et >> 5) * (kBK * 128);
-          const int ch = (et & 31) >> 2, w = et & 3;
+          const int ch = (et & 31) >> 3, w = et & 7;      // 32-byte chunk inside the 128 B row, word inside the chunk
 #pragma unroll 8
           for (int row = 0; row < kBK; ++row)
-            bs += *reinterpret_cast<const float*>(bt + row * 128 + ((ch ^ (row & 7)) << 4) + (w << 2));
+            bs += *reinterpret_cast<const float*>(bt + row * 128 + ((ch ^ (row & 3)) << 5) + (w << 2));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(s));
@@ -243,6 +244,7 @@ bool make_map_kmajor(CUtensorMap* m, const float* base, long long cols, long lon
 
 // MN-major operand: matrix [krows x ld] fp32 whose contiguous dimension is M/N -> 4D map
 // (32 floats, k-row, 32-float panel, feature), box 32 x 32 x npanels x 1  => shared memory [panel][k-row][128 B]
+// Swizzle: 128B span with 32B atoms (the only MN-major layout tcgen05 accepts for 32-bit operands).
 bool make_map_mnmajor(CUtensorMap* m, const float* base, long long cols, long long krows, long long ld, long long fs,
                       int nfeat, int npanels) {
   cuuint64_t dims[4] = {32, (cuuint64_t)krows, (cuuint64_t)(cols / 32), (cuuint64_t)nfeat};
@@ -250,7 +252,7 @@ bool make_map_mnmajor(CUtensorMap* m, const float* base, long long cols, long lo
   cuuint32_t box[4] = {32, (cuuint32_t)kBK, (cuuint32_t)npanels, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -112,13 +112,19 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major  operand tile [rows x 128 B]: 8-row groups of 1024 B;  SBO = 1024 (next 8 rows), LBO unused (=16 B).
 //   MN-major operand tile: panels of [k-rows x 128 B] (128 B = 32 fp32 / 64 bf16 along M/N);
 //                          SBO = 1024 (next 8 k-rows), LBO = panel stride (next 128 B worth of M/N).
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   fp32/tf32 MN-major operands must use LayoutType::SWIZZLE_128B_BASE32B (CUTLASS sm100_common.inl: "for mn-major
+//   tf32 operands, SW128_32B is the only available smem layout"): atoms of 4 k-rows x 128 B in which the 32-byte
+//   chunk index is XORed with (k-row % 4)  (cute Swizzle<2,5,2>; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+//   SBO = 512 (next 4 k-rows), LBO = panel stride.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = kLayoutSw128) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 

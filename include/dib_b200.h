@@ -145,6 +145,13 @@ uint64_t dib_launch_count(void);
 int dib_profile_enable(dib_model* h, int32_t on);
 int32_t dib_profile_read(dib_model* h, char* labels, size_t labels_bytes, float* ms, int32_t capacity);
 
+/* bring-up / unit-test hook: ONE GEMM problem through the tensor-core kernel (use_simt=0) or the fp32 SIMT kernel
+ * (use_simt=1); mode 0 FWD (bias = X, act), 1 DGRAD (X = activation source), 2 WGRAD (X = bias-grad partials).
+ * Synchronises the stream. */
+int dib_debug_gemm_tc(int32_t mode, const float* A, int32_t lda, const float* B, int32_t ldb, float* Cout, int32_t ldc,
+                      float* X, int32_t ldx, int32_t M, int32_t T, int32_t Ccols, int32_t R, int32_t act,
+                      int32_t nsplit, int32_t rows_per_split, int64_t split_stride, int32_t use_simt, void* stream);
+
 /* text of the last error raised on this thread ("" if none). */
 const char* dib_last_error(void);
 
