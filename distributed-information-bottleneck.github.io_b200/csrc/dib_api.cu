@@ -57,7 +57,7 @@ struct dib_model {
   Buf pe, enc_out, emb, pred, d_pred, d_emb, d_out;
   std::vector<Buf> enc_act, d_enc;  // index 1..L  (output of layer j-1)
   std::vector<Buf> int_act, d_int;  // index 1..Li
-  long long part_off = 0, kl_part_off = 0, loss_part_off = 0, acc_part_off = 0;
+  long long part_off = 0, kl_part_off = 0, loss_part_off = 0, acc_part_off = 0, wshadow_off = 0;
   int nblk_max = 0;
   // device tables
   DibGemmProblem* d_probs = nullptr;
@@ -67,6 +67,12 @@ struct dib_model {
   std::vector<int> enc_fwd, enc_dgrad, enc_wgrad;  // start index into d_probs per layer j
   std::vector<int> int_fwd, int_dgrad, int_wgrad;
   std::vector<int> enc_maxK;                        // max over features of fan-in of layer j
+  // fused per-feature encoder kernels (tensor-core mode; dib_enc_fused.cu)
+  bool fused_ok = false, fused_bwd_ok = false, force_unfused = false;
+  DibEncFusedDesc fdesc;
+  void* d_fused_tables = nullptr;
+  long long pack_off = 0;       // packed 16-bit encoder weights inside the workspace (float offset)
+  int kl_stride = 0, num_sms = 148, part_rows = kMaxSplits;
   // optional per-launch-group timing with CUDA events on the caller's stream (dib_profile_*)
   bool profiling = false;
   struct ProfRec { std::string label; cudaEvent_t a, b; };
@@ -115,10 +121,14 @@ void plan(dib_model* h) {
   h->d_out = make_buf(c, B, 2 * h->E, h->F);
   for (int j = 1; j <= h->L; ++j) h->d_enc[j] = make_buf(c, B, h->enc_arch[j - 1], h->F);
   h->nblk_max = (int)DIB_CEIL_DIV(B, (long long)kRowsPerBlock);
-  h->part_off = take(c, (long long)kMaxSplits * h->Pp);
-  h->kl_part_off = take(c, (long long)h->F * h->nblk_max);
+  h->part_rows = DIB_CEIL_DIV(h->num_sms, h->F) > kMaxSplits ? DIB_CEIL_DIV(h->num_sms, h->F) : kMaxSplits;
+  h->part_off = take(c, (long long)h->part_rows * h->Pp);
+  h->kl_stride = h->nblk_max > 192 ? h->nblk_max : 192;   // >= CTA slots per feature of the fused encoder kernels
+  h->kl_part_off = take(c, (long long)h->F * h->kl_stride);
   h->loss_part_off = take(c, h->nblk_max);
   h->acc_part_off = take(c, h->nblk_max);
+  h->wshadow_off = take(c, h->Pp);      // TF32-rounded copy of the parameters (tensor-core mode B operands)
+  h->pack_off = take(c, (long long)(dib_enc_fused_pack_bytes(h->F) + 3) / 4);
   h->ws_floats = c;
 }
 
@@ -247,12 +257,15 @@ int gemm(const Ctx& c, int mode, int first, int nprob, int maxC, int maxR, int n
   L.nsplit = nsplit; L.rows_per_split = rps; L.split_stride = c.h->Pp;
   L.alpha = c.h->alpha;
   float* part = c.ws + c.h->part_off;
+  const bool tc = c.h->precision == DIB_PREC_TF32;
+  L.round_out = tc ? 1 : 0;
   switch (mode) {
     case DIB_GEMM_FWD: L.baseA = c.ws; L.baseB = c.params; L.baseC = c.ws; L.baseX = nullptr; break;
     case DIB_GEMM_DGRAD: L.baseA = c.ws; L.baseB = c.params; L.baseC = c.ws; L.baseX = c.ws; break;
     default: L.baseA = c.ws; L.baseB = c.ws; L.baseC = part; L.baseX = part; break;
   }
-  if (c.h->precision == DIB_PREC_TF32 && dib_gemm_tc_eligible(mode, c.h->h_probs.data() + first, nprob, c.params)) {
+  if (tc && dib_gemm_tc_eligible(mode, c.h->h_probs.data() + first, nprob, c.params)) {
+    if (mode != DIB_GEMM_WGRAD) { L.baseB = c.ws + c.h->wshadow_off; L.baseBias = c.params; }
     DIB_CUDA_OK(dib_launch_gemm_tc(mode, L, c.h->h_probs.data() + first, c.st));
     return 0;
   }
@@ -262,7 +275,7 @@ int gemm(const Ctx& c, int mode, int first, int nprob, int maxC, int maxR, int n
 
 int check_call(const dib_model* h, const void* params, const void* x, int64_t n, const void* ws) {
   if (!h) return fail("null model handle");
-  if (!params || !x || !ws) return fail("null params / x / workspace pointer");
+  if (!params || !ws || (!x && n > 0)) return fail("null params / x / workspace pointer");
   if (n < 0 || n > h->maxB) return fail("n = " + std::to_string(n) + " exceeds config.max_batch = " + std::to_string(h->maxB));
   if (reinterpret_cast<uintptr_t>(ws) & 255) return fail("workspace must be 256-byte aligned");
   if (reinterpret_cast<uintptr_t>(params) & 15) return fail("params must be 16-byte aligned");
@@ -274,8 +287,36 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
                 uint64_t sample_offset, float inv_batch, bool training, float* user_pred, float* user_emb,
                 float* out_stats) {
   dib_model* h = c.h;
+  const int rnd = h->precision == DIB_PREC_TF32 ? 1 : 0;
+  if (rnd) {
+    prof_begin(c, "weights_tf32_shadow");
+    DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
+    prof_end(c);
+  }
+  // fused encoder path: only when the backward does not need the per-layer activations in HBM
+  const bool fused = h->fused_ok && rnd && (!training || h->fused_bwd_ok) && !h->force_unfused;
+  int nblk_kl = (int)DIB_CEIL_DIV((long long)c.n, (long long)kRowsPerBlock);
+  if (fused) {
+    const int ntiles = (int)DIB_CEIL_DIV((long long)c.n, 128ll);
+    long long want = (long long)h->F * ntiles;
+    DibEncFusedDesc d = h->fdesc;
+    d.grid = (int)(want < h->num_sms ? want : h->num_sms);
+    nblk_kl = DIB_CEIL_DIV(d.grid, h->F);
+    prof_begin(c, "enc_pack_weights");
+    DIB_CUDA_OK(dib_enc_fused_pack(d, c.params, c.ws + h->pack_off, c.st));
+    DIB_CUDA_OK(cudaMemsetAsync(c.ws + h->kl_part_off, 0, sizeof(float) * (size_t)h->F * h->kl_stride, c.st));
+    prof_end(c);
+    DibEncFusedIO io;
+    io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = c.n;
+    io.eps = eps; io.seed = seed; io.step = step; io.sample_offset = sample_offset;
+    io.emb = c.ws + h->emb.off; io.ldemb = h->emb.ld; io.user_emb = user_emb;
+    io.kl_part = c.ws + h->kl_part_off; io.kl_stride = h->kl_stride;
+    prof_begin(c, "enc_fused_fwd");
+    DIB_CUDA_OK(dib_enc_fused_forward(d, io, c.st));
+    prof_end(c);
+  } else {
   prof_begin(c, "pe");
-  DIB_CUDA_OK(dib_launch_pe(x, h->D, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, c.n, c.st));
+  DIB_CUDA_OK(dib_launch_pe(x, h->D, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, c.n, rnd, c.st));
   prof_end(c);
   for (int j = 0; j <= h->L; ++j) {
     prof_begin(c, "enc_fwd_l", j);
@@ -285,10 +326,11 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
   DibReparamArgs ra;
   ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
   ra.eps = eps; ra.seed = seed; ra.step = step; ra.sample_offset = sample_offset;
-  ra.F = h->F; ra.E = h->E; ra.n = c.n;
+  ra.F = h->F; ra.E = h->E; ra.n = c.n; ra.round_out = rnd;
   prof_begin(c, "reparam_kl_fwd");
-  DIB_CUDA_OK(dib_launch_reparam_fwd(ra, c.ws + h->emb.off, h->emb.ld, user_emb, c.ws + h->kl_part_off, h->nblk_max, c.st));
+  DIB_CUDA_OK(dib_launch_reparam_fwd(ra, c.ws + h->emb.off, h->emb.ld, user_emb, c.ws + h->kl_part_off, h->kl_stride, c.st));
   prof_end(c);
+  }
   for (int j = 0; j <= h->Li; ++j) {
     prof_begin(c, "int_fwd_l", j);
     if (gemm(c, DIB_GEMM_FWD, h->int_fwd[j], 1, int_fan_out(h, j), 0, 1, 0)) return 1;
@@ -297,9 +339,9 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
   prof_begin(c, "loss_stats");
   DIB_CUDA_OK(dib_launch_loss(h->loss, h->out_act, h->alpha, c.ws + h->pred.off, h->pred.ld, y, h->out, c.n, inv_batch,
                               training ? c.ws + h->d_pred.off : nullptr, user_pred, c.ws + h->loss_part_off,
-                              c.ws + h->acc_part_off, c.st));
+                              c.ws + h->acc_part_off, rnd, c.st));
   const int nblk = (int)DIB_CEIL_DIV((long long)c.n, (long long)kRowsPerBlock);
-  DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->nblk_max, nblk, c.ws + h->loss_part_off,
+  DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->kl_stride, nblk_kl, c.ws + h->loss_part_off,
                                         c.ws + h->acc_part_off, nblk, h->F, c.n, y != nullptr, out_stats, c.st));
   prof_end(c);
   return 0;
@@ -313,6 +355,13 @@ void dib_note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::m
 extern "C" {
 
 uint64_t dib_launch_count(void) { return g_launches.load(); }
+
+// bring-up switch: 1 = never use the fused encoder kernels (compare fused vs unfused tensor-core paths)
+int dib_debug_force_unfused(dib_model* h, int32_t on) {
+  if (!h) return fail("null model handle");
+  h->force_unfused = on != 0;
+  return 0;
+}
 
 int dib_profile_enable(dib_model* h, int32_t on) {
   if (!h) return fail("null model handle");
@@ -433,6 +482,12 @@ int dib_create(const dib_config* cfg, dib_model** out) {
     h->intB.push_back(add_var(0, int_fan_out(h, j)));
   }
   h->P = off; h->Pp = DIB_ROUND_UP(off, 64);
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || h->num_sms < 1)
+      h->num_sms = 148;
+  }
   plan(h);
 
   std::vector<DibGemmProblem> probs;
@@ -449,6 +504,35 @@ int dib_create(const dib_config* cfg, dib_model** out) {
     dib_destroy(h);
     return fail(msg);
   }
+  // ---- fused encoder kernels: two hidden layers of 128, E = 32, first-layer fan-in (+ bias column) <= 16
+  {
+    bool ok = h->precision != DIB_PREC_FP32 && h->L == 2 && h->enc_arch[0] == 128 && h->enc_arch[1] == 128 && h->E == 32;
+    for (int f = 0; ok && f < h->F; ++f) ok = h->w_in[f] + 1 <= 16;
+    if (ok) {
+      const int F = h->F;
+      std::vector<long long> tab(6 * (size_t)F);
+      std::vector<int> itab(2 * (size_t)F);
+      for (int f = 0; f < F; ++f) {
+        tab[0 * F + f] = h->encW[f][0]; tab[1 * F + f] = h->encB[f][0]; tab[2 * F + f] = h->encW[f][1];
+        tab[3 * F + f] = h->encB[f][1]; tab[4 * F + f] = h->encW[f][2]; tab[5 * F + f] = h->encB[f][2];
+        itab[f] = h->x_off[f]; itab[F + f] = h->fdims[f];
+      }
+      const size_t b1 = tab.size() * sizeof(long long), b2 = itab.size() * sizeof(int);
+      cudaError_t fe = cudaMalloc(&h->d_fused_tables, b1 + b2);
+      if (fe == cudaSuccess) fe = cudaMemcpy(h->d_fused_tables, tab.data(), b1, cudaMemcpyHostToDevice);
+      if (fe == cudaSuccess) fe = cudaMemcpy(static_cast<char*>(h->d_fused_tables) + b1, itab.data(), b2, cudaMemcpyHostToDevice);
+      if (fe == cudaSuccess) {
+        const long long* lt = static_cast<const long long*>(h->d_fused_tables);
+        const int* it = reinterpret_cast<const int*>(static_cast<const char*>(h->d_fused_tables) + b1);
+        DibEncFusedDesc& d = h->fdesc;
+        d.F = F; d.nfreq = h->nfreq; d.act = h->act; d.alpha = h->alpha; d.bf16 = 0;
+        d.w0_off = lt; d.b0_off = lt + F; d.w1_off = lt + 2 * F; d.b1_off = lt + 3 * F; d.w2_off = lt + 4 * F;
+        d.b2_off = lt + 5 * F; d.x_off = it; d.fdim = it + F;
+        h->fused_ok = true;
+        h->fused_bwd_ok = true;
+      }
+    }
+  }
   *out = h;
   return 0;
 }
@@ -458,6 +542,7 @@ void dib_destroy(dib_model* h) {
   if (h->d_probs) cudaFree(h->d_probs);
   if (h->d_col_src) cudaFree(h->d_col_src);
   if (h->d_col_freq) cudaFree(h->d_col_freq);
+  if (h->d_fused_tables) cudaFree(h->d_fused_tables);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
 }
@@ -496,8 +581,10 @@ int dib_encode_feature(dib_model* h, const float* params, int32_t feature, const
   if (n == 0) return 0;
   Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
   const int f = feature, wpad = DIB_ROUND_UP(h->w_in[f], 4);
+  const int rnd = h->precision == DIB_PREC_TF32 ? 1 : 0;
+  if (rnd) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
   DIB_CUDA_OK(dib_launch_pe(x_i, h->fdims[f], h->x_off[f], h->d_col_src, h->d_col_freq, h->pe_off[f], h->pe_off[f] + wpad,
-                            c.ws + h->pe.off, h->ldpe, 0, n, c.st));
+                            c.ws + h->pe.off, h->ldpe, 0, n, rnd, c.st));
   for (int j = 0; j <= h->L; ++j)
     if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j] + f, 1, enc_fan_out(h, j), 0, 1, 0)) return 1;
   DIB_CUDA_OK(dib_launch_copy2d(c.ws + h->enc_out.off + f * h->enc_out.feat_stride, h->enc_out.ld, out_mu_logvar,
@@ -533,10 +620,39 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
     if (gemm(c, DIB_GEMM_DGRAD, h->int_dgrad[j], 1, int_fan_in(h, j), 0, 1, 0)) return 1;
     prof_end(c);
   }
+  const bool fused = h->fused_ok && h->fused_bwd_ok && h->precision == DIB_PREC_TF32 && !h->force_unfused;
+  if (fused) {
+    const int ntiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
+    const long long want = (long long)h->F * ntiles;
+    DibEncFusedDesc d = h->fdesc;
+    d.grid = (int)(want < h->num_sms ? want : h->num_sms);
+    const int slots_max = DIB_CEIL_DIV(d.grid, h->F), slots_min = d.grid / h->F;
+    const long long p_enc = h->intW[0];              // encoder parameters occupy [0, p_enc)
+    float* part = c.ws + h->part_off;
+    if (slots_max > slots_min && slots_min >= 0)
+      DIB_CUDA_OK(cudaMemsetAsync(part + (long long)slots_min * h->Pp, 0,
+                                  sizeof(float) * (size_t)(slots_max - slots_min) * h->Pp, c.st));
+    DibEncFusedIO io;
+    io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = n;
+    io.eps = eps; io.seed = seed; io.step = step; io.sample_offset = sample_offset;
+    io.emb = nullptr; io.ldemb = 0; io.user_emb = nullptr; io.kl_part = nullptr; io.kl_stride = 0;
+    DibEncFusedBwdIO b;
+    b.d_emb = c.ws + h->d_emb.off; b.ldd = h->d_emb.ld; b.beta_dev = beta_dev; b.inv_batch = inv_global_batch;
+    b.gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
+    b.part = part; b.split_stride = h->Pp;
+    prof_begin(c, "enc_fused_bwd");
+    DIB_CUDA_OK(dib_enc_fused_backward(d, io, b, c.st));
+    prof_end(c);
+    prof_begin(c, "wgrad_split_reduce");
+    DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, slots_max, p_enc, grads_flat, c.st));
+    DIB_CUDA_OK(dib_launch_reduce_partials(part + p_enc, h->Pp, nsplit, h->P - p_enc, grads_flat + p_enc, c.st));
+    prof_end(c);
+    return 0;
+  }
   DibReparamArgs ra;
   ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
   ra.eps = eps; ra.seed = seed; ra.step = step; ra.sample_offset = sample_offset;
-  ra.F = h->F; ra.E = h->E; ra.n = n;
+  ra.F = h->F; ra.E = h->E; ra.n = n; ra.round_out = h->precision == DIB_PREC_TF32 ? 1 : 0;
   prof_begin(c, "reparam_kl_bwd");
   DIB_CUDA_OK(dib_launch_reparam_bwd(ra, c.ws + h->d_emb.off, h->d_emb.ld, beta_dev, inv_global_batch,
                                      c.ws + h->d_out.off, c.st));

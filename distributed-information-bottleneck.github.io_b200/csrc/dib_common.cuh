@@ -67,6 +67,15 @@ __device__ __forceinline__ void dib_philox_normal4(uint64_t seed, uint32_t step,
   n[0] = ra * ca; n[1] = ra * sa; n[2] = rb * cb; n[3] = rb * sb;
 }
 
+// round-to-nearest to the TF32 grid (10 explicit mantissa bits).  kind::tf32 MMAs ignore the low 13 bits of their
+// fp32 containers, i.e. TRUNCATE; producers round instead so that the operand error is unbiased (|rel| <= 2^-11).
+__device__ __forceinline__ float dib_round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float dib_maybe_round(float x, int on) { return on ? dib_round_tf32(x) : x; }
+
 __device__ __forceinline__ float dib_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

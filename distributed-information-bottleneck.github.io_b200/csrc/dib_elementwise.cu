@@ -28,7 +28,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* smem8) {
 // ------------------------------------------------------------------------------------------------
 __global__ void dib_pe_kernel(const float* __restrict__ x, int ldx, int x_col_shift, const int* __restrict__ col_src,
                               const int* __restrict__ col_freq, int col_begin, int ncols, float* __restrict__ pe,
-                              int ldpe, int pe_col_shift, long long n) {
+                              int ldpe, int pe_col_shift, long long n, int round_out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * ncols) return;
   const long long row = idx / ncols;
@@ -40,7 +40,7 @@ __global__ void dib_pe_kernel(const float* __restrict__ x, int ldx, int x_col_sh
     const int f = col_freq[col];
     v = f == 0 ? xv : sinf((float)f * xv);
   }
-  pe[row * ldpe + (col - pe_col_shift)] = v;
+  pe[row * ldpe + (col - pe_col_shift)] = dib_maybe_round(v, round_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -71,7 +71,7 @@ dib_reparam_fwd_kernel(DibReparamArgs a, float* __restrict__ emb, int ldemb, flo
           const float z = ep ? ep[e] : nrm[j];
           const float u = fmaf(s, z, mu);
           kl += 0.5f * (mu * mu + expf(lv) - lv - 1.f);
-          dst[e] = u;
+          dst[e] = dib_maybe_round(u, a.round_out);
           if (udst) udst[e] = u;
         }
       }
@@ -105,8 +105,8 @@ dib_reparam_bwd_kernel(DibReparamArgs a, const float* __restrict__ d_emb, int ld
         const float mu = o[e], lv = o[E + e], g = du[e];
         const float s = expf(0.5f * lv);
         const float z = ep ? ep[e] : nrm[j];
-        dq[e] = fmaf(bs, mu, g);
-        dq[E + e] = fmaf(g * z, 0.5f * s, bs * 0.5f * (expf(lv) - 1.f));
+        dq[e] = dib_maybe_round(fmaf(bs, mu, g), a.round_out);
+        dq[E + e] = dib_maybe_round(fmaf(g * z, 0.5f * s, bs * 0.5f * (expf(lv) - 1.f)), a.round_out);
       }
     }
   }
@@ -120,7 +120,7 @@ dib_reparam_bwd_kernel(DibReparamArgs a, const float* __restrict__ d_emb, int ld
 __global__ void __launch_bounds__(kRowsPerBlock)
 dib_loss_kernel(int loss, int out_act, float alpha, const float* __restrict__ pred, int ldp, const float* __restrict__ y,
                 int out_dim, long long n, float inv_batch, float* __restrict__ d_pred, float* __restrict__ user_pred,
-                float* __restrict__ loss_part, float* __restrict__ acc_part) {
+                float* __restrict__ loss_part, float* __restrict__ acc_part, int round_out) {
   __shared__ float red[8];
   const long long row = (long long)blockIdx.x * kRowsPerBlock + threadIdx.x;
   float l = 0.f, acc = 0.f;
@@ -143,7 +143,7 @@ dib_loss_kernel(int loss, int out_act, float alpha, const float* __restrict__ pr
           const float inv_se = 1.f / se;
           for (int j = 0; j < out_dim; ++j) {
             const float g = expf(z[j] - m) * inv_se - (j == label ? 1.f : 0.f);
-            dz[j] = g * inv_batch * dib_act_grad(out_act, z[j], alpha);
+            dz[j] = dib_maybe_round(g * inv_batch * dib_act_grad(out_act, z[j], alpha), round_out);
           }
         }
       } else {
@@ -160,7 +160,7 @@ dib_loss_kernel(int loss, int out_act, float alpha, const float* __restrict__ pr
             g = 2.f * d;
           }
           acc += ((zz > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f;
-          if (dz) dz[j] = g * inv_out * inv_batch * dib_act_grad(out_act, zz, alpha);
+          if (dz) dz[j] = dib_maybe_round(g * inv_out * inv_batch * dib_act_grad(out_act, zz, alpha), round_out);
         }
         l *= inv_out;
         acc *= inv_out;
@@ -199,6 +199,11 @@ __global__ void dib_reduce_partials_kernel(const float* __restrict__ part, long 
   float s = 0.f;
   for (int k = 0; k < nsplit; ++k) s += part[(long long)k * split_stride + i];
   out[i] = s;
+}
+
+__global__ void dib_round_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, long long count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = dib_round_tf32(src[i]);
 }
 
 __global__ void dib_copy2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int cols,
@@ -283,11 +288,12 @@ inline unsigned nblocks(long long work, int per) { return (unsigned)((work + per
 }  // namespace
 
 cudaError_t dib_launch_pe(const float* x, int ldx, int x_col_shift, const int* col_src, const int* col_freq,
-                          int col_begin, int col_end, float* pe, int ldpe, int pe_col_shift, int64_t n, cudaStream_t st) {
+                          int col_begin, int col_end, float* pe, int ldpe, int pe_col_shift, int64_t n, int round_out,
+                          cudaStream_t st) {
   const int ncols = col_end - col_begin;
   if (n <= 0 || ncols <= 0) return cudaSuccess;
   dib_pe_kernel<<<nblocks((long long)n * ncols, 256), 256, 0, st>>>(x, ldx, x_col_shift, col_src, col_freq, col_begin,
-                                                                   ncols, pe, ldpe, pe_col_shift, n);
+                                                                   ncols, pe, ldpe, pe_col_shift, n, round_out);
   dib_note_launch();
   return cudaGetLastError();
 }
@@ -312,10 +318,11 @@ cudaError_t dib_launch_reparam_bwd(const DibReparamArgs& a, const float* d_emb, 
 
 cudaError_t dib_launch_loss(int loss, int out_act, float alpha, const float* pred, int ldp, const float* y, int out_dim,
                             int64_t n, float inv_batch, float* d_pred, float* user_pred, float* loss_part,
-                            float* acc_part, cudaStream_t st) {
+                            float* acc_part, int round_out, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   dib_loss_kernel<<<nblocks(n, kRowsPerBlock), kRowsPerBlock, 0, st>>>(loss, out_act, alpha, pred, ldp, y, out_dim, n,
-                                                                      inv_batch, d_pred, user_pred, loss_part, acc_part);
+                                                                      inv_batch, d_pred, user_pred, loss_part, acc_part,
+                                                                      round_out);
   dib_note_launch();
   return cudaGetLastError();
 }
@@ -364,6 +371,13 @@ cudaError_t dib_launch_bhattacharyya(const float* mu_logvar, int64_t n, int E, f
 
 cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st) {
   dib_metrics_update_kernel<<<1, 256, 0, st>>>(stats, beta_dev, acc, F);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_round_copy(const float* src, float* dst, int64_t count, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  dib_round_copy_kernel<<<nblocks(count, 256), 256, 0, st>>>(src, dst, count);
   dib_note_launch();
   return cudaGetLastError();
 }

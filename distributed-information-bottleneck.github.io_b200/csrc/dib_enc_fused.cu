@@ -1,0 +1,798 @@
+// dib_enc_fused.cu -- the fused per-feature encoder kernels of the tensor-core mode (sm_100a).
+//
+// One persistent CTA per SM works on ONE feature at a time: the feature's encoder weights (positional-encoding
+// layer incl. its bias row, 128x128 hidden layer, 128x64 (mu|logvar) layer) are TMA-staged into shared memory
+// once and reused for every 128-sample tile of that feature.  Per tile the whole chain of models.py:101-112
+//     x column -> positional encoding -> Dense(128,act) -> Dense(128,act) -> Dense(2E) -> split (mu, logvar)
+//     -> u = mu + exp(logvar/2) eps -> KL partial sums -> emb[:, f*E:(f+1)*E]
+// runs on chip: the three contractions are tcgen05.mma instructions (16-bit operands with an 11-bit significand
+// = TF32's, fp32 accumulation in TMEM), the activations travel TMEM -> registers -> shared memory (as the next
+// MMA's swizzled A operand) and never touch HBM.  Only x (4 B/sample/feature) is read and emb is written.
+//
+// Operand layouts (16-bit): every activation/weight tile is [rows][64-element panels of 128 B] with the 16-byte
+// chunk index XORed with (row % 8) -- the SWIZZLE_128B pattern, which for 16-bit types is simultaneously a valid
+// K-major operand (rows = M/N, panel = K) and a valid MN-major operand (rows = K, panel = M/N).  That dual view is
+// what lets the backward kernel use one copy of h1/h2/dz/W for dgrad (reduction over features) and wgrad
+// (reduction over samples).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "dib_common.cuh"
+#include "dib_kernels.h"
+#include "dib_sm100.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int TM = 128;            // samples per tile (UMMA M)
+constexpr int HID = 128;           // hidden width of both encoder layers
+constexpr int EO = 64;             // 2 * embedding dim
+constexpr int K0 = 16;             // padded fan-in of the first layer: [pe (d*nfreq) | 1 (bias) | 0...]
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (1 + kEpiWarps);
+constexpr int kPanel = TM * 128;   // bytes of one 64-column panel of a 128-row tile (16 KB)
+
+// packed 16-bit weights in global memory, per feature (elements): W0p[16][128] | W1[128][128] | W2[128][64]
+constexpr int kW0Elems = K0 * HID, kW1Elems = HID * HID, kW2Elems = HID * EO;
+constexpr int kPackElems = kW0Elems + kW1Elems + kW2Elems;
+
+// shared memory map (bytes; operand tiles 1024-aligned)
+constexpr int kOffW1 = 0;
+constexpr int kOffW2 = kOffW1 + 2 * kPanel;        // 32 KB
+constexpr int kOffW0 = kOffW2 + kPanel;            // 16 KB
+constexpr int kOffA0 = kOffW0 + 2 * K0 * 128;      // 4 KB : W0p = 2 panels x 16 rows x 128 B
+constexpr int kOffH1 = kOffA0 + 2 * TM * 16;       // 4 KB : A0 = [2 k-halves][128 rows][16 B] (no swizzle)
+constexpr int kOffH2 = kOffH1 + 2 * kPanel;
+constexpr int kOffFwdEnd = kOffH2 + 2 * kPanel;
+// backward-only tiles
+constexpr int kOffDO = kOffFwdEnd;                 // [128 x 64]  one panel
+constexpr int kOffDZ2 = kOffDO + kPanel;           // [128 x 128] (dz1 aliases H2 once wgrad2 has drained)
+constexpr int kOffBwdEnd = kOffDZ2 + 2 * kPanel;
+
+struct EncFusedParams {
+  const float* x; int ldx;                 // [n, D]
+  const int* x_off;                        // [F] first x column of each feature
+  const int* fdim;                         // [F] d_i
+  int nfreq;                               // 1 + number of sinusoid blocks (1 = no positional encoding)
+  const float* params;                     // fp32 master parameters (biases b1, b2 are read from here)
+  const long long* b1_off; const long long* b2_off;   // [F] offsets of b1, b2 in params
+  const float* eps;                        // [n, F, E] or null -> Philox
+  unsigned long long seed; unsigned int step; unsigned long long sample_offset;
+  float* emb; int ldemb; float* user_emb;  // outputs (forward)
+  float* kl_part; int kl_stride;           // [F][kl_stride] per-(feature, slot) KL partial sums
+  int F; long long n; int act; float alpha;
+  int round_emb;
+};
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    const __half2 mx = __float2half2_rn(65504.f);
+    v = __hmax2(__hmin2(v, mx), __hneg2(mx));     // saturate instead of producing inf
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// address of the 16-byte chunk holding columns [8c, 8c+8) of row r in a [128 x 64k] swizzled tile
+__device__ __forceinline__ uint32_t tile_chunk_addr(uint32_t tile, int r, int col) {
+  const int panel = col >> 6, c = (col & 63) >> 3;
+  return tile + panel * kPanel + r * 128 + ((c ^ (r & 7)) << 4);
+}
+
+// TMEM -> (+bias, activation) -> 16-bit -> swizzled shared tile, for 64 columns [col0, col0+64) of row r
+template <bool BF16>
+__device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, uint32_t tile, int r, int col0, const float* bias_s,
+                                                 int act, float alpha) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + col0 + hh * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float z = __uint_as_float(v[j + k]);
+        if (bias_s) z += bias_s[col0 + hh * 32 + j + k];
+        f[k] = dib_act(act, z, alpha);
+      }
+      st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * 32 + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
+                   pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+    }
+  }
+}
+
+// first-layer operand row: [x_0..x_{d-1}, sin(2x).., sin(4x).., ..., 1, 0...] (models.py:22-23 + bias column)
+template <bool BF16>
+__device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, const float* xrow, int d, int nfreq) {
+  float f[8];
+  const int w_in = d * nfreq;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int col = khalf * 8 + k;
+    float v = 0.f;
+    if (col < w_in) {
+      const int blk = col / d, j = col - blk * d;
+      const float xv = xrow ? xrow[j] : 0.f;
+      v = blk == 0 ? xv : sinf((float)(1 << blk) * xv);
+    } else if (col == w_in) {
+      v = xrow ? 1.f : 0.f;          // bias column (rows past the batch end contribute nothing)
+    }
+    f[k] = v;
+  }
+  st_shared_v4(a0 + khalf * (TM * 16) + r * 16, pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
+               pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+}
+
+// ====================================================================================================
+// forward: x -> emb, KL partial sums
+// ====================================================================================================
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+dib_enc_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
+                         const __grid_constant__ CUtensorMap mapW2, const EncFusedParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
+  constexpr int kOffBias = kOffFwdEnd;                       // b1[128] b2[64] fp32
+  constexpr int kOffBar = kOffBias + (HID + EO) * 4;
+  float* bias1_s = reinterpret_cast<float*>(sg + kOffBias);
+  float* bias2_s = bias1_s + HID;
+  float* red_s = reinterpret_cast<float*>(sg + kOffBar + 128);          // [kEpiWarps]
+  const uint32_t bar = sb + kOffBar;
+  const uint32_t bar_w = bar, bar_a0 = bar + 8, bar_d0 = bar + 16, bar_h1 = bar + 24, bar_d1 = bar + 32,
+                 bar_h2 = bar + 40, bar_d2 = bar + 48, tmem_slot = bar + 56;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kOffBar + 56);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, c = blockIdx.x, F = P.F;
+  const int ntiles = (int)((P.n + TM - 1) / TM);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapW0); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a0, kEpiWarps); mbar_init(bar_h1, kEpiWarps); mbar_init(bar_h2, kEpiWarps);
+    mbar_init(bar_d0, 1); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot_g;
+  const uint32_t tD0 = tmem, tD1 = tmem + 128, tD2 = tmem + 256;
+
+  // work assignment: with G >= F CTAs, CTA c serves feature c % F as slot c / F of that feature's CTAs
+  int f_first, f_step, nslots, slot;
+  if (G >= F) { f_first = c % F; f_step = F * G; slot = c / F; nslots = (G - f_first + F - 1) / F; }
+  else { f_first = c; f_step = G; slot = 0; nslots = 1; }
+
+  constexpr uint32_t fmt = BF16 ? 1u : 0u;
+  constexpr uint32_t idesc0 = umma_idesc(fmt, 0, 1, HID);     // A K-major, B MN-major, N = 128
+  constexpr uint32_t idesc2 = umma_idesc(fmt, 0, 1, EO);      // N = 64
+  uint32_t it = 0, fit = 0;                                   // tile / feature iteration counters (barrier phases)
+
+  for (int f = f_first; f < F; f += f_step, ++fit) {
+    if (warp == 0) {
+      // ============================================================ weights + MMA issue (one thread)
+      if (lane == 0) {
+        mbar_expect_tx(bar_w, 2 * K0 * 128 + 2 * kPanel + kPanel);
+        tma_load_3d(sb + kOffW0, &mapW0, bar_w, 0, 0, f);
+        tma_load_3d(sb + kOffW0 + K0 * 128, &mapW0, bar_w, 64, 0, f);
+        tma_load_3d(sb + kOffW1, &mapW1, bar_w, 0, 0, f);
+        tma_load_3d(sb + kOffW1 + kPanel, &mapW1, bar_w, 64, 0, f);
+        tma_load_3d(sb + kOffW2, &mapW2, bar_w, 0, 0, f);
+        mbar_wait(bar_w, fit & 1);
+        for (int t = slot; t < ntiles; t += nslots, ++it) {
+          const uint32_t ph = it & 1;
+          mbar_wait(bar_a0, ph);
+          tc_fence_after_sync();
+          umma_f16<BF16>(tD0, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone),
+                         umma_smem_desc(sb + kOffW0, K0 * 128, 1024), idesc0, 0u);
+          umma_commit(bar_d0);
+          mbar_wait(bar_h1, ph);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < HID / 16; ++kk)
+            umma_f16<BF16>(tD1, umma_smem_desc(sb + kOffH1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
+                           umma_smem_desc(sb + kOffW1 + kk * 2048, kPanel, 1024), idesc0, kk > 0 ? 1u : 0u);
+          umma_commit(bar_d1);
+          mbar_wait(bar_h2, ph);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < HID / 16; ++kk)
+            umma_f16<BF16>(tD2, umma_smem_desc(sb + kOffH2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
+                           umma_smem_desc(sb + kOffW2 + kk * 2048, kPanel, 1024), idesc2, kk > 0 ? 1u : 0u);
+          umma_commit(bar_d2);
+          if (t + nslots >= ntiles) mbar_wait(bar_d2, ph);   // drain before the next feature's weights land
+        }
+      } else {
+        for (int t = slot; t < ntiles; t += nslots) ++it;
+      }
+      __syncwarp();
+    } else {
+      // ============================================================ epilogue warps
+      const int ew = warp - 1, q = warp & 3, hsel = ew >> 2;      // TMEM lane quarter, column half
+      const int et = ew * 32 + lane;                              // 0..255
+      const int r = q * 32 + lane;                                // row of the tile owned for TMEM reads
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      // per-feature constants
+      for (int i = et; i < HID + EO; i += kEpiWarps * 32)
+        bias1_s[i] = i < HID ? P.params[P.b1_off[f] + i] : P.params[P.b2_off[f] + (i - HID)];
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      const int d = P.fdim[f], xo = P.x_off[f];
+      float kl_acc = 0.f;
+      for (int t = slot; t < ntiles; t += nslots, ++it) {
+        const uint32_t ph = it & 1;
+        const long long row0 = (long long)t * TM;
+        // ---- stage 0: positional encoding of the x column -> A0
+        {
+          const int ar = et & (TM - 1), khalf = et >> 7;
+          const long long grow = row0 + ar;
+          write_a0_row<BF16>(sb + kOffA0, ar, khalf, grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, P.nfreq);
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a0);
+        }
+        // ---- layer 0 epilogue: relu(D0) -> H1   (bias folded into the GEMM through the ones column)
+        mbar_wait(bar_d0, ph);
+        tc_fence_after_sync();
+        epilogue_to_tile<BF16>(tD0 + lane_addr, sb + kOffH1, r, hsel * 64, nullptr, P.act, P.alpha);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_h1);
+        // ---- layer 1 epilogue: act(D1 + b1) -> H2
+        mbar_wait(bar_d1, ph);
+        tc_fence_after_sync();
+        epilogue_to_tile<BF16>(tD1 + lane_addr, sb + kOffH2, r, hsel * 64, bias1_s, P.act, P.alpha);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_h2);
+        // ---- layer 2 epilogue: (mu, logvar) -> reparameterise, KL, emb   (16 embedding dims per thread)
+        mbar_wait(bar_d2, ph);
+        tc_fence_after_sync();
+        {
+          uint32_t vm[16], vl[16];
+          tmem_ld_32x32b_x16(tD2 + lane_addr + hsel * 16, vm);
+          tmem_ld_32x32b_x16(tD2 + lane_addr + 32 + hsel * 16, vl);
+          tmem_ld_wait();
+          const long long grow = row0 + r;
+          if (grow < P.n) {
+            float* dst = P.emb + grow * P.ldemb + f * 32 + hsel * 16;
+            float* udst = P.user_emb ? P.user_emb + grow * ((long long)F * 32) + f * 32 + hsel * 16 : nullptr;
+            const float* ep = P.eps ? P.eps + (grow * F + f) * 32 + hsel * 16 : nullptr;
+#pragma unroll
+            for (int e0 = 0; e0 < 16; e0 += 4) {
+              float nrm[4];
+              if (ep) { const float4 e4 = *reinterpret_cast<const float4*>(ep + e0); nrm[0] = e4.x; nrm[1] = e4.y; nrm[2] = e4.z; nrm[3] = e4.w; }
+              else dib_philox_normal4(P.seed, P.step, P.sample_offset + (unsigned long long)grow, (uint32_t)f,
+                                      (uint32_t)(hsel * 4 + (e0 >> 2)), nrm);
+              float u[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float mu = __uint_as_float(vm[e0 + j]) + bias2_s[hsel * 16 + e0 + j];
+                const float lv = __uint_as_float(vl[e0 + j]) + bias2_s[32 + hsel * 16 + e0 + j];
+                const float s = expf(0.5f * lv);
+                u[j] = fmaf(s, nrm[j], mu);
+                kl_acc += 0.5f * (mu * mu + s * s - lv - 1.f);
+              }
+              if (udst) *reinterpret_cast<float4*>(udst + e0) = make_float4(u[0], u[1], u[2], u[3]);
+              if (P.round_emb) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) u[j] = dib_round_tf32(u[j]);
+              }
+              *reinterpret_cast<float4*>(dst + e0) = make_float4(u[0], u[1], u[2], u[3]);
+            }
+          }
+        }
+      }
+      // ---- per-(feature, slot) KL partial: fixed-order reduction over the 256 epilogue threads
+      kl_acc = dib_warp_sum(kl_acc);
+      if (lane == 0) red_s[ew] = kl_acc;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (et == 0) {
+        float s = 0.f;
+        for (int i = 0; i < kEpiWarps; ++i) s += red_s[i];
+        P.kl_part[(long long)f * P.kl_stride + slot] = s;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+}
+
+// ====================================================================================================
+// backward: recompute the forward chain on chip, then dgrad + wgrad of all three layers.
+//   d(mu)     = S*du + (beta*S/B)*mu                       (du = d loss / d u from the integration network)
+//   d(logvar) = S*du*eps*0.5*sigma + (beta*S/B)*0.5*(sigma^2-1)
+//   dz2 = (d(mu|logvar) W2^T) * act'(h2);  dz1 = (dz2 W1^T) * act'(h1)
+//   dW2 += h2^T d(mu|logvar);  dW1 += h1^T dz2;  [dW0;db0]^T += dz1^T [pe|1];  db1 = colsum dz2 (ones column of A0)
+// S is a power-of-two loss scale that keeps the 16-bit gradient operands in range (fp16); the fp32 accumulators
+// are multiplied by 1/S when they are flushed.  Weight-gradient accumulators live in TMEM for the whole feature.
+// TMEM columns: [0,128) D0/D1 | [128,256) D2, G2, G1 | [256,384) dW1 | [384,448) dW2 | [448,464) dW0p^T | [464,480) db1
+// ====================================================================================================
+struct EncFusedBwdParams {
+  EncFusedParams f;
+  const float* d_emb; int ldd;              // [n, ldd] gradient w.r.t. emb (already scaled by 1/B_global)
+  const float* beta_dev; float inv_batch; float gscale;
+  float* part; long long split_stride;      // weight-gradient partials [slot][P]
+  const long long* w0_off; const long long* b0_off; const long long* w1_off; const long long* w2_off;
+};
+
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t (&v)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+template <bool BF16>
+__device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b) {
+  if constexpr (BF16) { const float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); a = f.x; b = f.y; }
+  else { const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u)); a = f.x; b = f.y; }
+}
+
+// TMEM gradient g (64 columns) * act'(h from the shared tile `htile`) -> 16-bit -> shared tile `dtile`
+template <bool BF16>
+__device__ __forceinline__ void dgrad_epilogue(uint32_t taddr, uint32_t htile, uint32_t dtile, int r, int col0, int act,
+                                               float alpha) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + col0 + hh * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint32_t hv[4];
+      ld_shared_v4(tile_chunk_addr(htile, r, col0 + hh * 32 + j), hv);
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float h0, h1;
+        unpack2<BF16>(hv[k], h0, h1);
+        f[2 * k] = __uint_as_float(v[j + 2 * k]) * dib_act_grad(act, h0, alpha);
+        f[2 * k + 1] = __uint_as_float(v[j + 2 * k + 1]) * dib_act_grad(act, h1, alpha);
+      }
+      st_shared_v4(tile_chunk_addr(dtile, r, col0 + hh * 32 + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
+                   pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+    }
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
+                         const __grid_constant__ CUtensorMap mapW2, const EncFusedBwdParams Q) {
+  const EncFusedParams& P = Q.f;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
+  constexpr int kOffBias = kOffBwdEnd;
+  constexpr int kOffBar = kOffBias + (HID + EO) * 4;
+  float* bias1_s = reinterpret_cast<float*>(sg + kOffBias);
+  float* bias2_s = bias1_s + HID;
+  const uint32_t bar = sb + kOffBar;
+  const uint32_t bar_w = bar, bar_a0 = bar + 8, bar_d0 = bar + 16, bar_h1 = bar + 24, bar_d1 = bar + 32,
+                 bar_h2 = bar + 40, bar_d2 = bar + 48, bar_do = bar + 56, bar_g2 = bar + 64, bar_dz2 = bar + 72,
+                 bar_g1 = bar + 80, bar_dz1 = bar + 88, bar_wg = bar + 96, tmem_slot = bar + 104;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kOffBar + 104);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, c = blockIdx.x, F = P.F;
+  const int ntiles = (int)((P.n + TM - 1) / TM);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapW0); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a0, kEpiWarps); mbar_init(bar_h1, kEpiWarps); mbar_init(bar_h2, kEpiWarps);
+    mbar_init(bar_do, kEpiWarps); mbar_init(bar_dz2, kEpiWarps); mbar_init(bar_dz1, kEpiWarps);
+    mbar_init(bar_d0, 1); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_g2, 1); mbar_init(bar_g1, 1);
+    mbar_init(bar_wg, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot_g;
+  const uint32_t tR0 = tmem, tR1 = tmem + 128, tWG1 = tmem + 256, tWG2 = tmem + 384, tWG0 = tmem + 448, tWB1 = tmem + 464;
+
+  int f_first, f_step, nslots, slot;
+  if (G >= F) { f_first = c % F; f_step = F * G; slot = c / F; nslots = (G - f_first + F - 1) / F; }
+  else { f_first = c; f_step = G; slot = 0; nslots = 1; }
+
+  constexpr uint32_t fmt = BF16 ? 1u : 0u;
+  constexpr uint32_t id_kmn_128 = umma_idesc(fmt, 0, 1, HID), id_kmn_64 = umma_idesc(fmt, 0, 1, EO);
+  constexpr uint32_t id_kk_128 = umma_idesc(fmt, 0, 0, HID);
+  constexpr uint32_t id_mm_128 = umma_idesc(fmt, 1, 1, HID), id_mm_64 = umma_idesc(fmt, 1, 1, EO),
+                     id_mm_16 = umma_idesc(fmt, 1, 1, 16);
+  uint32_t it = 0, fit = 0;
+  const float S = Q.gscale, invS = 1.f / Q.gscale;
+
+  for (int f = f_first; f < F; f += f_step, ++fit) {
+    const bool any_tiles = slot < ntiles;
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_expect_tx(bar_w, 2 * K0 * 128 + 2 * kPanel + kPanel);
+        tma_load_3d(sb + kOffW0, &mapW0, bar_w, 0, 0, f);
+        tma_load_3d(sb + kOffW0 + K0 * 128, &mapW0, bar_w, 64, 0, f);
+        tma_load_3d(sb + kOffW1, &mapW1, bar_w, 0, 0, f);
+        tma_load_3d(sb + kOffW1 + kPanel, &mapW1, bar_w, 64, 0, f);
+        tma_load_3d(sb + kOffW2, &mapW2, bar_w, 0, 0, f);
+        mbar_wait(bar_w, fit & 1);
+        bool first = true;
+        for (int t = slot; t < ntiles; t += nslots, ++it, first = false) {
+          const uint32_t ph = it & 1;
+          // ---- recompute forward
+          mbar_wait(bar_a0, ph);
+          tc_fence_after_sync();
+          umma_f16<BF16>(tR0, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone),
+                         umma_smem_desc(sb + kOffW0, K0 * 128, 1024), id_kmn_128, 0u);
+          umma_commit(bar_d0);
+          mbar_wait(bar_h1, ph);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tR0, umma_smem_desc(sb + kOffH1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
+                           umma_smem_desc(sb + kOffW1 + kk * 2048, kPanel, 1024), id_kmn_128, kk > 0 ? 1u : 0u);
+          umma_commit(bar_d1);
+          mbar_wait(bar_h2, ph);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffH2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
+                           umma_smem_desc(sb + kOffW2 + kk * 2048, kPanel, 1024), id_kmn_64, kk > 0 ? 1u : 0u);
+          umma_commit(bar_d2);
+          // ---- layer 2 backward: G2 = dO W2^T ; dW2 += h2^T dO
+          mbar_wait(bar_do, ph);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffDO + kk * 32, 16, 1024),
+                           umma_smem_desc(sb + kOffW2 + kk * 32, 16, 1024), id_kk_128, kk > 0 ? 1u : 0u);
+          umma_commit(bar_g2);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWG2, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
+                           umma_smem_desc(sb + kOffDO + kk * 2048, kPanel, 1024), id_mm_64, (first && kk == 0) ? 0u : 1u);
+          // ---- layer 1 backward: G1 = dz2 W1^T ; dW1 += h1^T dz2 ; db1 += dz2^T [pe|1]
+          mbar_wait(bar_dz2, ph);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffDZ2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
+                           umma_smem_desc(sb + kOffW1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024), id_kk_128,
+                           kk > 0 ? 1u : 0u);
+          umma_commit(bar_g1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWG1, umma_smem_desc(sb + kOffH1 + kk * 2048, kPanel, 1024),
+                           umma_smem_desc(sb + kOffDZ2 + kk * 2048, kPanel, 1024), id_mm_128, (first && kk == 0) ? 0u : 1u);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWB1, umma_smem_desc(sb + kOffDZ2 + kk * 2048, kPanel, 1024),
+                           umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+                           (first && kk == 0) ? 0u : 1u);
+          // ---- layer 0 backward: [dW0;db0]^T += dz1^T [pe|1]     (dz1 lives in the H2 buffer)
+          mbar_wait(bar_dz1, ph);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWG0, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
+                           umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+                           (first && kk == 0) ? 0u : 1u);
+          umma_commit(bar_wg);
+          if (t + nslots >= ntiles) mbar_wait(bar_wg, ph);
+        }
+      } else {
+        for (int t = slot; t < ntiles; t += nslots) ++it;
+      }
+      __syncwarp();
+    } else {
+      const int ew = warp - 1, q = warp & 3, hsel = ew >> 2;
+      const int et = ew * 32 + lane;
+      const int r = q * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      for (int i = et; i < HID + EO; i += kEpiWarps * 32)
+        bias1_s[i] = i < HID ? P.params[P.b1_off[f] + i] : P.params[P.b2_off[f] + (i - HID)];
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      const int d = P.fdim[f], xo = P.x_off[f];
+      const float bs = Q.beta_dev[0] * Q.inv_batch * S;
+      float db2m[16], db2l[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { db2m[j] = 0.f; db2l[j] = 0.f; }
+      for (int t = slot; t < ntiles; t += nslots, ++it) {
+        const uint32_t ph = it & 1;
+        const long long row0 = (long long)t * TM;
+        {
+          const int ar = et & (TM - 1), khalf = et >> 7;
+          const long long grow = row0 + ar;
+          write_a0_row<BF16>(sb + kOffA0, ar, khalf, grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, P.nfreq);
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a0);
+        }
+        mbar_wait(bar_d0, ph);
+        tc_fence_after_sync();
+        epilogue_to_tile<BF16>(tR0 + lane_addr, sb + kOffH1, r, hsel * 64, nullptr, P.act, P.alpha);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_h1);
+        mbar_wait(bar_d1, ph);
+        tc_fence_after_sync();
+        epilogue_to_tile<BF16>(tR0 + lane_addr, sb + kOffH2, r, hsel * 64, bias1_s, P.act, P.alpha);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_h2);
+        // ---- (mu, logvar) -> d(mu), d(logvar) -> DO tile
+        mbar_wait(bar_d2, ph);
+        tc_fence_after_sync();
+        {
+          uint32_t vm[16], vl[16];
+          tmem_ld_32x32b_x16(tR1 + lane_addr + hsel * 16, vm);
+          tmem_ld_32x32b_x16(tR1 + lane_addr + 32 + hsel * 16, vl);
+          tmem_ld_wait();
+          const long long grow = row0 + r;
+          const bool valid = grow < P.n;
+          float dm[16], dl[16];
+          const float* du = Q.d_emb + (valid ? grow : 0) * Q.ldd + f * 32 + hsel * 16;
+          const float* ep = P.eps ? P.eps + ((valid ? grow : 0) * F + f) * 32 + hsel * 16 : nullptr;
+#pragma unroll
+          for (int e0 = 0; e0 < 16; e0 += 4) {
+            float nrm[4];
+            if (ep) { const float4 e4 = *reinterpret_cast<const float4*>(ep + e0); nrm[0] = e4.x; nrm[1] = e4.y; nrm[2] = e4.z; nrm[3] = e4.w; }
+            else dib_philox_normal4(P.seed, P.step, P.sample_offset + (unsigned long long)grow, (uint32_t)f,
+                                    (uint32_t)(hsel * 4 + (e0 >> 2)), nrm);
+            const float4 g4 = *reinterpret_cast<const float4*>(du + e0);
+            const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float mu = __uint_as_float(vm[e0 + j]) + bias2_s[hsel * 16 + e0 + j];
+              const float lv = __uint_as_float(vl[e0 + j]) + bias2_s[32 + hsel * 16 + e0 + j];
+              const float s = expf(0.5f * lv);
+              const float gs = g[j] * S;
+              const float a = valid ? fmaf(bs, mu, gs) : 0.f;
+              const float b = valid ? fmaf(gs * nrm[j], 0.5f * s, bs * 0.5f * (s * s - 1.f)) : 0.f;
+              dm[e0 + j] = a; dl[e0 + j] = b;
+              db2m[e0 + j] += a; db2l[e0 + j] += b;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            st_shared_v4(tile_chunk_addr(sb + kOffDO, r, hsel * 16 + j), pack2<BF16>(dm[j], dm[j + 1]),
+                         pack2<BF16>(dm[j + 2], dm[j + 3]), pack2<BF16>(dm[j + 4], dm[j + 5]), pack2<BF16>(dm[j + 6], dm[j + 7]));
+            st_shared_v4(tile_chunk_addr(sb + kOffDO, r, 32 + hsel * 16 + j), pack2<BF16>(dl[j], dl[j + 1]),
+                         pack2<BF16>(dl[j + 2], dl[j + 3]), pack2<BF16>(dl[j + 4], dl[j + 5]), pack2<BF16>(dl[j + 6], dl[j + 7]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_do);
+        // ---- dz2 = G2 * act'(h2)
+        mbar_wait(bar_g2, ph);
+        tc_fence_after_sync();
+        dgrad_epilogue<BF16>(tR1 + lane_addr, sb + kOffH2, sb + kOffDZ2, r, hsel * 64, P.act, P.alpha);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dz2);
+        // ---- dz1 = G1 * act'(h1)  -> H2 buffer (free: the dW2 MMAs that read h2 retired before G1 completed)
+        mbar_wait(bar_g1, ph);
+        tc_fence_after_sync();
+        dgrad_epilogue<BF16>(tR1 + lane_addr, sb + kOffH1, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dz1);
+        // the weight-gradient MMAs still read A0 / H1 / DZ2 / dz1: wait before the next tile overwrites them
+        mbar_wait(bar_wg, ph);
+        tc_fence_after_sync();
+      }
+      // ================= flush this (feature, slot)'s weight-gradient partials (scaled back by 1/S)
+      float* part = Q.part + (long long)slot * Q.split_stride;
+      const int w_in = d * P.nfreq;
+      {
+        // dW1[h1=r][h2 cols hsel*64..]
+        float* dst = part + Q.w1_off[f] + (long long)r * HID + hsel * 64;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          if (any_tiles) { tmem_ld_32x32b_x32(tWG1 + lane_addr + hsel * 64 + hh * 32, v); tmem_ld_wait(); }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + hh * 32 + j) = any_tiles
+                ? make_float4(__uint_as_float(v[j]) * invS, __uint_as_float(v[j + 1]) * invS,
+                              __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS)
+                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // dW2[h2=r][o cols hsel*32..]
+        float* dst2 = part + Q.w2_off[f] + (long long)r * EO + hsel * 32;
+        {
+          uint32_t v[32];
+          if (any_tiles) { tmem_ld_32x32b_x32(tWG2 + lane_addr + hsel * 32, v); tmem_ld_wait(); }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst2 + j) = any_tiles
+                ? make_float4(__uint_as_float(v[j]) * invS, __uint_as_float(v[j + 1]) * invS,
+                              __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS)
+                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (hsel == 0) {
+          // dW0[k][h1=r] (k < w_in), db0[r] = column w_in of dW0p^T; db1[h2=r] = column w_in of dz2^T [pe|1]
+          uint32_t v0[16], v1[16];
+          if (any_tiles) { tmem_ld_32x32b_x16(tWG0 + lane_addr, v0); tmem_ld_32x32b_x16(tWB1 + lane_addr, v1); tmem_ld_wait(); }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float val = any_tiles ? __uint_as_float(v0[k]) * invS : 0.f;
+            if (k < w_in) part[Q.w0_off[f] + (long long)k * HID + r] = val;
+            else if (k == w_in) part[Q.b0_off[f] + r] = val;
+          }
+          float b1v = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) if (k == w_in) b1v = any_tiles ? __uint_as_float(v1[k]) * invS : 0.f;
+          part[P.b1_off[f] + r] = b1v;
+        }
+      }
+      // db2: cross-row reduction of the per-thread column sums through shared memory (DZ2 region is idle now)
+      tc_fence_before_sync();
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      {
+        float* red = reinterpret_cast<float*>(sg + kOffDZ2);          // [128 rows][64 cols]
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { red[r * EO + hsel * 16 + j] = db2m[j]; red[r * EO + 32 + hsel * 16 + j] = db2l[j]; }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (et < EO) {
+          float s = 0.f;
+          for (int rr = 0; rr < TM; ++rr) s += red[rr * EO + et];
+          part[P.b2_off[f] + et] = s * invS;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// fp32 master parameters -> packed 16-bit per-feature weights [W0p | W1 | W2] (bias of layer 0 folded into W0p)
+// ----------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void dib_enc_pack_weights_kernel(const float* __restrict__ params, const long long* __restrict__ w0_off,
+                                            const long long* __restrict__ b0_off, const long long* __restrict__ w1_off,
+                                            const long long* __restrict__ w2_off, const int* __restrict__ fdim, int nfreq,
+                                            uint16_t* __restrict__ out) {
+  const int f = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kPackElems) return;
+  float v;
+  if (i < kW0Elems) {
+    const int k = i / HID, n = i - k * HID, w_in = fdim[f] * nfreq;
+    v = k < w_in ? params[w0_off[f] + (long long)k * HID + n] : (k == w_in ? params[b0_off[f] + n] : 0.f);
+  } else if (i < kW0Elems + kW1Elems) {
+    v = params[w1_off[f] + (i - kW0Elems)];
+  } else {
+    v = params[w2_off[f] + (i - kW0Elems - kW1Elems)];
+  }
+  uint16_t h;
+  if constexpr (BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); h = *reinterpret_cast<uint16_t*>(&b); }
+  else { __half b = __float2half_rn(v); h = *reinterpret_cast<uint16_t*>(&b); }
+  out[(long long)f * kPackElems + i] = h;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn2() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [rows x cols] 16-bit matrix per feature -> 3D map (col, row, feature), box 64 cols x rows x 1, SWIZZLE_128B
+bool make_wmap(CUtensorMap* m, const uint16_t* base, int cols, int rows, int nfeat, bool bf16) {
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nfeat};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)kPackElems * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return encode_fn2()(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                      const_cast<uint16_t*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+size_t dib_enc_fused_pack_bytes(int F) { return (size_t)F * kPackElems * 2; }
+
+cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, cudaStream_t st) {
+  dim3 grid(DIB_CEIL_DIV(kPackElems, 256), d.F);
+  if (d.bf16)
+    dib_enc_pack_weights_kernel<true><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.w2_off, d.fdim,
+                                                           d.nfreq, static_cast<uint16_t*>(packed));
+  else
+    dib_enc_pack_weights_kernel<false><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.w2_off, d.fdim,
+                                                            d.nfreq, static_cast<uint16_t*>(packed));
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_enc_fused_forward(const DibEncFusedDesc& d, const DibEncFusedIO& io, cudaStream_t st) {
+  if (!encode_fn2()) return cudaErrorNotSupported;
+  const uint16_t* pk = static_cast<const uint16_t*>(io.packed);
+  CUtensorMap m0, m1, m2;
+  if (!make_wmap(&m0, pk, HID, K0, d.F, d.bf16) || !make_wmap(&m1, pk + kW0Elems, HID, HID, d.F, d.bf16) ||
+      !make_wmap(&m2, pk + kW0Elems + kW1Elems, EO, HID, d.F, d.bf16))
+    return cudaErrorInvalidValue;
+  EncFusedParams P;
+  P.x = io.x; P.ldx = io.ldx; P.x_off = d.x_off; P.fdim = d.fdim; P.nfreq = d.nfreq; P.params = io.params;
+  P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step;
+  P.sample_offset = io.sample_offset; P.emb = io.emb; P.ldemb = io.ldemb; P.user_emb = io.user_emb;
+  P.kl_part = io.kl_part; P.kl_stride = io.kl_stride; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha;
+  P.round_emb = 1;
+  constexpr int smem = kOffFwdEnd + (HID + EO) * 4 + 256 + 1024;
+  static bool attr[2] = {false, false};
+  const int grid = d.grid;
+  if (d.bf16) {
+    if (!attr[1]) { cudaError_t e = cudaFuncSetAttribute(dib_enc_fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (e != cudaSuccess) return e; attr[1] = true; }
+    dib_enc_fused_fwd_kernel<true><<<grid, kThreads, smem, st>>>(m0, m1, m2, P);
+  } else {
+    if (!attr[0]) { cudaError_t e = cudaFuncSetAttribute(dib_enc_fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (e != cudaSuccess) return e; attr[0] = true; }
+    dib_enc_fused_fwd_kernel<false><<<grid, kThreads, smem, st>>>(m0, m1, m2, P);
+  }
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO& io, const DibEncFusedBwdIO& b,
+                                   cudaStream_t st) {
+  if (!encode_fn2()) return cudaErrorNotSupported;
+  const uint16_t* pk = static_cast<const uint16_t*>(io.packed);
+  CUtensorMap m0, m1, m2;
+  if (!make_wmap(&m0, pk, HID, K0, d.F, d.bf16) || !make_wmap(&m1, pk + kW0Elems, HID, HID, d.F, d.bf16) ||
+      !make_wmap(&m2, pk + kW0Elems + kW1Elems, EO, HID, d.F, d.bf16))
+    return cudaErrorInvalidValue;
+  EncFusedBwdParams Q;
+  EncFusedParams& P = Q.f;
+  P.x = io.x; P.ldx = io.ldx; P.x_off = d.x_off; P.fdim = d.fdim; P.nfreq = d.nfreq; P.params = io.params;
+  P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step;
+  P.sample_offset = io.sample_offset; P.emb = nullptr; P.ldemb = 0; P.user_emb = nullptr;
+  P.kl_part = nullptr; P.kl_stride = 0; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha; P.round_emb = 0;
+  Q.d_emb = b.d_emb; Q.ldd = b.ldd; Q.beta_dev = b.beta_dev; Q.inv_batch = b.inv_batch; Q.gscale = b.gscale;
+  Q.part = b.part; Q.split_stride = b.split_stride;
+  Q.w0_off = d.w0_off; Q.b0_off = d.b0_off; Q.w1_off = d.w1_off; Q.w2_off = d.w2_off;
+  constexpr int smem = kOffBwdEnd + (HID + EO) * 4 + 256 + 1024;
+  static bool attr[2] = {false, false};
+  if (d.bf16) {
+    if (!attr[1]) { cudaError_t e = cudaFuncSetAttribute(dib_enc_fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (e != cudaSuccess) return e; attr[1] = true; }
+    dib_enc_fused_bwd_kernel<true><<<d.grid, kThreads, smem, st>>>(m0, m1, m2, Q);
+  } else {
+    if (!attr[0]) { cudaError_t e = cudaFuncSetAttribute(dib_enc_fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (e != cudaSuccess) return e; attr[0] = true; }
+    dib_enc_fused_bwd_kernel<false><<<d.grid, kThreads, smem, st>>>(m0, m1, m2, Q);
+  }
+  dib_note_launch();
+  return cudaGetLastError();
+}

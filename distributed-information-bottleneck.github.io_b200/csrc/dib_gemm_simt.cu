@@ -30,7 +30,7 @@ template <int MODE, int BR, int BC, int BT, int TM, int TN>
 __global__ void __launch_bounds__((BR / TM) * (BC / TN))
 dib_gemm_simt_kernel(const DibGemmProblem* __restrict__ probs, const float* __restrict__ baseA,
                      const float* __restrict__ baseB, float* __restrict__ baseC, float* baseX,
-                     int M, int nsplit, int rows_per_split, long long split_stride, float alpha) {
+                     int M, int nsplit, int rows_per_split, long long split_stride, float alpha, int round_out) {
   constexpr int TX = BC / TN, TY = BR / TM, NT = TX * TY;
   constexpr int CM = TM >= 4 ? 4 : TM, NCM = TM / CM;   // row chunks of the per-thread micro tile
   constexpr int CN = TN >= 4 ? 4 : TN, NCN = TN / CN;   // column chunks
@@ -214,6 +214,7 @@ dib_gemm_simt_kernel(const DibGemmProblem* __restrict__ probs, const float* __re
         } else if constexpr (MODE == DIB_GEMM_DGRAD) {
           if (cc < C && p.act != DIB_ACT_LINEAR) v *= dib_act_grad(p.act, (baseX + p.x_off)[(long long)r * p.ldx + cc], alpha);
         }
+        if constexpr (MODE != DIB_GEMM_WGRAD) v = dib_maybe_round(v, round_out);
         vals[j] = cc < C ? v : 0.f;
       }
       float* dst = Out + (long long)r * ldc + c;
@@ -250,7 +251,7 @@ cudaError_t launch_cfg(const DibGemmLaunch& L, cudaStream_t st) {
     grid = dim3(DIB_CEIL_DIV(L.M, BR), DIB_CEIL_DIV(L.maxC, BC), L.nprob);
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
   dib_gemm_simt_kernel<MODE, BR, BC, BT, TM, TN><<<grid, NT, 0, st>>>(
-      L.probs, L.baseA, L.baseB, L.baseC, L.baseX, L.M, L.nsplit, L.rows_per_split, L.split_stride, L.alpha);
+      L.probs, L.baseA, L.baseB, L.baseC, L.baseX, L.M, L.nsplit, L.rows_per_split, L.split_stride, L.alpha, L.round_out);
   dib_note_launch();
   return cudaGetLastError();
 }

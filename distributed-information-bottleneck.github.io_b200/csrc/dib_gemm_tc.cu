@@ -39,7 +39,8 @@ template <int MODE, int BN>
 __global__ void __launch_bounds__(192, 1)
 dib_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    const DibGemmProblem* __restrict__ probs, const float* __restrict__ baseP, float* __restrict__ baseC,
-                   float* baseX, int M, int nsplit, int rows_per_split, long long split_stride, float alpha) {
+                   float* baseX, int M, int nsplit, int rows_per_split, long long split_stride, float alpha,
+                   int round_out) {
   using L = SmemLayout<BN>;
   constexpr bool A_MN = (MODE == DIB_GEMM_WGRAD), B_MN = (MODE != DIB_GEMM_DGRAD);
   extern __shared__ uint8_t smem_raw[];
@@ -176,10 +177,10 @@ dib_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
             float4 o;
-            o.x = dib_act(p.act, __uint_as_float(v[j + 0]) + b4.x, alpha);
-            o.y = dib_act(p.act, __uint_as_float(v[j + 1]) + b4.y, alpha);
-            o.z = dib_act(p.act, __uint_as_float(v[j + 2]) + b4.z, alpha);
-            o.w = dib_act(p.act, __uint_as_float(v[j + 3]) + b4.w, alpha);
+            o.x = dib_maybe_round(dib_act(p.act, __uint_as_float(v[j + 0]) + b4.x, alpha), round_out);
+            o.y = dib_maybe_round(dib_act(p.act, __uint_as_float(v[j + 1]) + b4.y, alpha), round_out);
+            o.z = dib_maybe_round(dib_act(p.act, __uint_as_float(v[j + 2]) + b4.z, alpha), round_out);
+            o.w = dib_maybe_round(dib_act(p.act, __uint_as_float(v[j + 3]) + b4.w, alpha), round_out);
             *reinterpret_cast<float4*>(dst + j) = o;
           }
         } else if constexpr (MODE == DIB_GEMM_DGRAD) {
@@ -193,6 +194,8 @@ dib_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
               o.x *= dib_act_grad(p.act, x4.x, alpha); o.y *= dib_act_grad(p.act, x4.y, alpha);
               o.z *= dib_act_grad(p.act, x4.z, alpha); o.w *= dib_act_grad(p.act, x4.w, alpha);
             }
+            o.x = dib_maybe_round(o.x, round_out); o.y = dib_maybe_round(o.y, round_out);
+            o.z = dib_maybe_round(o.z, round_out); o.w = dib_maybe_round(o.w, round_out);
             *reinterpret_cast<float4*>(dst + j) = o;
           }
         } else {
@@ -272,8 +275,8 @@ cudaError_t launch_tc(const DibGemmLaunch& L, const CUtensorMap& mapA, const CUt
   else
     grid = dim3(DIB_CEIL_DIV(L.M, kBM), DIB_CEIL_DIV(L.maxC, BN), L.nprob);
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return cudaSuccess;
-  kern<<<grid, 192, SL::kTotal, st>>>(mapA, mapB, L.probs, L.baseB, L.baseC, L.baseX, L.M, L.nsplit, L.rows_per_split,
-                                      L.split_stride, L.alpha);
+  kern<<<grid, 192, SL::kTotal, st>>>(mapA, mapB, L.probs, L.baseBias ? L.baseBias : L.baseB, L.baseC, L.baseX, L.M,
+                                      L.nsplit, L.rows_per_split, L.split_stride, L.alpha, L.round_out);
   dib_note_launch();
   return cudaGetLastError();
 }

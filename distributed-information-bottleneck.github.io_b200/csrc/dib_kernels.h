@@ -21,6 +21,8 @@ struct DibGemmLaunch {
   int rows_per_split;
   long long split_stride;
   float alpha;
+  int round_out = 0;              // round FWD / DGRAD outputs to the TF32 grid (tensor-core mode operands)
+  const float* baseBias = nullptr; // FWD bias base when baseB points at the TF32-rounded weight shadow
 };
 
 cudaError_t dib_launch_gemm_simt(int mode, const DibGemmLaunch& L, cudaStream_t st);
@@ -33,7 +35,7 @@ cudaError_t dib_launch_gemm_tc(int mode, const DibGemmLaunch& L, const DibGemmPr
 // positional encoding (models.py:22-23) into the padded first-layer operand; tables are per pe column.
 cudaError_t dib_launch_pe(const float* x, int ldx, int x_col_shift, const int* col_src, const int* col_freq,
                           int col_begin, int col_end, float* pe, int ldpe, int pe_col_shift, int64_t n,
-                          cudaStream_t st);
+                          int round_out, cudaStream_t st);
 
 struct DibReparamArgs {
   const float* enc_out;    // [F][feat_stride] rows of ldo floats: (mu[E] | logvar[E] | pad)
@@ -43,6 +45,7 @@ struct DibReparamArgs {
   uint64_t seed; uint32_t step; uint64_t sample_offset;
   int F, E;
   int64_t n;
+  int round_out = 0;
 };
 // u = mu + exp(logvar/2) eps (models.py:108); per-(block,feature) partial sums of the KL (models.py:111-112).
 cudaError_t dib_launch_reparam_fwd(const DibReparamArgs& a, float* emb, int ldemb, float* user_emb,
@@ -54,7 +57,9 @@ cudaError_t dib_launch_reparam_bwd(const DibReparamArgs& a, const float* d_emb, 
 // compiled loss + metrics=['accuracy'] + d(loss)/d(pre-activation output).
 cudaError_t dib_launch_loss(int loss, int out_act, float alpha, const float* pred, int ldp, const float* y, int out_dim,
                             int64_t n, float inv_batch, float* d_pred /*nullable*/, float* user_pred /*nullable*/,
-                            float* loss_part, float* acc_part, cudaStream_t st);
+                            float* loss_part, float* acc_part, int round_out, cudaStream_t st);
+
+cudaError_t dib_launch_round_copy(const float* src, float* dst, int64_t count, cudaStream_t st);
 
 cudaError_t dib_launch_finalize_stats(const float* kl_part, int nblk_stride, int nblk_kl, const float* loss_part,
                                       const float* acc_part, int nblk_loss, int F, int64_t n, int has_y,
@@ -72,3 +77,30 @@ cudaError_t dib_launch_bhattacharyya(const float* mu_logvar, int64_t n, int E, f
                                      cudaStream_t st);
 
 cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st);
+
+// ---- fused per-feature encoder kernels (dib_enc_fused.cu): x -> emb / KL without touching HBM in between ----
+struct DibEncFusedDesc {        // static per model; all pointers are DEVICE arrays of length F
+  int F = 0, nfreq = 1, act = 0, bf16 = 0, grid = 0;
+  float alpha = 0.2f;
+  const int* x_off = nullptr; const int* fdim = nullptr;
+  const long long* w0_off = nullptr; const long long* b0_off = nullptr; const long long* w1_off = nullptr;
+  const long long* b1_off = nullptr; const long long* w2_off = nullptr; const long long* b2_off = nullptr;
+};
+struct DibEncFusedIO {
+  const float* params; const void* packed;      // fp32 masters, packed 16-bit weights (dib_enc_fused_pack)
+  const float* x; int ldx; int64_t n;
+  const float* eps; uint64_t seed; uint32_t step; uint64_t sample_offset;
+  float* emb; int ldemb; float* user_emb;
+  float* kl_part; int kl_stride;
+};
+size_t dib_enc_fused_pack_bytes(int F);
+cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, cudaStream_t st);
+cudaError_t dib_enc_fused_forward(const DibEncFusedDesc& d, const DibEncFusedIO& io, cudaStream_t st);
+
+struct DibEncFusedBwdIO {
+  const float* d_emb; int ldd;          // gradient w.r.t. emb (scaled by 1/B_global)
+  const float* beta_dev; float inv_batch; float gscale;
+  float* part; long long split_stride;  // [slot][P] weight-gradient partials
+};
+cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO& io, const DibEncFusedBwdIO& b,
+                                   cudaStream_t st);

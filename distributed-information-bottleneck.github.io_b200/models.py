@@ -245,6 +245,8 @@ class DistributedIBNet:
             cfg = self._config(max_batch)
             _lib.check(self._lib.dib_create(ctypes.byref(cfg), ctypes.byref(h)))
             self._handle, self._handle_key, self._max_batch = h, key, max_batch
+            if getattr(self, "_force_unfused", False):
+                _lib.check(self._lib.dib_debug_force_unfused(h, 1))
             nbytes = int(self._lib.dib_workspace_bytes(h))
             self._workspace = None
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -377,8 +379,14 @@ class DistributedIBNet:
             xd = self._to_device(x, sum(self.feature_dimensionalities))
             yd = self._to_device(y, self._y_cols())
             e = self._to_device(eps) if eps is not None else None
-            self._backward(xd, yd, global_batch or xd.shape[0], e, sample_offset, step)
+            self._backward(xd, yd, global_batch or max(xd.shape[0], 1), e, sample_offset, step)
             return self._gradstats[:self._P].clone(), self._gradstats[self._P:].clone()
+
+    def debug_force_unfused(self, on=True, batch_hint=1):
+        """Bring-up switch: keep the tensor-core mode on the unfused kernels (fused-vs-unfused comparisons)."""
+        self._force_unfused = bool(on)
+        if self._handle is not None:
+            _lib.check(self._lib.dib_debug_force_unfused(self._handle, int(on)))
 
     def epoch_permutation(self, epoch, n):
         """The shuffle Model.fit applies in ``epoch`` (our RNG stream; Keras' own is irreproducible)."""

@@ -334,8 +334,9 @@ def adam_step(params, grads, st: AdamState, lr, beta_1=0.9, beta_2=0.999, epsilo
     st.t += 1
     dt = params.dtype.type
     lr_t = dt(lr) * dt(math.sqrt(1.0 - beta_2 ** st.t)) / dt(1.0 - beta_1 ** st.t)
-    st.m += (grads - st.m) * dt(1.0 - beta_1)
-    st.v += (grads * grads - st.v) * dt(1.0 - beta_2)
+    # Keras casts beta_1/beta_2 to the variable dtype first and forms (1 - beta) in that dtype
+    st.m += (grads - st.m) * (dt(1.0) - dt(beta_1))
+    st.v += (grads * grads - st.v) * (dt(1.0) - dt(beta_2))
     params -= lr_t * st.m / (np.sqrt(st.v) + dt(epsilon))
     return params
 
@@ -360,8 +361,9 @@ def fit(cfg: DIBConfig, flat_params, x, y, *, loss, epochs, batch_size, lr,
         (add_metric -> Mean with weight 1, models.py:115,121);
       * validation after every epoch with the same call() -- noise still sampled (train.py:264-265)
         -- in batches of batch_size, giving val_* twins.
-    eps_fn(step, global_sample_ids) -> eps [n, F, E]; step counts optimizer steps from 0 for
-    training batches; validation passes use step = 2**31 + epoch.
+    eps_fn(step, sample_ids) -> eps [n, F, E].  Noise contract of the engine: a training batch is keyed by
+    (optimizer step counted from 0, ROW POSITION inside the global batch); a validation pass is keyed by
+    (2**31 + epoch, row position inside the validation set).
     """
     p = np.array(flat_params, dtype=dtype, copy=True)
     st = AdamState(np.zeros_like(p), np.zeros_like(p))
@@ -381,7 +383,7 @@ def fit(cfg: DIBConfig, flat_params, x, y, *, loss, epochs, batch_size, lr,
         sums = dict(loss=0.0, acc=0.0, n=0, kl=np.zeros(F), nb=0)
         for b0 in range(0, N, batch_size):
             idx = perm[b0:b0 + batch_size]
-            eps = eps_fn(step, idx)
+            eps = eps_fn(step, np.arange(len(idx)))
             g, fr = train_grads(cfg, p, x[idx], y[idx], eps, beta, loss, dtype=dtype)
             adam_step(p, g.astype(dtype), st, lr, **adam_kwargs)
             n = len(idx)
