@@ -66,6 +66,10 @@ def algorithmic_macs(batch):
             macs[f"int_{kind}_l{j}"] = k * n * batch
     fwd = sum(v for k, v in macs.items() if "_fwd_" in k)
     train = sum(macs.values())
+    # fused per-feature encoder kernels: algorithmic work = the layers they replace (the backward kernel's on-chip
+    # recomputation of the forward is overhead, not algorithmic work)
+    macs["enc_fused_fwd"] = sum(v for k, v in macs.items() if k.startswith("enc_fwd_"))
+    macs["enc_fused_bwd"] = sum(v for k, v in macs.items() if k.startswith("enc_dgrad_") or k.startswith("enc_wgrad_"))
     return macs, fwd, train
 
 

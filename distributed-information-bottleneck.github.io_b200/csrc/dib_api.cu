@@ -123,7 +123,7 @@ void plan(dib_model* h) {
   h->nblk_max = (int)DIB_CEIL_DIV(B, (long long)kRowsPerBlock);
   h->part_rows = DIB_CEIL_DIV(h->num_sms, h->F) > kMaxSplits ? DIB_CEIL_DIV(h->num_sms, h->F) : kMaxSplits;
   h->part_off = take(c, (long long)h->part_rows * h->Pp);
-  h->kl_stride = h->nblk_max > 192 ? h->nblk_max : 192;   // >= CTA slots per feature of the fused encoder kernels
+  h->kl_stride = h->nblk_max > 2 * h->num_sms + 8 ? h->nblk_max : 2 * h->num_sms + 8;   // >= fused-kernel CTA slots per feature
   h->kl_part_off = take(c, (long long)h->F * h->kl_stride);
   h->loss_part_off = take(c, h->nblk_max);
   h->acc_part_off = take(c, h->nblk_max);
@@ -300,7 +300,8 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
     const int ntiles = (int)DIB_CEIL_DIV((long long)c.n, 128ll);
     long long want = (long long)h->F * ntiles;
     DibEncFusedDesc d = h->fdesc;
-    d.grid = (int)(want < h->num_sms ? want : h->num_sms);
+    const long long cap = (long long)h->num_sms * dib_enc_fused_fwd_ctas_per_sm();
+    d.grid = (int)(want < cap ? want : cap);
     nblk_kl = DIB_CEIL_DIV(d.grid, h->F);
     prof_begin(c, "enc_pack_weights");
     DIB_CUDA_OK(dib_enc_fused_pack(d, c.params, c.ws + h->pack_off, c.st));
@@ -596,7 +597,8 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
                    float inv_global_batch, const float* eps, uint64_t seed, uint32_t step, uint64_t sample_offset,
                    float* grads_flat, float* out_stats, void* workspace, void* stream) {
   if (check_call(h, params, x, n, workspace)) return 1;
-  if (!y || !beta_dev || !grads_flat || !out_stats) return fail("dib_train_step: y, beta_dev, grads_flat and out_stats are required");
+  if ((!y && n > 0) || !beta_dev || !grads_flat || !out_stats)
+    return fail("dib_train_step: y, beta_dev, grads_flat and out_stats are required");
   Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
   if (n == 0) {
     DIB_CUDA_OK(cudaMemsetAsync(grads_flat, 0, sizeof(float) * h->P, c.st));
@@ -629,9 +631,10 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
     const int slots_max = DIB_CEIL_DIV(d.grid, h->F), slots_min = d.grid / h->F;
     const long long p_enc = h->intW[0];              // encoder parameters occupy [0, p_enc)
     float* part = c.ws + h->part_off;
-    if (slots_max > slots_min && slots_min >= 0)
-      DIB_CUDA_OK(cudaMemsetAsync(part + (long long)slots_min * h->Pp, 0,
-                                  sizeof(float) * (size_t)(slots_max - slots_min) * h->Pp, c.st));
+    // features served by one CTA fewer leave their last slot unwritten: zero it (ENCODER range only -- the
+    // integration network's batch-split partials live in the same rows beyond p_enc)
+    for (int srow = slots_min; srow < slots_max; ++srow)
+      DIB_CUDA_OK(cudaMemsetAsync(part + (long long)srow * h->Pp, 0, sizeof(float) * (size_t)p_enc, c.st));
     DibEncFusedIO io;
     io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = n;
     io.eps = eps; io.seed = seed; io.step = step; io.sample_offset = sample_offset;

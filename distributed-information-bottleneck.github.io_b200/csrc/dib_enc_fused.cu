@@ -35,15 +35,20 @@ constexpr int kThreads = 32 * (1 + kEpiWarps);
 constexpr int kPanel = TM * 128;   // bytes of one 64-column panel of a 128-row tile (16 KB)
 
 // packed 16-bit weights in global memory, per feature (elements): W0p[16][128] | W1[128][128] | W2[128][64]
-constexpr int kW0Elems = K0 * HID, kW1Elems = HID * HID, kW2Elems = HID * EO;
-constexpr int kPackElems = kW0Elems + kW1Elems + kW2Elems;
+// followed by the bias carriers Bb1[16][128] | Bb2[16][64] whose only non-zero row (index w_in, the position of the
+// ones column in the first-layer operand) holds b1 / b2: one extra K=16 MMA step adds the bias for free.
+constexpr int kW0Elems = K0 * HID, kW1Elems = HID * HID, kW2Elems = HID * EO, kB1Elems = K0 * HID, kB2Elems = K0 * EO;
+constexpr int kPackElems = kW0Elems + kW1Elems + kW2Elems + kB1Elems + kB2Elems;
 
 // shared memory map (bytes; operand tiles 1024-aligned)
 constexpr int kOffW1 = 0;
 constexpr int kOffW2 = kOffW1 + 2 * kPanel;        // 32 KB
 constexpr int kOffW0 = kOffW2 + kPanel;            // 16 KB
-constexpr int kOffA0 = kOffW0 + 2 * K0 * 128;      // 4 KB : W0p = 2 panels x 16 rows x 128 B
-constexpr int kOffH1 = kOffA0 + 2 * TM * 16;       // 4 KB : A0 = [2 k-halves][128 rows][16 B] (no swizzle)
+constexpr int kOffBb1 = kOffW0 + 2 * K0 * 128;     // 4 KB : W0p = 2 panels x 16 rows x 128 B
+constexpr int kOffBb2 = kOffBb1 + 2 * K0 * 128;    // 4 KB : Bb1 likewise
+constexpr int kOffA0 = kOffBb2 + K0 * 128;         // 2 KB : Bb2 = 1 panel x 16 rows x 128 B
+constexpr int kOffH1 = kOffA0 + 2 * TM * 16 + 2048;// 4 KB : A0 = [2 k-halves][128 rows][16 B] (no swizzle); +2 KB keeps 1024-alignment
+constexpr int kOffFwdEnd1 = kOffH1 + 2 * kPanel;   // forward kernel: h2 overwrites h1 (its MMA has retired)
 constexpr int kOffH2 = kOffH1 + 2 * kPanel;
 constexpr int kOffFwdEnd = kOffH2 + 2 * kPanel;
 // backward-only tiles
@@ -66,17 +71,13 @@ struct EncFusedParams {
   int round_emb;
 };
 
+// two fp32 -> one 32-bit word of two 16-bit values (a in the low half), saturating instead of producing inf
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if constexpr (BF16) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-  } else {
-    __half2 v = __floats2half2_rn(a, b);
-    const __half2 mx = __float2half2_rn(65504.f);
-    v = __hmax2(__hmin2(v, mx), __hneg2(mx));     // saturate instead of producing inf
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
+  uint32_t r;
+  if constexpr (BF16) asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -89,10 +90,11 @@ __device__ __forceinline__ uint32_t tile_chunk_addr(uint32_t tile, int r, int co
   return tile + panel * kPanel + r * 128 + ((c ^ (r & 7)) << 4);
 }
 
-// TMEM -> (+bias, activation) -> 16-bit -> swizzled shared tile, for 64 columns [col0, col0+64) of row r
-template <bool BF16>
-__device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, uint32_t tile, int r, int col0, const float* bias_s,
-                                                 int act, float alpha) {
+// TMEM -> activation -> 16-bit -> swizzled shared tile, for 64 columns [col0, col0+64) of row r (bias is already in
+// the accumulator).  RELU fast path returns the 64-bit mask (h > 0) that the backward reuses as act'.
+template <bool BF16, bool RELU>
+__device__ __forceinline__ uint64_t epilogue_to_tile(uint32_t taddr, uint32_t tile, int r, int col0, int act, float alpha) {
+  uint64_t mask = 0;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     uint32_t v[32];
@@ -103,17 +105,23 @@ __device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, uint32_t tile, 
       float f[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float z = __uint_as_float(v[j + k]);
-        if (bias_s) z += bias_s[col0 + hh * 32 + j + k];
-        f[k] = dib_act(act, z, alpha);
+        const float z = __uint_as_float(v[j + k]);
+        if constexpr (RELU) {
+          f[k] = fmaxf(z, 0.f);
+          mask |= (uint64_t)(z > 0.f) << (hh * 32 + j + k);
+        } else {
+          f[k] = dib_act(act, z, alpha);
+        }
       }
       st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * 32 + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
                    pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
     }
   }
+  return mask;
 }
 
-// first-layer operand row: [x_0..x_{d-1}, sin(2x).., sin(4x).., ..., 1, 0...] (models.py:22-23 + bias column)
+// first-layer operand row: [x_0..x_{d-1}, sin(2x).., sin(4x).., ..., 1, 0...] (models.py:22-23 + the ones column
+// that carries every layer's bias through the bias-carrier matrices)
 template <bool BF16>
 __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, const float* xrow, int d, int nfreq) {
   float f[8];
@@ -127,7 +135,7 @@ __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, cons
       const float xv = xrow ? xrow[j] : 0.f;
       v = blk == 0 ? xv : sinf((float)(1 << blk) * xv);
     } else if (col == w_in) {
-      v = xrow ? 1.f : 0.f;          // bias column (rows past the batch end contribute nothing)
+      v = xrow ? 1.f : 0.f;          // rows past the batch end contribute nothing
     }
     f[k] = v;
   }
@@ -135,20 +143,65 @@ __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, cons
                pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
 }
 
-// ====================================================================================================
-// forward: x -> emb, KL partial sums
-// ====================================================================================================
+struct WeightMaps { CUtensorMap w0, w1, w2, b1, b2; };
+
+// one thread: stage a feature's packed weights (W0p, W1, W2, bias carriers) into shared memory
+__device__ __forceinline__ void load_weights(uint32_t sb, const WeightMaps& m, uint32_t bar, int f) {
+  mbar_expect_tx(bar, 2 * K0 * 128 + 2 * kPanel + kPanel + 2 * K0 * 128 + K0 * 128);
+  tma_load_3d(sb + kOffW0, &m.w0, bar, 0, 0, f);
+  tma_load_3d(sb + kOffW0 + K0 * 128, &m.w0, bar, 64, 0, f);
+  tma_load_3d(sb + kOffW1, &m.w1, bar, 0, 0, f);
+  tma_load_3d(sb + kOffW1 + kPanel, &m.w1, bar, 64, 0, f);
+  tma_load_3d(sb + kOffW2, &m.w2, bar, 0, 0, f);
+  tma_load_3d(sb + kOffBb1, &m.b1, bar, 0, 0, f);
+  tma_load_3d(sb + kOffBb1 + K0 * 128, &m.b1, bar, 64, 0, f);
+  tma_load_3d(sb + kOffBb2, &m.b2, bar, 0, 0, f);
+}
+
+// the three forward contractions of one tile, each preceded by its bias-carrier step (issued by one thread)
 template <bool BF16>
-__global__ void __launch_bounds__(kThreads, 1)
-dib_enc_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
-                         const __grid_constant__ CUtensorMap mapW2, const EncFusedParams P) {
+__device__ __forceinline__ void issue_layer0(uint32_t sb, uint32_t tD) {
+  constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, HID);
+  umma_f16<BF16>(tD, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffW0, K0 * 128, 1024), id, 0u);
+}
+template <bool BF16>
+__device__ __forceinline__ void issue_layer1(uint32_t sb, uint32_t tD, uint32_t h1) {
+  constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, HID);
+  umma_f16<BF16>(tD, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffBb1, K0 * 128, 1024), id, 0u);
+#pragma unroll
+  for (int kk = 0; kk < HID / 16; ++kk)
+    umma_f16<BF16>(tD, umma_smem_desc(h1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
+                   umma_smem_desc(sb + kOffW1 + kk * 2048, kPanel, 1024), id, 1u);
+}
+template <bool BF16>
+__device__ __forceinline__ void issue_layer2(uint32_t sb, uint32_t tD, uint32_t h2) {
+  constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, EO);
+  umma_f16<BF16>(tD, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffBb2, K0 * 128, 1024), id, 0u);
+#pragma unroll
+  for (int kk = 0; kk < HID / 16; ++kk)
+    umma_f16<BF16>(tD, umma_smem_desc(h2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
+                   umma_smem_desc(sb + kOffW2 + kk * 2048, kPanel, 1024), id, 1u);
+}
+
+#define DIB_EPI_SIGNAL(bar)            \
+  do {                                 \
+    fence_proxy_async_smem();          \
+    tc_fence_before_sync();            \
+    __syncwarp();                      \
+    if (lane == 0) mbar_arrive(bar);   \
+  } while (0)
+
+// ====================================================================================================
+// forward: x -> emb, KL partial sums.  96 KB of shared memory and 256 TMEM columns per CTA -> two CTAs per SM, so
+// one CTA's epilogue overlaps the other's MMAs.
+// ====================================================================================================
+template <bool BF16, bool RELU>
+__global__ void __launch_bounds__(kThreads, 2)
+dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFusedParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
-  constexpr int kOffBias = kOffFwdEnd;                       // b1[128] b2[64] fp32
-  constexpr int kOffBar = kOffBias + (HID + EO) * 4;
-  float* bias1_s = reinterpret_cast<float*>(sg + kOffBias);
-  float* bias2_s = bias1_s + HID;
+  constexpr int kOffBar = kOffFwdEnd1;
   float* red_s = reinterpret_cast<float*>(sg + kOffBar + 128);          // [kEpiWarps]
   const uint32_t bar = sb + kOffBar;
   const uint32_t bar_w = bar, bar_a0 = bar + 8, bar_d0 = bar + 16, bar_h1 = bar + 24, bar_d1 = bar + 32,
@@ -160,61 +213,39 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
   const int ntiles = (int)((P.n + TM - 1) / TM);
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&mapW0); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
+    tma_prefetch_desc(&maps.w0); tma_prefetch_desc(&maps.w1); tma_prefetch_desc(&maps.w2);
+    tma_prefetch_desc(&maps.b1); tma_prefetch_desc(&maps.b2);
     mbar_init(bar_w, 1);
     mbar_init(bar_a0, kEpiWarps); mbar_init(bar_h1, kEpiWarps); mbar_init(bar_h2, kEpiWarps);
     mbar_init(bar_d0, 1); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1);
     fence_barrier_init();
   }
-  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot_g;
-  const uint32_t tD0 = tmem, tD1 = tmem + 128, tD2 = tmem + 256;
+  const uint32_t tR0 = tmem, tR1 = tmem + 128;          // D0 and D1 share R0; D2 -> R1
+  const uint32_t hbuf = sb + kOffH1;                    // h1, then h2
 
-  // work assignment: with G >= F CTAs, CTA c serves feature c % F as slot c / F of that feature's CTAs
   int f_first, f_step, nslots, slot;
   if (G >= F) { f_first = c % F; f_step = F * G; slot = c / F; nslots = (G - f_first + F - 1) / F; }
   else { f_first = c; f_step = G; slot = 0; nslots = 1; }
-
-  constexpr uint32_t fmt = BF16 ? 1u : 0u;
-  constexpr uint32_t idesc0 = umma_idesc(fmt, 0, 1, HID);     // A K-major, B MN-major, N = 128
-  constexpr uint32_t idesc2 = umma_idesc(fmt, 0, 1, EO);      // N = 64
-  uint32_t it = 0, fit = 0;                                   // tile / feature iteration counters (barrier phases)
+  uint32_t it = 0, fit = 0;
 
   for (int f = f_first; f < F; f += f_step, ++fit) {
     if (warp == 0) {
-      // ============================================================ weights + MMA issue (one thread)
       if (lane == 0) {
-        mbar_expect_tx(bar_w, 2 * K0 * 128 + 2 * kPanel + kPanel);
-        tma_load_3d(sb + kOffW0, &mapW0, bar_w, 0, 0, f);
-        tma_load_3d(sb + kOffW0 + K0 * 128, &mapW0, bar_w, 64, 0, f);
-        tma_load_3d(sb + kOffW1, &mapW1, bar_w, 0, 0, f);
-        tma_load_3d(sb + kOffW1 + kPanel, &mapW1, bar_w, 64, 0, f);
-        tma_load_3d(sb + kOffW2, &mapW2, bar_w, 0, 0, f);
+        load_weights(sb, maps, bar_w, f);
         mbar_wait(bar_w, fit & 1);
         for (int t = slot; t < ntiles; t += nslots, ++it) {
           const uint32_t ph = it & 1;
-          mbar_wait(bar_a0, ph);
-          tc_fence_after_sync();
-          umma_f16<BF16>(tD0, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone),
-                         umma_smem_desc(sb + kOffW0, K0 * 128, 1024), idesc0, 0u);
-          umma_commit(bar_d0);
-          mbar_wait(bar_h1, ph);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int kk = 0; kk < HID / 16; ++kk)
-            umma_f16<BF16>(tD1, umma_smem_desc(sb + kOffH1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
-                           umma_smem_desc(sb + kOffW1 + kk * 2048, kPanel, 1024), idesc0, kk > 0 ? 1u : 0u);
-          umma_commit(bar_d1);
-          mbar_wait(bar_h2, ph);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int kk = 0; kk < HID / 16; ++kk)
-            umma_f16<BF16>(tD2, umma_smem_desc(sb + kOffH2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
-                           umma_smem_desc(sb + kOffW2 + kk * 2048, kPanel, 1024), idesc2, kk > 0 ? 1u : 0u);
-          umma_commit(bar_d2);
+          mbar_wait(bar_a0, ph); tc_fence_after_sync();
+          issue_layer0<BF16>(sb, tR0); umma_commit(bar_d0);
+          mbar_wait(bar_h1, ph); tc_fence_after_sync();
+          issue_layer1<BF16>(sb, tR0, hbuf); umma_commit(bar_d1);
+          mbar_wait(bar_h2, ph); tc_fence_after_sync();
+          issue_layer2<BF16>(sb, tR1, hbuf); umma_commit(bar_d2);
           if (t + nslots >= ntiles) mbar_wait(bar_d2, ph);   // drain before the next feature's weights land
         }
       } else {
@@ -222,54 +253,35 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
       }
       __syncwarp();
     } else {
-      // ============================================================ epilogue warps
       const int ew = warp - 1, q = warp & 3, hsel = ew >> 2;      // TMEM lane quarter, column half
-      const int et = ew * 32 + lane;                              // 0..255
-      const int r = q * 32 + lane;                                // row of the tile owned for TMEM reads
+      const int et = ew * 32 + lane;
+      const int r = q * 32 + lane;
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-      // per-feature constants
-      for (int i = et; i < HID + EO; i += kEpiWarps * 32)
-        bias1_s[i] = i < HID ? P.params[P.b1_off[f] + i] : P.params[P.b2_off[f] + (i - HID)];
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       const int d = P.fdim[f], xo = P.x_off[f];
       float kl_acc = 0.f;
       for (int t = slot; t < ntiles; t += nslots, ++it) {
         const uint32_t ph = it & 1;
         const long long row0 = (long long)t * TM;
-        // ---- stage 0: positional encoding of the x column -> A0
         {
           const int ar = et & (TM - 1), khalf = et >> 7;
           const long long grow = row0 + ar;
           write_a0_row<BF16>(sb + kOffA0, ar, khalf, grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, P.nfreq);
-          fence_proxy_async_smem();
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_a0);
+          DIB_EPI_SIGNAL(bar_a0);
         }
-        // ---- layer 0 epilogue: relu(D0) -> H1   (bias folded into the GEMM through the ones column)
-        mbar_wait(bar_d0, ph);
-        tc_fence_after_sync();
-        epilogue_to_tile<BF16>(tD0 + lane_addr, sb + kOffH1, r, hsel * 64, nullptr, P.act, P.alpha);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_h1);
-        // ---- layer 1 epilogue: act(D1 + b1) -> H2
-        mbar_wait(bar_d1, ph);
-        tc_fence_after_sync();
-        epilogue_to_tile<BF16>(tD1 + lane_addr, sb + kOffH2, r, hsel * 64, bias1_s, P.act, P.alpha);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_h2);
-        // ---- layer 2 epilogue: (mu, logvar) -> reparameterise, KL, emb   (16 embedding dims per thread)
-        mbar_wait(bar_d2, ph);
-        tc_fence_after_sync();
+        mbar_wait(bar_d0, ph); tc_fence_after_sync();
+        epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_h1);
+        mbar_wait(bar_d1, ph); tc_fence_after_sync();
+        epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_h2);
+        // ---- (mu, logvar) -> reparameterise, KL, emb   (16 embedding dims per thread)
+        mbar_wait(bar_d2, ph); tc_fence_after_sync();
         {
           uint32_t vm[16], vl[16];
-          tmem_ld_32x32b_x16(tD2 + lane_addr + hsel * 16, vm);
-          tmem_ld_32x32b_x16(tD2 + lane_addr + 32 + hsel * 16, vl);
+          tmem_ld_32x32b_x16(tR1 + lane_addr + hsel * 16, vm);
+          tmem_ld_32x32b_x16(tR1 + lane_addr + 32 + hsel * 16, vl);
           tmem_ld_wait();
+          tc_fence_before_sync();
           const long long grow = row0 + r;
           if (grow < P.n) {
             float* dst = P.emb + grow * P.ldemb + f * 32 + hsel * 16;
@@ -284,8 +296,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
               float u[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float mu = __uint_as_float(vm[e0 + j]) + bias2_s[hsel * 16 + e0 + j];
-                const float lv = __uint_as_float(vl[e0 + j]) + bias2_s[32 + hsel * 16 + e0 + j];
+                const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
                 const float s = expf(0.5f * lv);
                 u[j] = fmaf(s, nrm[j], mu);
                 kl_acc += 0.5f * (mu * mu + s * s - lv - 1.f);
@@ -314,7 +325,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 256); }
 }
 
 // ====================================================================================================
@@ -344,10 +355,11 @@ __device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b) {
   else { const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u)); a = f.x; b = f.y; }
 }
 
-// TMEM gradient g (64 columns) * act'(h from the shared tile `htile`) -> 16-bit -> shared tile `dtile`
-template <bool BF16>
+// TMEM gradient g (64 columns) * act'(h) -> 16-bit -> shared tile `dtile`; act' comes from the register mask kept by
+// the forward epilogue (RELU) or from the h values still sitting in the shared tile `htile`
+template <bool BF16, bool RELU>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t taddr, uint32_t htile, uint32_t dtile, int r, int col0, int act,
-                                               float alpha) {
+                                               float alpha, uint64_t mask) {
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     uint32_t v[32];
@@ -355,15 +367,20 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t taddr, uint32_t htile, u
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
-      uint32_t hv[4];
-      ld_shared_v4(tile_chunk_addr(htile, r, col0 + hh * 32 + j), hv);
       float f[8];
+      if constexpr (RELU) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float h0, h1;
-        unpack2<BF16>(hv[k], h0, h1);
-        f[2 * k] = __uint_as_float(v[j + 2 * k]) * dib_act_grad(act, h0, alpha);
-        f[2 * k + 1] = __uint_as_float(v[j + 2 * k + 1]) * dib_act_grad(act, h1, alpha);
+        for (int k = 0; k < 8; ++k) f[k] = ((mask >> (hh * 32 + j + k)) & 1ull) ? __uint_as_float(v[j + k]) : 0.f;
+      } else {
+        uint32_t hv[4];
+        ld_shared_v4(tile_chunk_addr(htile, r, col0 + hh * 32 + j), hv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float h0, h1;
+          unpack2<BF16>(hv[k], h0, h1);
+          f[2 * k] = __uint_as_float(v[j + 2 * k]) * dib_act_grad(act, h0, alpha);
+          f[2 * k + 1] = __uint_as_float(v[j + 2 * k + 1]) * dib_act_grad(act, h1, alpha);
+        }
       }
       st_shared_v4(tile_chunk_addr(dtile, r, col0 + hh * 32 + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
                    pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
@@ -371,18 +388,15 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t taddr, uint32_t htile, u
   }
 }
 
-template <bool BF16>
+// 9 warps are allocated as 12 (granularity 4): 65536 / (12*32) = 170 registers per thread is the launchable maximum
+template <bool BF16, bool RELU>
 __global__ void __launch_bounds__(kThreads, 1)
-dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
-                         const __grid_constant__ CUtensorMap mapW2, const EncFusedBwdParams Q) {
+dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFusedBwdParams Q) {
   const EncFusedParams& P = Q.f;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
-  constexpr int kOffBias = kOffBwdEnd;
-  constexpr int kOffBar = kOffBias + (HID + EO) * 4;
-  float* bias1_s = reinterpret_cast<float*>(sg + kOffBias);
-  float* bias2_s = bias1_s + HID;
+  constexpr int kOffBar = kOffBwdEnd;
   const uint32_t bar = sb + kOffBar;
   const uint32_t bar_w = bar, bar_a0 = bar + 8, bar_d0 = bar + 16, bar_h1 = bar + 24, bar_d1 = bar + 32,
                  bar_h2 = bar + 40, bar_d2 = bar + 48, bar_do = bar + 56, bar_g2 = bar + 64, bar_dz2 = bar + 72,
@@ -394,7 +408,8 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
   const int ntiles = (int)((P.n + TM - 1) / TM);
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&mapW0); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
+    tma_prefetch_desc(&maps.w0); tma_prefetch_desc(&maps.w1); tma_prefetch_desc(&maps.w2);
+    tma_prefetch_desc(&maps.b1); tma_prefetch_desc(&maps.b2);
     mbar_init(bar_w, 1);
     mbar_init(bar_a0, kEpiWarps); mbar_init(bar_h1, kEpiWarps); mbar_init(bar_h2, kEpiWarps);
     mbar_init(bar_do, kEpiWarps); mbar_init(bar_dz2, kEpiWarps); mbar_init(bar_dz1, kEpiWarps);
@@ -414,7 +429,6 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
   else { f_first = c; f_step = G; slot = 0; nslots = 1; }
 
   constexpr uint32_t fmt = BF16 ? 1u : 0u;
-  constexpr uint32_t id_kmn_128 = umma_idesc(fmt, 0, 1, HID), id_kmn_64 = umma_idesc(fmt, 0, 1, EO);
   constexpr uint32_t id_kk_128 = umma_idesc(fmt, 0, 0, HID);
   constexpr uint32_t id_mm_128 = umma_idesc(fmt, 1, 1, HID), id_mm_64 = umma_idesc(fmt, 1, 1, EO),
                      id_mm_16 = umma_idesc(fmt, 1, 1, 16);
@@ -425,39 +439,20 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
     const bool any_tiles = slot < ntiles;
     if (warp == 0) {
       if (lane == 0) {
-        mbar_expect_tx(bar_w, 2 * K0 * 128 + 2 * kPanel + kPanel);
-        tma_load_3d(sb + kOffW0, &mapW0, bar_w, 0, 0, f);
-        tma_load_3d(sb + kOffW0 + K0 * 128, &mapW0, bar_w, 64, 0, f);
-        tma_load_3d(sb + kOffW1, &mapW1, bar_w, 0, 0, f);
-        tma_load_3d(sb + kOffW1 + kPanel, &mapW1, bar_w, 64, 0, f);
-        tma_load_3d(sb + kOffW2, &mapW2, bar_w, 0, 0, f);
+        load_weights(sb, maps, bar_w, f);
         mbar_wait(bar_w, fit & 1);
         bool first = true;
         for (int t = slot; t < ntiles; t += nslots, ++it, first = false) {
           const uint32_t ph = it & 1;
           // ---- recompute forward
-          mbar_wait(bar_a0, ph);
-          tc_fence_after_sync();
-          umma_f16<BF16>(tR0, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone),
-                         umma_smem_desc(sb + kOffW0, K0 * 128, 1024), id_kmn_128, 0u);
-          umma_commit(bar_d0);
-          mbar_wait(bar_h1, ph);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tR0, umma_smem_desc(sb + kOffH1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
-                           umma_smem_desc(sb + kOffW1 + kk * 2048, kPanel, 1024), id_kmn_128, kk > 0 ? 1u : 0u);
-          umma_commit(bar_d1);
-          mbar_wait(bar_h2, ph);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffH2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
-                           umma_smem_desc(sb + kOffW2 + kk * 2048, kPanel, 1024), id_kmn_64, kk > 0 ? 1u : 0u);
-          umma_commit(bar_d2);
+          mbar_wait(bar_a0, ph); tc_fence_after_sync();
+          issue_layer0<BF16>(sb, tR0); umma_commit(bar_d0);
+          mbar_wait(bar_h1, ph); tc_fence_after_sync();
+          issue_layer1<BF16>(sb, tR0, sb + kOffH1); umma_commit(bar_d1);
+          mbar_wait(bar_h2, ph); tc_fence_after_sync();
+          issue_layer2<BF16>(sb, tR1, sb + kOffH2); umma_commit(bar_d2);
           // ---- layer 2 backward: G2 = dO W2^T ; dW2 += h2^T dO
-          mbar_wait(bar_do, ph);
-          tc_fence_after_sync();
+          mbar_wait(bar_do, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffDO + kk * 32, 16, 1024),
@@ -468,8 +463,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
             umma_f16<BF16>(tWG2, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
                            umma_smem_desc(sb + kOffDO + kk * 2048, kPanel, 1024), id_mm_64, (first && kk == 0) ? 0u : 1u);
           // ---- layer 1 backward: G1 = dz2 W1^T ; dW1 += h1^T dz2 ; db1 += dz2^T [pe|1]
-          mbar_wait(bar_dz2, ph);
-          tc_fence_after_sync();
+          mbar_wait(bar_dz2, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffDZ2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
@@ -486,8 +480,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
                            umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           // ---- layer 0 backward: [dW0;db0]^T += dz1^T [pe|1]     (dz1 lives in the H2 buffer)
-          mbar_wait(bar_dz1, ph);
-          tc_fence_after_sync();
+          mbar_wait(bar_dz1, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tWG0, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
@@ -505,9 +498,6 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
       const int et = ew * 32 + lane;
       const int r = q * 32 + lane;
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-      for (int i = et; i < HID + EO; i += kEpiWarps * 32)
-        bias1_s[i] = i < HID ? P.params[P.b1_off[f] + i] : P.params[P.b2_off[f] + (i - HID)];
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       const int d = P.fdim[f], xo = P.x_off[f];
       const float bs = Q.beta_dev[0] * Q.inv_batch * S;
       float db2m[16], db2l[16];
@@ -520,28 +510,16 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
           const int ar = et & (TM - 1), khalf = et >> 7;
           const long long grow = row0 + ar;
           write_a0_row<BF16>(sb + kOffA0, ar, khalf, grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, P.nfreq);
-          fence_proxy_async_smem();
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_a0);
+          DIB_EPI_SIGNAL(bar_a0);
         }
-        mbar_wait(bar_d0, ph);
-        tc_fence_after_sync();
-        epilogue_to_tile<BF16>(tR0 + lane_addr, sb + kOffH1, r, hsel * 64, nullptr, P.act, P.alpha);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_h1);
-        mbar_wait(bar_d1, ph);
-        tc_fence_after_sync();
-        epilogue_to_tile<BF16>(tR0 + lane_addr, sb + kOffH2, r, hsel * 64, bias1_s, P.act, P.alpha);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_h2);
+        mbar_wait(bar_d0, ph); tc_fence_after_sync();
+        const uint64_t m1 = epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH1, r, hsel * 64, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_h1);
+        mbar_wait(bar_d1, ph); tc_fence_after_sync();
+        const uint64_t m2 = epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_h2);
         // ---- (mu, logvar) -> d(mu), d(logvar) -> DO tile
-        mbar_wait(bar_d2, ph);
-        tc_fence_after_sync();
+        mbar_wait(bar_d2, ph); tc_fence_after_sync();
         {
           uint32_t vm[16], vl[16];
           tmem_ld_32x32b_x16(tR1 + lane_addr + hsel * 16, vm);
@@ -562,8 +540,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
             const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float mu = __uint_as_float(vm[e0 + j]) + bias2_s[hsel * 16 + e0 + j];
-              const float lv = __uint_as_float(vl[e0 + j]) + bias2_s[32 + hsel * 16 + e0 + j];
+              const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
               const float s = expf(0.5f * lv);
               const float gs = g[j] * S;
               const float a = valid ? fmaf(bs, mu, gs) : 0.f;
@@ -580,36 +557,23 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
                          pack2<BF16>(dl[j + 2], dl[j + 3]), pack2<BF16>(dl[j + 4], dl[j + 5]), pack2<BF16>(dl[j + 6], dl[j + 7]));
           }
         }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_do);
+        DIB_EPI_SIGNAL(bar_do);
         // ---- dz2 = G2 * act'(h2)
-        mbar_wait(bar_g2, ph);
-        tc_fence_after_sync();
-        dgrad_epilogue<BF16>(tR1 + lane_addr, sb + kOffH2, sb + kOffDZ2, r, hsel * 64, P.act, P.alpha);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dz2);
+        mbar_wait(bar_g2, ph); tc_fence_after_sync();
+        dgrad_epilogue<BF16, RELU>(tR1 + lane_addr, sb + kOffH2, sb + kOffDZ2, r, hsel * 64, P.act, P.alpha, m2);
+        DIB_EPI_SIGNAL(bar_dz2);
         // ---- dz1 = G1 * act'(h1)  -> H2 buffer (free: the dW2 MMAs that read h2 retired before G1 completed)
-        mbar_wait(bar_g1, ph);
-        tc_fence_after_sync();
-        dgrad_epilogue<BF16>(tR1 + lane_addr, sb + kOffH1, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dz1);
+        mbar_wait(bar_g1, ph); tc_fence_after_sync();
+        dgrad_epilogue<BF16, RELU>(tR1 + lane_addr, sb + kOffH1, sb + kOffH2, r, hsel * 64, P.act, P.alpha, m1);
+        DIB_EPI_SIGNAL(bar_dz1);
         // the weight-gradient MMAs still read A0 / H1 / DZ2 / dz1: wait before the next tile overwrites them
-        mbar_wait(bar_wg, ph);
-        tc_fence_after_sync();
+        mbar_wait(bar_wg, ph); tc_fence_after_sync();
       }
       // ================= flush this (feature, slot)'s weight-gradient partials (scaled back by 1/S)
       float* part = Q.part + (long long)slot * Q.split_stride;
       const int w_in = d * P.nfreq;
       {
-        // dW1[h1=r][h2 cols hsel*64..]
-        float* dst = part + Q.w1_off[f] + (long long)r * HID + hsel * 64;
+        float* dst = part + Q.w1_off[f] + (long long)r * HID + hsel * 64;          // dW1[h1=r][h2 cols hsel*64..]
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t v[32];
@@ -621,8 +585,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
                               __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS)
                 : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // dW2[h2=r][o cols hsel*32..]
-        float* dst2 = part + Q.w2_off[f] + (long long)r * EO + hsel * 32;
+        float* dst2 = part + Q.w2_off[f] + (long long)r * EO + hsel * 32;           // dW2[h2=r][o cols hsel*32..]
         {
           uint32_t v[32];
           if (any_tiles) { tmem_ld_32x32b_x32(tWG2 + lane_addr + hsel * 32, v); tmem_ld_wait(); }
@@ -672,29 +635,39 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid
 }
 
 // ----------------------------------------------------------------------------------------------------
-// fp32 master parameters -> packed 16-bit per-feature weights [W0p | W1 | W2] (bias of layer 0 folded into W0p)
+// fp32 master parameters -> packed 16-bit per-feature weights [W0p | W1 | W2 | Bb1 | Bb2]
+// (bias of layer 0 folded into W0p row w_in; b1 / b2 in row w_in of the bias carriers)
 // ----------------------------------------------------------------------------------------------------
 template <bool BF16>
 __global__ void dib_enc_pack_weights_kernel(const float* __restrict__ params, const long long* __restrict__ w0_off,
                                             const long long* __restrict__ b0_off, const long long* __restrict__ w1_off,
-                                            const long long* __restrict__ w2_off, const int* __restrict__ fdim, int nfreq,
+                                            const long long* __restrict__ b1_off, const long long* __restrict__ w2_off,
+                                            const long long* __restrict__ b2_off, const int* __restrict__ fdim, int nfreq,
                                             uint16_t* __restrict__ out) {
   const int f = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kPackElems) return;
+  const int idx = i, w_in = fdim[f] * nfreq;
   float v;
   if (i < kW0Elems) {
-    const int k = i / HID, n = i - k * HID, w_in = fdim[f] * nfreq;
+    const int k = i / HID, n = i - k * HID;
     v = k < w_in ? params[w0_off[f] + (long long)k * HID + n] : (k == w_in ? params[b0_off[f] + n] : 0.f);
-  } else if (i < kW0Elems + kW1Elems) {
-    v = params[w1_off[f] + (i - kW0Elems)];
+  } else if ((i -= kW0Elems) < kW1Elems) {
+    v = params[w1_off[f] + i];
+  } else if ((i -= kW1Elems) < kW2Elems) {
+    v = params[w2_off[f] + i];
+  } else if ((i -= kW2Elems) < kB1Elems) {
+    const int k = i / HID, n = i - k * HID;
+    v = k == w_in ? params[b1_off[f] + n] : 0.f;
   } else {
-    v = params[w2_off[f] + (i - kW0Elems - kW1Elems)];
+    i -= kB1Elems;
+    const int k = i / EO, n = i - k * EO;
+    v = k == w_in ? params[b2_off[f] + n] : 0.f;
   }
   uint16_t h;
   if constexpr (BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); h = *reinterpret_cast<uint16_t*>(&b); }
   else { __half b = __float2half_rn(v); h = *reinterpret_cast<uint16_t*>(&b); }
-  out[(long long)f * kPackElems + i] = h;
+  out[(long long)f * kPackElems + idx] = h;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -724,75 +697,77 @@ bool make_wmap(CUtensorMap* m, const uint16_t* base, int cols, int rows, int nfe
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool make_all_maps(WeightMaps* m, const void* packed, int F, bool bf16) {
+  const uint16_t* pk = static_cast<const uint16_t*>(packed);
+  return make_wmap(&m->w0, pk, HID, K0, F, bf16) && make_wmap(&m->w1, pk + kW0Elems, HID, HID, F, bf16) &&
+         make_wmap(&m->w2, pk + kW0Elems + kW1Elems, EO, HID, F, bf16) &&
+         make_wmap(&m->b1, pk + kW0Elems + kW1Elems + kW2Elems, HID, K0, F, bf16) &&
+         make_wmap(&m->b2, pk + kW0Elems + kW1Elems + kW2Elems + kB1Elems, EO, K0, F, bf16);
+}
+
+void fill_params(EncFusedParams& P, const DibEncFusedDesc& d, const DibEncFusedIO& io) {
+  P.x = io.x; P.ldx = io.ldx; P.x_off = d.x_off; P.fdim = d.fdim; P.nfreq = d.nfreq; P.params = io.params;
+  P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step;
+  P.sample_offset = io.sample_offset; P.emb = io.emb; P.ldemb = io.ldemb; P.user_emb = io.user_emb;
+  P.kl_part = io.kl_part; P.kl_stride = io.kl_stride; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha;
+  P.round_emb = 1;
+}
+
+template <typename K, typename A>
+cudaError_t launch_fused(K kern, int smem, int grid, const WeightMaps& m, const A& args, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, smem, st>>>(m, args);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 size_t dib_enc_fused_pack_bytes(int F) { return (size_t)F * kPackElems * 2; }
+int dib_enc_fused_fwd_ctas_per_sm() { return 2; }
 
 cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, cudaStream_t st) {
   dim3 grid(DIB_CEIL_DIV(kPackElems, 256), d.F);
   if (d.bf16)
-    dib_enc_pack_weights_kernel<true><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.w2_off, d.fdim,
-                                                           d.nfreq, static_cast<uint16_t*>(packed));
+    dib_enc_pack_weights_kernel<true><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.b1_off, d.w2_off,
+                                                           d.b2_off, d.fdim, d.nfreq, static_cast<uint16_t*>(packed));
   else
-    dib_enc_pack_weights_kernel<false><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.w2_off, d.fdim,
-                                                            d.nfreq, static_cast<uint16_t*>(packed));
+    dib_enc_pack_weights_kernel<false><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.b1_off, d.w2_off,
+                                                            d.b2_off, d.fdim, d.nfreq, static_cast<uint16_t*>(packed));
   dib_note_launch();
   return cudaGetLastError();
 }
 
 cudaError_t dib_enc_fused_forward(const DibEncFusedDesc& d, const DibEncFusedIO& io, cudaStream_t st) {
   if (!encode_fn2()) return cudaErrorNotSupported;
-  const uint16_t* pk = static_cast<const uint16_t*>(io.packed);
-  CUtensorMap m0, m1, m2;
-  if (!make_wmap(&m0, pk, HID, K0, d.F, d.bf16) || !make_wmap(&m1, pk + kW0Elems, HID, HID, d.F, d.bf16) ||
-      !make_wmap(&m2, pk + kW0Elems + kW1Elems, EO, HID, d.F, d.bf16))
-    return cudaErrorInvalidValue;
+  WeightMaps m;
+  if (!make_all_maps(&m, io.packed, d.F, d.bf16)) return cudaErrorInvalidValue;
   EncFusedParams P;
-  P.x = io.x; P.ldx = io.ldx; P.x_off = d.x_off; P.fdim = d.fdim; P.nfreq = d.nfreq; P.params = io.params;
-  P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step;
-  P.sample_offset = io.sample_offset; P.emb = io.emb; P.ldemb = io.ldemb; P.user_emb = io.user_emb;
-  P.kl_part = io.kl_part; P.kl_stride = io.kl_stride; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha;
-  P.round_emb = 1;
-  constexpr int smem = kOffFwdEnd + (HID + EO) * 4 + 256 + 1024;
-  static bool attr[2] = {false, false};
-  const int grid = d.grid;
-  if (d.bf16) {
-    if (!attr[1]) { cudaError_t e = cudaFuncSetAttribute(dib_enc_fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (e != cudaSuccess) return e; attr[1] = true; }
-    dib_enc_fused_fwd_kernel<true><<<grid, kThreads, smem, st>>>(m0, m1, m2, P);
-  } else {
-    if (!attr[0]) { cudaError_t e = cudaFuncSetAttribute(dib_enc_fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (e != cudaSuccess) return e; attr[0] = true; }
-    dib_enc_fused_fwd_kernel<false><<<grid, kThreads, smem, st>>>(m0, m1, m2, P);
-  }
-  dib_note_launch();
-  return cudaGetLastError();
+  fill_params(P, d, io);
+  constexpr int smem = kOffFwdEnd1 + 256 + 1024;
+  const bool relu = d.act == DIB_ACT_RELU;
+  if (d.bf16) return relu ? launch_fused(dib_enc_fused_fwd_kernel<true, true>, smem, d.grid, m, P, st)
+                          : launch_fused(dib_enc_fused_fwd_kernel<true, false>, smem, d.grid, m, P, st);
+  return relu ? launch_fused(dib_enc_fused_fwd_kernel<false, true>, smem, d.grid, m, P, st)
+              : launch_fused(dib_enc_fused_fwd_kernel<false, false>, smem, d.grid, m, P, st);
 }
 
 cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO& io, const DibEncFusedBwdIO& b,
                                    cudaStream_t st) {
   if (!encode_fn2()) return cudaErrorNotSupported;
-  const uint16_t* pk = static_cast<const uint16_t*>(io.packed);
-  CUtensorMap m0, m1, m2;
-  if (!make_wmap(&m0, pk, HID, K0, d.F, d.bf16) || !make_wmap(&m1, pk + kW0Elems, HID, HID, d.F, d.bf16) ||
-      !make_wmap(&m2, pk + kW0Elems + kW1Elems, EO, HID, d.F, d.bf16))
-    return cudaErrorInvalidValue;
+  WeightMaps m;
+  if (!make_all_maps(&m, io.packed, d.F, d.bf16)) return cudaErrorInvalidValue;
   EncFusedBwdParams Q;
-  EncFusedParams& P = Q.f;
-  P.x = io.x; P.ldx = io.ldx; P.x_off = d.x_off; P.fdim = d.fdim; P.nfreq = d.nfreq; P.params = io.params;
-  P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step;
-  P.sample_offset = io.sample_offset; P.emb = nullptr; P.ldemb = 0; P.user_emb = nullptr;
-  P.kl_part = nullptr; P.kl_stride = 0; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha; P.round_emb = 0;
+  fill_params(Q.f, d, io);
+  Q.f.round_emb = 0;
   Q.d_emb = b.d_emb; Q.ldd = b.ldd; Q.beta_dev = b.beta_dev; Q.inv_batch = b.inv_batch; Q.gscale = b.gscale;
   Q.part = b.part; Q.split_stride = b.split_stride;
   Q.w0_off = d.w0_off; Q.b0_off = d.b0_off; Q.w1_off = d.w1_off; Q.w2_off = d.w2_off;
-  constexpr int smem = kOffBwdEnd + (HID + EO) * 4 + 256 + 1024;
-  static bool attr[2] = {false, false};
-  if (d.bf16) {
-    if (!attr[1]) { cudaError_t e = cudaFuncSetAttribute(dib_enc_fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (e != cudaSuccess) return e; attr[1] = true; }
-    dib_enc_fused_bwd_kernel<true><<<d.grid, kThreads, smem, st>>>(m0, m1, m2, Q);
-  } else {
-    if (!attr[0]) { cudaError_t e = cudaFuncSetAttribute(dib_enc_fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); if (e != cudaSuccess) return e; attr[0] = true; }
-    dib_enc_fused_bwd_kernel<false><<<d.grid, kThreads, smem, st>>>(m0, m1, m2, Q);
-  }
-  dib_note_launch();
-  return cudaGetLastError();
+  constexpr int smem = kOffBwdEnd + 256 + 1024;
+  const bool relu = d.act == DIB_ACT_RELU;
+  if (d.bf16) return relu ? launch_fused(dib_enc_fused_bwd_kernel<true, true>, smem, d.grid, m, Q, st)
+                          : launch_fused(dib_enc_fused_bwd_kernel<true, false>, smem, d.grid, m, Q, st);
+  return relu ? launch_fused(dib_enc_fused_bwd_kernel<false, true>, smem, d.grid, m, Q, st)
+              : launch_fused(dib_enc_fused_bwd_kernel<false, false>, smem, d.grid, m, Q, st);
 }

@@ -94,6 +94,7 @@ struct DibEncFusedIO {
   float* kl_part; int kl_stride;
 };
 size_t dib_enc_fused_pack_bytes(int F);
+int dib_enc_fused_fwd_ctas_per_sm();
 cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, cudaStream_t st);
 cudaError_t dib_enc_fused_forward(const DibEncFusedDesc& d, const DibEncFusedIO& io, cudaStream_t st);
 
