@@ -127,7 +127,14 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def cpu_twin_rate(sample_rows, steps, warmup):
+_BEST_THREADS = None
+
+
+def cpu_twin_rate(sample_rows, steps, warmup, threads=None):
+    """samples/s of the reference graph's eager CPU twin.  `threads=None`: use the thread count that is fastest on
+    this host (a 128-thread pool on a shared box can be >100x slower than 16 threads for these small per-feature
+    ops, so "all the threads it can use" is found by a short probe rather than assumed to be os.cpu_count())."""
+    global _BEST_THREADS
     import torch
     from oracle import dib_oracle as O
     from oracle.torch_twin import time_train_steps
@@ -135,7 +142,18 @@ def cpu_twin_rate(sample_rows, steps, warmup):
     rng = np.random.default_rng(0)
     x = rng.standard_normal((sample_rows, F), dtype=np.float32)
     y = (x[:, 0] * x[:, 1] > 0).astype(np.float32)[:, None]
-    med, total, threads = time_train_steps(cfg, O.LOSS_BCE_LOGITS, x, y, LR, steps, warmup, threads=os.cpu_count())
+    if threads is None:
+        if _BEST_THREADS is None:
+            ncpu = os.cpu_count() or 1
+            cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
+            best = None
+            for c in cands:
+                med, _, _ = time_train_steps(cfg, O.LOSS_BCE_LOGITS, x[:2048], y[:2048], LR, 1, 1, threads=c)
+                if best is None or med < best[0]:
+                    best = (med, c)
+            _BEST_THREADS = best[1]
+        threads = _BEST_THREADS
+    med, total, threads = time_train_steps(cfg, O.LOSS_BCE_LOGITS, x, y, LR, steps, warmup, threads=threads)
     return sample_rows / med, med, threads
 
 

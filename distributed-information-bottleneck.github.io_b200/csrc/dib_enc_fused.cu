@@ -91,10 +91,11 @@ __device__ __forceinline__ uint32_t tile_chunk_addr(uint32_t tile, int r, int co
 }
 
 // TMEM -> activation -> 16-bit -> swizzled shared tile, for 64 columns [col0, col0+64) of row r (bias is already in
-// the accumulator).  RELU fast path returns the 64-bit mask (h > 0) that the backward reuses as act'.
+// the accumulator).  col0 is a multiple of 64, i.e. exactly one 128-byte panel row per thread.
 template <bool BF16, bool RELU>
-__device__ __forceinline__ uint64_t epilogue_to_tile(uint32_t taddr, uint32_t tile, int r, int col0, int act, float alpha) {
-  uint64_t mask = 0;
+__device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, uint32_t tile, int r, int col0, int act, float alpha) {
+  const uint32_t row_addr = tile + (col0 >> 6) * kPanel + r * 128;
+  const int r7 = r & 7;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     uint32_t v[32];
@@ -106,18 +107,12 @@ __device__ __forceinline__ uint64_t epilogue_to_tile(uint32_t taddr, uint32_t ti
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float z = __uint_as_float(v[j + k]);
-        if constexpr (RELU) {
-          f[k] = fmaxf(z, 0.f);
-          mask |= (uint64_t)(z > 0.f) << (hh * 32 + j + k);
-        } else {
-          f[k] = dib_act(act, z, alpha);
-        }
+        f[k] = RELU ? fmaxf(z, 0.f) : dib_act(act, z, alpha);
       }
-      st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * 32 + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
+      st_shared_v4(row_addr + ((((hh * 32 + j) >> 3) ^ r7) << 4), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
                    pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
     }
   }
-  return mask;
 }
 
 // first-layer operand row: [x_0..x_{d-1}, sin(2x).., sin(4x).., ..., 1, 0...] (models.py:22-23 + the ones column
@@ -237,16 +232,16 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
     if (warp == 0) {
       if (lane == 0) {
         load_weights(sb, maps, bar_w, f);
-        mbar_wait(bar_w, fit & 1);
+        mbar_wait_backoff(bar_w, fit & 1);
         for (int t = slot; t < ntiles; t += nslots, ++it) {
           const uint32_t ph = it & 1;
-          mbar_wait(bar_a0, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
           issue_layer0<BF16>(sb, tR0); umma_commit(bar_d0);
-          mbar_wait(bar_h1, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
           issue_layer1<BF16>(sb, tR0, hbuf); umma_commit(bar_d1);
-          mbar_wait(bar_h2, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
           issue_layer2<BF16>(sb, tR1, hbuf); umma_commit(bar_d2);
-          if (t + nslots >= ntiles) mbar_wait(bar_d2, ph);   // drain before the next feature's weights land
+          if (t + nslots >= ntiles) mbar_wait_backoff(bar_d2, ph);   // drain before the next feature's weights land
         }
       } else {
         for (int t = slot; t < ntiles; t += nslots) ++it;
@@ -337,6 +332,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
 // S is a power-of-two loss scale that keeps the 16-bit gradient operands in range (fp16); the fp32 accumulators
 // are multiplied by 1/S when they are flushed.  Weight-gradient accumulators live in TMEM for the whole feature.
 // TMEM columns: [0,128) D0/D1 | [128,256) D2, G2, G1 | [256,384) dW1 | [384,448) dW2 | [448,464) dW0p^T | [464,480) db1
+//               | [480,496) db2  (bias gradients = the ones column of [pe|1] used as the B operand: colsum for free)
 // ====================================================================================================
 struct EncFusedBwdParams {
   EncFusedParams f;
@@ -355,11 +351,27 @@ __device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b) {
   else { const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u)); a = f.x; b = f.y; }
 }
 
-// TMEM gradient g (64 columns) * act'(h) -> 16-bit -> shared tile `dtile`; act' comes from the register mask kept by
-// the forward epilogue (RELU) or from the h values still sitting in the shared tile `htile`
+// packed 16-bit pair p * (h > 0): relu' applied to two gradients at once (exact: multiplication by 1.0 / 0.0)
+template <bool BF16>
+__device__ __forceinline__ uint32_t relu_gate2(uint32_t p, uint32_t h) {
+  if constexpr (BF16) {
+    const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+    __nv_bfloat162 g = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&p), __hgt2(*reinterpret_cast<__nv_bfloat162*>(&h), z));
+    return *reinterpret_cast<uint32_t*>(&g);
+  } else {
+    const __half2 z = __float2half2_rn(0.f);
+    __half2 g = __hmul2(*reinterpret_cast<__half2*>(&p), __hgt2(*reinterpret_cast<__half2*>(&h), z));
+    return *reinterpret_cast<uint32_t*>(&g);
+  }
+}
+
+// TMEM gradient g (64 columns) * act'(h) -> 16-bit -> shared tile `dtile`; h is read back from the shared tile
+// `htile` that the forward epilogue wrote (relu: as a packed comparison, other activations through act'(h))
 template <bool BF16, bool RELU>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t taddr, uint32_t htile, uint32_t dtile, int r, int col0, int act,
-                                               float alpha, uint64_t mask) {
+                                               float alpha) {
+  const uint32_t off = (col0 >> 6) * kPanel + r * 128;
+  const int r7 = r & 7;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     uint32_t v[32];
@@ -367,28 +379,25 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t taddr, uint32_t htile, u
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
-      float f[8];
-      if constexpr (RELU) {
+      const uint32_t ch = off + ((((hh * 32 + j) >> 3) ^ r7) << 4);
+      uint32_t hv[4], o[4];
+      ld_shared_v4(htile + ch, hv);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = ((mask >> (hh * 32 + j + k)) & 1ull) ? __uint_as_float(v[j + k]) : 0.f;
-      } else {
-        uint32_t hv[4];
-        ld_shared_v4(tile_chunk_addr(htile, r, col0 + hh * 32 + j), hv);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 4; ++k) {
+        if constexpr (RELU) {
+          o[k] = relu_gate2<BF16>(pack2<BF16>(__uint_as_float(v[j + 2 * k]), __uint_as_float(v[j + 2 * k + 1])), hv[k]);
+        } else {
           float h0, h1;
           unpack2<BF16>(hv[k], h0, h1);
-          f[2 * k] = __uint_as_float(v[j + 2 * k]) * dib_act_grad(act, h0, alpha);
-          f[2 * k + 1] = __uint_as_float(v[j + 2 * k + 1]) * dib_act_grad(act, h1, alpha);
+          o[k] = pack2<BF16>(__uint_as_float(v[j + 2 * k]) * dib_act_grad(act, h0, alpha),
+                             __uint_as_float(v[j + 2 * k + 1]) * dib_act_grad(act, h1, alpha));
         }
       }
-      st_shared_v4(tile_chunk_addr(dtile, r, col0 + hh * 32 + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
-                   pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+      st_shared_v4(dtile + ch, o[0], o[1], o[2], o[3]);
     }
   }
 }
 
-// 9 warps are allocated as 12 (granularity 4): 65536 / (12*32) = 170 registers per thread is the launchable maximum
 template <bool BF16, bool RELU>
 __global__ void __launch_bounds__(kThreads, 1)
 dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFusedBwdParams Q) {
@@ -422,7 +431,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot_g;
-  const uint32_t tR0 = tmem, tR1 = tmem + 128, tWG1 = tmem + 256, tWG2 = tmem + 384, tWG0 = tmem + 448, tWB1 = tmem + 464;
+  const uint32_t tR0 = tmem, tR1 = tmem + 128, tWG1 = tmem + 256, tWG2 = tmem + 384, tWG0 = tmem + 448, tWB1 = tmem + 464, tWB2 = tmem + 480;
 
   int f_first, f_step, nslots, slot;
   if (G >= F) { f_first = c % F; f_step = F * G; slot = c / F; nslots = (G - f_first + F - 1) / F; }
@@ -440,19 +449,19 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
     if (warp == 0) {
       if (lane == 0) {
         load_weights(sb, maps, bar_w, f);
-        mbar_wait(bar_w, fit & 1);
+        mbar_wait_backoff(bar_w, fit & 1);
         bool first = true;
         for (int t = slot; t < ntiles; t += nslots, ++it, first = false) {
           const uint32_t ph = it & 1;
           // ---- recompute forward
-          mbar_wait(bar_a0, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
           issue_layer0<BF16>(sb, tR0); umma_commit(bar_d0);
-          mbar_wait(bar_h1, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
           issue_layer1<BF16>(sb, tR0, sb + kOffH1); umma_commit(bar_d1);
-          mbar_wait(bar_h2, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
           issue_layer2<BF16>(sb, tR1, sb + kOffH2); umma_commit(bar_d2);
           // ---- layer 2 backward: G2 = dO W2^T ; dW2 += h2^T dO
-          mbar_wait(bar_do, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_do, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffDO + kk * 32, 16, 1024),
@@ -462,8 +471,15 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tWG2, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
                            umma_smem_desc(sb + kOffDO + kk * 2048, kPanel, 1024), id_mm_64, (first && kk == 0) ? 0u : 1u);
+          // db2 += dO^T [pe|1]: M = 128 is formed by dO (64 columns) and the panel that follows it in shared memory
+          // (dz2, finite garbage at this point): TMEM lanes 64..127 of this accumulator are never read.
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWB2, umma_smem_desc(sb + kOffDO + kk * 2048, kPanel, 1024),
+                           umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+                           (first && kk == 0) ? 0u : 1u);
           // ---- layer 1 backward: G1 = dz2 W1^T ; dW1 += h1^T dz2 ; db1 += dz2^T [pe|1]
-          mbar_wait(bar_dz2, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_dz2, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffDZ2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
@@ -480,14 +496,14 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
                            umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           // ---- layer 0 backward: [dW0;db0]^T += dz1^T [pe|1]     (dz1 lives in the H2 buffer)
-          mbar_wait(bar_dz1, ph); tc_fence_after_sync();
+          mbar_wait_backoff(bar_dz1, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tWG0, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
                            umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           umma_commit(bar_wg);
-          if (t + nslots >= ntiles) mbar_wait(bar_wg, ph);
+          if (t + nslots >= ntiles) mbar_wait_backoff(bar_wg, ph);
         }
       } else {
         for (int t = slot; t < ntiles; t += nslots) ++it;
@@ -500,9 +516,6 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       const int d = P.fdim[f], xo = P.x_off[f];
       const float bs = Q.beta_dev[0] * Q.inv_batch * S;
-      float db2m[16], db2l[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { db2m[j] = 0.f; db2l[j] = 0.f; }
       for (int t = slot; t < ntiles; t += nslots, ++it) {
         const uint32_t ph = it & 1;
         const long long row0 = (long long)t * TM;
@@ -513,58 +526,59 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           DIB_EPI_SIGNAL(bar_a0);
         }
         mbar_wait(bar_d0, ph); tc_fence_after_sync();
-        const uint64_t m1 = epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH1, r, hsel * 64, P.act, P.alpha);
+        epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH1, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h1);
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
-        const uint64_t m2 = epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
+        epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h2);
-        // ---- (mu, logvar) -> d(mu), d(logvar) -> DO tile
+        // ---- (mu, logvar) -> d(mu), d(logvar) -> DO tile   (8 embedding dims at a time to bound live registers)
         mbar_wait(bar_d2, ph); tc_fence_after_sync();
         {
-          uint32_t vm[16], vl[16];
-          tmem_ld_32x32b_x16(tR1 + lane_addr + hsel * 16, vm);
-          tmem_ld_32x32b_x16(tR1 + lane_addr + 32 + hsel * 16, vl);
-          tmem_ld_wait();
           const long long grow = row0 + r;
           const bool valid = grow < P.n;
-          float dm[16], dl[16];
           const float* du = Q.d_emb + (valid ? grow : 0) * Q.ldd + f * 32 + hsel * 16;
           const float* ep = P.eps ? P.eps + ((valid ? grow : 0) * F + f) * 32 + hsel * 16 : nullptr;
+          const uint32_t do_row = sb + kOffDO + r * 128;
+          const int r7 = r & 7;
 #pragma unroll
-          for (int e0 = 0; e0 < 16; e0 += 4) {
-            float nrm[4];
-            if (ep) { const float4 e4 = *reinterpret_cast<const float4*>(ep + e0); nrm[0] = e4.x; nrm[1] = e4.y; nrm[2] = e4.z; nrm[3] = e4.w; }
-            else dib_philox_normal4(P.seed, P.step, P.sample_offset + (unsigned long long)grow, (uint32_t)f,
-                                    (uint32_t)(hsel * 4 + (e0 >> 2)), nrm);
-            const float4 g4 = *reinterpret_cast<const float4*>(du + e0);
-            const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+          for (int e8 = 0; e8 < 16; e8 += 8) {
+            uint32_t vm[8], vl[8];
+            tmem_ld_32x32b_x8(tR1 + lane_addr + hsel * 16 + e8, vm);
+            tmem_ld_32x32b_x8(tR1 + lane_addr + 32 + hsel * 16 + e8, vl);
+            tmem_ld_wait();
+            float dm[8], dl[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
-              const float s = expf(0.5f * lv);
-              const float gs = g[j] * S;
-              const float a = valid ? fmaf(bs, mu, gs) : 0.f;
-              const float b = valid ? fmaf(gs * nrm[j], 0.5f * s, bs * 0.5f * (s * s - 1.f)) : 0.f;
-              dm[e0 + j] = a; dl[e0 + j] = b;
-              db2m[e0 + j] += a; db2l[e0 + j] += b;
+            for (int e0 = 0; e0 < 8; e0 += 4) {
+              float nrm[4];
+              if (ep) { const float4 e4 = *reinterpret_cast<const float4*>(ep + e8 + e0); nrm[0] = e4.x; nrm[1] = e4.y; nrm[2] = e4.z; nrm[3] = e4.w; }
+              else dib_philox_normal4(P.seed, P.step, P.sample_offset + (unsigned long long)grow, (uint32_t)f,
+                                      (uint32_t)(hsel * 4 + ((e8 + e0) >> 2)), nrm);
+              const float4 g4 = *reinterpret_cast<const float4*>(du + e8 + e0);
+              const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
+                const float sg = expf(0.5f * lv);
+                const float gs = g[j] * S;
+                dm[e0 + j] = valid ? fmaf(bs, mu, gs) : 0.f;
+                dl[e0 + j] = valid ? fmaf(gs * nrm[j], 0.5f * sg, bs * 0.5f * (sg * sg - 1.f)) : 0.f;
+              }
             }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            st_shared_v4(tile_chunk_addr(sb + kOffDO, r, hsel * 16 + j), pack2<BF16>(dm[j], dm[j + 1]),
-                         pack2<BF16>(dm[j + 2], dm[j + 3]), pack2<BF16>(dm[j + 4], dm[j + 5]), pack2<BF16>(dm[j + 6], dm[j + 7]));
-            st_shared_v4(tile_chunk_addr(sb + kOffDO, r, 32 + hsel * 16 + j), pack2<BF16>(dl[j], dl[j + 1]),
-                         pack2<BF16>(dl[j + 2], dl[j + 3]), pack2<BF16>(dl[j + 4], dl[j + 5]), pack2<BF16>(dl[j + 6], dl[j + 7]));
+            const int cm = (hsel * 16 + e8) >> 3, cl = (32 + hsel * 16 + e8) >> 3;       // 16-byte chunk indices
+            st_shared_v4(do_row + ((cm ^ r7) << 4), pack2<BF16>(dm[0], dm[1]), pack2<BF16>(dm[2], dm[3]),
+                         pack2<BF16>(dm[4], dm[5]), pack2<BF16>(dm[6], dm[7]));
+            st_shared_v4(do_row + ((cl ^ r7) << 4), pack2<BF16>(dl[0], dl[1]), pack2<BF16>(dl[2], dl[3]),
+                         pack2<BF16>(dl[4], dl[5]), pack2<BF16>(dl[6], dl[7]));
           }
         }
         DIB_EPI_SIGNAL(bar_do);
         // ---- dz2 = G2 * act'(h2)
         mbar_wait(bar_g2, ph); tc_fence_after_sync();
-        dgrad_epilogue<BF16, RELU>(tR1 + lane_addr, sb + kOffH2, sb + kOffDZ2, r, hsel * 64, P.act, P.alpha, m2);
+        dgrad_epilogue<BF16, RELU>(tR1 + lane_addr, sb + kOffH2, sb + kOffDZ2, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_dz2);
         // ---- dz1 = G1 * act'(h1)  -> H2 buffer (free: the dW2 MMAs that read h2 retired before G1 completed)
         mbar_wait(bar_g1, ph); tc_fence_after_sync();
-        dgrad_epilogue<BF16, RELU>(tR1 + lane_addr, sb + kOffH1, sb + kOffH2, r, hsel * 64, P.act, P.alpha, m1);
+        dgrad_epilogue<BF16, RELU>(tR1 + lane_addr, sb + kOffH1, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_dz1);
         // the weight-gradient MMAs still read A0 / H1 / DZ2 / dz1: wait before the next tile overwrites them
         mbar_wait(bar_wg, ph); tc_fence_after_sync();
@@ -610,23 +624,18 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
 #pragma unroll
           for (int k = 0; k < 16; ++k) if (k == w_in) b1v = any_tiles ? __uint_as_float(v1[k]) * invS : 0.f;
           part[P.b1_off[f] + r] = b1v;
+          if (r < EO) {                                     // db2[o = r]: lanes 0..63 of the db2 accumulator
+            uint32_t v2[16];
+            if (any_tiles) { tmem_ld_32x32b_x16(tWB2 + lane_addr, v2); tmem_ld_wait(); }
+            float b2v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) if (k == w_in) b2v = any_tiles ? __uint_as_float(v2[k]) * invS : 0.f;
+            part[P.b2_off[f] + r] = b2v;
+          }
         }
       }
-      // db2: cross-row reduction of the per-thread column sums through shared memory (DZ2 region is idle now)
       tc_fence_before_sync();
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      {
-        float* red = reinterpret_cast<float*>(sg + kOffDZ2);          // [128 rows][64 cols]
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { red[r * EO + hsel * 16 + j] = db2m[j]; red[r * EO + 32 + hsel * 16 + j] = db2l[j]; }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        if (et < EO) {
-          float s = 0.f;
-          for (int rr = 0; rr < TM; ++rr) s += red[rr * EO + et];
-          part[P.b2_off[f] + et] = s * invS;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      }
     }
   }
   tc_fence_before_sync();
