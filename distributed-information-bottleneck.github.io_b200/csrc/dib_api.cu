@@ -68,11 +68,16 @@ struct dib_model {
   std::vector<int> int_fwd, int_dgrad, int_wgrad;
   std::vector<int> enc_maxK;                        // max over features of fan-in of layer j
   // fused per-feature encoder kernels (tensor-core mode; dib_enc_fused.cu)
-  bool fused_ok = false, fused_bwd_ok = false, force_unfused = false;
+  bool fused_ok = false, fused_bwd_ok = false, force_unfused = false, force_int32 = false;
   DibEncFusedDesc fdesc;
   void* d_fused_tables = nullptr;
   long long pack_off = 0;       // packed 16-bit encoder weights inside the workspace (float offset)
   int kl_stride = 0, num_sms = 148, part_rows = kMaxSplits;
+  // 16-bit integration network path (dib_int16.cu); offsets are FLOAT offsets into the workspace
+  bool int16_ok = false;
+  long long emb16_off = 0, demb16_off = 0, headpart_off = 0;
+  std::vector<long long> g16_off, dg16_off, w16_off;   // [1..Li], [1..Li], [0..Li-1]
+  int head_blocks = 0, lossacc_cap = 0;
   // optional per-launch-group timing with CUDA events on the caller's stream (dib_profile_*)
   bool profiling = false;
   struct ProfRec { std::string label; cudaEvent_t a, b; };
@@ -125,8 +130,22 @@ void plan(dib_model* h) {
   h->part_off = take(c, (long long)h->part_rows * h->Pp);
   h->kl_stride = h->nblk_max > 2 * h->num_sms + 8 ? h->nblk_max : 2 * h->num_sms + 8;   // >= fused-kernel CTA slots per feature
   h->kl_part_off = take(c, (long long)h->F * h->kl_stride);
-  h->loss_part_off = take(c, h->nblk_max);
-  h->acc_part_off = take(c, h->nblk_max);
+  h->head_blocks = dib_int16_head_blocks(h->num_sms);
+  h->lossacc_cap = h->nblk_max > h->head_blocks ? h->nblk_max : h->head_blocks;
+  h->loss_part_off = take(c, h->lossacc_cap);
+  h->acc_part_off = take(c, h->lossacc_cap);
+  {
+    const long long FE = (long long)h->F * h->E;
+    h->emb16_off = take(c, (B * FE + 1) / 2);
+    h->demb16_off = take(c, (B * FE + 1) / 2);
+    h->g16_off.assign(h->Li + 1, 0); h->dg16_off.assign(h->Li + 1, 0); h->w16_off.assign(h->Li + 1, 0);
+    for (int j = 1; j <= h->Li; ++j) {
+      h->g16_off[j] = take(c, (B * h->int_arch[j - 1] + 1) / 2);
+      h->dg16_off[j] = take(c, (B * h->int_arch[j - 1] + 1) / 2);
+    }
+    for (int j = 0; j < h->Li; ++j) h->w16_off[j] = take(c, ((long long)int_fan_in(h, j) * int_fan_out(h, j) + 1) / 2);
+    h->headpart_off = take(c, (long long)h->head_blocks * ((long long)(h->Li ? h->int_arch[h->Li - 1] : 1) * h->out + h->out));
+  }
   h->wshadow_off = take(c, h->Pp);      // TF32-rounded copy of the parameters (tensor-core mode B operands)
   h->pack_off = take(c, (long long)(dib_enc_fused_pack_bytes(h->F) + 3) / 4);
   h->ws_floats = c;
@@ -312,9 +331,36 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
     io.eps = eps; io.seed = seed; io.step = step; io.sample_offset = sample_offset;
     io.emb = c.ws + h->emb.off; io.ldemb = h->emb.ld; io.user_emb = user_emb;
     io.kl_part = c.ws + h->kl_part_off; io.kl_stride = h->kl_stride;
+    const bool i16 = h->int16_ok && !h->force_int32;
+    if (i16) { io.emb = nullptr; io.emb16 = c.ws + h->emb16_off; io.ldemb16 = h->F * h->E; }
     prof_begin(c, "enc_fused_fwd");
     DIB_CUDA_OK(dib_enc_fused_forward(d, io, c.st));
     prof_end(c);
+    if (i16) {
+      // ---------------- integration network on 16-bit activations + fused output head
+      prof_begin(c, "int16_pack_weights");
+      for (int j = 0; j < h->Li; ++j)
+        DIB_CUDA_OK(dib_int16_convert(c.params + h->intW[j], c.ws + h->w16_off[j], (long long)int_fan_in(h, j) * int_fan_out(h, j), c.st));
+      prof_end(c);
+      for (int j = 0; j < h->Li; ++j) {
+        prof_begin(c, "int16_fwd_l", j);
+        DIB_CUDA_OK(dib_int16_fwd(j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]), int_fan_in(h, j),
+                                  c.ws + h->w16_off[j], c.params + h->intB[j], c.ws + h->g16_off[j + 1], int_fan_out(h, j), c.n,
+                                  int_fan_in(h, j), int_fan_out(h, j), h->act, h->alpha, c.st));
+        prof_end(c);
+      }
+      const int Kh = h->int_arch[h->Li - 1];
+      const float gscale = training ? exp2f(ceilf(log2f(1.f / inv_batch))) : 1.f;
+      prof_begin(c, "int16_head_loss");
+      DIB_CUDA_OK(dib_int16_head(c.ws + h->g16_off[h->Li], Kh, Kh, c.params + h->intW[h->Li], c.params + h->intB[h->Li], h->out,
+                                 h->out_act, h->act, h->alpha, h->loss, y, c.n, inv_batch, gscale,
+                                 training ? (void*)(c.ws + h->dg16_off[h->Li]) : nullptr, Kh, user_pred, c.ws + h->headpart_off,
+                                 Kh * h->out + h->out, c.ws + h->loss_part_off, c.ws + h->acc_part_off, h->head_blocks, c.st));
+      DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->kl_stride, nblk_kl, c.ws + h->loss_part_off,
+                                            c.ws + h->acc_part_off, h->head_blocks, h->F, c.n, y != nullptr, out_stats, c.st));
+      prof_end(c);
+      return 0;
+    }
   } else {
   prof_begin(c, "pe");
   DIB_CUDA_OK(dib_launch_pe(x, h->D, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, c.n, rnd, c.st));
@@ -360,7 +406,8 @@ uint64_t dib_launch_count(void) { return g_launches.load(); }
 // bring-up switch: 1 = never use the fused encoder kernels (compare fused vs unfused tensor-core paths)
 int dib_debug_force_unfused(dib_model* h, int32_t on) {
   if (!h) return fail("null model handle");
-  h->force_unfused = on != 0;
+  h->force_unfused = (on & 1) != 0;      // bit 0: unfused encoder kernels
+  h->force_int32 = (on & 2) != 0;        // bit 1: integration network on the fp32-storage TF32 kernels
   return 0;
 }
 
@@ -531,6 +578,10 @@ int dib_create(const dib_config* cfg, dib_model** out) {
         d.b2_off = lt + 5 * F; d.x_off = it; d.fdim = it + F;
         h->fused_ok = true;
         h->fused_bwd_ok = true;
+        // 16-bit integration path: hidden widths multiples of 128, last hidden width 256, narrow output head
+        bool iok = h->Li >= 1 && (h->F * h->E) % 64 == 0 && h->int_arch[h->Li - 1] == 256 && h->out <= 16;
+        for (int j = 0; iok && j < h->Li; ++j) iok = h->int_arch[j] % 128 == 0 && (h->intB[j] & 3) == 0;
+        h->int16_ok = iok;
       }
     }
   }
@@ -613,6 +664,49 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
   rps = DIB_ROUND_UP(rps, 32);
   const int nsplit = (int)DIB_CEIL_DIV((long long)n, rps);
 
+  const bool fused_enc = h->fused_ok && h->fused_bwd_ok && h->precision == DIB_PREC_TF32 && !h->force_unfused;
+  if (fused_enc && h->int16_ok && !h->force_int32) {
+    const float gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
+    float* part = c.ws + h->part_off;
+    for (int j = h->Li - 1; j >= 0; --j) {
+      const void* in_j = j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]);
+      const int K = int_fan_in(h, j), N = int_fan_out(h, j);
+      prof_begin(c, "int16_wgrad_l", j);
+      DIB_CUDA_OK(dib_int16_wgrad(in_j, K, c.ws + h->dg16_off[j + 1], N, part + h->intW[j], part + h->intB[j], (int)n, K, N, nsplit,
+                                  (int)rps, h->Pp, 1.f / gscale, c.st));
+      prof_end(c);
+      prof_begin(c, "int16_dgrad_l", j);
+      DIB_CUDA_OK(dib_int16_dgrad(c.ws + h->dg16_off[j + 1], N, c.ws + h->w16_off[j], j > 0 ? (const void*)(c.ws + h->g16_off[j]) : nullptr,
+                                  K, j > 0 ? (void*)(c.ws + h->dg16_off[j]) : (void*)(c.ws + h->demb16_off), K, (int)n, K, N, h->act,
+                                  h->alpha, c.st));
+      prof_end(c);
+    }
+    const int ntiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
+    const long long want = (long long)h->F * ntiles;
+    DibEncFusedDesc d = h->fdesc;
+    d.grid = (int)(want < h->num_sms ? want : h->num_sms);
+    const int slots_max = DIB_CEIL_DIV(d.grid, h->F), slots_min = d.grid / h->F;
+    const long long p_enc = h->intW[0], p_head = h->intW[h->Li];
+    for (int srow = slots_min; srow < slots_max; ++srow)
+      DIB_CUDA_OK(cudaMemsetAsync(part + (long long)srow * h->Pp, 0, sizeof(float) * (size_t)p_enc, c.st));
+    DibEncFusedIO io;
+    io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = n;
+    io.eps = eps; io.seed = seed; io.step = step; io.sample_offset = sample_offset;
+    io.emb = nullptr; io.ldemb = 0; io.user_emb = nullptr; io.kl_part = nullptr; io.kl_stride = 0;
+    DibEncFusedBwdIO b;
+    b.d_emb = nullptr; b.ldd = 0; b.d_emb16 = c.ws + h->demb16_off; b.ldd16 = h->F * h->E;
+    b.beta_dev = beta_dev; b.inv_batch = inv_global_batch; b.gscale = gscale; b.part = part; b.split_stride = h->Pp;
+    prof_begin(c, "enc_fused_bwd");
+    DIB_CUDA_OK(dib_enc_fused_backward(d, io, b, c.st));
+    prof_end(c);
+    prof_begin(c, "wgrad_split_reduce");
+    DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, slots_max, p_enc, grads_flat, c.st));
+    DIB_CUDA_OK(dib_launch_reduce_partials(part + p_enc, h->Pp, nsplit, p_head - p_enc, grads_flat + p_enc, c.st));
+    const long long head_cnt = h->P - p_head;
+    DIB_CUDA_OK(dib_launch_reduce_partials(c.ws + h->headpart_off, head_cnt, h->head_blocks, head_cnt, grads_flat + p_head, c.st));
+    prof_end(c);
+    return 0;
+  }
   // integration network backward (GradientTape through models.py:122)
   for (int j = h->Li; j >= 0; --j) {
     prof_begin(c, "int_wgrad_l", j);

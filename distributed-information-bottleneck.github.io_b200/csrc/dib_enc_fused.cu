@@ -65,7 +65,8 @@ struct EncFusedParams {
   const long long* b1_off; const long long* b2_off;   // [F] offsets of b1, b2 in params
   const float* eps;                        // [n, F, E] or null -> Philox
   unsigned long long seed; unsigned int step; unsigned long long sample_offset;
-  float* emb; int ldemb; float* user_emb;  // outputs (forward)
+  float* emb; int ldemb; float* user_emb;  // outputs (forward); emb may be null when emb16 is given
+  __half* emb16; int ldemb16;              // fp16 copy of emb for the 16-bit integration path (or null)
   float* kl_part; int kl_stride;           // [F][kl_stride] per-(feature, slot) KL partial sums
   int F; long long n; int act; float alpha;
   int round_emb;
@@ -279,7 +280,8 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           tc_fence_before_sync();
           const long long grow = row0 + r;
           if (grow < P.n) {
-            float* dst = P.emb + grow * P.ldemb + f * 32 + hsel * 16;
+            float* dst = P.emb ? P.emb + grow * P.ldemb + f * 32 + hsel * 16 : nullptr;
+            __half* dst16 = P.emb16 ? P.emb16 + grow * P.ldemb16 + f * 32 + hsel * 16 : nullptr;
             float* udst = P.user_emb ? P.user_emb + grow * ((long long)F * 32) + f * 32 + hsel * 16 : nullptr;
             const float* ep = P.eps ? P.eps + (grow * F + f) * 32 + hsel * 16 : nullptr;
 #pragma unroll
@@ -297,11 +299,14 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
                 kl_acc += 0.5f * (mu * mu + s * s - lv - 1.f);
               }
               if (udst) *reinterpret_cast<float4*>(udst + e0) = make_float4(u[0], u[1], u[2], u[3]);
-              if (P.round_emb) {
+              if (dst16) *reinterpret_cast<uint2*>(dst16 + e0) = make_uint2(pack2<false>(u[0], u[1]), pack2<false>(u[2], u[3]));
+              if (dst) {
+                if (P.round_emb) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) u[j] = dib_round_tf32(u[j]);
+                  for (int j = 0; j < 4; ++j) u[j] = dib_round_tf32(u[j]);
+                }
+                *reinterpret_cast<float4*>(dst + e0) = make_float4(u[0], u[1], u[2], u[3]);
               }
-              *reinterpret_cast<float4*>(dst + e0) = make_float4(u[0], u[1], u[2], u[3]);
             }
           }
         }
@@ -337,6 +342,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
 struct EncFusedBwdParams {
   EncFusedParams f;
   const float* d_emb; int ldd;              // [n, ldd] gradient w.r.t. emb (already scaled by 1/B_global)
+  const __half* d_emb16; int ldd16;         // or: fp16 gradient already multiplied by the loss scale S
   const float* beta_dev; float inv_batch; float gscale;
   float* part; long long split_stride;      // weight-gradient partials [slot][P]
   const long long* w0_off; const long long* b0_off; const long long* w1_off; const long long* w2_off;
@@ -536,7 +542,8 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         {
           const long long grow = row0 + r;
           const bool valid = grow < P.n;
-          const float* du = Q.d_emb + (valid ? grow : 0) * Q.ldd + f * 32 + hsel * 16;
+          const float* du = Q.d_emb ? Q.d_emb + (valid ? grow : 0) * Q.ldd + f * 32 + hsel * 16 : nullptr;
+          const __half* du16 = Q.d_emb16 ? Q.d_emb16 + (valid ? grow : 0) * Q.ldd16 + f * 32 + hsel * 16 : nullptr;
           const float* ep = P.eps ? P.eps + ((valid ? grow : 0) * F + f) * 32 + hsel * 16 : nullptr;
           const uint32_t do_row = sb + kOffDO + r * 128;
           const int r7 = r & 7;
@@ -553,13 +560,20 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
               if (ep) { const float4 e4 = *reinterpret_cast<const float4*>(ep + e8 + e0); nrm[0] = e4.x; nrm[1] = e4.y; nrm[2] = e4.z; nrm[3] = e4.w; }
               else dib_philox_normal4(P.seed, P.step, P.sample_offset + (unsigned long long)grow, (uint32_t)f,
                                       (uint32_t)(hsel * 4 + ((e8 + e0) >> 2)), nrm);
-              const float4 g4 = *reinterpret_cast<const float4*>(du + e8 + e0);
-              const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+              float g[4];
+              if (du16) {
+                const uint2 gh = *reinterpret_cast<const uint2*>(du16 + e8 + e0);
+                uint32_t w0 = gh.x, w1 = gh.y;
+                unpack2<false>(w0, g[0], g[1]); unpack2<false>(w1, g[2], g[3]);
+              } else {
+                const float4 g4 = *reinterpret_cast<const float4*>(du + e8 + e0);
+                g[0] = g4.x * S; g[1] = g4.y * S; g[2] = g4.z * S; g[3] = g4.w * S;
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
                 const float sg = expf(0.5f * lv);
-                const float gs = g[j] * S;
+                const float gs = g[j];
                 dm[e0 + j] = valid ? fmaf(bs, mu, gs) : 0.f;
                 dl[e0 + j] = valid ? fmaf(gs * nrm[j], 0.5f * sg, bs * 0.5f * (sg * sg - 1.f)) : 0.f;
               }
@@ -719,7 +733,7 @@ void fill_params(EncFusedParams& P, const DibEncFusedDesc& d, const DibEncFusedI
   P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step;
   P.sample_offset = io.sample_offset; P.emb = io.emb; P.ldemb = io.ldemb; P.user_emb = io.user_emb;
   P.kl_part = io.kl_part; P.kl_stride = io.kl_stride; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha;
-  P.round_emb = 1;
+  P.round_emb = 1; P.emb16 = static_cast<__half*>(io.emb16); P.ldemb16 = io.ldemb16;
 }
 
 template <typename K, typename A>
@@ -770,6 +784,7 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
   EncFusedBwdParams Q;
   fill_params(Q.f, d, io);
   Q.f.round_emb = 0;
+  Q.d_emb16 = static_cast<const __half*>(b.d_emb16); Q.ldd16 = b.ldd16;
   Q.d_emb = b.d_emb; Q.ldd = b.ldd; Q.beta_dev = b.beta_dev; Q.inv_batch = b.inv_batch; Q.gscale = b.gscale;
   Q.part = b.part; Q.split_stride = b.split_stride;
   Q.w0_off = d.w0_off; Q.b0_off = d.b0_off; Q.w1_off = d.w1_off; Q.w2_off = d.w2_off;

@@ -1,0 +1,443 @@
+// dib_int16.cu -- the integration network (models.py:81-84,122) in the tensor-core mode: 16-bit activations in HBM
+// (emb, g_k, dz_k as fp16 -> half the traffic of the fp32 layout), tcgen05.mma kind::f16 with fp32 accumulation.
+//
+//   * dib_int16_gemm_kernel<MODE>: TMA-fed, mbarrier-pipelined 128 x 128 tile GEMM (K step 64 = one 128-byte swizzle
+//     span) with fused epilogues:  FWD  g = act(A W + b) -> fp16;  DGRAD  dz_in = (dz W^T) * act'(g_in) -> fp16;
+//     WGRAD  dW = g^T dz over a batch slice -> fp32 split partial (scaled back by 1/S), db = colsum dz from the smem tiles.
+//   * dib_int16_head_kernel: the narrow output layer (out <= 16) fused with everything around it -- logits, compiled
+//     loss + accuracy, d loss / d logits, the dgrad into the last hidden layer (incl. its act') and the output layer's
+//     own weight/bias gradients -- one pass over the last hidden activation.
+// Gradient operands are scaled by the power-of-two loss scale S (see dib_enc_fused.cu) to stay inside fp16 range.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "dib_common.cuh"
+#include "dib_kernels.h"
+#include "dib_sm100.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3;
+constexpr int kABytes = kBM * 128, kBBytes = kBN * 128, kStageBytes = kABytes + kBBytes;
+constexpr int kBarOff = kStages * kStageBytes;
+constexpr int kSmemTotal = kBarOff + 128 + 1024;
+
+struct Int16Args {
+  float* out32; __half* out16; int ldc;       // WGRAD partial base (fp32) | FWD/DGRAD output (fp16)
+  const __half* X; int ldx;                   // DGRAD: activation whose act' gates the gradient (or null)
+  const float* bias;                          // FWD
+  float* dbias;                               // WGRAD: bias-gradient partial base (or null)
+  int M, T, C, R, act;
+  float alpha, out_scale;
+  int nsplit, rows_per_split; long long split_stride;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void unpack_h2(uint32_t u, float& a, float& b) {
+  const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+  a = f.x; b = f.y;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(192, 1)
+dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Int16Args a) {
+  constexpr bool A_MN = (MODE == DIB_GEMM_WGRAD), B_MN = (MODE != DIB_GEMM_DGRAD);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t bar_base = sb + kBarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages), tmem_slot = bar_base + 8u * (2 * kStages + 1);
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kBarOff + 8 * (2 * kStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int split = 0, r0, c0;
+  if constexpr (MODE == DIB_GEMM_WGRAD) { split = blockIdx.z; c0 = blockIdx.x * kBN; r0 = blockIdx.y * kBM; }
+  else { r0 = blockIdx.x * kBM; c0 = blockIdx.y * kBN; }
+  const int R = (MODE == DIB_GEMM_WGRAD) ? a.R : a.M, C = a.C;
+  int t_begin = 0, t_end = a.T;
+  if constexpr (MODE == DIB_GEMM_WGRAD) { t_begin = split * a.rows_per_split; t_end = min(a.M, t_begin + a.rows_per_split); }
+  if (r0 >= R || c0 >= C) return;
+  const int ntiles = t_end > t_begin ? DIB_CEIL_DIV(t_end - t_begin, kBK) : 0;
+  const bool do_db = (MODE == DIB_GEMM_WGRAD) && (blockIdx.y == 0) && (a.dbias != nullptr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), do_db ? 5 : 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, kBN); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), kStageBytes);
+        const uint32_t a_dst = sb + s * kStageBytes, b_dst = a_dst + kABytes;
+        const int t0 = t_begin + it * kBK;
+        if constexpr (A_MN) tma_load_3d(a_dst, &mapA, full_bar(s), 0, t0, r0 / 64);
+        else                tma_load_2d(a_dst, &mapA, full_bar(s), t0, r0);
+        if constexpr (B_MN) tma_load_3d(b_dst, &mapB, full_bar(s), 0, t0, c0 / 64);
+        else                tma_load_2d(b_dst, &mapB, full_bar(s), t0, c0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(0u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBN);
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = sb + s * kStageBytes, b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int kk = 0; kk < kBK / 16; ++kk) {
+          // K-major: 32 B inside the swizzle span; MN-major (16-bit, SWIZZLE_128B): 16 k-rows = 2048 B, panels 8 KB apart
+          const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      if (ntiles > 0) umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3, et = (warp - 2) * 32 + lane;
+    if (do_db) {
+      float bs = 0.f;
+      for (int it = 0; it < ntiles; ++it) {
+        const int s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(full_bar(s), ph);
+        {
+          const uint8_t* bt = sg + s * kStageBytes + kABytes + (et >> 6) * (kBK * 128);   // panel of 64 columns
+          const int ch = (et & 63) >> 3, w = et & 7;
+#pragma unroll 8
+          for (int row = 0; row < kBK; ++row)
+            bs += __half2float(*reinterpret_cast<const __half*>(bt + row * 128 + ((ch ^ (row & 7)) << 4) + (w << 1)));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
+      }
+      if (c0 + et < C) (a.dbias + (long long)split * a.split_stride)[c0 + et] = bs * a.out_scale;
+    }
+    if (ntiles > 0) { mbar_wait(tmem_full_bar, 0); tc_fence_after_sync(); }
+    const int r = r0 + q * 32 + lane;
+#pragma unroll 1
+    for (int cc = 0; cc < kBN; cc += 32) {
+      uint32_t v[32];
+      if (ntiles > 0) { tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v); tmem_ld_wait(); }
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (r < R && c0 + cc < C) {          // C is a multiple of 64: a 32-column chunk is entirely inside or outside
+        const int c = c0 + cc;
+        if constexpr (MODE == DIB_GEMM_WGRAD) {
+          float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * a.out_scale, __uint_as_float(v[j + 1]) * a.out_scale,
+                                                              __uint_as_float(v[j + 2]) * a.out_scale, __uint_as_float(v[j + 3]) * a.out_scale);
+        } else {
+          __half* dst = a.out16 + (long long)r * a.ldc + c;
+          const __half* xs = (MODE == DIB_GEMM_DGRAD && a.X) ? a.X + (long long)r * a.ldx + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j + k]);
+            if constexpr (MODE == DIB_GEMM_FWD) {
+              const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c + j), b1 = *reinterpret_cast<const float4*>(a.bias + c + j + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = dib_act(a.act, f[k] + bb[k], a.alpha);
+            } else if (xs) {
+              const uint4 xv = *reinterpret_cast<const uint4*>(xs + j);
+              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float h0, h1;
+                unpack_h2(xw[k], h0, h1);
+                f[2 * k] *= dib_act_grad(a.act, h0, a.alpha);
+                f[2 * k + 1] *= dib_act_grad(a.act, h1, a.alpha);
+              }
+            }
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, kBN); }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// output head: one warp per row; lanes own 8 hidden units each (K = 256) or loop (K = multiple of 256)
+// ----------------------------------------------------------------------------------------------------
+constexpr int kHeadMaxOut = 16, kHeadWarps = 8;
+
+template <int KPT, int OUT>   // hidden units per lane (K / 32); compile-time bound of the output width (out_dim <= OUT)
+__global__ void __launch_bounds__(kHeadWarps * 32)
+dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float* __restrict__ Wc, const float* __restrict__ bc,
+                      int out_dim, int out_act, int hid_act, float alpha, int loss, const float* __restrict__ y, long long n,
+                      float inv_batch, float gscale, __half* __restrict__ dg, int lddg, float* __restrict__ user_pred,
+                      float* __restrict__ wpart, int wpart_stride, float* __restrict__ loss_part, float* __restrict__ acc_part) {
+  __shared__ float red[kHeadWarps][KPT * 32];
+  __shared__ float sred[kHeadWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kHeadWarps + warp, nw = gridDim.x * kHeadWarps;
+  float w[KPT][OUT], dw[KPT][OUT], db[OUT], bias[OUT];
+#pragma unroll
+  for (int o = 0; o < OUT; ++o) {
+    db[o] = 0.f;
+    bias[o] = o < out_dim ? bc[o] : 0.f;
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+      w[i][o] = o < out_dim ? Wc[(long long)(lane * KPT + i) * out_dim + o] : 0.f;
+      dw[i][o] = 0.f;
+    }
+  }
+  float lsum = 0.f, asum = 0.f;
+  const bool train = dg != nullptr;
+
+  for (long long row = gw; row < n; row += nw) {
+    float h[KPT];
+    {
+      const __half* src = g + row * ldg + lane * KPT;
+#pragma unroll
+      for (int i = 0; i < KPT; i += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+        unpack_h2(v.x, h[i], h[i + 1]); unpack_h2(v.y, h[i + 2], h[i + 3]);
+        unpack_h2(v.z, h[i + 4], h[i + 5]); unpack_h2(v.w, h[i + 6], h[i + 7]);
+      }
+    }
+    float z[OUT], dz[OUT];
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) s = fmaf(h[i], w[i][o], s);
+      z[o] = dib_act(out_act, dib_warp_sum(s) + bias[o], alpha);
+      dz[o] = 0.f;
+    }
+    // ---- compiled loss / metric / d loss / d z  (identical on all lanes)
+    if (y) {
+      float l = 0.f, acc = 0.f;
+      const float inv_out = 1.f / (float)out_dim;
+      if (loss == DIB_LOSS_SPARSE_CE_LOGITS) {
+        const int label = (int)y[row];
+        float m = z[0], zl = 0.f, se = 0.f; int am = 0;
+#pragma unroll
+        for (int o = 1; o < OUT; ++o) if (o < out_dim && z[o] > m) { m = z[o]; am = o; }
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) if (o < out_dim) { se += expf(z[o] - m); if (o == label) zl = z[o]; }
+        l = m + logf(se) - zl;
+        acc = am == label ? 1.f : 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) if (o < out_dim) dz[o] = expf(z[o] - m) / se - (o == label ? 1.f : 0.f);
+      } else {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) if (o < out_dim) {
+          const float t = y[row * out_dim + o];
+          if (loss == DIB_LOSS_BCE_LOGITS) { l += fmaxf(z[o], 0.f) - z[o] * t + log1pf(expf(-fabsf(z[o]))); dz[o] = (1.f / (1.f + expf(-z[o])) - t) * inv_out; }
+          else { const float d = z[o] - t; l += d * d; dz[o] = 2.f * d * inv_out; }
+          acc += ((z[o] > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f;
+        }
+        l *= inv_out; acc *= inv_out;
+      }
+      lsum += l; asum += acc;
+    }
+    if (user_pred) {
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) if (o < out_dim && lane == o) user_pred[row * out_dim + o] = z[o];
+    }
+    if (train) {
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) { dz[o] *= inv_batch * dib_act_grad(out_act, z[o], alpha); db[o] += dz[o]; }
+      float d[KPT];
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) { s = fmaf(dz[o], w[i][o], s); dw[i][o] = fmaf(h[i], dz[o], dw[i][o]); }
+        d[i] = s * gscale * dib_act_grad(hid_act, h[i], alpha);
+      }
+      __half* dst = dg + row * lddg + lane * KPT;
+#pragma unroll
+      for (int i = 0; i < KPT; i += 8)
+        *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_h2(d[i], d[i + 1]), pack_h2(d[i + 2], d[i + 3]),
+                                                        pack_h2(d[i + 4], d[i + 5]), pack_h2(d[i + 6], d[i + 7]));
+    }
+  }
+  // ---- per-block partials (fixed order over the block's warps): output-layer weight/bias gradients, loss, accuracy
+  if (train) {
+#pragma unroll
+    for (int o = 0; o < OUT; ++o) {
+      if (o < out_dim) {
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) red[warp][lane * KPT + i] = dw[i][o];
+      }
+      __syncthreads();
+      if (warp == 0 && o < out_dim) {
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+          float s = 0.f;
+          for (int ww = 0; ww < kHeadWarps; ++ww) s += red[ww][lane * KPT + i];
+          wpart[(long long)blockIdx.x * wpart_stride + (long long)(lane * KPT + i) * out_dim + o] = s;
+        }
+      }
+      __syncthreads();
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) red[warp][o] = db[o];
+    }
+    __syncthreads();
+    if (threadIdx.x < out_dim) {
+      float s = 0.f;
+      for (int ww = 0; ww < kHeadWarps; ++ww) s += red[ww][threadIdx.x];
+      wpart[(long long)blockIdx.x * wpart_stride + (long long)K * out_dim + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+  if (lane == 0) sred[warp] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) { float s = 0.f; for (int ww = 0; ww < kHeadWarps; ++ww) s += sred[ww]; loss_part[blockIdx.x] = s; }
+  __syncthreads();
+  if (lane == 0) sred[warp] = asum;
+  __syncthreads();
+  if (threadIdx.x == 0) { float s = 0.f; for (int ww = 0; ww < kHeadWarps; ++ww) s += sred[ww]; acc_part[blockIdx.x] = s; }
+}
+
+__global__ void dib_f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn3() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// K-major: [rows x ld] fp16, box 64 cols x brows
+bool map_k(CUtensorMap* m, const __half* base, long long cols, long long rows, long long ld, int brows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)brows}, es[2] = {1, 1};
+  return encode_fn3()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// MN-major: [krows x ld] fp16 whose contiguous dim is M/N -> (64, krow, panel), box 64 x 64 x npanels => smem [panel][krow][128 B]
+bool map_mn(CUtensorMap* m, const __half* base, long long cols, long long krows, long long ld, int npanels) {
+  cuuint64_t dims[3] = {64, (cuuint64_t)krows, (cuuint64_t)(cols / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)kBK, (cuuint32_t)npanels}, es[3] = {1, 1, 1};
+  return encode_fn3()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int MODE>
+cudaError_t launch16(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Args& a, dim3 grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dib_int16_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dib_int16_gemm_kernel<MODE><<<grid, 192, kSmemTotal, st>>>(mA, mB, a);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  dib_f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, static_cast<__half*>(dst16), n);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+// g_out[M x N] = act(g_in[M x K] W16[K x N] + bias)
+cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const float* bias, void* g_out, int ld_out, int M,
+                          int K, int N, int act, float alpha, cudaStream_t st) {
+  if (!encode_fn3()) return cudaErrorNotSupported;
+  CUtensorMap mA, mB;
+  if (!map_k(&mA, static_cast<const __half*>(g_in), K, M, ld_in, kBM) || !map_mn(&mB, static_cast<const __half*>(w16), N, K, N, kBN / 64))
+    return cudaErrorInvalidValue;
+  Int16Args a{};
+  a.out16 = static_cast<__half*>(g_out); a.ldc = ld_out; a.bias = bias; a.M = M; a.T = K; a.C = N; a.act = act; a.alpha = alpha;
+  a.out_scale = 1.f; a.nsplit = 1;
+  return launch16<DIB_GEMM_FWD>(mA, mB, a, dim3(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(N, kBN), 1), st);
+}
+
+// dz_in[M x K] = (dz[M x N] W16[K x N]^T) * act'(g_in[M x K])      (g_in may be null: no activation, e.g. d_emb)
+cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const void* g_in, int ld_g, void* dz_in, int ld_out,
+                            int M, int K, int N, int act, float alpha, cudaStream_t st) {
+  if (!encode_fn3()) return cudaErrorNotSupported;
+  CUtensorMap mA, mB;
+  if (!map_k(&mA, static_cast<const __half*>(dz), N, M, ld_dz, kBM) || !map_k(&mB, static_cast<const __half*>(w16), N, K, N, kBN))
+    return cudaErrorInvalidValue;
+  Int16Args a{};
+  a.out16 = static_cast<__half*>(dz_in); a.ldc = ld_out; a.X = static_cast<const __half*>(g_in); a.ldx = ld_g;
+  a.M = M; a.T = N; a.C = K; a.act = act; a.alpha = alpha; a.out_scale = 1.f; a.nsplit = 1;
+  return launch16<DIB_GEMM_DGRAD>(mA, mB, a, dim3(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(K, kBN), 1), st);
+}
+
+// dW[K x N] (fp32 split partials, * out_scale) = g_in[M x K]^T dz[M x N];  db = colsum dz
+cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
+                            int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, cudaStream_t st) {
+  if (!encode_fn3()) return cudaErrorNotSupported;
+  CUtensorMap mA, mB;
+  if (!map_mn(&mA, static_cast<const __half*>(g_in), K, M, ld_g, kBM / 64) || !map_mn(&mB, static_cast<const __half*>(dz), N, M, ld_dz, kBN / 64))
+    return cudaErrorInvalidValue;
+  Int16Args a{};
+  a.out32 = dW_part; a.ldc = N; a.dbias = db_part; a.M = M; a.T = 0; a.C = N; a.R = K; a.out_scale = out_scale;
+  a.nsplit = nsplit; a.rows_per_split = rows_per_split; a.split_stride = split_stride;
+  return launch16<DIB_GEMM_WGRAD>(mA, mB, a, dim3(DIB_CEIL_DIV(N, kBN), DIB_CEIL_DIV(K, kBM), nsplit), st);
+}
+
+int dib_int16_head_blocks(int num_sms) { return num_sms * 2; }
+
+cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const float* bc, int out_dim, int out_act, int hid_act,
+                           float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,
+                           float* user_pred, float* wpart, int wpart_stride, float* loss_part, float* acc_part, int nblocks,
+                           cudaStream_t st) {
+  if (out_dim > kHeadMaxOut || out_dim < 1 || K != 256) return cudaErrorInvalidValue;
+#define DIB_HEAD(OUT)                                                                                                   \
+  dib_int16_head_kernel<8, OUT><<<nblocks, kHeadWarps * 32, 0, st>>>(static_cast<const __half*>(g), ldg, K, Wc, bc, out_dim,      \
+      out_act, hid_act, alpha, loss, y, n, inv_batch, gscale, static_cast<__half*>(dg), lddg, user_pred, wpart, wpart_stride, \
+      loss_part, acc_part)
+  if (out_dim == 1) DIB_HEAD(1);
+  else if (out_dim == 2) DIB_HEAD(2);
+  else if (out_dim <= 4) DIB_HEAD(4);
+  else if (out_dim <= 8) DIB_HEAD(8);
+  else DIB_HEAD(16);
+#undef DIB_HEAD
+  dib_note_launch();
+  return cudaGetLastError();
+}

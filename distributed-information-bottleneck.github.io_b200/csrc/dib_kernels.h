@@ -92,6 +92,7 @@ struct DibEncFusedIO {
   const float* eps; uint64_t seed; uint32_t step; uint64_t sample_offset;
   float* emb; int ldemb; float* user_emb;
   float* kl_part; int kl_stride;
+  void* emb16 = nullptr; int ldemb16 = 0;   // optional fp16 copy of emb (16-bit integration path)
 };
 size_t dib_enc_fused_pack_bytes(int F);
 int dib_enc_fused_fwd_ctas_per_sm();
@@ -99,9 +100,24 @@ cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, vo
 cudaError_t dib_enc_fused_forward(const DibEncFusedDesc& d, const DibEncFusedIO& io, cudaStream_t st);
 
 struct DibEncFusedBwdIO {
-  const float* d_emb; int ldd;          // gradient w.r.t. emb (scaled by 1/B_global)
+  const float* d_emb; int ldd;          // gradient w.r.t. emb (scaled by 1/B_global), or null when d_emb16 is given
+  const void* d_emb16 = nullptr; int ldd16 = 0;   // fp16 gradient already multiplied by gscale
   const float* beta_dev; float inv_batch; float gscale;
   float* part; long long split_stride;  // [slot][P] weight-gradient partials
 };
 cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO& io, const DibEncFusedBwdIO& b,
                                    cudaStream_t st);
+
+// ---- 16-bit integration network path (dib_int16.cu) ----
+cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, cudaStream_t st);
+cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const float* bias, void* g_out, int ld_out, int M,
+                          int K, int N, int act, float alpha, cudaStream_t st);
+cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const void* g_in, int ld_g, void* dz_in, int ld_out,
+                            int M, int K, int N, int act, float alpha, cudaStream_t st);
+cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
+                            int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, cudaStream_t st);
+int dib_int16_head_blocks(int num_sms);
+cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const float* bc, int out_dim, int out_act, int hid_act,
+                           float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,
+                           float* user_pred, float* wpart, int wpart_stride, float* loss_part, float* acc_part, int nblocks,
+                           cudaStream_t st);

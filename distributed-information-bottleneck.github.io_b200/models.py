@@ -245,8 +245,8 @@ class DistributedIBNet:
             cfg = self._config(max_batch)
             _lib.check(self._lib.dib_create(ctypes.byref(cfg), ctypes.byref(h)))
             self._handle, self._handle_key, self._max_batch = h, key, max_batch
-            if getattr(self, "_force_unfused", False):
-                _lib.check(self._lib.dib_debug_force_unfused(h, 1))
+            if getattr(self, "_force_unfused", 0):
+                _lib.check(self._lib.dib_debug_force_unfused(h, int(self._force_unfused)))
             nbytes = int(self._lib.dib_workspace_bytes(h))
             self._workspace = None
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -384,7 +384,7 @@ class DistributedIBNet:
 
     def debug_force_unfused(self, on=True, batch_hint=1):
         """Bring-up switch: keep the tensor-core mode on the unfused kernels (fused-vs-unfused comparisons)."""
-        self._force_unfused = bool(on)
+        self._force_unfused = int(on)          # bit 0: unfused encoders, bit 1: fp32-storage integration network
         if self._handle is not None:
             _lib.check(self._lib.dib_debug_force_unfused(self._handle, int(on)))
 

@@ -152,7 +152,7 @@ int dib_debug_gemm_tc(int32_t mode, const float* A, int32_t lda, const float* B,
                       float* X, int32_t ldx, int32_t M, int32_t T, int32_t Ccols, int32_t R, int32_t act,
                       int32_t nsplit, int32_t rows_per_split, int64_t split_stride, int32_t use_simt, void* stream);
 
-/* bring-up switch: on=1 keeps the tensor-core mode on the unfused kernels (fused-vs-unfused comparisons). */
+/* bring-up switch (bit mask): 1 = unfused encoder kernels, 2 = integration network on fp32-storage TF32 kernels. */
 int dib_debug_force_unfused(dib_model* h, int32_t on);
 
 /* text of the last error raised on this thread ("" if none). */

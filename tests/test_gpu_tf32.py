@@ -80,11 +80,12 @@ def test_fused_encoder_kernels_match_unfused_and_fp32(shape):
     rng = np.random.default_rng(3)
     p = O.glorot_uniform_params(cfg, rng)
     p = p + (p == 0) * (0.05 * rng.standard_normal(p.size)).astype(np.float32)      # non-zero biases
-    for B in (128 * 3 + 17, 4096, 20000):
+    for B in (128 * 3 + 17, 4096 + 64):
         x = rng.standard_normal((B, D)).astype(np.float32)
         y = (x[:, 0] * x[:, 1] > 0).astype(np.float32)[:, None] if out == 1 else rng.standard_normal((B, out)).astype(np.float32)
         res = {}
-        for tag, prec, unfused in (("fp32", "fp32", False), ("tc_unfused", "tf32", True), ("tc_fused", "tf32", False)):
+        for tag, prec, unfused in (("fp32", "fp32", 0), ("tc_unfused", "tf32", 1), ("tc_fused_int32", "tf32", 2),
+                                   ("tc_fused", "tf32", 0)):
             m = build_model(cfg, precision=prec, loss=loss_name)
             m.debug_force_unfused(unfused)
             m.set_flat_weights(p)
@@ -93,7 +94,7 @@ def test_fused_encoder_kernels_match_unfused_and_fp32(shape):
             g, st = m.compute_gradients(x, y, step=5)
             res[tag] = (np.asarray(pred), g.cpu().numpy(), st.cpu().numpy())
         tol_g = TOL if B >= 4096 else 4 * TOL          # a few hundred samples: sign flips of single activations show
-        for tag in ("tc_unfused", "tc_fused"):
+        for tag in ("tc_unfused", "tc_fused_int32", "tc_fused"):
             assert rel_err(res[tag][0], res["fp32"][0]) < TOL, (tag, B)
             assert rel_err(res[tag][1], res["fp32"][1]) < tol_g, (tag, B)
             np.testing.assert_allclose(res[tag][2], res["fp32"][2], rtol=TOL, err_msg=f"{tag} {B}")
