@@ -188,10 +188,11 @@ def workload_config(n_gpus, precision):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DIB_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("DIB_PRECISION", "tf32"), choices=["tf32", "fp32"],
+                    help="tf32 = tensor-core mode (default, the headline); fp32 = exact CUDA-core parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -307,7 +307,8 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
                 float* out_stats) {
   dib_model* h = c.h;
   const int rnd = h->precision == DIB_PREC_TF32 ? 1 : 0;
-  if (rnd) {
+  const bool fast_path = h->fused_ok && rnd && (!training || h->fused_bwd_ok) && !h->force_unfused && h->int16_ok && !h->force_int32;
+  if (rnd && !fast_path) {
     prof_begin(c, "weights_tf32_shadow");
     DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
     prof_end(c);

@@ -196,8 +196,16 @@ __global__ void dib_reduce_partials_kernel(const float* __restrict__ part, long 
                                            long long count, float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  float s = 0.f;
-  for (int k = 0; k < nsplit; ++k) s += part[(long long)k * split_stride + i];
+  float s = 0.f;                       // fixed summation order (deterministic); loads batched 8 deep for latency
+  int k = 0;
+  for (; k + 8 <= nsplit; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = part[(long long)(k + u) * split_stride + i];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; k < nsplit; ++k) s += part[(long long)k * split_stride + i];
   out[i] = s;
 }
 

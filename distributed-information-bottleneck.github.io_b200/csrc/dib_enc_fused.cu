@@ -525,6 +525,15 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
       for (int t = slot; t < ntiles; t += nslots, ++it) {
         const uint32_t ph = it & 1;
         const long long row0 = (long long)t * TM;
+        // prefetch this thread's slice of the upstream gradient (32 B of fp16) long before the (mu, logvar) stage
+        uint4 dpre[2];
+        {
+          const long long g2 = row0 + r < P.n ? row0 + r : 0;
+          if (Q.d_emb16) {
+            const __half* src = Q.d_emb16 + g2 * Q.ldd16 + f * 32 + hsel * 16;
+            dpre[0] = *reinterpret_cast<const uint4*>(src); dpre[1] = *reinterpret_cast<const uint4*>(src + 8);
+          }
+        }
         {
           const int ar = et & (TM - 1), khalf = et >> 7;
           const long long grow = row0 + ar;
@@ -562,8 +571,8 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
                                       (uint32_t)(hsel * 4 + ((e8 + e0) >> 2)), nrm);
               float g[4];
               if (du16) {
-                const uint2 gh = *reinterpret_cast<const uint2*>(du16 + e8 + e0);
-                uint32_t w0 = gh.x, w1 = gh.y;
+                const uint4 gq = dpre[e8 >> 3];
+                uint32_t w0 = e0 == 0 ? gq.x : gq.z, w1 = e0 == 0 ? gq.y : gq.w;
                 unpack2<false>(w0, g[0], g[1]); unpack2<false>(w1, g[2], g[3]);
               } else {
                 const float4 g4 = *reinterpret_cast<const float4*>(du + e8 + e0);

@@ -190,7 +190,7 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 // ----------------------------------------------------------------------------------------------------
 constexpr int kHeadMaxOut = 16, kHeadWarps = 8;
 
-template <int KPT, int OUT>   // hidden units per lane (K / 32); compile-time bound of the output width (out_dim <= OUT)
+template <int KPT, int OUT, int ROWS>   // hidden units per lane (K / 32); bound of the output width; rows in flight per warp
 __global__ void __launch_bounds__(kHeadWarps * 32)
 dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float* __restrict__ Wc, const float* __restrict__ bc,
                       int out_dim, int out_act, int hid_act, float alpha, int loss, const float* __restrict__ y, long long n,
@@ -214,73 +214,82 @@ dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float*
   float lsum = 0.f, asum = 0.f;
   const bool train = dg != nullptr;
 
-  for (long long row = gw; row < n; row += nw) {
-    float h[KPT];
-    {
-      const __half* src = g + row * ldg + lane * KPT;
+  for (long long row0 = (long long)gw * ROWS; row0 < n; row0 += (long long)nw * ROWS) {
+    uint4 hv[ROWS][KPT / 8];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {                 // issue all loads of the row group first (memory-level parallelism)
+      const long long row = row0 + rr < n ? row0 + rr : n - 1;
+#pragma unroll
+      for (int i = 0; i < KPT; i += 8) hv[rr][i / 8] = *reinterpret_cast<const uint4*>(g + row * ldg + lane * KPT + i);
+    }
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      const long long row = row0 + rr;
+      if (row >= n) break;
+      float h[KPT];
 #pragma unroll
       for (int i = 0; i < KPT; i += 8) {
-        const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+        const uint4 v = hv[rr][i / 8];
         unpack_h2(v.x, h[i], h[i + 1]); unpack_h2(v.y, h[i + 2], h[i + 3]);
         unpack_h2(v.z, h[i + 4], h[i + 5]); unpack_h2(v.w, h[i + 6], h[i + 7]);
       }
-    }
-    float z[OUT], dz[OUT];
+      float z[OUT], dz[OUT];
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < KPT; ++i) s = fmaf(h[i], w[i][o], s);
-      z[o] = dib_act(out_act, dib_warp_sum(s) + bias[o], alpha);
-      dz[o] = 0.f;
-    }
-    // ---- compiled loss / metric / d loss / d z  (identical on all lanes)
-    if (y) {
-      float l = 0.f, acc = 0.f;
-      const float inv_out = 1.f / (float)out_dim;
-      if (loss == DIB_LOSS_SPARSE_CE_LOGITS) {
-        const int label = (int)y[row];
-        float m = z[0], zl = 0.f, se = 0.f; int am = 0;
-#pragma unroll
-        for (int o = 1; o < OUT; ++o) if (o < out_dim && z[o] > m) { m = z[o]; am = o; }
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) if (o < out_dim) { se += expf(z[o] - m); if (o == label) zl = z[o]; }
-        l = m + logf(se) - zl;
-        acc = am == label ? 1.f : 0.f;
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) if (o < out_dim) dz[o] = expf(z[o] - m) / se - (o == label ? 1.f : 0.f);
-      } else {
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) if (o < out_dim) {
-          const float t = y[row * out_dim + o];
-          if (loss == DIB_LOSS_BCE_LOGITS) { l += fmaxf(z[o], 0.f) - z[o] * t + log1pf(expf(-fabsf(z[o]))); dz[o] = (1.f / (1.f + expf(-z[o])) - t) * inv_out; }
-          else { const float d = z[o] - t; l += d * d; dz[o] = 2.f * d * inv_out; }
-          acc += ((z[o] > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f;
-        }
-        l *= inv_out; acc *= inv_out;
-      }
-      lsum += l; asum += acc;
-    }
-    if (user_pred) {
-#pragma unroll
-      for (int o = 0; o < OUT; ++o) if (o < out_dim && lane == o) user_pred[row * out_dim + o] = z[o];
-    }
-    if (train) {
-#pragma unroll
-      for (int o = 0; o < OUT; ++o) { dz[o] *= inv_batch * dib_act_grad(out_act, z[o], alpha); db[o] += dz[o]; }
-      float d[KPT];
-#pragma unroll
-      for (int i = 0; i < KPT; ++i) {
+      for (int o = 0; o < OUT; ++o) {
         float s = 0.f;
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) { s = fmaf(dz[o], w[i][o], s); dw[i][o] = fmaf(h[i], dz[o], dw[i][o]); }
-        d[i] = s * gscale * dib_act_grad(hid_act, h[i], alpha);
+        for (int i = 0; i < KPT; ++i) s = fmaf(h[i], w[i][o], s);
+        z[o] = dib_act(out_act, dib_warp_sum(s) + bias[o], alpha);
+        dz[o] = 0.f;
       }
-      __half* dst = dg + row * lddg + lane * KPT;
+      // ---- compiled loss / metric / d loss / d z  (identical on all lanes)
+      if (y) {
+        float l = 0.f, acc = 0.f;
+        const float inv_out = 1.f / (float)out_dim;
+        if (loss == DIB_LOSS_SPARSE_CE_LOGITS) {
+          const int label = (int)y[row];
+          float m = z[0], zl = 0.f, se = 0.f; int am = 0;
 #pragma unroll
-      for (int i = 0; i < KPT; i += 8)
-        *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_h2(d[i], d[i + 1]), pack_h2(d[i + 2], d[i + 3]),
-                                                        pack_h2(d[i + 4], d[i + 5]), pack_h2(d[i + 6], d[i + 7]));
+          for (int o = 1; o < OUT; ++o) if (o < out_dim && z[o] > m) { m = z[o]; am = o; }
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) if (o < out_dim) { se += expf(z[o] - m); if (o == label) zl = z[o]; }
+          l = m + logf(se) - zl;
+          acc = am == label ? 1.f : 0.f;
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) if (o < out_dim) dz[o] = expf(z[o] - m) / se - (o == label ? 1.f : 0.f);
+        } else {
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) if (o < out_dim) {
+            const float t = y[row * out_dim + o];
+            if (loss == DIB_LOSS_BCE_LOGITS) { l += fmaxf(z[o], 0.f) - z[o] * t + log1pf(expf(-fabsf(z[o]))); dz[o] = (1.f / (1.f + expf(-z[o])) - t) * inv_out; }
+            else { const float d = z[o] - t; l += d * d; dz[o] = 2.f * d * inv_out; }
+            acc += ((z[o] > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f;
+          }
+          l *= inv_out; acc *= inv_out;
+        }
+        lsum += l; asum += acc;
+      }
+      if (user_pred) {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) if (o < out_dim && lane == o) user_pred[row * out_dim + o] = z[o];
+      }
+      if (train) {
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) { dz[o] *= inv_batch * dib_act_grad(out_act, z[o], alpha); db[o] += dz[o]; }
+        float d[KPT];
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+          float s = 0.f;
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) { s = fmaf(dz[o], w[i][o], s); dw[i][o] = fmaf(h[i], dz[o], dw[i][o]); }
+          d[i] = s * gscale * dib_act_grad(hid_act, h[i], alpha);
+        }
+        __half* dst = dg + row * lddg + lane * KPT;
+#pragma unroll
+        for (int i = 0; i < KPT; i += 8)
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_h2(d[i], d[i + 1]), pack_h2(d[i + 2], d[i + 3]),
+                                                          pack_h2(d[i + 4], d[i + 5]), pack_h2(d[i + 6], d[i + 7]));
+      }
     }
   }
   // ---- per-block partials (fixed order over the block's warps): output-layer weight/bias gradients, loss, accuracy
@@ -421,7 +430,7 @@ cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_d
   return launch16<DIB_GEMM_WGRAD>(mA, mB, a, dim3(DIB_CEIL_DIV(N, kBN), DIB_CEIL_DIV(K, kBM), nsplit), st);
 }
 
-int dib_int16_head_blocks(int num_sms) { return num_sms * 2; }
+int dib_int16_head_blocks(int num_sms) { return num_sms * 4; }   // 32 warps per SM: the head is latency-bound per warp
 
 cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const float* bc, int out_dim, int out_act, int hid_act,
                            float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,
@@ -429,7 +438,7 @@ cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const
                            cudaStream_t st) {
   if (out_dim > kHeadMaxOut || out_dim < 1 || K != 256) return cudaErrorInvalidValue;
 #define DIB_HEAD(OUT)                                                                                                   \
-  dib_int16_head_kernel<8, OUT><<<nblocks, kHeadWarps * 32, 0, st>>>(static_cast<const __half*>(g), ldg, K, Wc, bc, out_dim,      \
+  dib_int16_head_kernel<8, OUT, (OUT <= 2 ? 4 : 1)><<<nblocks, kHeadWarps * 32, 0, st>>>(static_cast<const __half*>(g), ldg, K, Wc, bc, out_dim,      \
       out_act, hid_act, alpha, loss, y, n, inv_batch, gscale, static_cast<__half*>(dg), lddg, user_pred, wpart, wpart_stride, \
       loss_part, acc_part)
   if (out_dim == 1) DIB_HEAD(1);
