@@ -75,7 +75,8 @@ struct dib_model {
   int kl_stride = 0, num_sms = 148, part_rows = kMaxSplits;
   // 16-bit integration network path (dib_int16.cu); offsets are FLOAT offsets into the workspace
   bool int16_ok = false;
-  long long emb16_off = 0, demb16_off = 0, headpart_off = 0;
+  long long emb16_off = 0, demb16_off = 0, headpart_off = 0, dbpart_off = 0;
+  int head_stride = 0, dbpart_stride = 0;
   std::vector<long long> g16_off, dg16_off, w16_off;   // [1..Li], [1..Li], [0..Li-1]
   int head_blocks = 0, lossacc_cap = 0;
   // optional per-launch-group timing with CUDA events on the caller's stream (dib_profile_*)
@@ -144,7 +145,13 @@ void plan(dib_model* h) {
       h->dg16_off[j] = take(c, (B * h->int_arch[j - 1] + 1) / 2);
     }
     for (int j = 0; j < h->Li; ++j) h->w16_off[j] = take(c, ((long long)int_fan_in(h, j) * int_fan_out(h, j) + 1) / 2);
-    h->headpart_off = take(c, (long long)h->head_blocks * ((long long)(h->Li ? h->int_arch[h->Li - 1] : 1) * h->out + h->out));
+    const int Kh = h->Li ? h->int_arch[h->Li - 1] : 1;
+    h->head_stride = Kh * h->out + h->out + Kh;          // [dWc | dbc | column sums of dg (bias grad of the last hidden layer)]
+    h->headpart_off = take(c, (long long)h->head_blocks * h->head_stride);
+    int wmax = 1;
+    for (int j = 0; j < h->Li; ++j) if (h->int_arch[j] > wmax) wmax = h->int_arch[j];
+    h->dbpart_stride = wmax;                             // dgrad-epilogue column sums: [row tile][width]
+    h->dbpart_off = take(c, (long long)DIB_CEIL_DIV(B, 128ll) * wmax);
   }
   h->wshadow_off = take(c, h->Pp);      // TF32-rounded copy of the parameters (tensor-core mode B operands)
   h->pack_off = take(c, (long long)(dib_enc_fused_pack_bytes(h->F) + 3) / 4);
@@ -356,7 +363,7 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
       DIB_CUDA_OK(dib_int16_head(c.ws + h->g16_off[h->Li], Kh, Kh, c.params + h->intW[h->Li], c.params + h->intB[h->Li], h->out,
                                  h->out_act, h->act, h->alpha, h->loss, y, c.n, inv_batch, gscale,
                                  training ? (void*)(c.ws + h->dg16_off[h->Li]) : nullptr, Kh, user_pred, c.ws + h->headpart_off,
-                                 Kh * h->out + h->out, c.ws + h->loss_part_off, c.ws + h->acc_part_off, h->head_blocks, c.st));
+                                 h->head_stride, c.ws + h->loss_part_off, c.ws + h->acc_part_off, h->head_blocks, c.st));
       DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->kl_stride, nblk_kl, c.ws + h->loss_part_off,
                                             c.ws + h->acc_part_off, h->head_blocks, h->F, c.n, y != nullptr, out_stats, c.st));
       prof_end(c);
@@ -669,17 +676,24 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
   if (fused_enc && h->int16_ok && !h->force_int32) {
     const float gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
     float* part = c.ws + h->part_off;
+    const int Kh = h->int_arch[h->Li - 1];
+    const int row_tiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
+    // bias gradient of the last hidden layer: column sums of dg accumulated by the output head
+    DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off + (long long)Kh * h->out + h->out, h->head_stride, h->head_blocks, Kh,
+                                       1.f / gscale, grads_flat + h->intB[h->Li - 1], c.st));
     for (int j = h->Li - 1; j >= 0; --j) {
       const void* in_j = j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]);
       const int K = int_fan_in(h, j), N = int_fan_out(h, j);
       prof_begin(c, "int16_wgrad_l", j);
-      DIB_CUDA_OK(dib_int16_wgrad(in_j, K, c.ws + h->dg16_off[j + 1], N, part + h->intW[j], part + h->intB[j], (int)n, K, N, nsplit,
+      DIB_CUDA_OK(dib_int16_wgrad(in_j, K, c.ws + h->dg16_off[j + 1], N, part + h->intW[j], nullptr, (int)n, K, N, nsplit,
                                   (int)rps, h->Pp, 1.f / gscale, c.st));
       prof_end(c);
       prof_begin(c, "int16_dgrad_l", j);
       DIB_CUDA_OK(dib_int16_dgrad(c.ws + h->dg16_off[j + 1], N, c.ws + h->w16_off[j], j > 0 ? (const void*)(c.ws + h->g16_off[j]) : nullptr,
                                   K, j > 0 ? (void*)(c.ws + h->dg16_off[j]) : (void*)(c.ws + h->demb16_off), K, (int)n, K, N, h->act,
-                                  h->alpha, c.st));
+                                  h->alpha, j > 0 ? c.ws + h->dbpart_off : nullptr, c.st));
+      if (j > 0)   // bias gradient of layer j-1 = column sums of the gradient this dgrad just produced
+        DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->dbpart_off, K, row_tiles, K, 1.f / gscale, grads_flat + h->intB[j - 1], c.st));
       prof_end(c);
     }
     const int ntiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
@@ -702,9 +716,10 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
     prof_end(c);
     prof_begin(c, "wgrad_split_reduce");
     DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, slots_max, p_enc, grads_flat, c.st));
-    DIB_CUDA_OK(dib_launch_reduce_partials(part + p_enc, h->Pp, nsplit, p_head - p_enc, grads_flat + p_enc, c.st));
-    const long long head_cnt = h->P - p_head;
-    DIB_CUDA_OK(dib_launch_reduce_partials(c.ws + h->headpart_off, head_cnt, h->head_blocks, head_cnt, grads_flat + p_head, c.st));
+    for (int j = 0; j < h->Li; ++j)     // hidden-layer kernels: batch-split partials (their biases were reduced above)
+      DIB_CUDA_OK(dib_launch_reduce_partials(part + h->intW[j], h->Pp, nsplit, (long long)int_fan_in(h, j) * int_fan_out(h, j),
+                                             grads_flat + h->intW[j], c.st));
+    DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off, h->head_stride, h->head_blocks, h->P - p_head, 1.f, grads_flat + p_head, c.st));
     prof_end(c);
     return 0;
   }

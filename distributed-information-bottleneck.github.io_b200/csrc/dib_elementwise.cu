@@ -209,6 +209,34 @@ __global__ void dib_reduce_partials_kernel(const float* __restrict__ part, long 
   out[i] = s;
 }
 
+// out[i] = scale * sum_rows part[row][i] for MANY rows and few columns: 32 outputs x 8 row lanes per block, fixed order
+__global__ void __launch_bounds__(256)
+dib_reduce_tall_kernel(const float* __restrict__ part, long long row_stride, int nrows, long long count, float scale,
+                       float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (i < count) {
+    int r = ty;
+    for (; r + 56 < nrows; r += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part[(long long)(r + 8 * u) * row_stride + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; r < nrows; r += 8) s += part[(long long)r * row_stride + i];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < count) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k][tx];
+    out[i] = t * scale;
+  }
+}
+
 __global__ void dib_round_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, long long count) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) dst[i] = dib_round_tf32(src[i]);
@@ -386,6 +414,14 @@ cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev,
 cudaError_t dib_launch_round_copy(const float* src, float* dst, int64_t count, cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   dib_round_copy_kernel<<<nblocks(count, 256), 256, 0, st>>>(src, dst, count);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int nrows, int64_t count, float scale, float* out,
+                                   cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  dib_reduce_tall_kernel<<<nblocks(count, 32), 256, 0, st>>>(part, row_stride, nrows, count, scale, out);
   dib_note_launch();
   return cudaGetLastError();
 }

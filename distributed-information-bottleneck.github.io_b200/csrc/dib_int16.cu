@@ -28,7 +28,7 @@ struct Int16Args {
   float* out32; __half* out16; int ldc;       // WGRAD partial base (fp32) | FWD/DGRAD output (fp16)
   const __half* X; int ldx;                   // DGRAD: activation whose act' gates the gradient (or null)
   const float* bias;                          // FWD
-  float* dbias;                               // WGRAD: bias-gradient partial base (or null)
+  float* dbias;                               // DGRAD: column sums of the produced gradient per 128-row tile [tiles_r][C] (or null)
   int M, T, C, R, act;
   float alpha, out_scale;
   int nsplit, rows_per_split; long long split_stride;
@@ -44,8 +44,11 @@ __device__ __forceinline__ void unpack_h2(uint32_t u, float& a, float& b) {
   a = f.x; b = f.y;
 }
 
+// Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the shared-memory stage ring runs across tiles and the
+// fp32 accumulator is double-buffered in TMEM (2 x 128 columns), so the epilogue of tile i overlaps the mainloop of
+// tile i+1.  Warp roles: 0 TMA producer | 1 MMA issuer (+ TMEM owner) | 2..5 epilogue.
 template <int MODE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Int16Args a) {
   constexpr bool A_MN = (MODE == DIB_GEMM_WGRAD), B_MN = (MODE != DIB_GEMM_DGRAD);
   extern __shared__ uint8_t smem_raw[];
@@ -54,135 +57,214 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   const uint32_t bar_base = sb + kBarOff;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages), tmem_slot = bar_base + 8u * (2 * kStages + 1);
-  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kBarOff + 8 * (2 * kStages + 1));
+  auto tfull_bar = [&](int acc) { return bar_base + 8u * (2 * kStages + acc); };
+  auto tempty_bar = [&](int acc) { return bar_base + 8u * (2 * kStages + 2 + acc); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kBarOff + 8 * (2 * kStages + 4));
 
+  __shared__ float colsum_s[4][kBN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int split = 0, r0, c0;
-  if constexpr (MODE == DIB_GEMM_WGRAD) { split = blockIdx.z; c0 = blockIdx.x * kBN; r0 = blockIdx.y * kBM; }
-  else { r0 = blockIdx.x * kBM; c0 = blockIdx.y * kBN; }
   const int R = (MODE == DIB_GEMM_WGRAD) ? a.R : a.M, C = a.C;
-  int t_begin = 0, t_end = a.T;
-  if constexpr (MODE == DIB_GEMM_WGRAD) { t_begin = split * a.rows_per_split; t_end = min(a.M, t_begin + a.rows_per_split); }
-  if (r0 >= R || c0 >= C) return;
-  const int ntiles = t_end > t_begin ? DIB_CEIL_DIV(t_end - t_begin, kBK) : 0;
-  const bool do_db = (MODE == DIB_GEMM_WGRAD) && (blockIdx.y == 0) && (a.dbias != nullptr);
+  const int tiles_r = DIB_CEIL_DIV(R, kBM), tiles_c = DIB_CEIL_DIV(C, kBN);
+  const int nsp = (MODE == DIB_GEMM_WGRAD) ? a.nsplit : 1;
+  const int ntile = tiles_r * tiles_c * nsp;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), do_db ? 5 : 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int acc = 0; acc < 2; ++acc) { mbar_init(tfull_bar(acc), 1); mbar_init(tempty_bar(acc), 4); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, kBN); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 2 * kBN); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_g;
 
+  auto decode = [&](int tile, int& r0, int& c0, int& split, int& t_begin, int& nk) {
+    const int per = tiles_r * tiles_c;
+    split = tile / per;
+    const int rem = tile - split * per;
+    r0 = (rem / tiles_c) * kBM; c0 = (rem % tiles_c) * kBN;
+    int t_end;
+    if (MODE == DIB_GEMM_WGRAD) { t_begin = split * a.rows_per_split; t_end = min(a.M, t_begin + a.rows_per_split); }
+    else { t_begin = 0; t_end = a.T; }
+    nk = t_end > t_begin ? DIB_CEIL_DIV(t_end - t_begin, kBK) : 0;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < ntiles; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), kStageBytes);
-        const uint32_t a_dst = sb + s * kStageBytes, b_dst = a_dst + kABytes;
-        const int t0 = t_begin + it * kBK;
-        if constexpr (A_MN) tma_load_3d(a_dst, &mapA, full_bar(s), 0, t0, r0 / 64);
-        else                tma_load_2d(a_dst, &mapA, full_bar(s), t0, r0);
-        if constexpr (B_MN) tma_load_3d(b_dst, &mapB, full_bar(s), 0, t0, c0 / 64);
-        else                tma_load_2d(b_dst, &mapB, full_bar(s), t0, c0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        int r0, c0, split, t_begin, nk;
+        decode(tile, r0, c0, split, t_begin, nk);
+        for (int k = 0; k < nk; ++k, ++it) {
+          const int s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), kStageBytes);
+          const uint32_t a_dst = sb + s * kStageBytes, b_dst = a_dst + kABytes;
+          const int t0 = t_begin + k * kBK;
+          if constexpr (A_MN) tma_load_3d(a_dst, &mapA, full_bar(s), 0, t0, r0 / 64);
+          else                tma_load_2d(a_dst, &mapA, full_bar(s), t0, r0);
+          if constexpr (B_MN) tma_load_3d(b_dst, &mapB, full_bar(s), 0, t0, c0 / 64);
+          else                tma_load_2d(b_dst, &mapB, full_bar(s), t0, c0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(0u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBN);
-      for (int it = 0; it < ntiles; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(full_bar(s), ph);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        int r0, c0, split, t_begin, nk;
+        decode(tile, r0, c0, split, t_begin, nk);
+        if (nk == 0) continue;
+        const int acc = lt & 1;
+        mbar_wait(tempty_bar(acc), ((lt >> 1) & 1) ^ 1);           // the epilogue has drained this accumulator
         tc_fence_after_sync();
-        const uint32_t a_addr = sb + s * kStageBytes, b_addr = a_addr + kABytes;
+        const uint32_t d_tmem = tmem_base + acc * kBN;
+        for (int k = 0; k < nk; ++k, ++it) {
+          const int s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = sb + s * kStageBytes, b_addr = a_addr + kABytes;
 #pragma unroll
-        for (int kk = 0; kk < kBK / 16; ++kk) {
-          // K-major: 32 B inside the swizzle span; MN-major (16-bit, SWIZZLE_128B): 16 k-rows = 2048 B, panels 8 KB apart
-          const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kBK / 16; ++kk) {
+            // K-major: 32 B inside the swizzle span; MN-major (16-bit, SWIZZLE_128B): 16 k-rows = 2048 B, panels 8 KB apart
+            const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
         }
-        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(acc));
+        ++lt;
       }
-      if (ntiles > 0) umma_commit(tmem_full_bar);
     }
   } else {
-    const int q = warp & 3, et = (warp - 2) * 32 + lane;
-    if (do_db) {
-      float bs = 0.f;
-      for (int it = 0; it < ntiles; ++it) {
-        const int s = it % kStages, ph = (it / kStages) & 1;
-        mbar_wait(full_bar(s), ph);
-        {
-          const uint8_t* bt = sg + s * kStageBytes + kABytes + (et >> 6) * (kBK * 128);   // panel of 64 columns
-          const int ch = (et & 63) >> 3, w = et & 7;
-#pragma unroll 8
-          for (int row = 0; row < kBK; ++row)
-            bs += __half2float(*reinterpret_cast<const __half*>(bt + row * 128 + ((ch ^ (row & 7)) << 4) + (w << 1)));
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar(s));
-      }
-      if (c0 + et < C) (a.dbias + (long long)split * a.split_stride)[c0 + et] = bs * a.out_scale;
-    }
-    if (ntiles > 0) { mbar_wait(tmem_full_bar, 0); tc_fence_after_sync(); }
-    const int r = r0 + q * 32 + lane;
+    const int q = warp & 3;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+      int r0, c0, split, t_begin, nk;
+      decode(tile, r0, c0, split, t_begin, nk);
+      const int acc = lt & 1;
+      if (nk > 0) { mbar_wait(tfull_bar(acc), (lt >> 1) & 1); tc_fence_after_sync(); }
+      const int r = r0 + q * 32 + lane;
 #pragma unroll 1
-    for (int cc = 0; cc < kBN; cc += 32) {
-      uint32_t v[32];
-      if (ntiles > 0) { tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v); tmem_ld_wait(); }
-      else {
+      for (int cc = 0; cc < kBN; cc += 32) {
+        uint32_t v[32];
+        if (nk > 0) { tmem_ld_32x32b_x32(tmem_base + acc * kBN + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v); tmem_ld_wait(); }
+        else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      if (r < R && c0 + cc < C) {          // C is a multiple of 64: a 32-column chunk is entirely inside or outside
-        const int c = c0 + cc;
-        if constexpr (MODE == DIB_GEMM_WGRAD) {
-          float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (r < R && c0 + cc < C) {          // C is a multiple of 64: a 32-column chunk is entirely inside or outside
+          const int c = c0 + cc;
+          if constexpr (MODE == DIB_GEMM_WGRAD) {
+            float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * a.out_scale, __uint_as_float(v[j + 1]) * a.out_scale,
-                                                              __uint_as_float(v[j + 2]) * a.out_scale, __uint_as_float(v[j + 3]) * a.out_scale);
-        } else {
-          __half* dst = a.out16 + (long long)r * a.ldc + c;
-          const __half* xs = (MODE == DIB_GEMM_DGRAD && a.X) ? a.X + (long long)r * a.ldx + c : nullptr;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * a.out_scale, __uint_as_float(v[j + 1]) * a.out_scale,
+                                                                __uint_as_float(v[j + 2]) * a.out_scale, __uint_as_float(v[j + 3]) * a.out_scale);
+          } else {
+            __half* dst = a.out16 + (long long)r * a.ldc + c;
+            const __half* xs = (MODE == DIB_GEMM_DGRAD && a.X) ? a.X + (long long)r * a.ldx + c : nullptr;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float f[8];
+            for (int j = 0; j < 32; j += 8) {
+              float f[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j + k]);
-            if constexpr (MODE == DIB_GEMM_FWD) {
-              const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c + j), b1 = *reinterpret_cast<const float4*>(a.bias + c + j + 4);
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j + k]);
+              if constexpr (MODE == DIB_GEMM_FWD) {
+                const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c + j), b1 = *reinterpret_cast<const float4*>(a.bias + c + j + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int k = 0; k < 8; ++k) f[k] = dib_act(a.act, f[k] + bb[k], a.alpha);
-            } else if (xs) {
-              const uint4 xv = *reinterpret_cast<const uint4*>(xs + j);
-              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                for (int k = 0; k < 8; ++k) f[k] = dib_act(a.act, f[k] + bb[k], a.alpha);
+              } else if (xs) {
+                const uint4 xv = *reinterpret_cast<const uint4*>(xs + j);
+                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float h0, h1;
-                unpack_h2(xw[k], h0, h1);
-                f[2 * k] *= dib_act_grad(a.act, h0, a.alpha);
-                f[2 * k + 1] *= dib_act_grad(a.act, h1, a.alpha);
+                for (int k = 0; k < 4; ++k) {
+                  float h0, h1;
+                  unpack_h2(xw[k], h0, h1);
+                  f[2 * k] *= dib_act_grad(a.act, h0, a.alpha);
+                  f[2 * k + 1] *= dib_act_grad(a.act, h1, a.alpha);
+                }
+              }
+              *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+              if constexpr (MODE == DIB_GEMM_DGRAD) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[j + k] = __float_as_uint(f[k]);     // keep the gated fp32 values for the column sums
               }
             }
-            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          }
+        } else if constexpr (MODE == DIB_GEMM_DGRAD) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;                                  // rows / columns outside the matrix add nothing
+        }
+        if constexpr (MODE == DIB_GEMM_DGRAD) {
+          if (a.dbias) {
+            // bias gradient of the layer below = column sums of the gradient just produced: 32 values per lane are
+            // transpose-reduced over the warp's 32 rows in 31 shuffles; lane L ends up with column L of this chunk
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+              for (int i = 0; i < o; ++i) {
+                const bool up = (lane & o) != 0;
+                const float send = up ? w[i] : w[i + o], keep = up ? w[i + o] : w[i];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              }
+            }
+            colsum_s[q][cc + lane] = w[0];
           }
         }
+      }
+      if constexpr (MODE == DIB_GEMM_DGRAD) {
+        if (a.dbias) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int et = (warp - 2) * 32 + lane;               // one column of the tile per epilogue thread
+          if (c0 + et < C)
+            a.dbias[(long long)(r0 / kBM) * C + c0 + et] = (colsum_s[0][et] + colsum_s[1][et]) + (colsum_s[2][et] + colsum_s[3][et]);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+      if (nk > 0) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        ++lt;
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, kBN); }
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 2 * kBN); }
+}
+
+// bias gradient of a hidden layer: column sums of the fp16 gradient over one batch slice -> fp32 split partial.
+// grid (C / 64, nsplit), 256 threads: lane pairs of columns (half2), 8 row lanes, fixed-order combine.
+__global__ void __launch_bounds__(256)
+dib_int16_colsum_kernel(const __half* __restrict__ dz, int ld, int M, int C, int rows_per_split, float scale,
+                        float* __restrict__ out, long long split_stride) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + tx * 2, split = blockIdx.y;
+  const int t0 = split * rows_per_split, t1 = min(M, t0 + rows_per_split);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C)
+    for (int row = t0 + ty; row < t1; row += 8) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(dz + (long long)row * ld + c));
+      s0 += f.x; s1 += f.y;
+    }
+  red[ty][tx * 2] = s0; red[ty][tx * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < C) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    out[(long long)split * split_stride + blockIdx.x * 64 + threadIdx.x] = s * scale;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -200,7 +282,9 @@ dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float*
   __shared__ float sred[kHeadWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * kHeadWarps + warp, nw = gridDim.x * kHeadWarps;
-  float w[KPT][OUT], dw[KPT][OUT], db[OUT], bias[OUT];
+  float w[KPT][OUT], dw[KPT][OUT], db[OUT], bias[OUT], dbh[KPT];
+#pragma unroll
+  for (int i = 0; i < KPT; ++i) dbh[i] = 0.f;
 #pragma unroll
   for (int o = 0; o < OUT; ++o) {
     db[o] = 0.f;
@@ -283,6 +367,7 @@ dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float*
 #pragma unroll
           for (int o = 0; o < OUT; ++o) { s = fmaf(dz[o], w[i][o], s); dw[i][o] = fmaf(h[i], dz[o], dw[i][o]); }
           d[i] = s * gscale * dib_act_grad(hid_act, h[i], alpha);
+          dbh[i] += d[i];
         }
         __half* dst = dg + row * lddg + lane * KPT;
 #pragma unroll
@@ -311,6 +396,19 @@ dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float*
       }
       __syncthreads();
     }
+    // bias gradient of the last hidden layer (column sums of dg, still multiplied by gscale) -> wpart[K*out+out + k]
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) red[warp][lane * KPT + i] = dbh[i];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) {
+        float s = 0.f;
+        for (int ww = 0; ww < kHeadWarps; ++ww) s += red[ww][lane * KPT + i];
+        wpart[(long long)blockIdx.x * wpart_stride + (long long)K * out_dim + out_dim + lane * KPT + i] = s;
+      }
+    }
+    __syncthreads();
     if (lane == 0) {
 #pragma unroll
       for (int o = 0; o < OUT; ++o) red[warp][o] = db[o];
@@ -369,8 +467,13 @@ bool map_mn(CUtensorMap* m, const __half* base, long long cols, long long krows,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int g_num_sms16 = 0;
 template <int MODE>
-cudaError_t launch16(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Args& a, dim3 grid, cudaStream_t st) {
+cudaError_t launch16(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Args& a, dim3 tiles, cudaStream_t st) {
+  if (!g_num_sms16) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms16, cudaDevAttrMultiProcessorCount, dev); }
+  const long long nt = (long long)tiles.x * tiles.y * tiles.z;
+  if (nt <= 0) return cudaSuccess;
+  dim3 grid((unsigned)(nt < 2ll * g_num_sms16 ? nt : 2ll * g_num_sms16));
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(dib_int16_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
@@ -406,14 +509,14 @@ cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const fl
 
 // dz_in[M x K] = (dz[M x N] W16[K x N]^T) * act'(g_in[M x K])      (g_in may be null: no activation, e.g. d_emb)
 cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const void* g_in, int ld_g, void* dz_in, int ld_out,
-                            int M, int K, int N, int act, float alpha, cudaStream_t st) {
+                            int M, int K, int N, int act, float alpha, float* colsum_part, cudaStream_t st) {
   if (!encode_fn3()) return cudaErrorNotSupported;
   CUtensorMap mA, mB;
   if (!map_k(&mA, static_cast<const __half*>(dz), N, M, ld_dz, kBM) || !map_k(&mB, static_cast<const __half*>(w16), N, K, N, kBN))
     return cudaErrorInvalidValue;
   Int16Args a{};
   a.out16 = static_cast<__half*>(dz_in); a.ldc = ld_out; a.X = static_cast<const __half*>(g_in); a.ldx = ld_g;
-  a.M = M; a.T = N; a.C = K; a.act = act; a.alpha = alpha; a.out_scale = 1.f; a.nsplit = 1;
+  a.M = M; a.T = N; a.C = K; a.act = act; a.alpha = alpha; a.out_scale = 1.f; a.nsplit = 1; a.dbias = colsum_part;
   return launch16<DIB_GEMM_DGRAD>(mA, mB, a, dim3(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(K, kBN), 1), st);
 }
 
@@ -425,12 +528,13 @@ cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_d
   if (!map_mn(&mA, static_cast<const __half*>(g_in), K, M, ld_g, kBM / 64) || !map_mn(&mB, static_cast<const __half*>(dz), N, M, ld_dz, kBN / 64))
     return cudaErrorInvalidValue;
   Int16Args a{};
-  a.out32 = dW_part; a.ldc = N; a.dbias = db_part; a.M = M; a.T = 0; a.C = N; a.R = K; a.out_scale = out_scale;
+  a.out32 = dW_part; a.ldc = N; a.dbias = nullptr; a.M = M; a.T = 0; a.C = N; a.R = K; a.out_scale = out_scale;
   a.nsplit = nsplit; a.rows_per_split = rows_per_split; a.split_stride = split_stride;
+  (void)db_part;   // bias gradients come from the kernel that PRODUCES dz (dgrad epilogue / output head), not from here
   return launch16<DIB_GEMM_WGRAD>(mA, mB, a, dim3(DIB_CEIL_DIV(N, kBN), DIB_CEIL_DIV(K, kBM), nsplit), st);
 }
 
-int dib_int16_head_blocks(int num_sms) { return num_sms * 4; }   // 32 warps per SM: the head is latency-bound per warp
+int dib_int16_head_blocks(int num_sms) { return num_sms * 2; }
 
 cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const float* bc, int out_dim, int out_act, int hid_act,
                            float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,

@@ -112,8 +112,11 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
 cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, cudaStream_t st);
 cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const float* bias, void* g_out, int ld_out, int M,
                           int K, int N, int act, float alpha, cudaStream_t st);
+// colsum_part (nullable): [ceil(M/128)][K] per-row-tile column sums of dz_in = bias-gradient partials of the layer below
 cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const void* g_in, int ld_g, void* dz_in, int ld_out,
-                            int M, int K, int N, int act, float alpha, cudaStream_t st);
+                            int M, int K, int N, int act, float alpha, float* colsum_part, cudaStream_t st);
+cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int nrows, int64_t count, float scale, float* out,
+                                   cudaStream_t st);
 cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
                             int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, cudaStream_t st);
 int dib_int16_head_blocks(int num_sms);
