@@ -85,7 +85,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                 stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -242,10 +242,10 @@ def main():
                           global_batch=BATCH * world, sample_offset=rank * BATCH)
 
     # ---------------- device-resident timed region -> value
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # sampled under load: warm-up + timed region
     for i in range(args.warmup):
         device_step(i)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = int(lib.dib_launch_count())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -260,18 +260,23 @@ def main():
     value = BATCH * world / (ms_per_step * 1e-3)
 
     # ---------------- end to end through the public API from pinned host buffers -> e2e
-    for i in range(2):
-        model.train_on_batch(xs_h[i], ys_h[i])
+    for i in range(3):
+        model.train_on_batch(xs_h[i], ys_h[i], sync=False).get()
     barrier()
     ev0.record()
+    pend = []
     for i in range(args.steps):
-        out = model.train_on_batch(xs_h[i % N_DISTINCT_BATCHES], ys_h[i % N_DISTINCT_BATCHES])
+        # every step: pinned host batch -> H2D (copy stream) -> step -> async D2H of the metrics into pinned memory
+        pend.append(model.train_on_batch(xs_h[i % N_DISTINCT_BATCHES], ys_h[i % N_DISTINCT_BATCHES], sync=False))
+        if len(pend) > 4:
+            pend.pop(0).get()            # the host reads every step's result, a few steps behind the device
+    out = [p.get() for p in pend][-1]
     ev1.record()
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     e2e = {"value": BATCH * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(xs_h[0].numel() * 4 + ys_h[0].numel() * 4),
-           "d2h_bytes_per_step": int((F + 3) * 4), "api": "DistributedIBNet.train_on_batch(host x, host y) -> metrics dict",
+           "d2h_bytes_per_step": int((F + 3) * 4), "api": "DistributedIBNet.train_on_batch(host x, host y, sync=False).get() -> metrics dict (H2D on a copy stream, D2H async)",
            "last_loss": out["loss"]}
 
     # ---------------- per-launch-group CUDA-event profile of the same steps -> roofline (rank 0)

@@ -442,24 +442,71 @@ class DistributedIBNet:
     def _sync_lr(self):
         self._lr_dev.fill_(float(self.optimizer.learning_rate))
 
-    def train_on_batch(self, x, y, return_dict=True):
-        """One optimizer step on a (host or device) batch; returns the batch metrics (forces a D2H read)."""
+    def train_on_batch(self, x, y, return_dict=True, sync=True):
+        """One optimizer step on a (host or device) batch.
+
+        ``sync=True`` (Keras behaviour): returns the batch metrics (dict, or the scalar loss) -- forces the D2H read.
+        ``sync=False``: returns a :class:`PendingBatchResult`; host batches are staged through a copy stream with two
+        device slots and the metrics are copied to pinned memory asynchronously, so the H2D copy of call k+1 overlaps
+        the compute of call k.  ``result.get()`` (or the next sync point) yields the same dict."""
         if self.optimizer is None:
             raise RuntimeError("call compile() first")
         with torch.cuda.device(self.device):
             self._sync_lr()
-            xd = self._to_device(x, sum(self.feature_dimensionalities))
-            yd = self._to_device(y, self._y_cols())
+            D = sum(self.feature_dimensionalities)
             world, rank = parallel.world_and_rank(self.process_group)
-            n = xd.shape[0]
-            stats = self._train_step(xd, yd, global_batch=n * world, sample_offset=rank * n)
-            s = stats.detach().cpu().numpy().astype(np.float64)
-        F = self.number_features
-        nn = max(s[F + 2], 1.0)
-        out = {"loss": float((s[F] + float(self.beta.value()) * s[:F].sum()) / nn), "accuracy": float(s[F + 1] / nn)}
-        for i in range(F):
-            out[f"KL{i}"] = float(s[i] / nn)
+            host_x = not (isinstance(x, torch.Tensor) and x.is_cuda)
+            if sync or not host_x:
+                xd, yd = self._to_device(x, D), self._to_device(y, self._y_cols())
+                n = xd.shape[0]
+                stats = self._train_step(xd, yd, global_batch=n * world, sample_offset=rank * n)
+                res = PendingBatchResult(self, stats.detach().clone() if not sync else stats, None, None)
+            else:
+                xd, yd, slot = self._stage_async(x, y, D)
+                n = xd.shape[0]
+                stats = self._train_step(xd, yd, global_batch=n * world, sample_offset=rank * n)
+                st = self._staging
+                st["done"][slot].record(torch.cuda.current_stream())          # slot may be overwritten after this
+                hi = (st["k"] - 1) % len(st["stats_host"])
+                if st["pending"][hi] is not None:
+                    st["pending"][hi].get()                                   # its pinned buffer is about to be reused
+                host = st["stats_host"][hi]
+                host.copy_(stats, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                res = PendingBatchResult(self, None, host, ev)
+                st["pending"][hi] = res
+        if not sync:
+            return res
+        out = res.get()
         return out if return_dict else out["loss"]
+
+    def _stage_async(self, x, y, D):
+        """H2D of a host batch on the copy stream into one of two device slots; the compute stream waits on it."""
+        xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        yt = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+        n, yc = xt.shape[0], self._y_cols()
+        st = getattr(self, "_staging", None)
+        if st is None or st["n"] != n:
+            st = dict(n=n, k=0, stream=torch.cuda.Stream(device=self.device),
+                      x=[torch.empty(n, D, dtype=torch.float32, device=self.device) for _ in range(2)],
+                      y=[torch.empty((n, yc) if yc > 0 else (n,), dtype=torch.float32, device=self.device) for _ in range(2)],
+                      done=[torch.cuda.Event() for _ in range(2)], copied=[torch.cuda.Event() for _ in range(2)],
+                      stats_host=[torch.empty(self.number_features + 3, dtype=torch.float32).pin_memory() for _ in range(8)],
+                      pending=[None] * 8, used=[False, False])
+            self._staging = st
+        slot = st["k"] % 2
+        st["k"] += 1
+        cs = st["stream"]
+        if st["used"][slot]:
+            cs.wait_event(st["done"][slot])                   # the step that read this slot two calls ago has finished
+        with torch.cuda.stream(cs):
+            st["x"][slot].copy_(xt.reshape(n, D), non_blocking=True)
+            st["y"][slot].copy_(yt.reshape(st["y"][slot].shape), non_blocking=True)
+            st["copied"][slot].record(cs)
+        torch.cuda.current_stream().wait_event(st["copied"][slot])
+        st["used"][slot] = True
+        return st["x"][slot], st["y"][slot], slot
 
     def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose='auto', callbacks=None, validation_data=None,
             shuffle=True, initial_epoch=0, **_):
@@ -549,6 +596,33 @@ class DistributedIBNet:
             outs.append(np.asarray(self(x[b0:b0 + int(batch_size)], training=False)) if not isinstance(x, torch.Tensor)
                         else self(x[b0:b0 + int(batch_size)], training=False))
         return torch.cat(outs) if isinstance(x, torch.Tensor) else np.concatenate(outs)
+
+
+class PendingBatchResult:
+    """Metrics of one ``train_on_batch(..., sync=False)`` call; ``get()`` waits for the asynchronous D2H copy."""
+
+    def __init__(self, model, stats_dev, stats_host, event):
+        self._m, self._dev, self._host, self._ev = model, stats_dev, stats_host, event
+        self._beta = float(model.beta.value())
+        self._out = None
+
+    def get(self):
+        if self._out is None:
+            if self._ev is not None:
+                self._ev.synchronize()
+                s = self._host.numpy().astype(np.float64)            # copy out of the pinned buffer
+            else:
+                s = self._dev.detach().cpu().numpy().astype(np.float64)
+            F = self._m.number_features
+            nn = max(s[F + 2], 1.0)
+            out = {"loss": float((s[F] + self._beta * s[:F].sum()) / nn), "accuracy": float(s[F + 1] / nn)}
+            for i in range(F):
+                out[f"KL{i}"] = float(s[i] / nn)
+            self._out = out
+        return self._out
+
+    def __getitem__(self, k):
+        return self.get()[k]
 
 
 class InfoBottleneckAnnealingCallback(Callback):
