@@ -174,20 +174,21 @@ dib_loss_kernel(int loss, int out_act, float alpha, const float* __restrict__ pr
   if (threadIdx.x == 0) { loss_part[blockIdx.x] = ls; acc_part[blockIdx.x] = as; }
 }
 
-// stats = [ sum_b KL_i (F) | sum_b task loss | sum_b accuracy | n ]; one block, fixed summation order.
+// stats = [ sum_b KL_i (F) | sum_b task loss | sum_b accuracy | n ]; one block, one WARP per item (fixed lane-strided
+// order + fixed shuffle tree -> deterministic), no block-wide barriers.
 __global__ void __launch_bounds__(256)
 dib_finalize_stats_kernel(const float* __restrict__ kl_part, int nblk_stride, int nblk_kl, const float* __restrict__ loss_part,
                           const float* __restrict__ acc_part, int nblk_loss, int F, long long n, int has_y,
                           float* __restrict__ out) {
-  __shared__ float red[8];
-  for (int item = 0; item < F + 2; ++item) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int item = warp; item < F + 2; item += nwarps) {
     const float* src; int cnt;
     if (item < F) { src = kl_part + (long long)item * nblk_stride; cnt = nblk_kl; }
     else { src = item == F ? loss_part : acc_part; cnt = has_y ? nblk_loss : 0; }
     float v = 0.f;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) v += src[i];
-    const float s = block_sum_256(v, red);
-    if (threadIdx.x == 0) out[item] = s;
+    for (int i = lane; i < cnt; i += 32) v += src[i];
+    v = dib_warp_sum(v);
+    if (lane == 0) out[item] = v;
   }
   if (threadIdx.x == 0) out[F + 2] = (float)n;
 }

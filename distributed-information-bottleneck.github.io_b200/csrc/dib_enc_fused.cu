@@ -48,13 +48,15 @@ constexpr int kOffBb1 = kOffW0 + 2 * K0 * 128;     // 4 KB : W0p = 2 panels x 16
 constexpr int kOffBb2 = kOffBb1 + 2 * K0 * 128;    // 4 KB : Bb1 likewise
 constexpr int kOffA0 = kOffBb2 + K0 * 128;         // 2 KB : Bb2 = 1 panel x 16 rows x 128 B
 constexpr int kOffH1 = kOffA0 + 2 * TM * 16 + 2048;// 4 KB : A0 = [2 k-halves][128 rows][16 B] (no swizzle); +2 KB keeps 1024-alignment
-constexpr int kOffFwdEnd1 = kOffH1 + 2 * kPanel;   // forward kernel: h2 overwrites h1 (its MMA has retired)
+constexpr int kOffFwdA0b = kOffH1 + 2 * kPanel;    // forward kernel: h2 overwrites h1 (its MMA has retired); second A0 buffer
+constexpr int kOffFwdEnd1 = kOffFwdA0b + 2 * TM * 16;
 constexpr int kOffH2 = kOffH1 + 2 * kPanel;
 constexpr int kOffFwdEnd = kOffH2 + 2 * kPanel;
 // backward-only tiles
 constexpr int kOffDO = kOffFwdEnd;                 // [128 x 64]  one panel
 constexpr int kOffDZ2 = kOffDO + kPanel;           // [128 x 128] (dz1 aliases H2 once wgrad2 has drained)
-constexpr int kOffBwdEnd = kOffDZ2 + 2 * kPanel;
+constexpr int kOffBwdA0b = kOffDZ2 + 2 * kPanel;    // second A0 buffer (the next tile's operand is staged while this one runs)
+constexpr int kOffBwdEnd = kOffBwdA0b + 2 * TM * 16;
 
 struct EncFusedParams {
   const float* x; int ldx;                 // [n, D]
@@ -117,9 +119,15 @@ __device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, uint32_t tile, 
 }
 
 // first-layer operand row: [x_0..x_{d-1}, sin(2x).., sin(4x).., ..., 1, 0...] (models.py:22-23 + the ones column
-// that carries every layer's bias through the bias-carrier matrices)
+// that carries every layer's bias through the bias-carrier matrices).  xv = the row's (prefetched) feature values.
+constexpr int kMaxFeatDim = 3;     // d * nfreq + 1 <= 16 and nfreq >= 1
+__device__ __forceinline__ void load_x(const float* xrow, int d, float (&xv)[kMaxFeatDim]) {
+#pragma unroll
+  for (int j = 0; j < kMaxFeatDim; ++j) xv[j] = (xrow && j < d) ? xrow[j] : 0.f;
+}
 template <bool BF16>
-__device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, const float* xrow, int d, int nfreq) {
+__device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, bool valid, const float (&xv)[kMaxFeatDim], int d,
+                                             int nfreq) {
   float f[8];
   const int w_in = d * nfreq;
 #pragma unroll
@@ -128,10 +136,12 @@ __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, cons
     float v = 0.f;
     if (col < w_in) {
       const int blk = col / d, j = col - blk * d;
-      const float xv = xrow ? xrow[j] : 0.f;
-      v = blk == 0 ? xv : sinf((float)(1 << blk) * xv);
+      float xj = xv[0];
+#pragma unroll
+      for (int q = 1; q < kMaxFeatDim; ++q) if (j == q) xj = xv[q];
+      v = blk == 0 ? xj : sinf((float)(1 << blk) * xj);
     } else if (col == w_in) {
-      v = xrow ? 1.f : 0.f;          // rows past the batch end contribute nothing
+      v = valid ? 1.f : 0.f;          // rows past the batch end contribute nothing
     }
     f[k] = v;
   }
@@ -156,23 +166,23 @@ __device__ __forceinline__ void load_weights(uint32_t sb, const WeightMaps& m, u
 
 // the three forward contractions of one tile, each preceded by its bias-carrier step (issued by one thread)
 template <bool BF16>
-__device__ __forceinline__ void issue_layer0(uint32_t sb, uint32_t tD) {
+__device__ __forceinline__ void issue_layer0(uint32_t sb, uint32_t tD, uint32_t a0) {
   constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, HID);
-  umma_f16<BF16>(tD, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffW0, K0 * 128, 1024), id, 0u);
+  umma_f16<BF16>(tD, umma_smem_desc(a0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffW0, K0 * 128, 1024), id, 0u);
 }
 template <bool BF16>
-__device__ __forceinline__ void issue_layer1(uint32_t sb, uint32_t tD, uint32_t h1) {
+__device__ __forceinline__ void issue_layer1(uint32_t sb, uint32_t tD, uint32_t h1, uint32_t a0) {
   constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, HID);
-  umma_f16<BF16>(tD, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffBb1, K0 * 128, 1024), id, 0u);
+  umma_f16<BF16>(tD, umma_smem_desc(a0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffBb1, K0 * 128, 1024), id, 0u);
 #pragma unroll
   for (int kk = 0; kk < HID / 16; ++kk)
     umma_f16<BF16>(tD, umma_smem_desc(h1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
                    umma_smem_desc(sb + kOffW1 + kk * 2048, kPanel, 1024), id, 1u);
 }
 template <bool BF16>
-__device__ __forceinline__ void issue_layer2(uint32_t sb, uint32_t tD, uint32_t h2) {
+__device__ __forceinline__ void issue_layer2(uint32_t sb, uint32_t tD, uint32_t h2, uint32_t a0) {
   constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, EO);
-  umma_f16<BF16>(tD, umma_smem_desc(sb + kOffA0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffBb2, K0 * 128, 1024), id, 0u);
+  umma_f16<BF16>(tD, umma_smem_desc(a0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffBb2, K0 * 128, 1024), id, 0u);
 #pragma unroll
   for (int kk = 0; kk < HID / 16; ++kk)
     umma_f16<BF16>(tD, umma_smem_desc(h2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
@@ -237,11 +247,12 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         for (int t = slot; t < ntiles; t += nslots, ++it) {
           const uint32_t ph = it & 1;
           mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
-          issue_layer0<BF16>(sb, tR0); umma_commit(bar_d0);
+          const uint32_t a0 = sb + ((it & 1) ? kOffFwdA0b : kOffA0);
+          issue_layer0<BF16>(sb, tR0, a0); umma_commit(bar_d0);
           mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
-          issue_layer1<BF16>(sb, tR0, hbuf); umma_commit(bar_d1);
+          issue_layer1<BF16>(sb, tR0, hbuf, a0); umma_commit(bar_d1);
           mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
-          issue_layer2<BF16>(sb, tR1, hbuf); umma_commit(bar_d2);
+          issue_layer2<BF16>(sb, tR1, hbuf, a0); umma_commit(bar_d2);
           if (t + nslots >= ntiles) mbar_wait_backoff(bar_d2, ph);   // drain before the next feature's weights land
         }
       } else {
@@ -255,18 +266,27 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       const int d = P.fdim[f], xo = P.x_off[f];
       float kl_acc = 0.f;
+      const int ar = et & (TM - 1), khalf = et >> 7;             // first-layer operand: row / k-half staged by this thread
+      float xv[kMaxFeatDim];
+      if (slot < ntiles) {                                       // operand of the first tile
+        const long long grow = (long long)slot * TM + ar;
+        load_x(grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, xv);
+        write_a0_row<BF16>(sb + ((it & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow < P.n, xv, d, P.nfreq);
+        DIB_EPI_SIGNAL(bar_a0);
+      }
       for (int t = slot; t < ntiles; t += nslots, ++it) {
         const uint32_t ph = it & 1;
         const long long row0 = (long long)t * TM;
-        {
-          const int ar = et & (TM - 1), khalf = et >> 7;
-          const long long grow = row0 + ar;
-          write_a0_row<BF16>(sb + kOffA0, ar, khalf, grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, P.nfreq);
-          DIB_EPI_SIGNAL(bar_a0);
-        }
+        const bool has_next = t + nslots < ntiles;
+        const long long grow_n = (long long)(t + nslots) * TM + ar;
+        if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv);   // prefetch the next tile's x
         mbar_wait(bar_d0, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h1);
+        if (has_next) {      // stage the next tile's operand in the other A0 buffer: its layer-0 MMA then runs early
+          write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
+          DIB_EPI_SIGNAL(bar_a0);
+        }
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h2);
@@ -461,11 +481,12 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           const uint32_t ph = it & 1;
           // ---- recompute forward
           mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
-          issue_layer0<BF16>(sb, tR0); umma_commit(bar_d0);
+          const uint32_t a0 = sb + ((it & 1) ? kOffBwdA0b : kOffA0);
+          issue_layer0<BF16>(sb, tR0, a0); umma_commit(bar_d0);
           mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
-          issue_layer1<BF16>(sb, tR0, sb + kOffH1); umma_commit(bar_d1);
+          issue_layer1<BF16>(sb, tR0, sb + kOffH1, a0); umma_commit(bar_d1);
           mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
-          issue_layer2<BF16>(sb, tR1, sb + kOffH2); umma_commit(bar_d2);
+          issue_layer2<BF16>(sb, tR1, sb + kOffH2, a0); umma_commit(bar_d2);
           // ---- layer 2 backward: G2 = dO W2^T ; dW2 += h2^T dO
           mbar_wait_backoff(bar_do, ph); tc_fence_after_sync();
 #pragma unroll
@@ -482,7 +503,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tWB2, umma_smem_desc(sb + kOffDO + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           // ---- layer 1 backward: G1 = dz2 W1^T ; dW1 += h1^T dz2 ; db1 += dz2^T [pe|1]
           mbar_wait_backoff(bar_dz2, ph); tc_fence_after_sync();
@@ -499,14 +520,14 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tWB1, umma_smem_desc(sb + kOffDZ2 + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           // ---- layer 0 backward: [dW0;db0]^T += dz1^T [pe|1]     (dz1 lives in the H2 buffer)
           mbar_wait_backoff(bar_dz1, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tWG0, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(sb + kOffA0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           umma_commit(bar_wg);
           if (t + nslots >= ntiles) mbar_wait_backoff(bar_wg, ph);
@@ -522,6 +543,14 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       const int d = P.fdim[f], xo = P.x_off[f];
       const float bs = Q.beta_dev[0] * Q.inv_batch * S;
+      const int ar = et & (TM - 1), khalf = et >> 7;             // first-layer operand: row / k-half staged by this thread
+      float xv[kMaxFeatDim];
+      if (slot < ntiles) {                                       // operand of the first tile
+        const long long grow0 = (long long)slot * TM + ar;
+        load_x(grow0 < P.n ? P.x + grow0 * P.ldx + xo : nullptr, d, xv);
+        write_a0_row<BF16>(sb + ((it & 1) ? kOffBwdA0b : kOffA0), ar, khalf, grow0 < P.n, xv, d, P.nfreq);
+        DIB_EPI_SIGNAL(bar_a0);
+      }
       for (int t = slot; t < ntiles; t += nslots, ++it) {
         const uint32_t ph = it & 1;
         const long long row0 = (long long)t * TM;
@@ -534,15 +563,16 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
             dpre[0] = *reinterpret_cast<const uint4*>(src); dpre[1] = *reinterpret_cast<const uint4*>(src + 8);
           }
         }
-        {
-          const int ar = et & (TM - 1), khalf = et >> 7;
-          const long long grow = row0 + ar;
-          write_a0_row<BF16>(sb + kOffA0, ar, khalf, grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, P.nfreq);
-          DIB_EPI_SIGNAL(bar_a0);
-        }
+        const bool has_next = t + nslots < ntiles;
+        const long long grow_n = (long long)(t + nslots) * TM + ar;
+        if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv);   // prefetch the next tile's x
         mbar_wait(bar_d0, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH1, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h1);
+        if (has_next) {      // stage the next tile's first-layer operand in the other A0 buffer
+          write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffBwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
+          DIB_EPI_SIGNAL(bar_a0);
+        }
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h2);
