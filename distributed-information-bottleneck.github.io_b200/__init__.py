@@ -7,9 +7,9 @@ backed by hand-written sm_100a CUDA kernels behind the C ABI of include/dib_b200
 from . import keras_compat, models, parallel, utils                              # noqa: F401
 from .keras_compat import Adam, Callback, History, losses, optimizers           # noqa: F401
 from .models import (DistributedIBNet, InfoBottleneckAnnealingCallback, PositionalEncoding,   # noqa: F401
-                     SaveCompressionMatricesCallback, StashEmbeddingsCallback)
+                     SaveCompressionMatricesCallback, StashEmbeddingsCallback, InfoPerFeatureCallback)
 from ._lib import DibError, library_path                                         # noqa: F401
 
 __all__ = ["DistributedIBNet", "PositionalEncoding", "InfoBottleneckAnnealingCallback",
-           "SaveCompressionMatricesCallback", "StashEmbeddingsCallback", "Adam", "optimizers", "losses",
+           "SaveCompressionMatricesCallback", "StashEmbeddingsCallback", "InfoPerFeatureCallback", "Adam", "optimizers", "losses",
            "Callback", "History", "models", "utils", "parallel", "keras_compat", "DibError", "library_path"]

@@ -801,6 +801,15 @@ int dib_metrics_update(const float* stats, const float* beta_dev, float* acc, in
   return 0;
 }
 
+int dib_mi_sandwich_bounds(const float* mu_logvar, int64_t n, int32_t embedding_dimension, const float* eps, uint64_t seed,
+                           uint32_t step, float* row_scratch, float* out_lower_upper, void* stream) {
+  if (!mu_logvar || !row_scratch || !out_lower_upper || n < 1 || n > 0x7fffffffll || embedding_dimension < 1)
+    return fail("dib_mi_sandwich_bounds: bad arguments");
+  DIB_CUDA_OK(dib_launch_mi_sandwich(mu_logvar, n, embedding_dimension, eps, seed, step, row_scratch, out_lower_upper,
+                                     static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int dib_bhattacharyya(const float* mu_logvar, int64_t n, int32_t embedding_dimension, float* out_dist,
                       float* out_compression, void* stream) {
   if (!mu_logvar || n < 0 || embedding_dimension < 1) return fail("dib_bhattacharyya: bad arguments");

@@ -320,6 +320,79 @@ __global__ void dib_metrics_update_kernel(const float* __restrict__ stats, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// next row f1 -- utils.py:36-65 compute_batch: InfoNCE / leave-one-out bounds of one encoder on one batch.
+// One block per sample i: u_i = mu_i + sigma_i eps_i in shared memory, threads stride over j, log-space
+// (max, sum) reduction for logsumexp over all j and over j != i.  row_out[i] = (lower_i, upper_i).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dib_mi_rows_kernel(const float* __restrict__ ml, int n, int E, const float* __restrict__ eps, unsigned long long seed,
+                   unsigned int step, float* __restrict__ row_out) {
+  extern __shared__ float u_s[];            // [E]
+  __shared__ float red_m[8], red_s[8], red_s2[8], s_diag;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  for (int e = tid; e < E; e += blockDim.x) {
+    float z;
+    if (eps) z = eps[(long long)i * E + e];
+    else { float nrm[4]; dib_philox_normal4(seed, step, (unsigned long long)i, 0u, (unsigned)(e >> 2), nrm); z = nrm[e & 3]; }
+    u_s[e] = fmaf(expf(0.5f * ml[(long long)i * 2 * E + E + e]), z, ml[(long long)i * 2 * E + e]);
+  }
+  __syncthreads();
+  const float cst = -0.5f * (float)E * 1.8378770664093453f;       // -E/2 log(2 pi)
+  // pass 1: log p_ij for this thread's j's, running max
+  float lmax = -INFINITY;
+  for (int j = tid; j < n; j += blockDim.x) {
+    const float* mj = ml + (long long)j * 2 * E;
+    float q = 0.f, sl = 0.f;
+    for (int e = 0; e < E; ++e) { const float lv = mj[E + e], dlt = u_s[e] - mj[e]; q = fmaf(dlt * dlt, expf(-lv), q); sl += lv; }
+    const float lp = -0.5f * q - 0.5f * sl + cst;
+    if (j == i) s_diag = lp;
+    lmax = fmaxf(lmax, lp);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if ((tid & 31) == 0) red_m[tid >> 5] = lmax;
+  __syncthreads();
+  float m = red_m[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, red_m[w]);
+  // pass 2: sums of exp(lp - m) over all j and over j != i (recomputing lp keeps registers/smem independent of n)
+  float s_all = 0.f, s_off = 0.f;
+  for (int j = tid; j < n; j += blockDim.x) {
+    const float* mj = ml + (long long)j * 2 * E;
+    float q = 0.f, sl = 0.f;
+    for (int e = 0; e < E; ++e) { const float lv = mj[E + e], dlt = u_s[e] - mj[e]; q = fmaf(dlt * dlt, expf(-lv), q); sl += lv; }
+    const float ex = expf(-0.5f * q - 0.5f * sl + cst - m);
+    s_all += ex;
+    if (j != i) s_off += ex;
+  }
+  s_all = dib_warp_sum(s_all); s_off = dib_warp_sum(s_off);
+  if ((tid & 31) == 0) { red_s[tid >> 5] = s_all; red_s2[tid >> 5] = s_off; }
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { a += red_s[w]; b += red_s2[w]; }
+    const float logn = logf((float)n);
+    row_out[2 * i] = s_diag - (m + logf(a) - logn);              // InfoNCE term      (utils.py:59-61)
+    row_out[2 * i + 1] = s_diag - (m + logf(b) - logn);          // leave-one-out term (utils.py:63-64; still / bs)
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dib_mi_mean_kernel(const float* __restrict__ row_out, int n, float* __restrict__ out2) {
+  __shared__ double red[2][8];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { a += (double)row_out[2 * i]; b += (double)row_out[2 * i + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sa = 0.0, sb2 = 0.0;
+    for (int w = 0; w < 8; ++w) { sa += red[0][w]; sb2 += red[1][w]; }
+    out2[0] = (float)(sa / n); out2[1] = (float)(sb2 / n);
+  }
+}
+
 inline unsigned nblocks(long long work, int per) { return (unsigned)((work + per - 1) / per); }
 
 }  // namespace
@@ -423,6 +496,16 @@ cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int 
                                    cudaStream_t st) {
   if (count <= 0) return cudaSuccess;
   dib_reduce_tall_kernel<<<nblocks(count, 32), 256, 0, st>>>(part, row_stride, nrows, count, scale, out);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_mi_sandwich(const float* mu_logvar, int64_t n, int E, const float* eps, uint64_t seed, uint32_t step,
+                                   float* row_scratch, float* out2, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  dib_mi_rows_kernel<<<(unsigned)n, 256, E * sizeof(float), st>>>(mu_logvar, (int)n, E, eps, seed, step, row_scratch);
+  dib_note_launch();
+  dib_mi_mean_kernel<<<1, 256, 0, st>>>(row_scratch, (int)n, out2);
   dib_note_launch();
   return cudaGetLastError();
 }

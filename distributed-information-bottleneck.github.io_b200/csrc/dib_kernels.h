@@ -124,3 +124,6 @@ cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const
                            float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,
                            float* user_pred, float* wpart, int wpart_stride, float* loss_part, float* acc_part, int nblocks,
                            cudaStream_t st);
+
+cudaError_t dib_launch_mi_sandwich(const float* mu_logvar, int64_t n, int E, const float* eps, uint64_t seed, uint32_t step,
+                                   float* row_scratch, float* out2, cudaStream_t st);

@@ -36,7 +36,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // for a lone control thread that shares its scheduler with working warps: back off between polls
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+  while (!mbar_try_wait(bar, parity)) {}   // try_wait itself suspends for a bounded time; an extra nanosleep only adds hop latency
 }
 
 // ------------------------------------------------------------------------------------------------ TMA

@@ -708,3 +708,35 @@ class StashEmbeddingsCallback(Callback):
                 o = np.asarray(m.feature_encoders[i](x[:, offs[i]:offs[i + 1]]))
                 self.mus_for_later.append(o[:, :E])
                 self.logvars_for_later.append(o[:, E:])
+
+
+class InfoPerFeatureCallback(Callback):
+    """Callback to compute the information contained in each compression channel during training (models.py:188-223;
+    the shipped version passes wrong keyword names to utils -- this follows the corrected copy in nb-radial cell 5).
+    ``self.bounds`` collects [lower, upper] (nats) per feature each time it fires, feature-major like the reference."""
+
+    def __init__(self, save_frequency, tf_dataset_validation, evaluation_batch_size=None, number_evaluation_batches=None,
+                 info_bound_batch_size=1024, info_bound_number_batches=8, seed=0):
+        super().__init__()
+        self.save_frequency = save_frequency
+        data = tf_dataset_validation[0] if isinstance(tf_dataset_validation, (tuple, list)) else tf_dataset_validation
+        self.x_validation = data                                     # the reference maps (x, y) -> x
+        self.bounds = []
+        self.evaluation_batch_size = evaluation_batch_size or info_bound_batch_size
+        self.number_evaluation_batches = number_evaluation_batches or info_bound_number_batches
+        self.seed = seed
+
+    def on_epoch_end(self, epoch, logs=None):
+        if (epoch % self.save_frequency) != 0:
+            return
+        from . import utils
+        m = self.model
+        x = self.x_validation
+        xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        offs = np.cumsum([0] + list(m.feature_dimensionalities))
+        for i in range(m.number_features):
+            lo_up = utils.estimate_mi_sandwich_bounds(m.feature_encoders[i], xt[:, offs[i]:offs[i + 1]],
+                                                      evaluation_batch_size=self.evaluation_batch_size,
+                                                      number_evaluation_batches=self.number_evaluation_batches,
+                                                      seed=self.seed + epoch)
+            self.bounds.append([float(lo_up[0]), float(lo_up[1])])

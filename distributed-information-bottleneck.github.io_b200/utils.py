@@ -67,3 +67,44 @@ def compression_matrix(feature_encoder, feature_inps):
         _lib.check(lib.dib_bhattacharyya(_lib.ptr(o), n, E, _lib.ptr(dist), _lib.ptr(comp),
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return comp.cpu().numpy(), dist.cpu().numpy()
+
+
+def mi_sandwich_batch(mu_logvar, eps=None, seed=0, step=0):
+    """One batch of utils.py:36-65 on the GPU (dib_mi_sandwich_bounds): (InfoNCE lower, leave-one-out upper) in nats.
+    ``mu_logvar`` [n, 2E] on the device; ``eps`` [n, E] or None (Philox)."""
+    lib = _lib.load()
+    n, E = mu_logvar.shape[0], mu_logvar.shape[1] // 2
+    dev = mu_logvar.device
+    scratch = torch.empty(2 * n, dtype=torch.float32, device=dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    e = None if eps is None else _dev(eps, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dib_mi_sandwich_bounds(_lib.ptr(mu_logvar), n, E, _lib.ptr(e), int(seed), int(step) & 0xFFFFFFFF,
+                                              _lib.ptr(scratch), _lib.ptr(out),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
+
+
+def estimate_mi_sandwich_bounds(encoder, dataset, evaluation_batch_size=1024, number_evaluation_batches=8, seed=0):
+    """utils.py:10-73: upper and lower bounds of the information transmitted by one feature encoder.
+
+    ``encoder`` is ``model.feature_encoders[i]``; ``dataset`` the rows of that feature ([N, d_i] array or tensor; a
+    ``(x, y)`` tuple is accepted and y dropped, as the reference's callback does).  Batches are drawn like the
+    reference's ``repeat().shuffle().batch().take()``: ``number_evaluation_batches`` batches of
+    ``evaluation_batch_size`` rows sampled (with our seeded RNG; the reference's shuffle is unseeded) from the
+    repeated data.  Returns np.array([lower, upper]) in nats, the mean over batches."""
+    if isinstance(dataset, (tuple, list)):
+        dataset = dataset[0]
+    model = encoder._model
+    x = _dev(dataset, model.device)
+    if x.dim() == 1:
+        x = x[:, None]
+    N = x.shape[0]
+    gen = torch.Generator(device=model.device)
+    gen.manual_seed(int(seed))
+    outs = []
+    for b in range(int(number_evaluation_batches)):
+        idx = torch.randint(0, N, (int(evaluation_batch_size),), generator=gen, device=model.device)
+        o = model._encode_feature(encoder.index, x.index_select(0, idx))
+        outs.append(mi_sandwich_batch(o, None, seed=(int(seed) << 8) + encoder.index, step=b))
+    return torch.stack(outs).mean(0).double().cpu().numpy()

@@ -136,6 +136,12 @@ int dib_metrics_update(const float* stats, const float* beta_dev, float* acc, in
 int dib_bhattacharyya(const float* mu_logvar, int64_t n, int32_t embedding_dimension,
                       float* out_dist, float* out_compression, void* stream);
 
+/* NEXT ROW f1 -- utils.estimate_mi_sandwich_bounds' per-batch kernel (utils.py:36-65): InfoNCE lower and leave-one-out
+ * upper bound (nats) of I(U;X) for one encoder on one batch of n samples.  mu_logvar [n, 2E] (dib_encode_feature
+ * output); eps [n, E] or NULL -> Philox(seed, step, row, feature 0, dim); row_scratch [2n] floats; out [2]. */
+int dib_mi_sandwich_bounds(const float* mu_logvar, int64_t n, int32_t embedding_dimension, const float* eps, uint64_t seed,
+                           uint32_t step, float* row_scratch, float* out_lower_upper, void* stream);
+
 /* ---- observability (no reference counterpart) ---------------------------------------------------------
  * dib_launch_count: kernels launched by this library in this process.
  * dib_profile_enable(h,1): bracket every launch group of subsequent forward/train_step calls with CUDA events

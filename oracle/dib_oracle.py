@@ -456,3 +456,43 @@ def boolean_circuit_truth_table():
     x = 2 * tt[:, :10] - 1                                             # data.py:56
     y = tt[:, -1]
     return x.astype(np.float32), y.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# next row f1: InfoNCE / leave-one-out sandwich bounds on I(U;X) of one encoder (utils.py:10-73)
+# ----------------------------------------------------------------------------------------------
+def mi_sandwich_batch(mu, logvar, eps):
+    """utils.py:36-65 ``compute_batch`` with the sample u = mu + exp(logvar/2)*eps explicit, evaluated in log space
+    (the reference forms the densities directly in float64; identical up to underflow):
+        log p(u_i|x_j) = -1/2 sum_e ((u_i - mu_j)/sigma_j)^2 - 1/2 sum_e logvar_j - E/2 log(2 pi)          (:48-57)
+        InfoNCE lower  = mean_i [ log p_ii - log mean_j p_ij ]                                            (:59-61)
+        LOO upper      = mean_i [ log p_ii - log ( (1/bs) sum_{j != i} p_ij ) ]    (diagonal zeroed, still /bs; :63-64)
+    Returns (lower, upper) in nats."""
+    mu, logvar, eps = [np.asarray(a, dtype=np.float64) for a in (mu, logvar, eps)]
+    bs, E = mu.shape
+    sig = np.exp(logvar / 2.0)
+    u = mu + sig * eps
+    nd = (u[:, None, :] - mu[None, :, :]) / sig[None, :, :]
+    logp = -0.5 * (nd ** 2).sum(-1) - 0.5 * logvar.sum(-1)[None, :] - 0.5 * E * np.log(2.0 * np.pi)
+    diag = np.diag(logp)
+
+    def lse(a):
+        m = a.max(axis=1, keepdims=True)
+        return (m + np.log(np.exp(a - m).sum(axis=1, keepdims=True)))[:, 0]
+    lower = np.mean(diag - (lse(logp) - np.log(bs)))
+    off = logp.copy()
+    off[np.arange(bs), np.arange(bs)] = -np.inf
+    upper = np.mean(diag - (lse(off) - np.log(bs)))
+    return float(lower), float(upper)
+
+
+def estimate_mi_sandwich_bounds(cfg: DIBConfig, flat_params, feature_ind, x_i, batches, eps_list, dtype=np.float64):
+    """utils.py:10-73: average of compute_batch over the given batches (lists of row indices into x_i) with the given
+    noise; the reference draws the batches with an unseeded tf.data shuffle, so batch composition is an input here."""
+    encoders, _ = unflatten(cfg, np.asarray(flat_params, dtype=dtype))
+    E = cfg.feature_embedding_dimension
+    out = []
+    for idx, eps in zip(batches, eps_list):
+        o = encoder_forward(cfg, encoders[feature_ind], np.asarray(x_i, dtype=dtype)[idx])
+        out.append(mi_sandwich_batch(o[:, :E], o[:, E:], eps))
+    return np.mean(np.asarray(out), axis=0)

@@ -131,6 +131,24 @@ def _split(x, sizes, axis=-1):
     return np.split(x, np.cumsum(sizes)[:-1], axis=axis)
 
 
+class _Dataset:
+    """tf.data.Dataset stand-in: repeat/shuffle/batch/take over the rows of an array; the (random, unseeded in the
+    reference) shuffle is replaced by the identity so that the batches are the consecutive row blocks."""
+    def __init__(self, arr, bs=None, n=None):
+        self.arr, self.bs, self.n = arr, bs, n
+
+    def repeat(self): return self
+    def shuffle(self, _): return self
+    def batch(self, bs): return _Dataset(self.arr, bs, self.n)
+    def take(self, n): return _Dataset(self.arr, self.bs, n)
+
+    def __iter__(self):
+        N = self.arr.shape[0]
+        for b in range(self.n):
+            idx = (np.arange(self.bs) + b * self.bs) % N
+            yield self.arr[idx]
+
+
 def _random_normal(shape, mean=0.0, stddev=1.0, dtype=None):
     return mean + stddev * EPS.pop(tuple(int(s) for s in shape))
 
@@ -147,7 +165,11 @@ def install_tf_shim():
     tf.cast = lambda x, dt: np.asarray(x).astype(dt)
     tf.Variable = _Variable
     tf.function = lambda f=None, **k: f if f is not None else (lambda g: g)
-    tf.math = types.SimpleNamespace(sin=np.sin, log=lambda v: np.log(np.float32(v)))
+    tf.math = types.SimpleNamespace(sin=np.sin, log=lambda v: np.log(v) if isinstance(v, np.ndarray) and v.dtype == np.float64
+                                    else np.log(np.float32(v)))
+    tf.reshape = lambda x, shape: np.reshape(x, [int(s) for s in shape])
+    tf.eye = lambda n, dtype=None: np.eye(int(n), dtype=dtype)
+    tf.linalg = types.SimpleNamespace(diag_part=lambda x: np.diag(x).copy())   # tf tensors are immutable: no view
     tf.random = types.SimpleNamespace(normal=_random_normal)
     keras = types.SimpleNamespace(
         layers=types.SimpleNamespace(Layer=_Layer, Input=_Input, Dense=_Dense),
@@ -285,6 +307,22 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_bhattacharyya.npz"), mu=mu, lv=lv, D=D, mu2=mu2, lv2=lv2,
                         D2=D2, mu3=mu3, lv3=lv3, mu4=mu4, lv4=lv4, D34=D34)
     print("bhattacharyya KAT off-diagonal:", D2[0, 1], np.exp(-D2[0, 1]))
+
+    # --- MI sandwich bounds through the reference's utils.estimate_mi_sandwich_bounds (utils.py:10-73) ---
+    rng = np.random.default_rng(31)
+    bs, E, nb = 64, 8, 3
+    x_feat = rng.standard_normal((bs * nb, 1))
+    Wenc = rng.standard_normal((1, 2 * E)) * 0.8
+    benc = rng.standard_normal(2 * E) * 0.3
+    encoder = lambda xb: np.concatenate([np.tanh(xb @ Wenc[:, :E] + benc[:E]) * 2.0, xb @ Wenc[:, E:] * 0.3 + benc[E:] - 1.0], -1)
+    eps_mi = [rng.standard_normal((bs, E)) for _ in range(nb)]
+    EPS.q = [e.copy() for e in eps_mi]
+    bounds = utils.estimate_mi_sandwich_bounds(encoder, _Dataset(x_feat), evaluation_batch_size=bs, number_evaluation_batches=nb)
+    assert not EPS.q
+    enc_out = encoder(x_feat)
+    np.savez_compressed(os.path.join(HERE, "ref_mi_sandwich.npz"), mu=enc_out[:, :E], lv=enc_out[:, E:], eps=np.stack(eps_mi),
+                        bounds=np.asarray(bounds), bs=bs, nb=nb)
+    print("MI sandwich (nats) lower/upper:", bounds)
 
 
 if __name__ == "__main__":

@@ -256,3 +256,32 @@ def test_compression_matrix_callback(tmp_path):
     np.testing.assert_allclose(rec["compression_matrix"], ref, rtol=1e-4, atol=1e-5)
     assert os.path.exists(os.path.join(str(tmp_path), f"feature_3_log10beta_{np.log10(1e-3):.3f}.npz"))
     assert len(stash.mus_for_later) == 10 and stash.mus_for_later[0].shape == (32, 4)
+
+
+def test_mi_sandwich_bounds_kernel_and_callback(golden_dir):
+    """next row f1: dib_mi_sandwich_bounds against the reference-code golden, the oracle with explicit and with Philox
+    noise, and InfoPerFeatureCallback end to end on the Boolean circuit (binary features carry <= 1 bit each)."""
+    import dib_b200
+    from dib_b200 import utils
+    z = np.load(os.path.join(golden_dir, "ref_mi_sandwich.npz"))
+    bs, nb = int(z["bs"]), int(z["nb"])
+    dev = torch.device("cuda")
+    outs = []
+    for b in range(nb):
+        ml = torch.from_numpy(np.concatenate([z["mu"][b * bs:(b + 1) * bs], z["lv"][b * bs:(b + 1) * bs]], -1)).float().to(dev)
+        outs.append(utils.mi_sandwich_batch(ml, z["eps"][b]).cpu().numpy())
+    np.testing.assert_allclose(np.mean(outs, 0), z["bounds"], rtol=2e-5)
+    rng = np.random.default_rng(1)
+    n, E = 700, 32
+    mu, lv = rng.standard_normal((n, E)), rng.standard_normal((n, E)) * 0.5 - 1.0
+    ml = torch.from_numpy(np.concatenate([mu, lv], -1)).float().to(dev)
+    got = utils.mi_sandwich_batch(ml, None, seed=77, step=3).cpu().numpy()
+    eps = philox.normal_noise(77, 3, np.arange(n), 1, E, dtype=np.float64)[:, 0, :]
+    np.testing.assert_allclose(got, O.mi_sandwich_batch(mu.astype(np.float32), lv.astype(np.float32), eps), rtol=1e-4, atol=1e-4)
+    x, y = O.boolean_circuit_truth_table()
+    cfg = O.DIBConfig([1] * 10, [32], [32], 1, feature_embedding_dimension=8)
+    m = build_model(cfg, lr=3e-3)
+    cb = dib_b200.InfoPerFeatureCallback(1, (x, y), evaluation_batch_size=256, number_evaluation_batches=2)
+    m.fit(x, y, epochs=2, batch_size=256, callbacks=[dib_b200.InfoBottleneckAnnealingCallback(1e-4, 1e-3, 0, 2), cb])
+    bounds = np.asarray(cb.bounds).reshape(2, 10, 2) / np.log(2)
+    assert np.all(bounds[..., 0] <= bounds[..., 1] + 1e-4) and np.all(bounds[..., 0] < 1.0 + 1e-3) and np.all(bounds > -1e-3)

@@ -194,3 +194,22 @@ def test_numpy_backward_matches_torch_autograd_twin():
     np.testing.assert_allclose(twin.flat_grads().numpy(), g, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(float(total), fr.loss, rtol=1e-12)
     np.testing.assert_allclose(kls.detach().numpy(), fr.kl_per_feature, rtol=1e-12)
+
+
+def test_mi_sandwich_matches_reference_code_and_closed_forms(golden_dir):
+    """next row f1: the oracle against utils.estimate_mi_sandwich_bounds executed from the reference (golden) and two
+    closed forms: identical conditionals -> lower 0, upper log(bs/(bs-1)); k well separated clusters -> ~log k."""
+    z = np.load(os.path.join(golden_dir, "ref_mi_sandwich.npz"))
+    bs, nb = int(z["bs"]), int(z["nb"])
+    out = [O.mi_sandwich_batch(z["mu"][b * bs:(b + 1) * bs], z["lv"][b * bs:(b + 1) * bs], z["eps"][b]) for b in range(nb)]
+    np.testing.assert_allclose(np.mean(out, 0), z["bounds"], rtol=1e-10)
+    rng = np.random.default_rng(0)
+    bs, E = 32, 4
+    lo, up = O.mi_sandwich_batch(np.zeros((bs, E)), np.zeros((bs, E)), rng.standard_normal((bs, E)))
+    np.testing.assert_allclose([lo, up], [0.0, np.log(bs / (bs - 1))], atol=1e-12)
+    k, bs = 4, 512
+    lab = np.arange(bs) % k
+    mu = np.stack([np.cos(2 * np.pi * lab / k), np.sin(2 * np.pi * lab / k)], -1) * 50.0
+    lo, up = O.mi_sandwich_batch(mu, np.zeros((bs, 2)), rng.standard_normal((bs, 2)))
+    np.testing.assert_allclose(lo, np.log(k), atol=1e-6)
+    assert up >= lo - 1e-9
