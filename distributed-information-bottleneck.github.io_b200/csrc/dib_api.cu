@@ -64,6 +64,7 @@ struct dib_model {
   std::vector<DibGemmProblem> h_probs;
   int* d_col_src = nullptr;
   int* d_col_freq = nullptr;
+  int* d_col_feat = nullptr;   // feature owning each first-layer operand column (row gather of dib_compression_matrices)
   std::vector<int> enc_fwd, enc_dgrad, enc_wgrad;  // start index into d_probs per layer j
   std::vector<int> int_fwd, int_dgrad, int_wgrad;
   std::vector<int> enc_maxK;                        // max over features of fan-in of layer j
@@ -507,7 +508,7 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   for (int d : h->int_arch) if (d < 1) { delete h; return fail("dib_create: integration width < 1"); }
 
   // first-layer operand layout: per feature a zero-padded block of width round_up(d_i * nfreq, 4)
-  std::vector<int> col_src, col_freq;
+  std::vector<int> col_src, col_freq, col_feat;
   h->D = 0;
   for (int f = 0; f < h->F; ++f) {
     const int d = h->fdims[f], w = d * h->nfreq;
@@ -517,6 +518,7 @@ int dib_create(const dib_config* cfg, dib_model** out) {
     for (int blk = 0; blk < h->nfreq; ++blk)
       for (int k = 0; k < d; ++k) { col_src.push_back(h->D + k); col_freq.push_back(blk == 0 ? 0 : (1 << blk)); }
     while (col_src.size() % 4) { col_src.push_back(-1); col_freq.push_back(0); }
+    col_feat.resize(col_src.size(), f);
     h->D += d;
   }
   h->ldpe = (int)col_src.size();
@@ -552,9 +554,11 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   cudaError_t e = cudaMalloc(&h->d_probs, probs.size() * sizeof(DibGemmProblem));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_col_src, col_src.size() * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_col_freq, col_freq.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_col_feat, col_feat.size() * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_probs, probs.data(), probs.size() * sizeof(DibGemmProblem), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_col_src, col_src.data(), col_src.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_col_freq, col_freq.data(), col_freq.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_col_feat, col_feat.data(), col_feat.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     std::string msg = std::string("dib_create: CUDA error: ") + cudaGetErrorString(e);
     dib_destroy(h);
@@ -602,6 +606,7 @@ void dib_destroy(dib_model* h) {
   if (h->d_probs) cudaFree(h->d_probs);
   if (h->d_col_src) cudaFree(h->d_col_src);
   if (h->d_col_freq) cudaFree(h->d_col_freq);
+  if (h->d_col_feat) cudaFree(h->d_col_feat);
   if (h->d_fused_tables) cudaFree(h->d_fused_tables);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
@@ -813,8 +818,46 @@ int dib_mi_sandwich_bounds(const float* mu_logvar, int64_t n, int32_t embedding_
 int dib_bhattacharyya(const float* mu_logvar, int64_t n, int32_t embedding_dimension, float* out_dist,
                       float* out_compression, void* stream) {
   if (!mu_logvar || n < 0 || embedding_dimension < 1) return fail("dib_bhattacharyya: bad arguments");
-  DIB_CUDA_OK(dib_launch_bhattacharyya(mu_logvar, n, embedding_dimension, out_dist, out_compression,
-                                       static_cast<cudaStream_t>(stream)));
+  const int64_t ld = 2 * (int64_t)embedding_dimension;
+  DIB_CUDA_OK(dib_launch_pairwise_gauss(0, mu_logvar, ld, 0, n, mu_logvar, ld, 0, n, embedding_dimension, 1, out_dist,
+                                        out_compression, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int dib_pairwise_gaussian(int32_t kind, const float* mu_logvar_1, int64_t n, const float* mu_logvar_2, int64_t m,
+                          int32_t embedding_dimension, float* out, float* out_exp_neg, void* stream) {
+  if ((kind != 0 && kind != 1) || n < 0 || m < 0 || embedding_dimension < 1 ||
+      ((!mu_logvar_1 || !mu_logvar_2) && n > 0 && m > 0))
+    return fail("dib_pairwise_gaussian: bad arguments");
+  const int64_t ld = 2 * (int64_t)embedding_dimension;
+  DIB_CUDA_OK(dib_launch_pairwise_gauss(kind, mu_logvar_1, ld, 0, n, mu_logvar_2, ld, 0, m, embedding_dimension, 1, out,
+                                        out_exp_neg, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int dib_compression_matrices(dib_model* h, const float* params, const float* x, int64_t n_total, const int32_t* row_index,
+                             int64_t n, float* out_mu_logvar, float* out_dist, float* out_compression, void* workspace,
+                             void* stream) {
+  if (check_call(h, params, x, n, workspace)) return 1;
+  if (n_total < 0 || (!row_index && n > n_total) || (row_index && n > 0 && n_total < 1))
+    return fail("dib_compression_matrices: rows out of range");
+  if (n == 0) return 0;
+  Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
+  const int rnd = h->precision == DIB_PREC_TF32 ? 1 : 0;
+  if (rnd) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
+  // all F encoders as ONE grouped problem per layer (the reference loops over features in Python, visualization.py:14-35)
+  DIB_CUDA_OK(dib_launch_pe(x, h->D, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, n, rnd, c.st,
+                            row_index, h->d_col_feat, n_total));
+  for (int j = 0; j <= h->L; ++j)
+    if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j], h->F, enc_fan_out(h, j), 0, 1, 0)) return 1;
+  const float* eo = c.ws + h->enc_out.off;
+  if (out_mu_logvar)
+    for (int f = 0; f < h->F; ++f)
+      DIB_CUDA_OK(dib_launch_copy2d(eo + f * h->enc_out.feat_stride, h->enc_out.ld, out_mu_logvar + (int64_t)f * n * 2 * h->E,
+                                    2 * h->E, 2 * h->E, n, c.st));
+  if (out_dist || out_compression)
+    DIB_CUDA_OK(dib_launch_pairwise_gauss(0, eo, h->enc_out.ld, h->enc_out.feat_stride, n, eo, h->enc_out.ld,
+                                          h->enc_out.feat_stride, n, h->E, h->F, out_dist, out_compression, c.st));
   return 0;
 }
 

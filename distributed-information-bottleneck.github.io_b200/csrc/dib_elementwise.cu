@@ -28,7 +28,8 @@ __device__ __forceinline__ float block_sum_256(float v, float* smem8) {
 // ------------------------------------------------------------------------------------------------
 __global__ void dib_pe_kernel(const float* __restrict__ x, int ldx, int x_col_shift, const int* __restrict__ col_src,
                               const int* __restrict__ col_freq, int col_begin, int ncols, float* __restrict__ pe,
-                              int ldpe, int pe_col_shift, long long n, int round_out) {
+                              int ldpe, int pe_col_shift, long long n, int round_out,
+                              const int* __restrict__ row_index, const int* __restrict__ col_feat, long long n_src) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * ncols) return;
   const long long row = idx / ncols;
@@ -36,7 +37,12 @@ __global__ void dib_pe_kernel(const float* __restrict__ x, int ldx, int x_col_sh
   const int src = col_src[col];
   float v = 0.f;
   if (src >= 0) {
-    const float xv = x[row * ldx + (src - x_col_shift)];
+    long long srow = row;
+    if (row_index) {   // per-feature row gather (visualization.py:17-28 picks different rows for every feature)
+      srow = row_index[(long long)col_feat[col] * n + row];
+      srow = srow < 0 ? 0 : (srow >= n_src ? n_src - 1 : srow);
+    }
+    const float xv = x[srow * ldx + (src - x_col_shift)];
     const int f = col_freq[col];
     v = f == 0 ? xv : sinf((float)f * xv);
   }
@@ -278,26 +284,41 @@ dib_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __res
 __global__ void dib_inc_step_kernel(int32_t* step_dev) { step_dev[0] += 1; }
 
 // ------------------------------------------------------------------------------------------------
-// utils.py:177-212 in closed form, + exp(-D) (visualization.py:34).  One thread per (i, j).
+// utils.py:177-212 (Bhattacharyya, mode 0) and utils.py:213-247 (KL(1||2), mode 1) between two sets of diagonal
+// Gaussians in closed form, + exp(-D) (visualization.py:34).  One thread per (i, j); blockIdx.y = group (feature).
 // ------------------------------------------------------------------------------------------------
-__global__ void dib_bhattacharyya_kernel(const float* __restrict__ ml, long long n, int E, float* __restrict__ out_dist,
-                                         float* __restrict__ out_comp) {
+__global__ void dib_pairwise_gauss_kernel(int mode, const float* __restrict__ ml1, long long ld1, long long gstride1,
+                                          long long n, const float* __restrict__ ml2, long long ld2, long long gstride2,
+                                          long long m, int E, float* __restrict__ out_dist, float* __restrict__ out_comp) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * n) return;
-  const long long i = idx / n, j = idx % n;
-  const float* a = ml + i * 2 * E;
-  const float* b = ml + j * 2 * E;
-  float t1 = 0.f, t2 = 0.f;
-  for (int e = 0; e < E; ++e) {
-    const float d = a[e] - b[e];
-    const float la = a[E + e], lb = b[E + e];
-    const float sbar = 0.5f * (expf(la) + expf(lb));
-    t1 += d * d / sbar;
-    t2 += logf(sbar) - 0.5f * (la + lb);
+  if (idx >= n * m) return;
+  const long long g = blockIdx.y;
+  const long long i = idx / m, j = idx % m;
+  const float* a = ml1 + g * gstride1 + i * ld1;
+  const float* b = ml2 + g * gstride2 + j * ld2;
+  float D;
+  if (mode == 0) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int e = 0; e < E; ++e) {
+      const float d = a[e] - b[e];
+      const float la = a[E + e], lb = b[E + e];
+      const float sbar = 0.5f * (expf(la) + expf(lb));
+      t1 += d * d / sbar;
+      t2 += logf(sbar) - 0.5f * (la + lb);
+    }
+    D = 0.125f * t1 + 0.5f * t2;
+  } else {
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) {
+      const float d = b[e] - a[e];
+      const float la = a[E + e], lb = b[E + e];
+      acc += (lb - la - 1.f) + expf(la - lb) + d * d * expf(-lb);
+    }
+    D = 0.5f * acc;
   }
-  const float D = 0.125f * t1 + 0.5f * t2;
-  if (out_dist) out_dist[idx] = D;
-  if (out_comp) out_comp[idx] = expf(-D);
+  const long long o = g * n * m + idx;
+  if (out_dist) out_dist[o] = D;
+  if (out_comp) out_comp[o] = expf(-D);
 }
 
 // Keras Mean-metric aggregation over the batches of an epoch (see dib_metrics_update in dib_b200.h).
@@ -399,11 +420,12 @@ inline unsigned nblocks(long long work, int per) { return (unsigned)((work + per
 
 cudaError_t dib_launch_pe(const float* x, int ldx, int x_col_shift, const int* col_src, const int* col_freq,
                           int col_begin, int col_end, float* pe, int ldpe, int pe_col_shift, int64_t n, int round_out,
-                          cudaStream_t st) {
+                          cudaStream_t st, const int* row_index, const int* col_feat, int64_t n_src) {
   const int ncols = col_end - col_begin;
   if (n <= 0 || ncols <= 0) return cudaSuccess;
   dib_pe_kernel<<<nblocks((long long)n * ncols, 256), 256, 0, st>>>(x, ldx, x_col_shift, col_src, col_freq, col_begin,
-                                                                   ncols, pe, ldpe, pe_col_shift, n, round_out);
+                                                                   ncols, pe, ldpe, pe_col_shift, n, round_out,
+                                                                   row_index, col_feat, n_src);
   dib_note_launch();
   return cudaGetLastError();
 }
@@ -471,10 +493,12 @@ cudaError_t dib_launch_adam(float* params, const float* grads, float* m, float* 
   return cudaGetLastError();
 }
 
-cudaError_t dib_launch_bhattacharyya(const float* mu_logvar, int64_t n, int E, float* out_dist, float* out_comp,
-                                     cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
-  dib_bhattacharyya_kernel<<<nblocks((long long)n * n, 128), 128, 0, st>>>(mu_logvar, n, E, out_dist, out_comp);
+cudaError_t dib_launch_pairwise_gauss(int mode, const float* ml1, int64_t ld1, int64_t gstride1, int64_t n,
+                                      const float* ml2, int64_t ld2, int64_t gstride2, int64_t m, int E, int groups,
+                                      float* out_dist, float* out_comp, cudaStream_t st) {
+  if (n <= 0 || m <= 0 || groups <= 0) return cudaSuccess;
+  dim3 grid(nblocks((long long)n * m, 128), groups);
+  dib_pairwise_gauss_kernel<<<grid, 128, 0, st>>>(mode, ml1, ld1, gstride1, n, ml2, ld2, gstride2, m, E, out_dist, out_comp);
   dib_note_launch();
   return cudaGetLastError();
 }

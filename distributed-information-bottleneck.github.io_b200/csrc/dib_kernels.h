@@ -35,7 +35,8 @@ cudaError_t dib_launch_gemm_tc(int mode, const DibGemmLaunch& L, const DibGemmPr
 // positional encoding (models.py:22-23) into the padded first-layer operand; tables are per pe column.
 cudaError_t dib_launch_pe(const float* x, int ldx, int x_col_shift, const int* col_src, const int* col_freq,
                           int col_begin, int col_end, float* pe, int ldpe, int pe_col_shift, int64_t n,
-                          int round_out, cudaStream_t st);
+                          int round_out, cudaStream_t st, const int* row_index = nullptr,
+                          const int* col_feat = nullptr, int64_t n_src = 0);
 
 struct DibReparamArgs {
   const float* enc_out;    // [F][feat_stride] rows of ldo floats: (mu[E] | logvar[E] | pad)
@@ -73,8 +74,11 @@ cudaError_t dib_launch_copy2d(const float* src, int lds, float* dst, int ldd, in
 cudaError_t dib_launch_adam(float* params, const float* grads, float* m, float* v, int64_t count,
                             const float* lr_dev, int32_t* step_dev, float b1, float b2, float eps, cudaStream_t st);
 
-cudaError_t dib_launch_bhattacharyya(const float* mu_logvar, int64_t n, int E, float* out_dist, float* out_comp,
-                                     cudaStream_t st);
+// mode 0: Bhattacharyya distance, 1: KL(1||2); ml* rows are (mu[E] | logvar[E]) with leading dimension ld*, `groups`
+// independent problems gstride* floats apart; outputs [groups, n, m].
+cudaError_t dib_launch_pairwise_gauss(int mode, const float* ml1, int64_t ld1, int64_t gstride1, int64_t n,
+                                      const float* ml2, int64_t ld2, int64_t gstride2, int64_t m, int E, int groups,
+                                      float* out_dist, float* out_comp, cudaStream_t st);
 
 cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st);
 

@@ -348,6 +348,35 @@ class DistributedIBNet:
                                                     _lib.ptr(out), _lib.ptr(self._workspace), _stream()))
         return out
 
+    def compression_matrices(self, x, row_index=None, want=("mu_logvar", "dist", "comp")):
+        """All features at once (dib_compression_matrices; visualization.py:14-35 loops over features in Python):
+        rows ``row_index[i]`` of ``x`` -> encoder i -> Bhattacharyya -> exp(-D).  ``row_index``: [F, n] integer array or
+        None (= all rows of x for every feature).  Returns a dict of device tensors for the names in ``want``:
+        mu_logvar [F, n, 2E], dist [F, n, n], comp [F, n, n]."""
+        t = self._to_device(x, sum(self.feature_dimensionalities))
+        F, E = self.number_features, self.feature_embedding_dimension
+        if row_index is None:
+            n, idx = t.shape[0], None
+        else:
+            idx = torch.as_tensor(np.ascontiguousarray(row_index), dtype=torch.int32).to(self.device).contiguous()
+            if idx.dim() != 2 or idx.shape[0] != F:
+                raise ValueError("row_index must have shape [number_features, n]")
+            n = idx.shape[1]
+        self._ensure_handle(max(n, 1))
+        out = {}
+        if "mu_logvar" in want:
+            out["mu_logvar"] = torch.empty(F, n, 2 * E, dtype=torch.float32, device=self.device)
+        if "dist" in want:
+            out["dist"] = torch.empty(F, n, n, dtype=torch.float32, device=self.device)
+        if "comp" in want:
+            out["comp"] = torch.empty(F, n, n, dtype=torch.float32, device=self.device)
+        opt = lambda k: _lib.ptr(out[k]) if k in out else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dib_compression_matrices(self._handle, _lib.ptr(self._params), _lib.ptr(t), t.shape[0],
+                                                          _lib.ptr(idx) if idx is not None else None, n, opt("mu_logvar"),
+                                                          opt("dist"), opt("comp"), _lib.ptr(self._workspace), _stream()))
+        return out
+
     def _backward(self, x, y, global_batch, eps=None, sample_offset=0, step=None):
         """dib_train_step: forward + reverse mode into self._gradstats = [grads (P) || stats (F+3)]."""
         n = x.shape[0]
@@ -650,8 +679,8 @@ class InfoBottleneckAnnealingCallback(Callback):
 class SaveCompressionMatricesCallback(Callback):
     """Callback to save compression scheme matrices during training (models.py:152-186; the intended behaviour is
     the inline copy at train.py:251-261 -- the shipped on_epoch_end raises NameError).  For every feature: pick
-    <=128 rows as visualization.py:17-28 does, encoder forward, Bhattacharyya matrix, exp(-D) (all on the GPU via
-    dib_encode_feature + dib_bhattacharyya).  The reference renders a PNG with matplotlib, which is not available
+    <=128 rows as visualization.py:17-28 does, encoder forward, Bhattacharyya matrix, exp(-D) (all features in one
+    device call, dib_compression_matrices).  The reference renders a PNG with matplotlib, which is not available
     here; the numeric artefact is saved as ``feature_{i}_log10beta_{x:.3f}.npz`` (same stem) and kept in
     ``self.matrices``."""
 
@@ -676,12 +705,17 @@ class SaveCompressionMatricesCallback(Callback):
         offs = np.cumsum([0] + list(model.feature_dimensionalities))
         if self.outdir:
             os.makedirs(self.outdir, exist_ok=True)
-        for i in range(model.number_features):
-            feat, raw = xp[:, offs[i]:offs[i + 1]], xr[:, offs[i]:offs[i + 1]]
-            inds, sorted_raw = utils.select_display_rows(raw, self.max_number_to_display, self.rng)
-            comp, dist = utils.compression_matrix(model.feature_encoders[i], feat[inds])
-            rec = dict(epoch=epoch, feature=i, beta=beta_value, compression_matrix=comp, bhattacharyya=dist,
-                       raw_values=sorted_raw)
+        # row selection per feature on the host (visualization.py:17-28), then ONE device call for all features
+        picks = [utils.select_display_rows(xr[:, offs[i]:offs[i + 1]], self.max_number_to_display, self.rng)
+                 for i in range(model.number_features)]
+        n = max(len(inds) for inds, _ in picks)
+        row_index = np.stack([np.concatenate([inds, np.full(n - len(inds), inds[-1])]) for inds, _ in picks])
+        res = model.compression_matrices(xp, row_index, want=("dist", "comp"))
+        comp_all, dist_all = res["comp"].cpu().numpy(), res["dist"].cpu().numpy()
+        for i, (inds, sorted_raw) in enumerate(picks):
+            k = len(inds)
+            rec = dict(epoch=epoch, feature=i, beta=beta_value, compression_matrix=comp_all[i, :k, :k],
+                       bhattacharyya=dist_all[i, :k, :k], raw_values=sorted_raw)
             self.matrices.append(rec)
             if self.outdir:
                 np.savez(os.path.join(self.outdir, f'feature_{i}_log10beta_{np.log10(beta_value):.3f}.npz'), **rec)
@@ -701,13 +735,11 @@ class StashEmbeddingsCallback(Callback):
     def on_epoch_end(self, epoch, logs=None):
         if (epoch > self.save_start) and ((epoch % self.save_frequency) == 0):
             m = self.model
-            x = np.asarray(self.x_in.cpu() if isinstance(self.x_in, torch.Tensor) else self.x_in)
-            offs = np.cumsum([0] + list(m.feature_dimensionalities))
             E = m.feature_embedding_dimension
+            o = m.compression_matrices(self.x_in, None, want=("mu_logvar",))["mu_logvar"].cpu().numpy()
             for i in range(m.number_features):
-                o = np.asarray(m.feature_encoders[i](x[:, offs[i]:offs[i + 1]]))
-                self.mus_for_later.append(o[:, :E])
-                self.logvars_for_later.append(o[:, E:])
+                self.mus_for_later.append(o[i, :, :E])
+                self.logvars_for_later.append(o[i, :, E:])
 
 
 class InfoPerFeatureCallback(Callback):

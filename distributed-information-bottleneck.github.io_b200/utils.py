@@ -15,29 +15,34 @@ def _dev(a, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
-def bhattacharyya_dist_mat(mus1, logvars1, mus2=None, logvars2=None, device=None):
-    """utils.py:177-212 (Bhattacharyya distances between diagonal Gaussians) on the GPU via dib_bhattacharyya.
-    The CUDA kernel computes the square self-distance matrix of one set (the only way the reference calls it,
-    visualization.py:33); for two different sets the rows are stacked and the off-diagonal block returned."""
+def _pairwise(kind, mus1, logvars1, mus2, logvars2, device):
     if not torch.cuda.is_available():
         raise _lib.DibError("dib_b200 needs a CUDA device; there is no CPU path")
     lib = _lib.load()
-    device = device or torch.device("cuda", torch.cuda.current_device())
-    m1, l1 = _dev(mus1, device), _dev(logvars1, device)
+    device = device or (mus1.device if isinstance(mus1, torch.Tensor) and mus1.is_cuda
+                        else torch.device("cuda", torch.cuda.current_device()))
+    ml1 = torch.cat([_dev(mus1, device), _dev(logvars1, device)], dim=1).contiguous()
     same = mus2 is None or (mus2 is mus1 and logvars2 is logvars1)
-    if same:
-        ml = torch.cat([m1, l1], dim=1).contiguous()
-    else:
-        m2, l2 = _dev(mus2, device), _dev(logvars2, device)
-        ml = torch.cat([torch.cat([m1, l1], dim=1), torch.cat([m2, l2], dim=1)], dim=0).contiguous()
-    n, E = ml.shape[0], m1.shape[1]
-    out = torch.empty(n, n, dtype=torch.float32, device=device)
+    ml2 = ml1 if same else torch.cat([_dev(mus2, device), _dev(logvars2, device)], dim=1).contiguous()
+    if ml1.shape[1] != ml2.shape[1]:
+        raise ValueError("embedding dimensions differ")
+    n, m, E = ml1.shape[0], ml2.shape[0], ml1.shape[1] // 2
+    out = torch.empty(n, m, dtype=torch.float32, device=device)
     with torch.cuda.device(device):
-        _lib.check(lib.dib_bhattacharyya(_lib.ptr(ml), n, E, _lib.ptr(out), None,
-                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-    if not same:
-        out = out[:m1.shape[0], m1.shape[0]:]
+        _lib.check(lib.dib_pairwise_gaussian(kind, _lib.ptr(ml1), n, _lib.ptr(ml2), m, E, _lib.ptr(out), None,
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return out if isinstance(mus1, torch.Tensor) else out.cpu().numpy()
+
+
+def bhattacharyya_dist_mat(mus1, logvars1, mus2=None, logvars2=None, device=None):
+    """utils.py:177-212 (Bhattacharyya distances between diagonal Gaussians, [N, M]) on the GPU in the O(N*M*E)
+    closed form (dib_pairwise_gaussian kind 0)."""
+    return _pairwise(0, mus1, logvars1, mus2, logvars2, device)
+
+
+def kl_divergence_mat(mus1, logvars1, mus2=None, logvars2=None, device=None):
+    """utils.py:213-247: KL(N(mus1_i, e^logvars1_i) || N(mus2_j, e^logvars2_j)), [N, M] (dib_pairwise_gaussian kind 1)."""
+    return _pairwise(1, mus1, logvars1, mus2, logvars2, device)
 
 
 def select_display_rows(inp_features_raw, max_number_to_display=128, rng=None):

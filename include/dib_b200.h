@@ -136,6 +136,22 @@ int dib_metrics_update(const float* stats, const float* beta_dev, float* acc, in
 int dib_bhattacharyya(const float* mu_logvar, int64_t n, int32_t embedding_dimension,
                       float* out_dist, float* out_compression, void* stream);
 
+/* NEXT ROW f2 -- pairwise closed forms between two sets of diagonal Gaussians, rows (mu || logvar):
+ *   kind 0: utils.bhattacharyya_dist_mat(mus1, logvars1, mus2, logvars2)  (utils.py:177-212)
+ *   kind 1: utils.kl_divergence_mat(mus1, logvars1, mus2, logvars2) = KL(N1_i || N2_j)  (utils.py:213-247)
+ * mu_logvar_1 [n, 2E], mu_logvar_2 [m, 2E] -> out [n, m] and/or out_exp_neg [n, m] = exp(-out) (either may be NULL). */
+int dib_pairwise_gaussian(int32_t kind, const float* mu_logvar_1, int64_t n, const float* mu_logvar_2, int64_t m,
+                          int32_t embedding_dimension, float* out, float* out_exp_neg, void* stream);
+
+/* NEXT ROW f2 -- visualization.save_compression_matrices (visualization.py:14-35) / SaveCompressionMatricesCallback
+ * (models.py:152-186) / StashEmbeddingsCallback (nb-radial cell 5) for ALL features in one call: for feature i take
+ * rows row_index[i, 0..n) of x [n_total, sum d_i] (row_index: device int32 [F, n], NULL = rows 0..n-1 for every
+ * feature), run encoder i without noise, then Bhattacharyya and exp(-D).  Outputs (each may be NULL):
+ * out_mu_logvar [F, n, 2E], out_dist [F, n, n], out_compression [F, n, n].  n <= config.max_batch. */
+int dib_compression_matrices(dib_model* h, const float* params, const float* x, int64_t n_total,
+                             const int32_t* row_index, int64_t n, float* out_mu_logvar, float* out_dist,
+                             float* out_compression, void* workspace, void* stream);
+
 /* NEXT ROW f1 -- utils.estimate_mi_sandwich_bounds' per-batch kernel (utils.py:36-65): InfoNCE lower and leave-one-out
  * upper bound (nats) of I(U;X) for one encoder on one batch of n samples.  mu_logvar [n, 2E] (dib_encode_feature
  * output); eps [n, E] or NULL -> Philox(seed, step, row, feature 0, dim); row_scratch [2n] floats; out [2]. */

@@ -433,6 +433,34 @@ def bhattacharyya_dist_mat(mus1, logvars1, mus2, logvars2):
     return term1 + term2
 
 
+def kl_divergence_mat(mus1, logvars1, mus2, logvars2):
+    """utils.py:213-247 in closed form: KL(N1_i || N2_j) =
+       1/2 [ sum lv2_j - sum lv1_i - E + sum_e exp(lv1_i - lv2_j) + sum_e (mu2_j - mu1_i)^2 exp(-lv2_j) ]."""
+    mus1, logvars1, mus2, logvars2 = [np.asarray(a, dtype=np.float64) for a in (mus1, logvars1, mus2, logvars2)]
+    E = mus1.shape[1]
+    d = mus2[None, :, :] - mus1[:, None, :]
+    term1 = np.exp(logvars1[:, None, :] - logvars2[None, :, :]).sum(-1)
+    term2 = (d * d * np.exp(-logvars2)[None, :, :]).sum(-1)
+    return 0.5 * (logvars2.sum(-1)[None, :] - logvars1.sum(-1)[:, None] - E + term1 + term2)
+
+
+def compression_matrices(cfg: DIBConfig, flat_params, x, row_index=None, dtype=np.float64):
+    """visualization.save_compression_matrices (visualization.py:14-35) for every feature: rows row_index[i] of x
+    -> encoder i -> Bhattacharyya -> exp(-D).  Returns (mu_logvar [F,n,2E], dist [F,n,n], comp [F,n,n])."""
+    encoders, _ = unflatten(cfg, np.asarray(flat_params, dtype=dtype))
+    x = np.asarray(x, dtype=dtype)
+    E = cfg.feature_embedding_dimension
+    offs = np.cumsum([0] + list(cfg.feature_dimensionalities))
+    outs, dists = [], []
+    for i in range(cfg.number_features):
+        rows = x if row_index is None else x[np.asarray(row_index[i])]
+        o = encoder_forward(cfg, encoders[i], rows[:, offs[i]:offs[i + 1]])
+        outs.append(o)
+        dists.append(bhattacharyya_dist_mat(o[:, :E], o[:, E:], o[:, :E], o[:, E:]))
+    dists = np.stack(dists)
+    return np.stack(outs), dists, np.exp(-dists)
+
+
 def compression_matrix(cfg: DIBConfig, flat_params, feature_ind, x_rows, dtype=np.float64):
     """visualization.py:31-34: encoder forward (no noise) -> Bhattacharyya -> exp(-D)."""
     encoders, _ = unflatten(cfg, np.asarray(flat_params, dtype=dtype))

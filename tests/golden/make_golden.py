@@ -308,6 +308,16 @@ def main():
                         D2=D2, mu3=mu3, lv3=lv3, mu4=mu4, lv4=lv4, D34=D34)
     print("bhattacharyya KAT off-diagonal:", D2[0, 1], np.exp(-D2[0, 1]))
 
+    # --- KL matrix through the reference's utils.kl_divergence_mat (utils.py:213-247) ---
+    rng = np.random.default_rng(22)
+    kmu1, klv1 = rng.standard_normal((9, 6)), rng.standard_normal((9, 6)) * 0.6
+    kmu2, klv2 = rng.standard_normal((4, 6)), rng.standard_normal((4, 6)) * 0.6 - 0.3
+    KL12 = utils.kl_divergence_mat(kmu1, klv1, kmu2, klv2)
+    KL11 = utils.kl_divergence_mat(kmu1, klv1, kmu1, klv1)
+    np.savez_compressed(os.path.join(HERE, "ref_kl_divergence.npz"), mu1=kmu1, lv1=klv1, mu2=kmu2, lv2=klv2, KL12=KL12,
+                        KL11=KL11)
+    print("kl_divergence_mat[0,:3]:", KL12[0, :3])
+
     # --- MI sandwich bounds through the reference's utils.estimate_mi_sandwich_bounds (utils.py:10-73) ---
     rng = np.random.default_rng(31)
     bs, E, nb = 64, 8, 3

@@ -258,6 +258,39 @@ def test_compression_matrix_callback(tmp_path):
     assert len(stash.mus_for_later) == 10 and stash.mus_for_later[0].shape == (32, 4)
 
 
+def test_kl_divergence_mat_matches_reference_golden(golden_dir):
+    """next row f2: utils.kl_divergence_mat (utils.py:213-247) through dib_pairwise_gaussian."""
+    from dib_b200 import utils
+    z = np.load(os.path.join(golden_dir, "ref_kl_divergence.npz"))
+    np.testing.assert_allclose(utils.kl_divergence_mat(z["mu1"], z["lv1"], z["mu2"], z["lv2"]), z["KL12"], rtol=3e-5, atol=3e-5)
+    K11 = utils.kl_divergence_mat(z["mu1"], z["lv1"])
+    np.testing.assert_allclose(K11, z["KL11"], rtol=3e-5, atol=3e-5)
+    np.testing.assert_allclose(np.diag(K11), 0, atol=1e-5)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 5e-3)])
+def test_compression_matrices_all_features_in_one_call(precision, tol):
+    """next row f2: dib_compression_matrices (all encoders as one grouped problem + batched Bhattacharyya) against the
+    oracle's per-feature loop (visualization.py:14-35), with per-feature row gathers and without."""
+    rng = np.random.default_rng(5)
+    cfg = O.DIBConfig([2, 1, 3, 1], [64, 32], [32], 1, feature_embedding_dimension=8)
+    m = build_model(cfg, precision=precision, seed=3)
+    x = rng.standard_normal((300, 7)).astype(np.float32)
+    row_index = np.stack([rng.choice(300, 96) for _ in range(4)])
+    got = m.compression_matrices(x, row_index)
+    ml, dist, comp = O.compression_matrices(cfg, m.get_flat_weights(), x, row_index)
+    assert rel_err(got["mu_logvar"].cpu().numpy(), ml) < tol
+    np.testing.assert_allclose(got["comp"].cpu().numpy(), comp, atol=10 * tol)
+    if precision == "fp32":
+        np.testing.assert_allclose(got["dist"].cpu().numpy(), dist, rtol=1e-4, atol=1e-4)
+    got = m.compression_matrices(x[:50], None, want=("mu_logvar",))
+    assert set(got) == {"mu_logvar"}
+    assert rel_err(got["mu_logvar"].cpu().numpy(), O.compression_matrices(cfg, m.get_flat_weights(), x[:50])[0]) < tol
+    for i in range(4):                                                   # same numbers as the per-feature a15 contract
+        o = m.feature_encoders[i](x[:50, sum(cfg.feature_dimensionalities[:i]):sum(cfg.feature_dimensionalities[:i + 1])])
+        np.testing.assert_allclose(np.asarray(o), got["mu_logvar"][i].cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
 def test_mi_sandwich_bounds_kernel_and_callback(golden_dir):
     """next row f1: dib_mi_sandwich_bounds against the reference-code golden, the oracle with explicit and with Philox
     noise, and InfoPerFeatureCallback end to end on the Boolean circuit (binary features carry <= 1 bit each)."""

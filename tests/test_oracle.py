@@ -55,6 +55,22 @@ def test_kl_closed_form_kat():
     np.testing.assert_allclose(per_row.mean(), 1.98746673, rtol=1e-8)
 
 
+def test_kl_divergence_mat_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_kl_divergence.npz"))
+    np.testing.assert_allclose(O.kl_divergence_mat(z["mu1"], z["lv1"], z["mu2"], z["lv2"]), z["KL12"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(O.kl_divergence_mat(z["mu1"], z["lv1"], z["mu1"], z["lv1"]), z["KL11"], rtol=1e-10, atol=1e-11)
+
+
+def test_compression_matrices_agree_with_single_feature_path():
+    rng = np.random.default_rng(2)
+    cfg = O.DIBConfig([2, 1], [8], [8], 1, feature_embedding_dimension=4)
+    p = O.glorot_uniform_params(cfg, np.random.default_rng(0))
+    x = rng.standard_normal((20, 3))
+    idx = np.stack([rng.choice(20, 6), rng.choice(20, 6)])
+    _, _, comp = O.compression_matrices(cfg, p, x, idx)
+    np.testing.assert_allclose(comp[1], O.compression_matrix(cfg, p, 1, x[idx[1], 2:3]), rtol=1e-12)
+
+
 def test_bhattacharyya_golden_and_kat(golden_dir):
     z = np.load(os.path.join(golden_dir, "ref_bhattacharyya.npz"))
     np.testing.assert_allclose(O.bhattacharyya_dist_mat(z["mu"], z["lv"], z["mu"], z["lv"]), z["D"], rtol=1e-9, atol=1e-10)
