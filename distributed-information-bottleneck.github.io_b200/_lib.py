@@ -9,7 +9,7 @@ from . import build as _build
 ABI_VERSION = 1
 
 ACTIVATIONS = {None: 0, "linear": 0, "relu": 1, "tanh": 2, "leaky_relu": 3, "sigmoid": 4, "elu": 5}
-LOSSES = {"bce_logits": 0, "sparse_ce_logits": 1, "mse": 2}
+LOSSES = {"bce_logits": 0, "sparse_ce_logits": 1, "mse": 2, "external": 3}
 PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
 
 
@@ -54,6 +54,9 @@ SIGNATURES = {
     "dib_bhattacharyya": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "dib_pairwise_gaussian": (c_int32, [c_int32, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                         c_void_p]),
+    "dib_scaled_similarity": (c_int32, [c_int32, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p]),
+    "dib_infonce_head": (c_int32, [c_int32, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
     "dib_compression_matrices": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p]),
     "dib_mi_sandwich_bounds": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p]),

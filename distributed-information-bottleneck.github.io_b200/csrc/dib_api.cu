@@ -490,7 +490,7 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   if (cfg->activation_fn < 0 || cfg->activation_fn > DIB_ACT_ELU || cfg->output_activation_fn < 0 ||
       cfg->output_activation_fn > DIB_ACT_ELU)
     return fail("dib_create: unknown activation");
-  if (cfg->loss < 0 || cfg->loss > DIB_LOSS_MSE) return fail("dib_create: unknown loss");
+  if (cfg->loss < 0 || cfg->loss > DIB_LOSS_EXTERNAL) return fail("dib_create: unknown loss");
   dib_model* h = new (std::nothrow) dib_model();
   if (!h) return fail("dib_create: out of host memory");
   h->F = cfg->number_features; h->L = cfg->number_encoder_layers; h->Li = cfg->number_integration_layers;
@@ -591,7 +591,9 @@ int dib_create(const dib_config* cfg, dib_model** out) {
         h->fused_ok = true;
         h->fused_bwd_ok = true;
         // 16-bit integration path: hidden widths multiples of 128, last hidden width 256, narrow output head
-        bool iok = h->Li >= 1 && (h->F * h->E) % 64 == 0 && h->int_arch[h->Li - 1] == 256 && h->out <= 16;
+        // (the fused head owns the compiled loss, so a caller-owned loss takes the TF32 integration kernels)
+        bool iok = h->Li >= 1 && (h->F * h->E) % 64 == 0 && h->int_arch[h->Li - 1] == 256 && h->out <= 16 &&
+                   h->loss != DIB_LOSS_EXTERNAL;
         for (int j = 0; iok && j < h->Li; ++j) iok = h->int_arch[j] % 128 == 0 && (h->intB[j] & 3) == 0;
         h->int16_ok = iok;
       }
@@ -832,6 +834,24 @@ int dib_pairwise_gaussian(int32_t kind, const float* mu_logvar_1, int64_t n, con
   const int64_t ld = 2 * (int64_t)embedding_dimension;
   DIB_CUDA_OK(dib_launch_pairwise_gauss(kind, mu_logvar_1, ld, 0, n, mu_logvar_2, ld, 0, m, embedding_dimension, 1, out,
                                         out_exp_neg, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int dib_scaled_similarity(int32_t kind, const float* e1, int64_t n, const float* e2, int64_t m, int32_t d, float temperature,
+                          float* out, void* stream) {
+  if (kind < 0 || kind > 4 || n < 0 || m < 0 || d < 1 || !(temperature > 0.f) || ((!e1 || !e2 || !out) && n > 0 && m > 0))
+    return fail("dib_scaled_similarity: bad arguments");
+  DIB_CUDA_OK(dib_launch_similarity(kind, e1, n, e2, m, d, temperature, out, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int dib_infonce_head(int32_t kind, const float* e1, const float* e2, int64_t n, int32_t d, float temperature, float* scratch,
+                     float* out_loss, float* d_e1, float* d_e2, void* stream) {
+  if (kind < 0 || kind > 4 || n < 1 || n > 32768 || d < 1 || d > 512 || !(temperature > 0.f) || !e1 || !e2 || !scratch ||
+      !out_loss)
+    return fail("dib_infonce_head: bad arguments (1 <= n <= 32768, 1 <= d <= 512, temperature > 0)");
+  DIB_CUDA_OK(dib_launch_infonce_head(kind, e1, e2, n, d, temperature, scratch, out_loss, d_e1, d_e2,
+                                      static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -135,7 +135,12 @@ dib_loss_kernel(int loss, int out_act, float alpha, const float* __restrict__ pr
     float* dz = d_pred ? d_pred + row * ldp : nullptr;
     if (user_pred)
       for (int j = 0; j < out_dim; ++j) user_pred[row * out_dim + j] = z[j];
-    if (y) {
+    if (y && loss == DIB_LOSS_EXTERNAL) {
+      // the caller's d(task loss)/d(prediction); only the output activation's derivative is applied here
+      if (dz)
+        for (int j = 0; j < out_dim; ++j)
+          dz[j] = dib_maybe_round(y[row * out_dim + j] * dib_act_grad(out_act, z[j], alpha), round_out);
+    } else if (y) {
       const float inv_out = 1.f / (float)out_dim;
       if (loss == DIB_LOSS_SPARSE_CE_LOGITS) {
         const int label = (int)y[row];

@@ -80,6 +80,12 @@ cudaError_t dib_launch_pairwise_gauss(int mode, const float* ml1, int64_t ld1, i
                                       const float* ml2, int64_t ld2, int64_t gstride2, int64_t m, int E, int groups,
                                       float* out_dist, float* out_comp, cudaStream_t st);
 
+// next row f3 (dib_infonce.cu): kind 0 l2sq | 1 l2 | 2 l1 | 3 linf | 4 cosine
+cudaError_t dib_launch_similarity(int kind, const float* e1, int64_t n, const float* e2, int64_t m, int d, float temperature,
+                                  float* out, cudaStream_t st);
+cudaError_t dib_launch_infonce_head(int kind, const float* e1, const float* e2, int64_t n, int d, float temperature,
+                                    float* scratch, float* out_loss, float* d_e1, float* d_e2, cudaStream_t st);
+
 cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st);
 
 // ---- fused per-feature encoder kernels (dib_enc_fused.cu): x -> emb / KL without touching HBM in between ----

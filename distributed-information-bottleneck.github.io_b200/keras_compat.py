@@ -72,6 +72,8 @@ def resolve_loss(loss):
             return "mse"
         if key in ("bce_logits", "sparse_ce_logits"):
             return key
+        if key in ("external", "custom"):       # GradientTape-style loops: the caller owns the task loss
+            return "external"
     raise ValueError(f"unsupported loss {loss!r}")
 
 

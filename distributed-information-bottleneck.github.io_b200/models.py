@@ -389,6 +389,20 @@ class DistributedIBNet:
             int(sample_offset), _lib.ptr(self._gradstats), _lib.ptr(self._gradstats[P:]), _lib.ptr(self._workspace),
             _stream()))
 
+    def apply_gradients(self, flat_grads):
+        """optimizer.apply_gradients(zip(grads, model.trainable_variables)) of the custom loops (train.py:217-219,
+        nb-bool cell 6): one Keras-Adam update of the flat parameter buffer with caller-supplied gradients."""
+        g = torch.as_tensor(flat_grads, dtype=torch.float32).to(self.device).contiguous()
+        if g.numel() != self._P:
+            raise ValueError(f"expected {self._P} gradient values, got {g.numel()}")
+        opt = self.optimizer
+        self._sync_lr()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dib_adam_step(
+                _lib.ptr(self._params), _lib.ptr(g), _lib.ptr(self._m), _lib.ptr(self._v), self._P,
+                _lib.ptr(self._lr_dev), _lib.ptr(self._step_dev), opt.beta_1, opt.beta_2, opt.epsilon, _stream()))
+        self._train_step_count += 1
+
     def _train_step(self, x, y, global_batch, eps=None, sample_offset=0):
         """backward, all-reduce over the data-parallel group (one flat collective: grads || stats), Keras-Adam."""
         P = self._P

@@ -113,3 +113,53 @@ def estimate_mi_sandwich_bounds(encoder, dataset, evaluation_batch_size=1024, nu
         o = model._encode_feature(encoder.index, x.index_select(0, idx))
         outs.append(mi_sandwich_batch(o, None, seed=(int(seed) << 8) + encoder.index, step=b))
     return torch.stack(outs).mean(0).double().cpu().numpy()
+
+
+SIMILARITY_TYPES = {"l2sq": 0, "l2": 1, "l1": 2, "linf": 3, "cosine": 4}
+
+
+def _similarity_kind(similarity_type):
+    if similarity_type not in SIMILARITY_TYPES:
+        raise ValueError(f"Similarity type not implemented: {similarity_type}")      # utils.py:172
+    return SIMILARITY_TYPES[similarity_type]
+
+
+def get_scaled_similarity(embeddings1, embeddings2, similarity_type, temperature):
+    """utils.py:127-175 on the GPU (dib_scaled_similarity): [N, d], [M, d] -> [N, M] similarities / temperature."""
+    kind = _similarity_kind(similarity_type)
+    if not torch.cuda.is_available():
+        raise _lib.DibError("dib_b200 needs a CUDA device; there is no CPU path")
+    lib = _lib.load()
+    device = (embeddings1.device if isinstance(embeddings1, torch.Tensor) and embeddings1.is_cuda
+              else torch.device("cuda", torch.cuda.current_device()))
+    e1, e2 = _dev(embeddings1, device), _dev(embeddings2, device)
+    if e1.shape[1] != e2.shape[1]:
+        raise ValueError("embedding dimensions differ")
+    out = torch.empty(e1.shape[0], e2.shape[0], dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(lib.dib_scaled_similarity(kind, _lib.ptr(e1), e1.shape[0], _lib.ptr(e2), e2.shape[0], e1.shape[1],
+                                             float(temperature), _lib.ptr(out),
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out if isinstance(embeddings1, torch.Tensor) else out.cpu().numpy()
+
+
+def infonce_loss_and_grads(embeddings1, embeddings2, similarity_type, temperature, want_grads=True):
+    """The InfoNCE head of the custom loop (train.py:203-213) with its reverse mode (dib_infonce_head).
+    Returns (loss [1], d loss/d embeddings1, d loss/d embeddings2) as device tensors (grads None if not wanted)."""
+    kind = _similarity_kind(similarity_type)
+    lib = _lib.load()
+    device = (embeddings1.device if isinstance(embeddings1, torch.Tensor) and embeddings1.is_cuda
+              else torch.device("cuda", torch.cuda.current_device()))
+    e1, e2 = _dev(embeddings1, device), _dev(embeddings2, device)
+    if e1.shape != e2.shape:
+        raise ValueError("the InfoNCE loss needs two [n, d] batches of equal shape (train.py:222-223)")
+    n, d = e1.shape
+    scratch = torch.empty(n * n + 4 * n, dtype=torch.float32, device=device)
+    loss = torch.empty(1, dtype=torch.float32, device=device)
+    d1 = torch.empty_like(e1) if want_grads else None
+    d2 = torch.empty_like(e2) if want_grads else None
+    with torch.cuda.device(device):
+        _lib.check(lib.dib_infonce_head(kind, _lib.ptr(e1), _lib.ptr(e2), n, d, float(temperature), _lib.ptr(scratch),
+                                        _lib.ptr(loss), _lib.ptr(d1), _lib.ptr(d2),
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return loss, d1, d2

@@ -46,7 +46,12 @@ enum dib_activation {
 enum dib_loss {
   DIB_LOSS_BCE_LOGITS = 0,       /* tf.keras.losses.BinaryCrossentropy(from_logits=True)            */
   DIB_LOSS_SPARSE_CE_LOGITS = 1, /* tf.keras.losses.SparseCategoricalCrossentropy(from_logits=True) */
-  DIB_LOSS_MSE = 2
+  DIB_LOSS_MSE = 2,
+  /* NEXT ROW f3 -- custom training steps (GradientTape loops: train.py:201-220 InfoNCE, nb-bool cell 6, nb-particle
+   * cell 7): the CALLER owns the task loss.  dib_forward returns the predictions; in dib_train_step the `y` argument
+   * is reinterpreted as d(task loss)/d(predictions) [n, out], already carrying the caller's batch-mean scaling (it is
+   * NOT multiplied by inv_global_batch; the beta*KL term still is).  Task-loss and accuracy statistics are 0. */
+  DIB_LOSS_EXTERNAL = 3
 };
 
 /* arithmetic of the dense contractions. FP32 = CUDA-core FMA (parity path).  The tensor-core modes
@@ -151,6 +156,18 @@ int dib_pairwise_gaussian(int32_t kind, const float* mu_logvar_1, int64_t n, con
 int dib_compression_matrices(dib_model* h, const float* params, const float* x, int64_t n_total,
                              const int32_t* row_index, int64_t n, float* out_mu_logvar, float* out_dist,
                              float* out_compression, void* workspace, void* stream);
+
+/* NEXT ROW f3 -- utils.get_scaled_similarity (utils.py:127-175; distances utils.py:75-125):
+ * kind 0 'l2sq' | 1 'l2' | 2 'l1' | 3 'linf' | 4 'cosine';  e1 [n, d], e2 [m, d] -> out [n, m] = similarity / temperature. */
+int dib_scaled_similarity(int32_t kind, const float* e1, int64_t n, const float* e2, int64_t m, int32_t d,
+                          float temperature, float* out, void* stream);
+
+/* NEXT ROW f3 -- the InfoNCE head of the custom training loop (train.py:203-213) and its reverse mode (train.py:216-219):
+ *   S = get_scaled_similarity(e1, e2);  out_loss[0] = mean_i CE(i, S[i,:]) + mean_i CE(i, S^T[i,:])   (nats)
+ *   d_e1, d_e2 [n, d] = d loss / d e1, d e2 (either may be NULL).  e1 = model(x) (feed d_e1 to dib_train_step of a
+ *   DIB_LOSS_EXTERNAL model), e2 = the caller's output encoder.  scratch: n*n + 4n floats.  n <= 32768, d <= 512. */
+int dib_infonce_head(int32_t kind, const float* e1, const float* e2, int64_t n, int32_t d, float temperature,
+                     float* scratch, float* out_loss, float* d_e1, float* d_e2, void* stream);
 
 /* NEXT ROW f1 -- utils.estimate_mi_sandwich_bounds' per-batch kernel (utils.py:36-65): InfoNCE lower and leave-one-out
  * upper bound (nats) of I(U;X) for one encoder on one batch of n samples.  mu_logvar [n, 2E] (dib_encode_feature

@@ -262,7 +262,7 @@ def forward(cfg: DIBConfig, flat_params, x, eps, beta, y=None, loss=None, keep=F
     kls = np.asarray(kls, dtype=dtype)
     res = ForwardResult(pred=pred, emb=emb, kl_per_feature=kls, task_loss=float("nan"),
                         loss=float("nan"), acc_sum=float("nan"))
-    if y is not None:
+    if y is not None and loss != "external":
         res.task_loss = float(task_loss_per_sample(loss, pred, y).mean())
         res.loss = res.task_loss + float(beta) * float(kls.sum())     # models.py:118
         res.acc_sum = accuracy_count(loss, pred, y)
@@ -282,7 +282,8 @@ def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.flo
     eps = np.asarray(eps, dtype=dtype)
     # integration network backward
     int_acts, integration = c["int_acts"], c["integration"]
-    dz = task_loss_grad(loss, fr.pred, y) / B
+    # loss == "external": y is the caller's d(task loss)/d(pred), already batch-scaled (custom GradientTape loops)
+    dz = np.asarray(y, dtype=dtype).reshape(fr.pred.shape) if loss == "external" else task_loss_grad(loss, fr.pred, y) / B
     dz = dz * act_grad_from_output(cfg.output_activation_fn, int_acts[-1], cfg.leaky_alpha)
     int_grads = [None] * len(integration)
     for k in reversed(range(len(integration))):
@@ -468,6 +469,71 @@ def compression_matrix(cfg: DIBConfig, flat_params, feature_ind, x_rows, dtype=n
     E = cfg.feature_embedding_dimension
     mu, lv = o[:, :E], o[:, E:]
     return np.exp(-bhattacharyya_dist_mat(mu, lv, mu, lv))
+
+
+# ----------------------------------------------------------------------------------------------
+# next row f3: InfoNCE head of the custom training loop (train.py:201-213, utils.py:75-175)
+# ----------------------------------------------------------------------------------------------
+SIMILARITY_TYPES = ("l2sq", "l2", "l1", "linf", "cosine")
+
+
+def get_scaled_similarity(embeddings1, embeddings2, similarity_type, temperature):
+    """utils.py:127-175 (+ the pairwise distances utils.py:75-125): [N, d], [M, d] -> [N, M] similarities / temperature."""
+    a, b = np.asarray(embeddings1, dtype=np.float64), np.asarray(embeddings2, dtype=np.float64)
+    diff = a[:, None, :] - b[None, :, :]
+    if similarity_type in ("l2sq", "l2"):
+        # the reference expands |a|^2 + |b|^2 - 2ab and clamps at 0 (utils.py:85-90)
+        d2 = np.maximum((a * a).sum(-1)[:, None] + (b * b).sum(-1)[None, :] - 2.0 * a @ b.T, 0.0)
+        sim = -d2 if similarity_type == "l2sq" else -np.sqrt(d2 + 1e-9)
+    elif similarity_type == "l1":
+        sim = -np.abs(diff).sum(-1)
+    elif similarity_type == "linf":
+        sim = -np.abs(diff).max(-1)
+    elif similarity_type == "cosine":
+        sim = (a / np.linalg.norm(a, axis=-1, keepdims=True)) @ (b / np.linalg.norm(b, axis=-1, keepdims=True)).T
+    else:
+        raise ValueError(f"Similarity type not implemented: {similarity_type}")
+    return sim / temperature
+
+
+def _logsumexp(s, axis):
+    m = s.max(axis=axis, keepdims=True)
+    return (m + np.log(np.exp(s - m).sum(axis=axis, keepdims=True))).squeeze(axis)
+
+
+def infonce_loss_and_grads(embeddings1, embeddings2, similarity_type, temperature):
+    """train.py:203-213: S = get_scaled_similarity(e1, e2); loss = mean_i CE(i, S[i,:]) + mean_i CE(i, S^T[i,:]).
+    Returns (loss, d loss/d e1, d loss/d e2, S) with the analytic reverse mode GradientTape would produce."""
+    a, b = np.asarray(embeddings1, dtype=np.float64), np.asarray(embeddings2, dtype=np.float64)
+    n = a.shape[0]
+    assert b.shape[0] == n, "the InfoNCE loss needs full, equal batches (train.py:222-223)"
+    T = float(temperature)
+    S = get_scaled_similarity(a, b, similarity_type, T)
+    row, col = _logsumexp(S, 1), _logsumexp(S, 0)
+    diag = np.diag(S)
+    loss = float((row - diag).mean() + (col - diag).mean())
+    dS = (np.exp(S - row[:, None]) + np.exp(S - col[None, :]) - 2.0 * np.eye(n)) / n
+    diff = a[:, None, :] - b[None, :, :]
+    if similarity_type == "l2sq":
+        g = -2.0 * diff / T                                          # d s_ij / d a_i  (= -d s_ij / d b_j)
+    elif similarity_type == "l2":
+        g = -diff / (-S * T)[:, :, None] / T                         # sqrt(d2 + eps) = -S T
+    elif similarity_type == "l1":
+        g = -np.sign(diff) / T
+    elif similarity_type == "linf":
+        k = np.abs(diff).argmax(-1)
+        g = np.zeros_like(diff)
+        ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        g[ii, jj, k] = -np.sign(diff[ii, jj, k]) / T
+    if similarity_type == "cosine":
+        na, nb = np.linalg.norm(a, axis=-1), np.linalg.norm(b, axis=-1)
+        ah, bh = a / na[:, None], b / nb[:, None]
+        c = ah @ bh.T
+        ga = (bh[None, :, :] - c[:, :, None] * ah[:, None, :]) / na[:, None, None] / T
+        gb = (ah[:, None, :] - c[:, :, None] * bh[None, :, :]) / nb[None, :, None] / T
+    else:
+        ga, gb = g, -g
+    return loss, np.einsum("ij,ijk->ik", dS, ga), np.einsum("ij,ijk->jk", dS, gb), S
 
 
 # ----------------------------------------------------------------------------------------------

@@ -160,7 +160,12 @@ def install_tf_shim():
     tf.split = _split
     tf.exp, tf.square = np.exp, np.square
     tf.reduce_mean = lambda x, axis=None: np.mean(x, axis=axis)
-    tf.reduce_sum = lambda x, axis=None: np.sum(np.asarray(x), axis=axis)
+    tf.reduce_sum = lambda x, axis=None, keepdims=False: np.sum(np.asarray(x), axis=axis, keepdims=keepdims)
+    tf.reduce_max = lambda x, axis=None: np.max(np.asarray(x), axis=axis)
+    tf.expand_dims = lambda x, axis: np.expand_dims(x, axis)
+    tf.maximum, tf.abs, tf.sqrt = np.maximum, np.abs, np.sqrt
+    tf.matmul = lambda a, b, transpose_b=False: np.matmul(a, np.swapaxes(b, -1, -2) if transpose_b else b)
+    tf.tile = lambda x, reps: np.tile(x, [int(r) for r in reps])
     tf.shape = lambda x: x.shape
     tf.cast = lambda x, dt: np.asarray(x).astype(dt)
     tf.Variable = _Variable
@@ -169,7 +174,12 @@ def install_tf_shim():
                                     else np.log(np.float32(v)))
     tf.reshape = lambda x, shape: np.reshape(x, [int(s) for s in shape])
     tf.eye = lambda n, dtype=None: np.eye(int(n), dtype=dtype)
-    tf.linalg = types.SimpleNamespace(diag_part=lambda x: np.diag(x).copy())   # tf tensors are immutable: no view
+    def _normalize(x, ord=2, axis=-1):
+        assert ord == 2
+        nrm = np.sqrt(np.sum(np.square(x), axis=axis, keepdims=True))
+        return x / nrm, nrm
+    tf.linalg = types.SimpleNamespace(diag_part=lambda x: np.diag(x).copy(),   # tf tensors are immutable: no view
+                                      normalize=_normalize)
     tf.random = types.SimpleNamespace(normal=_random_normal)
     keras = types.SimpleNamespace(
         layers=types.SimpleNamespace(Layer=_Layer, Input=_Input, Dense=_Dense),
@@ -317,6 +327,15 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_kl_divergence.npz"), mu1=kmu1, lv1=klv1, mu2=kmu2, lv2=klv2, KL12=KL12,
                         KL11=KL11)
     print("kl_divergence_mat[0,:3]:", KL12[0, :3])
+
+    # --- similarity matrices through the reference's utils.get_scaled_similarity (utils.py:75-175) ---
+    rng = np.random.default_rng(41)
+    e1, e2 = rng.standard_normal((11, 6)), rng.standard_normal((7, 6))
+    sims = {"e1": e1, "e2": e2, "temperature": np.float64(0.7)}
+    for kind in ("l2sq", "l2", "l1", "linf", "cosine"):
+        sims[kind] = utils.get_scaled_similarity(e1, e2, kind, 0.7)
+    np.savez_compressed(os.path.join(HERE, "ref_scaled_similarity.npz"), **sims)
+    print("similarity l2sq[0,:3]:", sims["l2sq"][0, :3], "cosine[0,:3]:", sims["cosine"][0, :3])
 
     # --- MI sandwich bounds through the reference's utils.estimate_mi_sandwich_bounds (utils.py:10-73) ---
     rng = np.random.default_rng(31)

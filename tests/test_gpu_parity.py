@@ -318,3 +318,82 @@ def test_mi_sandwich_bounds_kernel_and_callback(golden_dir):
     m.fit(x, y, epochs=2, batch_size=256, callbacks=[dib_b200.InfoBottleneckAnnealingCallback(1e-4, 1e-3, 0, 2), cb])
     bounds = np.asarray(cb.bounds).reshape(2, 10, 2) / np.log(2)
     assert np.all(bounds[..., 0] <= bounds[..., 1] + 1e-4) and np.all(bounds[..., 0] < 1.0 + 1e-3) and np.all(bounds > -1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# next row f3: custom training steps -- caller-owned loss (DIB_LOSS_EXTERNAL) and the InfoNCE head
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("tf32", 5e-3)])
+def test_external_loss_gradients_match_oracle(precision, tol):
+    """dib_train_step with loss = external: y carries d(task)/d(pred); checked against the oracle fed the same upstream
+    gradient, and against the compiled-MSE step of the same model (identical by construction)."""
+    rng = np.random.default_rng(11)
+    cfg = O.DIBConfig([1] * 4, [128, 128], [256, 256], 8, feature_embedding_dimension=32, output_activation_fn="tanh")
+    B = 256
+    x = rng.standard_normal((B, 4)).astype(np.float32)
+    eps = rng.standard_normal((B, 4, 32)).astype(np.float32)
+    d_pred = (rng.standard_normal((B, 8)) / B).astype(np.float32)
+    m = build_model(cfg, precision=precision, loss="external", seed=2)
+    m.beta.assign(0.05)
+    p = m.get_flat_weights()
+    g, stats = m.compute_gradients(x, d_pred, eps=eps)
+    g_ref, fr = O.train_grads(cfg, p, x, d_pred, eps, 0.05, "external")
+    assert rel_err(g.cpu().numpy(), g_ref) < tol
+    st = stats.cpu().numpy()
+    np.testing.assert_allclose(st[:4] / B, fr.kl_per_feature, rtol=10 * tol)
+    assert st[4] == 0 and st[5] == 0 and st[6] == B
+    pred = np.asarray(m(x, eps=eps))
+    assert rel_err(pred, fr.pred) < tol
+    m2 = build_model(cfg, precision=precision, loss="mse", seed=2)
+    m2.beta.assign(0.05)
+    y = rng.standard_normal((B, 8)).astype(np.float32)
+    g_mse, _ = m2.compute_gradients(x, y, eps=eps)
+    d_mse = (O.task_loss_grad("mse", pred.astype(np.float64), y) / B).astype(np.float32)
+    g_ext, _ = m.compute_gradients(x, d_mse, eps=eps)
+    assert rel_err(g_ext.cpu().numpy(), g_mse.cpu().numpy()) < max(tol, 2e-4)
+
+
+def test_scaled_similarity_and_infonce_head(golden_dir):
+    from dib_b200 import utils
+    z = np.load(os.path.join(golden_dir, "ref_scaled_similarity.npz"))
+    for kind in O.SIMILARITY_TYPES:
+        got = utils.get_scaled_similarity(z["e1"], z["e2"], kind, float(z["temperature"]))
+        np.testing.assert_allclose(got, z[kind], rtol=2e-5, atol=2e-5)
+    with pytest.raises(ValueError):
+        utils.get_scaled_similarity(z["e1"], z["e2"], "hamming", 1.0)
+    rng = np.random.default_rng(8)
+    for n, d in ((300, 32), (129, 200), (5, 3)):
+        a, b = rng.standard_normal((n, d)).astype(np.float32), rng.standard_normal((n, d)).astype(np.float32)
+        for kind in O.SIMILARITY_TYPES:
+            T = 0.3 if kind == "cosine" else 2.0 * np.sqrt(d)
+            loss, da, db = utils.infonce_loss_and_grads(a, b, kind, T)
+            l_ref, da_ref, db_ref, _ = O.infonce_loss_and_grads(a, b, kind, T)
+            np.testing.assert_allclose(loss.item(), l_ref, rtol=2e-5)
+            assert rel_err(da.cpu().numpy(), da_ref) < 1e-4, (kind, n, d)
+            assert rel_err(db.cpu().numpy(), db_ref) < 1e-4, (kind, n, d)
+
+
+def test_infonce_custom_loop_trains():
+    """train.py:201-220 end to end: model(x) -> InfoNCE head against an output encoder -> d_pred -> dib_train_step
+    (external loss) -> apply_gradients.  The output encoder here is a fixed linear map (the reference trains an MLP;
+    any torch module can own that side).  The loss must fall well below its chance level 2 ln(n)."""
+    import dib_b200
+    from dib_b200 import utils
+    rng = np.random.default_rng(0)
+    n, F, d = 256, 4, 16
+    x = rng.standard_normal((n * 8, F)).astype(np.float32)
+    y = np.stack([x[:, 0] * x[:, 1], np.sin(2 * x[:, 2]), x[:, 3]], -1).astype(np.float32)
+    Wy = (rng.standard_normal((3, d)) * 0.8).astype(np.float32)
+    cfg = O.DIBConfig([1] * F, [64, 64], [128], d, feature_embedding_dimension=8)
+    m = build_model(cfg, loss="external", lr=2e-3, seed=1)
+    m.beta.assign(1e-4)
+    losses = []
+    for step in range(60):
+        sl = slice((step % 8) * n, (step % 8 + 1) * n)
+        e1 = m(torch.from_numpy(x[sl]).cuda(), step=step)                       # forward with this step's noise
+        e2 = torch.from_numpy(y[sl] @ Wy).cuda()
+        loss, d_e1, _ = utils.infonce_loss_and_grads(e1, e2, "l2sq", 4.0)
+        g, _ = m.compute_gradients(x[sl], d_e1, step=step)                      # same (seed, step) -> same noise
+        m.apply_gradients(g)
+        losses.append(loss.item())
+    assert losses[0] > 0.9 * 2 * np.log(n) * 0.5 and np.mean(losses[-5:]) < 0.8 * np.mean(losses[:5])

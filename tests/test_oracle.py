@@ -71,6 +71,47 @@ def test_compression_matrices_agree_with_single_feature_path():
     np.testing.assert_allclose(comp[1], O.compression_matrix(cfg, p, 1, x[idx[1], 2:3]), rtol=1e-12)
 
 
+def test_scaled_similarity_golden_and_infonce_grads_vs_autograd(golden_dir):
+    """next row f3: similarity matrices against the reference's utils.get_scaled_similarity; the analytic InfoNCE
+    gradients against torch autograd of the same loss (train.py:203-213)."""
+    import torch
+    z = np.load(os.path.join(golden_dir, "ref_scaled_similarity.npz"))
+    for kind in O.SIMILARITY_TYPES:
+        np.testing.assert_allclose(O.get_scaled_similarity(z["e1"], z["e2"], kind, float(z["temperature"])), z[kind],
+                                   rtol=1e-9, atol=1e-9)
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal((9, 5)), rng.standard_normal((9, 5))
+    for kind in O.SIMILARITY_TYPES:
+        loss, da, db, _ = O.infonce_loss_and_grads(a, b, kind, 0.5)
+        ta, tb = torch.tensor(a, requires_grad=True), torch.tensor(b, requires_grad=True)
+        diff = ta[:, None, :] - tb[None, :, :]
+        if kind == "l2sq": S = -(diff ** 2).sum(-1)
+        elif kind == "l2": S = -torch.sqrt((diff ** 2).sum(-1) + 1e-9)
+        elif kind == "l1": S = -diff.abs().sum(-1)
+        elif kind == "linf": S = -diff.abs().amax(-1)
+        else: S = torch.nn.functional.normalize(ta, dim=-1, eps=0) @ torch.nn.functional.normalize(tb, dim=-1, eps=0).T
+        S = S / 0.5
+        lab = torch.arange(9)
+        tl = torch.nn.functional.cross_entropy(S, lab) + torch.nn.functional.cross_entropy(S.T, lab)
+        tl.backward()
+        np.testing.assert_allclose(loss, tl.item(), rtol=1e-10)
+        np.testing.assert_allclose(da, ta.grad.numpy(), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(db, tb.grad.numpy(), rtol=1e-8, atol=1e-10)
+
+
+def test_external_loss_gradients_equal_compiled_loss_gradients():
+    """next row f3: handing the oracle d(task)/d(pred) of the compiled loss reproduces the compiled-loss gradients."""
+    rng = np.random.default_rng(3)
+    cfg = O.DIBConfig([1, 2], [8], [8], 2, feature_embedding_dimension=4, output_activation_fn="tanh")
+    p = O.glorot_uniform_params(cfg, np.random.default_rng(1)).astype(np.float64)
+    x, y = rng.standard_normal((12, 3)), rng.standard_normal((12, 2))
+    eps = rng.standard_normal((12, 2, 4))
+    g_ref, fr = O.train_grads(cfg, p, x, y, eps, 0.3, "mse")
+    d_pred = O.task_loss_grad("mse", fr.pred, y) / 12
+    g_ext, _ = O.train_grads(cfg, p, x, d_pred, eps, 0.3, "external")
+    np.testing.assert_allclose(g_ext, g_ref, rtol=1e-12, atol=1e-14)
+
+
 def test_bhattacharyya_golden_and_kat(golden_dir):
     z = np.load(os.path.join(golden_dir, "ref_bhattacharyya.npz"))
     np.testing.assert_allclose(O.bhattacharyya_dist_mat(z["mu"], z["lv"], z["mu"], z["lv"]), z["D"], rtol=1e-9, atol=1e-10)
