@@ -4,7 +4,7 @@ Drop-in for the hot path of distributed-information-bottleneck.github.io: ``mode
 ``model.compile`` / ``model.fit`` / ``InfoBottleneckAnnealingCallback`` / ``SaveCompressionMatricesCallback``,
 backed by hand-written sm_100a CUDA kernels behind the C ABI of include/dib_b200.h.
 """
-from . import keras_compat, models, parallel, utils                              # noqa: F401
+from . import ctw, keras_compat, models, parallel, utils                              # noqa: F401
 from .keras_compat import Adam, Callback, History, losses, optimizers           # noqa: F401
 from .models import (DistributedIBNet, InfoBottleneckAnnealingCallback, PositionalEncoding,   # noqa: F401
                      SaveCompressionMatricesCallback, StashEmbeddingsCallback, InfoPerFeatureCallback)

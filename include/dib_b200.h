@@ -175,6 +175,16 @@ int dib_infonce_head(int32_t kind, const float* e1, const float* e2, int64_t n, 
 int dib_mi_sandwich_bounds(const float* mu_logvar, int64_t n, int32_t embedding_dimension, const float* eps, uint64_t seed,
                            uint32_t step, float* row_scratch, float* out_lower_upper, void* stream);
 
+/* NEXT ROW f4 -- ctw.estimate_entropy(seq, alphabet_size) (chaos/ctw.pyx:2-3 -> chaos/cppctw.cpp:163-171): infinite-depth
+ * Context-Tree-Weighting entropy-rate estimate in bits/symbol.  HOST functions on HOST memory (the suffix-tree build is
+ * irregular pointer chasing; SURVEY 8f keeps it on the CPU): symbols are int8 in [0, alphabet_size), alphabet_size <= 127.
+ * The batch form runs `count` independent sequences (sequences + offsets[i] .. offsets[i+1]) on num_threads host threads
+ * (<= 0: all cores).  Results are bit-identical to the reference (double carrying a float-rounded value). */
+int dib_ctw_estimate_entropy(const int8_t* sequence, int64_t length, int32_t alphabet_size, double* out_bits_per_symbol);
+int dib_ctw_estimate_entropy_batch(const int8_t* sequences, const int64_t* offsets, int32_t count, int32_t alphabet_size,
+                                   int32_t num_threads, double* out_bits_per_symbol);
+const char* dib_ctw_last_error(void);
+
 /* ---- observability (no reference counterpart) ---------------------------------------------------------
  * dib_launch_count: kernels launched by this library in this process.
  * dib_profile_enable(h,1): bracket every launch group of subsequent forward/train_step calls with CUDA events
