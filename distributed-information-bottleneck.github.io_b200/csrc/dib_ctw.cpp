@@ -82,22 +82,24 @@ struct ContextTree {
   double root_code_length() {
     const double beta = 1. / A;                                    // cppctw.cpp:166
     const double lg_ab = std::lgamma(A * beta), lg_b = std::lgamma(beta), ln2 = std::log(2);
-    std::vector<double> lg_cache;                                  // lgamma(c + beta)
+    std::vector<double> lg_cache, lg_total_cache;                  // lgamma(c + beta), lgamma(total + A beta)
     int sg = 0;
-    auto lg_count = [&](int32_t c) {
-      if ((size_t)c >= lg_cache.size()) lg_cache.resize((size_t)c + 64, std::numeric_limits<double>::quiet_NaN());
-      double& v = lg_cache[c];
-      if (std::isnan(v)) v = lgamma_r(c + beta, &sg);
+    auto memo = [&](std::vector<double>& cache, int64_t c, double offset) {
+      if ((size_t)c >= cache.size()) cache.resize((size_t)c + 64, std::numeric_limits<double>::quiet_NaN());
+      double& v = cache[c];
+      if (std::isnan(v)) v = lgamma_r((double)c + offset, &sg);
       return v;
     };
+    auto lg_count = [&](int32_t c) { return memo(lg_cache, c, beta); };
     const int32_t nn = (int32_t)tail_pos.size();
     std::vector<double> weighted(nn);
     for (int32_t node = nn - 1; node >= 0; --node) {
       const int32_t* cnt = &counts[(size_t)node * A];
       const int32_t* ch = &child[(size_t)node * A];
-      double total = 0.;
-      for (int i = 0; i < A; ++i) total += cnt[i];
-      double le = lgamma_r(total + A * beta, &sg) - lg_ab;
+      int64_t itotal = 0;
+      for (int i = 0; i < A; ++i) itotal += cnt[i];
+      const double total = (double)itotal;
+      double le = memo(lg_total_cache, itotal, A * beta) - lg_ab;
       for (int i = 0; i < A; ++i) le -= lg_count(cnt[i]) - lg_b;
       le /= ln2;
       double lc = 0.;

@@ -358,7 +358,8 @@ class DistributedIBNet:
         if row_index is None:
             n, idx = t.shape[0], None
         else:
-            idx = torch.as_tensor(np.ascontiguousarray(row_index), dtype=torch.int32).to(self.device).contiguous()
+            idx = row_index if isinstance(row_index, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(row_index))
+            idx = idx.to(device=self.device, dtype=torch.int32).contiguous()
             if idx.dim() != 2 or idx.shape[0] != F:
                 raise ValueError("row_index must have shape [number_features, n]")
             n = idx.shape[1]
