@@ -56,7 +56,9 @@ constexpr int kOffFwdEnd = kOffH2 + 2 * kPanel;
 constexpr int kOffDO = kOffFwdEnd;                 // [128 x 64]  one panel
 constexpr int kOffDZ2 = kOffDO + kPanel;           // [128 x 128] (dz1 aliases H2 once wgrad2 has drained)
 constexpr int kOffBwdA0b = kOffDZ2 + 2 * kPanel;    // second A0 buffer (the next tile's operand is staged while this one runs)
-constexpr int kOffBwdEnd = kOffBwdA0b + 2 * TM * 16;
+constexpr int kOffBwdH1b = kOffBwdA0b + 2 * TM * 16; // second h1 buffer: the next tile's first epilogue does not wait for this tile's dW1
+constexpr int kOffBwdEnd = kOffBwdH1b + 2 * kPanel;
+static_assert(kOffBwdH1b % 1024 == 0, "operand tiles must be 1024-byte aligned");
 
 struct EncFusedParams {
   const float* x; int ldx;                 // [n, D]
@@ -95,24 +97,23 @@ __device__ __forceinline__ uint32_t tile_chunk_addr(uint32_t tile, int r, int co
 
 // TMEM -> activation -> 16-bit -> swizzled shared tile, for 64 columns [col0, col0+64) of row r (bias is already in
 // the accumulator).  col0 is a multiple of 64, i.e. exactly one 128-byte panel row per thread.
-template <bool BF16, bool RELU>
+template <bool BF16, bool RELU, int NC = 64>
 __device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, uint32_t tile, int r, int col0, int act, float alpha) {
-  const uint32_t row_addr = tile + (col0 >> 6) * kPanel + r * 128;
-  const int r7 = r & 7;
+  constexpr int CH = 32;                      // columns per TMEM load
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(taddr + col0 + hh * 32, v);
+  for (int hh = 0; hh < NC / CH; ++hh) {
+    uint32_t v[CH];
+    tmem_ld_32x32b_x32(taddr + col0 + hh * CH, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
+    for (int j = 0; j < CH; j += 8) {
       float f[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float z = __uint_as_float(v[j + k]);
         f[k] = RELU ? fmaxf(z, 0.f) : dib_act(act, z, alpha);
       }
-      st_shared_v4(row_addr + ((((hh * 32 + j) >> 3) ^ r7) << 4), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
+      st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * CH + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
                    pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
     }
   }
@@ -147,6 +148,28 @@ __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, bool
   }
   st_shared_v4(a0 + khalf * (TM * 16) + r * 16, pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
                pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+}
+
+// eps for embedding dims [dim0, dim0 + 8) of one row (dim0 a multiple of 8; eps_row points at dim0): explicit tensor or
+// Philox (same keying as dib_elementwise.cu: counter word = dim / 4).
+// Generated in the idle windows while the tensor pipe runs layers 1/2, not on the critical path behind D2.
+__device__ __forceinline__ void noise8(const float* eps_row, unsigned long long seed, unsigned int step,
+                                       unsigned long long grow, int f, int dim0, bool valid, float (&nrm)[8]) {
+  if (eps_row) {
+    if (valid) {
+      const float4 a = *reinterpret_cast<const float4*>(eps_row), b = *reinterpret_cast<const float4*>(eps_row + 4);
+      nrm[0] = a.x; nrm[1] = a.y; nrm[2] = a.z; nrm[3] = a.w; nrm[4] = b.x; nrm[5] = b.y; nrm[6] = b.z; nrm[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nrm[j] = 0.f;
+    }
+  } else {
+    float lo[4], hi[4];
+    dib_philox_normal4(seed, step, grow, (uint32_t)f, (uint32_t)(dim0 >> 2), lo);
+    dib_philox_normal4(seed, step, grow, (uint32_t)f, (uint32_t)((dim0 >> 2) + 1), hi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { nrm[j] = lo[j]; nrm[4 + j] = hi[j]; }
+  }
 }
 
 struct WeightMaps { CUtensorMap w0, w1, w2, b1, b2; };
@@ -280,6 +303,10 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         const bool has_next = t + nslots < ntiles;
         const long long grow_n = (long long)(t + nslots) * TM + ar;
         if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv);   // prefetch the next tile's x
+        const long long grow = row0 + r;
+        const bool valid = grow < P.n;
+        const float* ep = (P.eps && valid) ? P.eps + (grow * F + f) * 32 + hsel * 16 : P.eps;
+        float nrmA[8], nrmB[8];
         mbar_wait(bar_d0, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h1);
@@ -287,9 +314,11 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
           DIB_EPI_SIGNAL(bar_a0);
         }
+        noise8(ep, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, hsel * 16, valid, nrmA);   // while layer 1 runs
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h2);
+        noise8(ep ? ep + 8 : nullptr, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, hsel * 16 + 8, valid, nrmB);   // while layer 2 runs
         // ---- (mu, logvar) -> reparameterise, KL, emb   (16 embedding dims per thread)
         mbar_wait(bar_d2, ph); tc_fence_after_sync();
         {
@@ -298,24 +327,18 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           tmem_ld_32x32b_x16(tR1 + lane_addr + 32 + hsel * 16, vl);
           tmem_ld_wait();
           tc_fence_before_sync();
-          const long long grow = row0 + r;
-          if (grow < P.n) {
+          if (valid) {
             float* dst = P.emb ? P.emb + grow * P.ldemb + f * 32 + hsel * 16 : nullptr;
             __half* dst16 = P.emb16 ? P.emb16 + grow * P.ldemb16 + f * 32 + hsel * 16 : nullptr;
             float* udst = P.user_emb ? P.user_emb + grow * ((long long)F * 32) + f * 32 + hsel * 16 : nullptr;
-            const float* ep = P.eps ? P.eps + (grow * F + f) * 32 + hsel * 16 : nullptr;
 #pragma unroll
             for (int e0 = 0; e0 < 16; e0 += 4) {
-              float nrm[4];
-              if (ep) { const float4 e4 = *reinterpret_cast<const float4*>(ep + e0); nrm[0] = e4.x; nrm[1] = e4.y; nrm[2] = e4.z; nrm[3] = e4.w; }
-              else dib_philox_normal4(P.seed, P.step, P.sample_offset + (unsigned long long)grow, (uint32_t)f,
-                                      (uint32_t)(hsel * 4 + (e0 >> 2)), nrm);
               float u[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
                 const float s = expf(0.5f * lv);
-                u[j] = fmaf(s, nrm[j], mu);
+                u[j] = fmaf(s, e0 < 8 ? nrmA[e0 + j] : nrmB[e0 - 8 + j], mu);
                 kl_acc += 0.5f * (mu * mu + s * s - lv - 1.f);
               }
               if (udst) *reinterpret_cast<float4*>(udst + e0) = make_float4(u[0], u[1], u[2], u[3]);
@@ -393,19 +416,18 @@ __device__ __forceinline__ uint32_t relu_gate2(uint32_t p, uint32_t h) {
 
 // TMEM gradient g (64 columns) * act'(h) -> 16-bit -> shared tile `dtile`; h is read back from the shared tile
 // `htile` that the forward epilogue wrote (relu: as a packed comparison, other activations through act'(h))
-template <bool BF16, bool RELU>
+template <bool BF16, bool RELU, int NC = 64>
 __device__ __forceinline__ void dgrad_epilogue(uint32_t taddr, uint32_t htile, uint32_t dtile, int r, int col0, int act,
                                                float alpha) {
-  const uint32_t off = (col0 >> 6) * kPanel + r * 128;
-  const int r7 = r & 7;
+  constexpr int CH = 32;
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(taddr + col0 + hh * 32, v);
+  for (int hh = 0; hh < NC / CH; ++hh) {
+    uint32_t v[CH];
+    tmem_ld_32x32b_x32(taddr + col0 + hh * CH, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const uint32_t ch = off + ((((hh * 32 + j) >> 3) ^ r7) << 4);
+    for (int j = 0; j < CH; j += 8) {
+      const uint32_t ch = tile_chunk_addr(0u, r, col0 + hh * CH + j);
       uint32_t hv[4], o[4];
       ld_shared_v4(htile + ch, hv);
 #pragma unroll
@@ -424,10 +446,14 @@ __device__ __forceinline__ void dgrad_epilogue(uint32_t taddr, uint32_t htile, u
   }
 }
 
-template <bool BF16, bool RELU>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW epilogue warps (8 or 16): 4 TMEM lane quarters x CS = EW/4 column slices.  16 warps halve the columns per thread
+// (fewer live registers) and double the warps per scheduler that hide the TMEM / shared-memory / SFU latencies.
+template <bool BF16, bool RELU, int EW>
+__global__ void __launch_bounds__(32 * (1 + EW), 1)
 dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFusedBwdParams Q) {
   const EncFusedParams& P = Q.f;
+  constexpr int CS = EW / 4, NC = HID / CS, ND = 32 / CS, NW2 = EO / CS;   // column slices; columns / emb dims / dW2 columns per thread
+  static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
@@ -446,8 +472,8 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
     tma_prefetch_desc(&maps.w0); tma_prefetch_desc(&maps.w1); tma_prefetch_desc(&maps.w2);
     tma_prefetch_desc(&maps.b1); tma_prefetch_desc(&maps.b2);
     mbar_init(bar_w, 1);
-    mbar_init(bar_a0, kEpiWarps); mbar_init(bar_h1, kEpiWarps); mbar_init(bar_h2, kEpiWarps);
-    mbar_init(bar_do, kEpiWarps); mbar_init(bar_dz2, kEpiWarps); mbar_init(bar_dz1, kEpiWarps);
+    mbar_init(bar_a0, EW); mbar_init(bar_h1, EW); mbar_init(bar_h2, EW);
+    mbar_init(bar_do, EW); mbar_init(bar_dz2, EW); mbar_init(bar_dz1, EW);
     mbar_init(bar_d0, 1); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_g2, 1); mbar_init(bar_g1, 1);
     mbar_init(bar_wg, 1);
     fence_barrier_init();
@@ -477,14 +503,17 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         load_weights(sb, maps, bar_w, f);
         mbar_wait_backoff(bar_w, fit & 1);
         bool first = true;
+        if (any_tiles) {     // layer 0 of the feature's first tile; every later tile's layer 0 is issued one tile ahead (below)
+          mbar_wait_backoff(bar_a0, it & 1); tc_fence_after_sync();
+          issue_layer0<BF16>(sb, tR0, sb + ((it & 1) ? kOffBwdA0b : kOffA0)); umma_commit(bar_d0);
+        }
         for (int t = slot; t < ntiles; t += nslots, ++it, first = false) {
           const uint32_t ph = it & 1;
           // ---- recompute forward
-          mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
           const uint32_t a0 = sb + ((it & 1) ? kOffBwdA0b : kOffA0);
-          issue_layer0<BF16>(sb, tR0, a0); umma_commit(bar_d0);
+          const uint32_t h1buf = sb + ((it & 1) ? kOffBwdH1b : kOffH1);
           mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
-          issue_layer1<BF16>(sb, tR0, sb + kOffH1, a0); umma_commit(bar_d1);
+          issue_layer1<BF16>(sb, tR0, h1buf, a0); umma_commit(bar_d1);
           mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
           issue_layer2<BF16>(sb, tR1, sb + kOffH2, a0); umma_commit(bar_d2);
           // ---- layer 2 backward: G2 = dO W2^T ; dW2 += h2^T dO
@@ -515,13 +544,19 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           umma_commit(bar_g1);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWG1, umma_smem_desc(sb + kOffH1 + kk * 2048, kPanel, 1024),
+            umma_f16<BF16>(tWG1, umma_smem_desc(h1buf + kk * 2048, kPanel, 1024),
                            umma_smem_desc(sb + kOffDZ2 + kk * 2048, kPanel, 1024), id_mm_128, (first && kk == 0) ? 0u : 1u);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_f16<BF16>(tWB1, umma_smem_desc(sb + kOffDZ2 + kk * 2048, kPanel, 1024),
                            umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
+          // ---- the NEXT tile's layer 0 (its operand was staged long ago; R0 is free since this tile's h2 epilogue):
+          // its first epilogue then follows this tile's last one without an MMA round trip in between
+          if (t + nslots < ntiles) {
+            mbar_wait_backoff(bar_a0, ph ^ 1); tc_fence_after_sync();
+            issue_layer0<BF16>(sb, tR0, sb + (((it + 1) & 1) ? kOffBwdA0b : kOffA0)); umma_commit(bar_d0);
+          }
           // ---- layer 0 backward: [dW0;db0]^T += dz1^T [pe|1]     (dz1 lives in the H2 buffer)
           mbar_wait_backoff(bar_dz1, ph); tc_fence_after_sync();
 #pragma unroll
@@ -537,68 +572,77 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
       }
       __syncwarp();
     } else {
-      const int ew = warp - 1, q = warp & 3, hsel = ew >> 2;
+      const int ew = warp - 1, q = warp & 3, csel = ew >> 2;
       const int et = ew * 32 + lane;
       const int r = q * 32 + lane;
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       const int d = P.fdim[f], xo = P.x_off[f];
       const float bs = Q.beta_dev[0] * Q.inv_batch * S;
-      const int ar = et & (TM - 1), khalf = et >> 7;             // first-layer operand: row / k-half staged by this thread
+      const int ar = et & (TM - 1), khalf = (et >> 7) & 1;             // first-layer operand: row / k-half staged by this thread
+      const bool stager = et < 2 * TM;                           // 256 (row, k-half) slots of A0
       float xv[kMaxFeatDim];
       if (slot < ntiles) {                                       // operand of the first tile
         const long long grow0 = (long long)slot * TM + ar;
-        load_x(grow0 < P.n ? P.x + grow0 * P.ldx + xo : nullptr, d, xv);
-        write_a0_row<BF16>(sb + ((it & 1) ? kOffBwdA0b : kOffA0), ar, khalf, grow0 < P.n, xv, d, P.nfreq);
+        if (stager) {
+          load_x(grow0 < P.n ? P.x + grow0 * P.ldx + xo : nullptr, d, xv);
+          write_a0_row<BF16>(sb + ((it & 1) ? kOffBwdA0b : kOffA0), ar, khalf, grow0 < P.n, xv, d, P.nfreq);
+        }
         DIB_EPI_SIGNAL(bar_a0);
       }
       for (int t = slot; t < ntiles; t += nslots, ++it) {
         const uint32_t ph = it & 1;
         const long long row0 = (long long)t * TM;
         // prefetch this thread's slice of the upstream gradient (32 B of fp16) long before the (mu, logvar) stage
-        uint4 dpre[2];
+        uint4 dpre[ND / 8];
         {
           const long long g2 = row0 + r < P.n ? row0 + r : 0;
           if (Q.d_emb16) {
-            const __half* src = Q.d_emb16 + g2 * Q.ldd16 + f * 32 + hsel * 16;
-            dpre[0] = *reinterpret_cast<const uint4*>(src); dpre[1] = *reinterpret_cast<const uint4*>(src + 8);
+            const __half* src = Q.d_emb16 + g2 * Q.ldd16 + f * 32 + csel * ND;
+#pragma unroll
+            for (int u = 0; u < ND / 8; ++u) dpre[u] = *reinterpret_cast<const uint4*>(src + u * 8);
           }
         }
         const bool has_next = t + nslots < ntiles;
         const long long grow_n = (long long)(t + nslots) * TM + ar;
-        if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv);   // prefetch the next tile's x
+        if (has_next && stager) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv);   // prefetch the next tile's x
+        const uint32_t h1buf = sb + ((it & 1) ? kOffBwdH1b : kOffH1);
+        const long long grow = row0 + r;
+        const bool valid = grow < P.n;
+        const float* ep = (P.eps && valid) ? P.eps + (grow * F + f) * 32 + csel * ND : P.eps;
+        float nrm[ND];
         mbar_wait(bar_d0, ph); tc_fence_after_sync();
-        epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH1, r, hsel * 64, P.act, P.alpha);
+        epilogue_to_tile<BF16, RELU, NC>(tR0 + lane_addr, h1buf, r, csel * NC, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h1);
+        noise8(ep, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, csel * ND, valid,
+               *reinterpret_cast<float(*)[8]>(&nrm[0]));                                                  // while layer 1 runs
+        mbar_wait(bar_d1, ph); tc_fence_after_sync();
+        // the previous tile's weight-gradient MMAs read H2 (dz1), DO, DZ2 and the other A0 buffer: retired from here on
+        if (t != slot) { mbar_wait(bar_wg, ph ^ 1); tc_fence_after_sync(); }
+        epilogue_to_tile<BF16, RELU, NC>(tR0 + lane_addr, sb + kOffH2, r, csel * NC, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_h2);
         if (has_next) {      // stage the next tile's first-layer operand in the other A0 buffer
-          write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffBwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
+          if (stager) write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffBwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
           DIB_EPI_SIGNAL(bar_a0);
         }
-        mbar_wait(bar_d1, ph); tc_fence_after_sync();
-        epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
-        DIB_EPI_SIGNAL(bar_h2);
+        if constexpr (ND == 16)
+          noise8(ep ? ep + 8 : nullptr, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, csel * ND + 8, valid,
+                 *reinterpret_cast<float(*)[8]>(&nrm[ND - 8]));                                           // while layer 2 runs
         // ---- (mu, logvar) -> d(mu), d(logvar) -> DO tile   (8 embedding dims at a time to bound live registers)
         mbar_wait(bar_d2, ph); tc_fence_after_sync();
         {
-          const long long grow = row0 + r;
-          const bool valid = grow < P.n;
-          const float* du = Q.d_emb ? Q.d_emb + (valid ? grow : 0) * Q.ldd + f * 32 + hsel * 16 : nullptr;
-          const __half* du16 = Q.d_emb16 ? Q.d_emb16 + (valid ? grow : 0) * Q.ldd16 + f * 32 + hsel * 16 : nullptr;
-          const float* ep = P.eps ? P.eps + ((valid ? grow : 0) * F + f) * 32 + hsel * 16 : nullptr;
+          const float* du = Q.d_emb ? Q.d_emb + (valid ? grow : 0) * Q.ldd + f * 32 + csel * ND : nullptr;
+          const bool du16 = Q.d_emb16 != nullptr;
           const uint32_t do_row = sb + kOffDO + r * 128;
           const int r7 = r & 7;
 #pragma unroll
-          for (int e8 = 0; e8 < 16; e8 += 8) {
+          for (int e8 = 0; e8 < ND; e8 += 8) {
             uint32_t vm[8], vl[8];
-            tmem_ld_32x32b_x8(tR1 + lane_addr + hsel * 16 + e8, vm);
-            tmem_ld_32x32b_x8(tR1 + lane_addr + 32 + hsel * 16 + e8, vl);
+            tmem_ld_32x32b_x8(tR1 + lane_addr + csel * ND + e8, vm);
+            tmem_ld_32x32b_x8(tR1 + lane_addr + 32 + csel * ND + e8, vl);
             tmem_ld_wait();
             float dm[8], dl[8];
 #pragma unroll
             for (int e0 = 0; e0 < 8; e0 += 4) {
-              float nrm[4];
-              if (ep) { const float4 e4 = *reinterpret_cast<const float4*>(ep + e8 + e0); nrm[0] = e4.x; nrm[1] = e4.y; nrm[2] = e4.z; nrm[3] = e4.w; }
-              else dib_philox_normal4(P.seed, P.step, P.sample_offset + (unsigned long long)grow, (uint32_t)f,
-                                      (uint32_t)(hsel * 4 + ((e8 + e0) >> 2)), nrm);
               float g[4];
               if (du16) {
                 const uint4 gq = dpre[e8 >> 3];
@@ -613,11 +657,12 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
                 const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
                 const float sg = expf(0.5f * lv);
                 const float gs = g[j];
+                const float nz = nrm[e8 + e0 + j];
                 dm[e0 + j] = valid ? fmaf(bs, mu, gs) : 0.f;
-                dl[e0 + j] = valid ? fmaf(gs * nrm[j], 0.5f * sg, bs * 0.5f * (sg * sg - 1.f)) : 0.f;
+                dl[e0 + j] = valid ? fmaf(gs * nz, 0.5f * sg, bs * 0.5f * (sg * sg - 1.f)) : 0.f;
               }
             }
-            const int cm = (hsel * 16 + e8) >> 3, cl = (32 + hsel * 16 + e8) >> 3;       // 16-byte chunk indices
+            const int cm = (csel * ND + e8) >> 3, cl = (32 + csel * ND + e8) >> 3;       // 16-byte chunk indices
             st_shared_v4(do_row + ((cm ^ r7) << 4), pack2<BF16>(dm[0], dm[1]), pack2<BF16>(dm[2], dm[3]),
                          pack2<BF16>(dm[4], dm[5]), pack2<BF16>(dm[6], dm[7]));
             st_shared_v4(do_row + ((cl ^ r7) << 4), pack2<BF16>(dl[0], dl[1]), pack2<BF16>(dl[2], dl[3]),
@@ -627,24 +672,24 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         DIB_EPI_SIGNAL(bar_do);
         // ---- dz2 = G2 * act'(h2)
         mbar_wait(bar_g2, ph); tc_fence_after_sync();
-        dgrad_epilogue<BF16, RELU>(tR1 + lane_addr, sb + kOffH2, sb + kOffDZ2, r, hsel * 64, P.act, P.alpha);
+        dgrad_epilogue<BF16, RELU, NC>(tR1 + lane_addr, sb + kOffH2, sb + kOffDZ2, r, csel * NC, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_dz2);
         // ---- dz1 = G1 * act'(h1)  -> H2 buffer (free: the dW2 MMAs that read h2 retired before G1 completed)
         mbar_wait(bar_g1, ph); tc_fence_after_sync();
-        dgrad_epilogue<BF16, RELU>(tR1 + lane_addr, sb + kOffH1, sb + kOffH2, r, hsel * 64, P.act, P.alpha);
+        dgrad_epilogue<BF16, RELU, NC>(tR1 + lane_addr, h1buf, sb + kOffH2, r, csel * NC, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_dz1);
-        // the weight-gradient MMAs still read A0 / H1 / DZ2 / dz1: wait before the next tile overwrites them
-        mbar_wait(bar_wg, ph); tc_fence_after_sync();
       }
+      // every weight-gradient MMA of this feature has retired before the accumulators are read back
+      if (any_tiles) { mbar_wait(bar_wg, (it - 1) & 1); tc_fence_after_sync(); }
       // ================= flush this (feature, slot)'s weight-gradient partials (scaled back by 1/S)
       float* part = Q.part + (long long)slot * Q.split_stride;
       const int w_in = d * P.nfreq;
       {
-        float* dst = part + Q.w1_off[f] + (long long)r * HID + hsel * 64;          // dW1[h1=r][h2 cols hsel*64..]
+        float* dst = part + Q.w1_off[f] + (long long)r * HID + csel * NC;          // dW1[h1=r][h2 cols csel*NC..]
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+        for (int hh = 0; hh < NC / 32; ++hh) {
           uint32_t v[32];
-          if (any_tiles) { tmem_ld_32x32b_x32(tWG1 + lane_addr + hsel * 64 + hh * 32, v); tmem_ld_wait(); }
+          if (any_tiles) { tmem_ld_32x32b_x32(tWG1 + lane_addr + csel * NC + hh * 32, v); tmem_ld_wait(); }
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(dst + hh * 32 + j) = any_tiles
@@ -652,18 +697,19 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
                               __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS)
                 : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float* dst2 = part + Q.w2_off[f] + (long long)r * EO + hsel * 32;           // dW2[h2=r][o cols hsel*32..]
-        {
-          uint32_t v[32];
-          if (any_tiles) { tmem_ld_32x32b_x32(tWG2 + lane_addr + hsel * 32, v); tmem_ld_wait(); }
+        float* dst2 = part + Q.w2_off[f] + (long long)r * EO + csel * NW2;          // dW2[h2=r][o cols csel*NW2..]
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst2 + j) = any_tiles
+        for (int hh = 0; hh < NW2 / 16; ++hh) {
+          uint32_t v[16];
+          if (any_tiles) { tmem_ld_32x32b_x16(tWG2 + lane_addr + csel * NW2 + hh * 16, v); tmem_ld_wait(); }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst2 + hh * 16 + j) = any_tiles
                 ? make_float4(__uint_as_float(v[j]) * invS, __uint_as_float(v[j + 1]) * invS,
                               __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS)
                 : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (hsel == 0) {
+        if (csel == 0) {
           // dW0[k][h1=r] (k < w_in), db0[r] = column w_in of dW0p^T; db1[h2=r] = column w_in of dz2^T [pe|1]
           uint32_t v0[16], v1[16];
           if (any_tiles) { tmem_ld_32x32b_x16(tWG0 + lane_addr, v0); tmem_ld_32x32b_x16(tWB1 + lane_addr, v1); tmem_ld_wait(); }
@@ -688,7 +734,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         }
       }
       tc_fence_before_sync();
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
   }
   tc_fence_before_sync();
@@ -776,10 +822,10 @@ void fill_params(EncFusedParams& P, const DibEncFusedDesc& d, const DibEncFusedI
 }
 
 template <typename K, typename A>
-cudaError_t launch_fused(K kern, int smem, int grid, const WeightMaps& m, const A& args, cudaStream_t st) {
+cudaError_t launch_fused(K kern, int smem, int grid, const WeightMaps& m, const A& args, cudaStream_t st, int threads = kThreads) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, smem, st>>>(m, args);
+  kern<<<grid, threads, smem, st>>>(m, args);
   dib_note_launch();
   return cudaGetLastError();
 }
@@ -829,8 +875,9 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
   Q.w0_off = d.w0_off; Q.b0_off = d.b0_off; Q.w1_off = d.w1_off; Q.w2_off = d.w2_off;
   constexpr int smem = kOffBwdEnd + 256 + 1024;
   const bool relu = d.act == DIB_ACT_RELU;
-  if (d.bf16) return relu ? launch_fused(dib_enc_fused_bwd_kernel<true, true>, smem, d.grid, m, Q, st)
-                          : launch_fused(dib_enc_fused_bwd_kernel<true, false>, smem, d.grid, m, Q, st);
-  return relu ? launch_fused(dib_enc_fused_bwd_kernel<false, true>, smem, d.grid, m, Q, st)
-              : launch_fused(dib_enc_fused_bwd_kernel<false, false>, smem, d.grid, m, Q, st);
+  if (d.bf16) return cudaErrorNotSupported;            // bf16 operands: forward only (gradients need fp16's mantissa)
+  // 8 epilogue warps.  The 16-warp instantiation (<.., 16>, 32 columns per thread) was measured slower on B200
+  // (0.498 vs 0.467 ms at C0): 17 warps cap the kernel at 96 registers and the spills outweigh the extra latency hiding.
+  return relu ? launch_fused(dib_enc_fused_bwd_kernel<false, true, 8>, smem, d.grid, m, Q, st, 32 * 9)
+              : launch_fused(dib_enc_fused_bwd_kernel<false, false, 8>, smem, d.grid, m, Q, st, 32 * 9);
 }
