@@ -323,7 +323,7 @@ def test_mi_sandwich_bounds_kernel_and_callback(golden_dir):
 # ---------------------------------------------------------------------------------------------------------
 # next row f3: custom training steps -- caller-owned loss (DIB_LOSS_EXTERNAL) and the InfoNCE head
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("tf32", 5e-3)])    # fp32: sums over 4160 rows vs float64
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 5e-3)])    # fp32 sums over 4160 rows vs float64
 def test_external_loss_gradients_match_oracle(precision, tol):
     """dib_train_step with loss = external: y carries d(task)/d(pred).  The upstream gradient is the MSE gradient against
     random targets, so the step must equal (a) the oracle fed the same upstream gradient and (b) the compiled-MSE step
@@ -351,7 +351,8 @@ def test_external_loss_gradients_match_oracle(precision, tol):
     m2 = build_model(cfg, precision=precision, loss="mse", seed=2)
     m2.beta.assign(0.05)
     g_mse, _ = m2.compute_gradients(x, y, eps=eps)
-    assert rel_err(g.cpu().numpy(), g_mse.cpu().numpy()) < max(2 * tol, 2e-4)
+    # same kernels, same summation order: the caller-owned and the compiled loss agree far tighter than either with float64
+    assert rel_err(g.cpu().numpy(), g_mse.cpu().numpy()) < (2e-5 if precision == "fp32" else 2 * tol)
 
 
 def test_scaled_similarity_and_infonce_head(golden_dir):
