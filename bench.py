@@ -161,9 +161,11 @@ def run_reference(args, rank):
     """The reference graph's CPU twin (oracle/torch_twin.py; TensorFlow is not installable here) on the host cores."""
     if rank != 0:
         return
-    # bounded sample: probe a small batch, then size the per-step sample for ~1.5 s per step
+    # bounded sample: probe a small batch, then size the per-step sample so that the whole run (warm-up + timed steps)
+    # takes about 90 s of CPU time, at most one full batch and at most ~1.5 s per step
     _, probe, _ = cpu_twin_rate(4096, 1, 1)
-    rows = int(min(BATCH, max(4096, 2 ** int(np.log2(max(1.5 / probe, 1.0) * 4096)))))
+    per_step = min(1.5, 90.0 / max(args.steps + args.warmup, 1))
+    rows = int(min(BATCH, max(1024, 2 ** int(np.log2(max(per_step / probe, 0.25) * 4096)))))
     rate, med, threads = cpu_twin_rate(rows, args.steps, args.warmup)
     sample = f"{rows} of {BATCH} rows per step, {args.steps} timed steps, PyTorch-CPU eager twin of models.py (TF unavailable)"
     line = {
