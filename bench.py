@@ -73,6 +73,28 @@ def algorithmic_macs(batch):
     return macs, fwd, train
 
 
+NCU_KERNEL_OF_GROUP = {"enc_fused_bwd": "dib_enc_fused_bwd_kernel", "enc_fused_fwd": "dib_enc_fused_fwd_kernel"}
+
+
+def ncu_dram_traffic(group):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same command (profiles/r01_final_ncu_full.txt); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_final_ncu_full.txt")
+    kern = NCU_KERNEL_OF_GROUP.get(group)
+    if not kern or not os.path.exists(path):
+        return None
+    total, inside, scale = 0.0, False, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(path):
+        if line.startswith("## "):
+            if inside:
+                break
+            inside = kern in line
+        elif inside and ("dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line):
+            parts = line.split()
+            total += float(parts[1]) * scale.get(parts[2], 1.0)
+    return total or None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md 'clocks' line)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -308,7 +330,8 @@ def main():
         ach = 2 * macs[top] / (avg[top] * 1e-3) / 1e12
         step_ach = 2 * train_macs / (ms_per_step * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"], "traffic": ncu_dram_traffic(top),
+                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_final_ncu_full.txt)",
                     "peak_source": f"{peaks['source']} bf16 dense sustained (MEASURED_PEAKS.json); math runs as {args.precision}",
                     "kernel_ms": avg[top], "kernel_share_of_step": avg[top] / sum(avg.values()),
                     "step_achieved_tflops": step_ach, "step_frac": step_ach / peaks["tflops_sustained"],
