@@ -202,11 +202,14 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, precision):
-    return {"workload": "C0: 16 scalar features x batch 65536/GPU, PE(4 freq) -> enc[128,128] -> E=32 -> int[256,256] -> 1, "
+def workload_config(n_gpus, precision, per_gpu=None):
+    per_gpu = BATCH if per_gpu is None else per_gpu
+    return {"workload": f"C0: 16 scalar features x batch {per_gpu}/GPU, PE(4 freq) -> enc[128,128] -> E=32 -> int[256,256] -> 1, "
                         "BCE-from-logits + beta*KL, Keras-Adam",
-            "global_batch": BATCH * n_gpus, "per_gpu_batch": BATCH, "parallelism": f"dp{n_gpus}", "precision": precision,
-            "l2": "per-step working set (activations ~3 GB fp32 path) >> 126 MB L2; 16 distinct input batches rotate"}
+            "global_batch": per_gpu * n_gpus, "per_gpu_batch": per_gpu, "parallelism": f"dp{n_gpus}", "precision": precision,
+            "l2": "no explicit flush: every step streams its intermediates through the 126 MB L2 (tensor-core path ~0.33 GB of "
+                  "fp16 activations/gradients/partials per 65536 rows, fp32 path ~3 GB), evicting the 16 rotating input "
+                  "batches between their uses"}
 
 
 def main():
@@ -218,6 +221,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("DIB_PRECISION", "tf32"), choices=["tf32", "fp32"],
                     help="tf32 = tensor-core mode (default, the headline); fp32 = exact CUDA-core parity path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): 65536 rows per GPU; strong: the 65536-row global batch is "
+                         "split over the GPUs (SURVEY 8d 'the metric as stated')")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,6 +244,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    PB = BATCH // world if args.scaling == "strong" else BATCH          # rows per GPU per step
     lib = _lib.load()
 
     model = dib_b200.DistributedIBNet([1] * F, ENC, INT, OUT, use_positional_encoding=True,
@@ -246,7 +253,7 @@ def main():
     model.compile(optimizer=dib_b200.Adam(LR), loss=dib_b200.losses.BinaryCrossentropy(from_logits=True),
                   metrics=["accuracy"])
     model.beta.assign(1e-3)
-    xs_h, ys_h = synth_batches(rank, N_DISTINCT_BATCHES, BATCH, pinned=True)
+    xs_h, ys_h = synth_batches(rank, N_DISTINCT_BATCHES, PB, pinned=True)
     xs_d = [x.cuda(non_blocking=True) for x in xs_h]
     ys_d = [y.cuda(non_blocking=True) for y in ys_h]
     torch.cuda.synchronize()
@@ -265,7 +272,7 @@ def main():
 
     def device_step(i):
         model._train_step(xs_d[i % N_DISTINCT_BATCHES], ys_d[i % N_DISTINCT_BATCHES],
-                          global_batch=BATCH * world, sample_offset=rank * BATCH)
+                          global_batch=PB * world, sample_offset=rank * PB)
 
     # ---------------- device-resident timed region -> value
     sampler = ClockSampler(local_rank) if rank == 0 else None      # sampled under load: warm-up + timed region
@@ -283,7 +290,7 @@ def main():
     launches = int(lib.dib_launch_count()) - launches0
     clocks = sampler.stop() if sampler else None
     ms_per_step = ms_total / args.steps
-    value = BATCH * world / (ms_per_step * 1e-3)
+    value = PB * world / (ms_per_step * 1e-3)
 
     # ---------------- end to end through the public API from pinned host buffers -> e2e
     for i in range(3):
@@ -300,7 +307,7 @@ def main():
     ev1.record()
     barrier()
     e2e_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-    e2e = {"value": BATCH * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+    e2e = {"value": PB * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(xs_h[0].numel() * 4 + ys_h[0].numel() * 4),
            "d2h_bytes_per_step": int((F + 3) * 4), "api": "DistributedIBNet.train_on_batch(host x, host y, sync=False).get() -> metrics dict (H2D on a copy stream, D2H async)",
            "last_loss": out["loss"]}
@@ -309,11 +316,11 @@ def main():
     roofline = None
     if rank == 0:
         import ctypes
-        model._ensure_handle(BATCH)
+        model._ensure_handle(PB)
         _lib.check(lib.dib_profile_enable(model._handle, 1))
         nprof = min(args.steps, 5)
         for i in range(nprof):
-            model._backward(xs_d[i], ys_d[i], global_batch=BATCH * world, sample_offset=rank * BATCH)
+            model._backward(xs_d[i], ys_d[i], global_batch=PB * world, sample_offset=rank * PB)
         cap = 4096
         ms = (ctypes.c_float * cap)()
         labels = ctypes.create_string_buffer(1 << 16)
@@ -324,7 +331,7 @@ def main():
         for nm, t in zip(names, list(ms)[:n]):
             groups.setdefault(nm, []).append(float(t))
         avg = {k: float(np.mean(v)) for k, v in groups.items()}
-        macs, fwd_macs, train_macs = algorithmic_macs(BATCH)
+        macs, fwd_macs, train_macs = algorithmic_macs(PB)
         top = max((k for k in avg if k in macs), key=lambda k: avg[k])
         peaks = measured_peaks()
         ach = 2 * macs[top] / (avg[top] * 1e-3) / 1e12
@@ -336,7 +343,7 @@ def main():
                     "kernel_ms": avg[top], "kernel_share_of_step": avg[top] / sum(avg.values()),
                     "step_achieved_tflops": step_ach, "step_frac": step_ach / peaks["tflops_sustained"],
                     "algorithmic_gflop_per_step": 2 * train_macs / 1e9,
-                    "hbm_algorithmic_gbs": (68 * BATCH + 7 * model.count_params() * 4) / (ms_per_step * 1e-3) / 1e9,
+                    "hbm_algorithmic_gbs": (68 * PB + 7 * model.count_params() * 4) / (ms_per_step * 1e-3) / 1e9,
                     "hbm_peak_gbs": peaks["hbm_gbs"],
                     "group_ms": {k: round(v, 4) for k, v in sorted(avg.items(), key=lambda kv: -kv[1])}}
     barrier()
@@ -352,9 +359,9 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision],
-            "data": "synthetic", "config": workload_config(world, args.precision), "clocks": clocks, "e2e": e2e,
+            "data": "synthetic", "config": workload_config(world, args.precision, PB), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "library": os.path.relpath(_lib.library_path(), ROOT), "build": lib.dib_build_info().decode(),
         }
