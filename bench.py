@@ -199,7 +199,7 @@ def run_reference(args, rank):
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus, precision, per_gpu=None):
@@ -212,7 +212,26 @@ def workload_config(n_gpus, precision, per_gpu=None):
                   "batches between their uses"}
 
 
+JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries print there too (NCCL's version banner, torchrun notices), so
+    keep a private handle on the real stdout for the result and point fd 1 at stderr for everything else."""
+    global JSON_OUT
+    if JSON_OUT is None:
+        sys.stdout.flush()
+        JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    JSON_OUT.write(json.dumps(line) + "\n")
+    JSON_OUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -240,8 +259,6 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
     PB = BATCH // world if args.scaling == "strong" else BATCH          # rows per GPU per step
@@ -365,7 +382,7 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "library": os.path.relpath(_lib.library_path(), ROOT), "build": lib.dib_build_info().decode(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
