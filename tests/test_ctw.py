@@ -74,3 +74,24 @@ def test_entropy_rate_properties(ctw):
     for _ in range(50000):                                                    # sticky two-state chain, H = h(0.05)
         markov.append(markov[-1] ^ int(rng.random() < 0.05))
     assert abs(ctw.estimate_entropy(markov, 2) - (-(0.05 * np.log2(0.05) + 0.95 * np.log2(0.95)))) < 0.02
+
+
+def test_random_small_sequences_against_python_restatement(ctw):
+    """hypothesis-style sweep (seeded): many short sequences over small alphabets, incl. long runs and periodic pieces
+    that exercise the lazy tail extension; library == Python restatement == (when built) the reference, bit for bit."""
+    rng = np.random.default_rng(2024)
+    for trial in range(300):
+        A = int(rng.integers(1, 6))
+        n = int(rng.integers(1, 90))
+        kind = trial % 3
+        if kind == 0:
+            seq = rng.integers(0, A, n)
+        elif kind == 1:                                                       # runs
+            seq = np.repeat(rng.integers(0, A, max(n // 7, 1)), 7)[:n]
+        else:                                                                 # periodic with a defect
+            seq = np.tile(rng.integers(0, A, int(rng.integers(1, 5))), n)[:n]
+            seq[int(rng.integers(0, n))] = int(rng.integers(0, A))
+        got = ctw.estimate_entropy(seq, A)
+        assert got == ctw_oracle.estimate_entropy(seq, A), (trial, A, seq.tolist())
+        if ctw_oracle.reference_available():
+            assert got == ctw_oracle.reference_estimate_entropy(seq, A), (trial, A, seq.tolist())
