@@ -2,8 +2,8 @@
 // Reference: chaos/cppctw.cpp (ctw.estimate_entropy(seq, alphabet_size), chaos/ctw.pyx:2-3) -- the reference's only
 // native code.  It is an irregular, pointer-chasing suffix-tree build: it stays on the HOST (a GPU version is not
 // justified); what changes here is the data structure and the batching:
-//   * nodes live in one arena (flat int32 arrays: counts[node][A], child[node][A], tail position/symbol) instead of a
-//     heap object with two std::vectors per node -> no per-node allocation, indices instead of pointers;
+//   * nodes live in one arena (one contiguous int32 record per node: counts[A] | child[A] | tail position | tail symbol)
+//     instead of a heap object with two std::vectors per node -> no per-node allocation, indices instead of pointers;
 //   * a child is always created after its parent, so the code-length pass is ONE reverse sweep over the arena
 //     (children before parents) -- no recursion (the reference recurses as deep as the tree: ~N for a constant sequence);
 //   * lgamma(c + beta) is memoised per count (same argument -> bit-identical value);
@@ -28,52 +28,57 @@ constexpr int kMaxCreateDepth = 512;     // cppctw.cpp:13
 int fail_ctw(const std::string& m);
 
 struct ContextTree {
-  int A;
-  std::vector<int32_t> counts, child;     // [node * A + symbol]
-  std::vector<int32_t> tail_pos;          // > 0: this leaf stands for the context continuing before sequence[tail_pos]
-  std::vector<int8_t> tail_sym;           // the one symbol counted so far along that continuation
+  int A, S;                               // alphabet size; int32 words per node
+  // one record per node, contiguous: counts[A] | child[A] | tail position | tail symbol -- a visit touches one or two
+  // cache lines instead of three arrays.  tail position > 0: this leaf stands for the context continuing before
+  // sequence[tail position]; tail symbol: the one symbol counted so far along that continuation.
+  std::vector<int32_t> pool;
+  int32_t nodes = 0;
 
-  explicit ContextTree(int alphabet) : A(alphabet) { add_node(-1, -1); }
+  explicit ContextTree(int alphabet) : A(alphabet), S(2 * alphabet + 2) { add_node(-1, -1); }
 
-  int32_t add_node(int32_t pos, int8_t sym) {
-    const int32_t id = (int32_t)tail_pos.size();
-    counts.insert(counts.end(), A, 0);
-    child.insert(child.end(), A, -1);
-    tail_pos.push_back(pos);
-    tail_sym.push_back(sym);
-    return id;
+  int32_t* rec(int32_t node) { return pool.data() + (size_t)node * S; }
+  const int32_t* rec(int32_t node) const { return pool.data() + (size_t)node * S; }
+
+  int32_t add_node(int32_t pos, int32_t sym) {
+    const size_t base = pool.size();
+    pool.resize(base + S);
+    int32_t* r = pool.data() + base;
+    for (int i = 0; i < A; ++i) { r[i] = 0; r[A + i] = -1; }
+    r[2 * A] = pos; r[2 * A + 1] = sym;
+    return nodes++;
   }
 
-  void reserve(size_t nodes) {
-    counts.reserve(nodes * A); child.reserve(nodes * A); tail_pos.reserve(nodes); tail_sym.reserve(nodes);
-  }
+  void reserve(size_t n) { pool.reserve(n * S); }
 
   // cppctw.cpp:106-154
   void insert_all(const int8_t* s, int64_t n) {
+    const int TP = 2 * A, TS = 2 * A + 1;
     for (int64_t t = 0; t < n; ++t) {
-      const int8_t cur = s[t];
+      const int cur = s[t];
       int32_t node = 0;
-      counts[cur] += 1;
+      rec(0)[cur] += 1;
       for (int64_t c = t - 1; c >= 0; --c) {
-        if (tail_pos[node] > 0) {                        // push the pending continuation one symbol deeper
-          const int32_t p = tail_pos[node] - 1;
-          const int8_t ts = tail_sym[node];
-          const int32_t nn = add_node(p, ts);
-          child[(size_t)node * A + s[p]] = nn;
-          counts[(size_t)nn * A + ts] += 1;
-          tail_pos[node] = -1; tail_sym[node] = -1;
+        int32_t* r = rec(node);
+        if (r[TP] > 0) {                                 // push the pending continuation one symbol deeper
+          const int32_t p = r[TP] - 1, ts = r[TS];
+          r[TP] = -1; r[TS] = -1;
+          const int32_t nn = add_node(p, ts);            // may move the pool: re-derive the record pointers
+          rec(node)[A + s[p]] = nn;
+          rec(nn)[ts] += 1;
+          r = rec(node);
         }
-        const int8_t ctx = s[c];
-        const int32_t nxt = child[(size_t)node * A + ctx];
+        const int ctx = s[c];
+        const int32_t nxt = r[A + ctx];
         if (nxt < 0) {
           if (t - c > kMaxCreateDepth) break;
           const int32_t nn = c > 0 ? add_node((int32_t)c, cur) : add_node(-1, -1);
-          child[(size_t)node * A + ctx] = nn;
-          counts[(size_t)nn * A + cur] += 1;
+          rec(node)[A + ctx] = nn;
+          rec(nn)[cur] += 1;
           break;
         }
         node = nxt;
-        counts[(size_t)node * A + cur] += 1;
+        rec(node)[cur] += 1;
       }
     }
   }
@@ -91,11 +96,11 @@ struct ContextTree {
       return v;
     };
     auto lg_count = [&](int32_t c) { return memo(lg_cache, c, beta); };
-    const int32_t nn = (int32_t)tail_pos.size();
+    const int32_t nn = nodes;
     std::vector<double> weighted(nn);
     for (int32_t node = nn - 1; node >= 0; --node) {
-      const int32_t* cnt = &counts[(size_t)node * A];
-      const int32_t* ch = &child[(size_t)node * A];
+      const int32_t* cnt = rec(node);
+      const int32_t* ch = cnt + A;
       int64_t itotal = 0;
       for (int i = 0; i < A; ++i) itotal += cnt[i];
       const double total = (double)itotal;
