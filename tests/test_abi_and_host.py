@@ -94,3 +94,23 @@ def test_select_display_rows():
     raw = np.random.default_rng(0).standard_normal((500, 1))
     inds, vals = utils.select_display_rows(raw, 128, np.random.default_rng(1))
     assert len(inds) == 128 and np.all(np.diff(vals) >= 0) and np.allclose(raw[inds, 0], vals)
+
+
+def test_bench_accounting_matches_survey_numbers():
+    """bench.py's algorithmic work model against SURVEY.md section 8d: C0 forward 600 320 MAC/sample, train
+    1 790 720 MAC/sample = 234.7 GFLOP per 65 536-row step; and the ncu traffic lookup parses the committed capture."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    macs, fwd, train = bench.algorithmic_macs(65536)
+    assert fwd == 600320 * 65536 and train == 1790720 * 65536
+    assert abs(2 * train / 1e9 - 234.7) < 0.05
+    assert macs["enc_fused_fwd"] == 16 * 25216 * 65536
+    assert macs["enc_fused_bwd"] == 16 * (25216 + 128 * 128 + 128 * 64) * 65536
+    t = bench.ncu_dram_traffic("enc_fused_bwd")
+    assert t is None or 1e6 < t < 1e9
+    cfg = bench.workload_config(2, "tf32", 32768)
+    assert cfg["global_batch"] == 65536 and cfg["per_gpu_batch"] == 32768 and cfg["parallelism"] == "dp2"
