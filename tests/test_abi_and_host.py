@@ -114,3 +114,29 @@ def test_bench_accounting_matches_survey_numbers():
     assert t is None or 1e6 < t < 1e9
     cfg = bench.workload_config(2, "tf32", 32768)
     assert cfg["global_batch"] == 65536 and cfg["per_gpu_batch"] == 32768 and cfg["parallelism"] == "dp2"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/dib_b200.h must compile as C99 (no C++-isms outside the extern "C" guard) and a C
+    program must link against the library and reach a host-only entry point (the CTW estimator needs no GPU)."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "dib_b200.h")
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    from dib_b200 import _lib
+    lib_dir = os.path.dirname(_lib.library_path())
+    src = tmp_path / "main.c"
+    src.write_text('#include <stdio.h>\n#include "dib_b200.h"\n'
+                   'int main(void) { const int8_t s[4] = {1, 0, 0, 1}; double h = 0.0;\n'
+                   '  if (dib_ctw_estimate_entropy(s, 4, 2, &h)) { puts(dib_ctw_last_error()); return 1; }\n'
+                   '  printf("%.17g %s\\n", h, dib_build_info()); return 0; }\n')
+    exe = tmp_path / "main"
+    subprocess.run([gcc, "-std=c99", str(src), "-I", os.path.join(root, "include"), "-L", lib_dir, "-ldib_b200",
+                    "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert float(out[0]) == 1.0232774019241333 and "sm_100a" in " ".join(out[1:])
