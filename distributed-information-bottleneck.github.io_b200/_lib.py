@@ -10,7 +10,9 @@ ABI_VERSION = 1
 
 ACTIVATIONS = {None: 0, "linear": 0, "relu": 1, "tanh": 2, "leaky_relu": 3, "sigmoid": 4, "elu": 5}
 LOSSES = {"bce_logits": 0, "sparse_ce_logits": 1, "mse": 2, "external": 3}
-PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+# 'fp16' / 'bf16': fused 16-bit-operand tcgen05 kernels (fp32 accumulate); 'tf32': kind::tf32 GEMMs on fp32 storage;
+# 'fp32': exact CUDA-core FMA parity path.  See enum dib_precision in include/dib_b200.h.
+PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
 
 
 class DibConfig(ctypes.Structure):
@@ -72,6 +74,7 @@ SIGNATURES = {
     "dib_debug_force_unfused": (c_int32, [c_void_p, c_int32]),
     "dib_last_error": (c_char_p, []),
     "dib_build_info": (c_char_p, []),
+    "dib_model_info": (c_int32, [c_void_p, c_char_p, c_size_t]),
 }
 
 _lib = None

@@ -88,6 +88,11 @@ struct dib_model {
 
 namespace {
 
+// precision modes: FP32 = CUDA-core FMA; TF32 = kind::tf32 grouped GEMMs on fp32 storage; FP16 / BF16 = the fused
+// 16-bit-operand kernels (dib_enc_fused.cu, dib_int16.cu) where the shapes allow, kind::tf32 GEMMs elsewhere
+bool is_tc(const dib_model* h) { return h->precision != DIB_PREC_FP32; }
+bool want16(const dib_model* h) { return h->precision == DIB_PREC_FP16 || h->precision == DIB_PREC_BF16; }
+
 int enc_fan_in(const dib_model* h, int f, int j) { return j == 0 ? h->w_in[f] : h->enc_arch[j - 1]; }
 int enc_fan_out(const dib_model* h, int j) { return j < h->L ? h->enc_arch[j] : 2 * h->E; }
 int int_fan_in(const dib_model* h, int j) { return j == 0 ? h->F * h->E : h->int_arch[j - 1]; }
@@ -284,7 +289,7 @@ int gemm(const Ctx& c, int mode, int first, int nprob, int maxC, int maxR, int n
   L.nsplit = nsplit; L.rows_per_split = rps; L.split_stride = c.h->Pp;
   L.alpha = c.h->alpha;
   float* part = c.ws + c.h->part_off;
-  const bool tc = c.h->precision == DIB_PREC_TF32;
+  const bool tc = is_tc(c.h);
   L.round_out = tc ? 1 : 0;
   switch (mode) {
     case DIB_GEMM_FWD: L.baseA = c.ws; L.baseB = c.params; L.baseC = c.ws; L.baseX = nullptr; break;
@@ -314,7 +319,7 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
                 uint64_t sample_offset, float inv_batch, bool training, float* user_pred, float* user_emb,
                 float* out_stats) {
   dib_model* h = c.h;
-  const int rnd = h->precision == DIB_PREC_TF32 ? 1 : 0;
+  const int rnd = is_tc(h) ? 1 : 0;
   const bool fast_path = h->fused_ok && rnd && (!training || h->fused_bwd_ok) && !h->force_unfused && h->int16_ok && !h->force_int32;
   if (rnd && !fast_path) {
     prof_begin(c, "weights_tf32_shadow");
@@ -346,16 +351,17 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
     DIB_CUDA_OK(dib_enc_fused_forward(d, io, c.st));
     prof_end(c);
     if (i16) {
+      const int bf = h->precision == DIB_PREC_BF16 ? 1 : 0;
       // ---------------- integration network on 16-bit activations + fused output head
       prof_begin(c, "int16_pack_weights");
       for (int j = 0; j < h->Li; ++j)
-        DIB_CUDA_OK(dib_int16_convert(c.params + h->intW[j], c.ws + h->w16_off[j], (long long)int_fan_in(h, j) * int_fan_out(h, j), c.st));
+        DIB_CUDA_OK(dib_int16_convert(c.params + h->intW[j], c.ws + h->w16_off[j], (long long)int_fan_in(h, j) * int_fan_out(h, j), bf, c.st));
       prof_end(c);
       for (int j = 0; j < h->Li; ++j) {
         prof_begin(c, "int16_fwd_l", j);
         DIB_CUDA_OK(dib_int16_fwd(j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]), int_fan_in(h, j),
                                   c.ws + h->w16_off[j], c.params + h->intB[j], c.ws + h->g16_off[j + 1], int_fan_out(h, j), c.n,
-                                  int_fan_in(h, j), int_fan_out(h, j), h->act, h->alpha, c.st));
+                                  int_fan_in(h, j), int_fan_out(h, j), h->act, h->alpha, bf, c.st));
         prof_end(c);
       }
       const int Kh = h->int_arch[h->Li - 1];
@@ -364,7 +370,7 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
       DIB_CUDA_OK(dib_int16_head(c.ws + h->g16_off[h->Li], Kh, Kh, c.params + h->intW[h->Li], c.params + h->intB[h->Li], h->out,
                                  h->out_act, h->act, h->alpha, h->loss, y, c.n, inv_batch, gscale,
                                  training ? (void*)(c.ws + h->dg16_off[h->Li]) : nullptr, Kh, user_pred, c.ws + h->headpart_off,
-                                 h->head_stride, c.ws + h->loss_part_off, c.ws + h->acc_part_off, h->head_blocks, c.st));
+                                 h->head_stride, c.ws + h->loss_part_off, c.ws + h->acc_part_off, h->head_blocks, bf, c.st));
       DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->kl_stride, nblk_kl, c.ws + h->loss_part_off,
                                             c.ws + h->acc_part_off, h->head_blocks, h->F, c.n, y != nullptr, out_stats, c.st));
       prof_end(c);
@@ -475,7 +481,28 @@ int dib_debug_gemm_tc(int32_t mode, const float* A, int32_t lda, const float* B,
 
 const char* dib_last_error(void) { return g_last_error.c_str(); }
 
-const char* dib_build_info(void) { return "dib_b200 abi=1 arch=sm_100a paths=fp32-simt,tf32-tcgen05"; }
+const char* dib_build_info(void) {
+  return "dib_b200 abi=1 arch=sm_100a paths=fp32-simt,tf32-tcgen05,fp16-fused-tcgen05,bf16-fused-tcgen05";
+}
+
+int32_t dib_model_info(const dib_model* h, char* out, size_t out_bytes) {
+  if (!h || !out || out_bytes < 2) { fail("dib_model_info: bad arguments"); return -1; }
+  static const char* pn[] = {"fp32", "tf32", "bf16", "fp16"};
+  const bool fused = h->fused_ok && h->fused_bwd_ok && !h->force_unfused;
+  const bool i16 = fused && h->int16_ok && !h->force_int32;
+  const char* k16 = h->precision == DIB_PREC_BF16 ? "bf16" : "f16";
+  std::string s = std::string("precision=") + pn[h->precision];
+  if (!is_tc(h)) s += " encoders=simt-fp32 integration=simt-fp32 operands=fp32 accumulate=fp32";
+  else {
+    s += fused ? std::string(" encoders=fused-tcgen05-") + k16 : std::string(" encoders=grouped-tcgen05-tf32");
+    s += i16 ? std::string(" integration=int16-tcgen05-") + k16 : std::string(" integration=tcgen05-tf32");
+    s += fused ? std::string(" operands=") + (h->precision == DIB_PREC_BF16 ? "bf16" : "fp16") : std::string(" operands=tf32");
+    s += " accumulate=fp32";
+  }
+  const size_t k = s.size() < out_bytes - 1 ? s.size() : out_bytes - 1;
+  memcpy(out, s.data(), k); out[k] = 0;
+  return (int32_t)k;
+}
 
 int dib_create(const dib_config* cfg, dib_model** out) {
   if (!cfg || !out) return fail("dib_create: null argument");
@@ -485,8 +512,8 @@ int dib_create(const dib_config* cfg, dib_model** out) {
       cfg->max_batch < 1 || cfg->number_encoder_layers < 0 || cfg->number_integration_layers < 0)
     return fail("dib_create: invalid sizes");
   if (cfg->max_batch > 0x7fffffffll) return fail("dib_create: max_batch too large");
-  if (cfg->precision != DIB_PREC_FP32 && cfg->precision != DIB_PREC_TF32)
-    return fail("dib_create: precision must be DIB_PREC_FP32 or DIB_PREC_TF32 in this build");
+  if (cfg->precision < DIB_PREC_FP32 || cfg->precision > DIB_PREC_FP16)
+    return fail("dib_create: unknown precision");
   if (cfg->activation_fn < 0 || cfg->activation_fn > DIB_ACT_ELU || cfg->output_activation_fn < 0 ||
       cfg->output_activation_fn > DIB_ACT_ELU)
     return fail("dib_create: unknown activation");
@@ -566,7 +593,7 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   }
   // ---- fused encoder kernels: two hidden layers of 128, E = 32, first-layer fan-in (+ bias column) <= 16
   {
-    bool ok = h->precision != DIB_PREC_FP32 && h->L == 2 && h->enc_arch[0] == 128 && h->enc_arch[1] == 128 && h->E == 32;
+    bool ok = want16(h) && h->L == 2 && h->enc_arch[0] == 128 && h->enc_arch[1] == 128 && h->E == 32;
     for (int f = 0; ok && f < h->F; ++f) ok = h->w_in[f] + 1 <= 16;
     if (ok) {
       const int F = h->F;
@@ -585,7 +612,7 @@ int dib_create(const dib_config* cfg, dib_model** out) {
         const long long* lt = static_cast<const long long*>(h->d_fused_tables);
         const int* it = reinterpret_cast<const int*>(static_cast<const char*>(h->d_fused_tables) + b1);
         DibEncFusedDesc& d = h->fdesc;
-        d.F = F; d.nfreq = h->nfreq; d.act = h->act; d.alpha = h->alpha; d.bf16 = 0;
+        d.F = F; d.nfreq = h->nfreq; d.act = h->act; d.alpha = h->alpha; d.bf16 = h->precision == DIB_PREC_BF16 ? 1 : 0;
         d.w0_off = lt; d.b0_off = lt + F; d.w1_off = lt + 2 * F; d.b1_off = lt + 3 * F; d.w2_off = lt + 4 * F;
         d.b2_off = lt + 5 * F; d.x_off = it; d.fdim = it + F;
         h->fused_ok = true;
@@ -648,7 +675,7 @@ int dib_encode_feature(dib_model* h, const float* params, int32_t feature, const
   if (n == 0) return 0;
   Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
   const int f = feature, wpad = DIB_ROUND_UP(h->w_in[f], 4);
-  const int rnd = h->precision == DIB_PREC_TF32 ? 1 : 0;
+  const int rnd = is_tc(h) ? 1 : 0;
   if (rnd) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
   DIB_CUDA_OK(dib_launch_pe(x_i, h->fdims[f], h->x_off[f], h->d_col_src, h->d_col_freq, h->pe_off[f], h->pe_off[f] + wpad,
                             c.ws + h->pe.off, h->ldpe, 0, n, rnd, c.st));
@@ -679,8 +706,9 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
   rps = DIB_ROUND_UP(rps, 32);
   const int nsplit = (int)DIB_CEIL_DIV((long long)n, rps);
 
-  const bool fused_enc = h->fused_ok && h->fused_bwd_ok && h->precision == DIB_PREC_TF32 && !h->force_unfused;
+  const bool fused_enc = h->fused_ok && h->fused_bwd_ok && !h->force_unfused;
   if (fused_enc && h->int16_ok && !h->force_int32) {
+    const int bf = h->precision == DIB_PREC_BF16 ? 1 : 0;
     const float gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
     float* part = c.ws + h->part_off;
     const int Kh = h->int_arch[h->Li - 1];
@@ -693,12 +721,12 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
       const int K = int_fan_in(h, j), N = int_fan_out(h, j);
       prof_begin(c, "int16_wgrad_l", j);
       DIB_CUDA_OK(dib_int16_wgrad(in_j, K, c.ws + h->dg16_off[j + 1], N, part + h->intW[j], nullptr, (int)n, K, N, nsplit,
-                                  (int)rps, h->Pp, 1.f / gscale, c.st));
+                                  (int)rps, h->Pp, 1.f / gscale, bf, c.st));
       prof_end(c);
       prof_begin(c, "int16_dgrad_l", j);
       DIB_CUDA_OK(dib_int16_dgrad(c.ws + h->dg16_off[j + 1], N, c.ws + h->w16_off[j], j > 0 ? (const void*)(c.ws + h->g16_off[j]) : nullptr,
                                   K, j > 0 ? (void*)(c.ws + h->dg16_off[j]) : (void*)(c.ws + h->demb16_off), K, (int)n, K, N, h->act,
-                                  h->alpha, j > 0 ? c.ws + h->dbpart_off : nullptr, c.st));
+                                  h->alpha, j > 0 ? c.ws + h->dbpart_off : nullptr, bf, c.st));
       if (j > 0)   // bias gradient of layer j-1 = column sums of the gradient this dgrad just produced
         DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->dbpart_off, K, row_tiles, K, 1.f / gscale, grads_flat + h->intB[j - 1], c.st));
       prof_end(c);
@@ -739,7 +767,7 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
     if (gemm(c, DIB_GEMM_DGRAD, h->int_dgrad[j], 1, int_fan_in(h, j), 0, 1, 0)) return 1;
     prof_end(c);
   }
-  const bool fused = h->fused_ok && h->fused_bwd_ok && h->precision == DIB_PREC_TF32 && !h->force_unfused;
+  const bool fused = h->fused_ok && h->fused_bwd_ok && !h->force_unfused;
   if (fused) {
     const int ntiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
     const long long want = (long long)h->F * ntiles;
@@ -772,7 +800,7 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
   DibReparamArgs ra;
   ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
   ra.eps = eps; ra.seed = seed; ra.step = step; ra.sample_offset = sample_offset;
-  ra.F = h->F; ra.E = h->E; ra.n = n; ra.round_out = h->precision == DIB_PREC_TF32 ? 1 : 0;
+  ra.F = h->F; ra.E = h->E; ra.n = n; ra.round_out = is_tc(h) ? 1 : 0;
   prof_begin(c, "reparam_kl_bwd");
   DIB_CUDA_OK(dib_launch_reparam_bwd(ra, c.ws + h->d_emb.off, h->d_emb.ld, beta_dev, inv_global_batch,
                                      c.ws + h->d_out.off, c.st));
@@ -863,7 +891,7 @@ int dib_compression_matrices(dib_model* h, const float* params, const float* x, 
     return fail("dib_compression_matrices: rows out of range");
   if (n == 0) return 0;
   Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
-  const int rnd = h->precision == DIB_PREC_TF32 ? 1 : 0;
+  const int rnd = is_tc(h) ? 1 : 0;
   if (rnd) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
   // all F encoders as ONE grouped problem per layer (the reference loops over features in Python, visualization.py:14-35)
   DIB_CUDA_OK(dib_launch_pe(x, h->D, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, n, rnd, c.st,

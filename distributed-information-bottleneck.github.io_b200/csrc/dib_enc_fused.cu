@@ -70,7 +70,7 @@ struct EncFusedParams {
   const float* eps;                        // [n, F, E] or null -> Philox
   unsigned long long seed; unsigned int step; unsigned long long sample_offset;
   float* emb; int ldemb; float* user_emb;  // outputs (forward); emb may be null when emb16 is given
-  __half* emb16; int ldemb16;              // fp16 copy of emb for the 16-bit integration path (or null)
+  uint16_t* emb16; int ldemb16;            // 16-bit (fp16 / bf16) copy of emb for the 16-bit integration path (or null)
   float* kl_part; int kl_stride;           // [F][kl_stride] per-(feature, slot) KL partial sums
   int F; long long n; int act; float alpha;
   int round_emb;
@@ -329,7 +329,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           tc_fence_before_sync();
           if (valid) {
             float* dst = P.emb ? P.emb + grow * P.ldemb + f * 32 + hsel * 16 : nullptr;
-            __half* dst16 = P.emb16 ? P.emb16 + grow * P.ldemb16 + f * 32 + hsel * 16 : nullptr;
+            uint16_t* dst16 = P.emb16 ? P.emb16 + grow * P.ldemb16 + f * 32 + hsel * 16 : nullptr;
             float* udst = P.user_emb ? P.user_emb + grow * ((long long)F * 32) + f * 32 + hsel * 16 : nullptr;
 #pragma unroll
             for (int e0 = 0; e0 < 16; e0 += 4) {
@@ -342,7 +342,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
                 kl_acc += 0.5f * (mu * mu + s * s - lv - 1.f);
               }
               if (udst) *reinterpret_cast<float4*>(udst + e0) = make_float4(u[0], u[1], u[2], u[3]);
-              if (dst16) *reinterpret_cast<uint2*>(dst16 + e0) = make_uint2(pack2<false>(u[0], u[1]), pack2<false>(u[2], u[3]));
+              if (dst16) *reinterpret_cast<uint2*>(dst16 + e0) = make_uint2(pack2<BF16>(u[0], u[1]), pack2<BF16>(u[2], u[3]));
               if (dst) {
                 if (P.round_emb) {
 #pragma unroll
@@ -385,7 +385,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
 struct EncFusedBwdParams {
   EncFusedParams f;
   const float* d_emb; int ldd;              // [n, ldd] gradient w.r.t. emb (already scaled by 1/B_global)
-  const __half* d_emb16; int ldd16;         // or: fp16 gradient already multiplied by the loss scale S
+  const uint16_t* d_emb16; int ldd16;       // or: 16-bit gradient already multiplied by the loss scale S
   const float* beta_dev; float inv_batch; float gscale;
   float* part; long long split_stride;      // weight-gradient partials [slot][P]
   const long long* w0_off; const long long* b0_off; const long long* w1_off; const long long* w2_off;
@@ -597,7 +597,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         {
           const long long g2 = row0 + r < P.n ? row0 + r : 0;
           if (Q.d_emb16) {
-            const __half* src = Q.d_emb16 + g2 * Q.ldd16 + f * 32 + csel * ND;
+            const uint16_t* src = Q.d_emb16 + g2 * Q.ldd16 + f * 32 + csel * ND;
 #pragma unroll
             for (int u = 0; u < ND / 8; ++u) dpre[u] = *reinterpret_cast<const uint4*>(src + u * 8);
           }
@@ -647,7 +647,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
               if (du16) {
                 const uint4 gq = dpre[e8 >> 3];
                 uint32_t w0 = e0 == 0 ? gq.x : gq.z, w1 = e0 == 0 ? gq.y : gq.w;
-                unpack2<false>(w0, g[0], g[1]); unpack2<false>(w1, g[2], g[3]);
+                unpack2<BF16>(w0, g[0], g[1]); unpack2<BF16>(w1, g[2], g[3]);
               } else {
                 const float4 g4 = *reinterpret_cast<const float4*>(du + e8 + e0);
                 g[0] = g4.x * S; g[1] = g4.y * S; g[2] = g4.z * S; g[3] = g4.w * S;
@@ -818,7 +818,7 @@ void fill_params(EncFusedParams& P, const DibEncFusedDesc& d, const DibEncFusedI
   P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step;
   P.sample_offset = io.sample_offset; P.emb = io.emb; P.ldemb = io.ldemb; P.user_emb = io.user_emb;
   P.kl_part = io.kl_part; P.kl_stride = io.kl_stride; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha;
-  P.round_emb = 1; P.emb16 = static_cast<__half*>(io.emb16); P.ldemb16 = io.ldemb16;
+  P.round_emb = 1; P.emb16 = static_cast<uint16_t*>(io.emb16); P.ldemb16 = io.ldemb16;
 }
 
 template <typename K, typename A>
@@ -869,13 +869,15 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
   EncFusedBwdParams Q;
   fill_params(Q.f, d, io);
   Q.f.round_emb = 0;
-  Q.d_emb16 = static_cast<const __half*>(b.d_emb16); Q.ldd16 = b.ldd16;
+  Q.d_emb16 = static_cast<const uint16_t*>(b.d_emb16); Q.ldd16 = b.ldd16;
   Q.d_emb = b.d_emb; Q.ldd = b.ldd; Q.beta_dev = b.beta_dev; Q.inv_batch = b.inv_batch; Q.gscale = b.gscale;
   Q.part = b.part; Q.split_stride = b.split_stride;
   Q.w0_off = d.w0_off; Q.b0_off = d.b0_off; Q.w1_off = d.w1_off; Q.w2_off = d.w2_off;
   constexpr int smem = kOffBwdEnd + 256 + 1024;
   const bool relu = d.act == DIB_ACT_RELU;
-  if (d.bf16) return cudaErrorNotSupported;            // bf16 operands: forward only (gradients need fp16's mantissa)
+  if (d.bf16)    // bf16 operands end to end (7-bit mantissa gradients: the usual bf16-training trade, BASELINE config 4)
+    return relu ? launch_fused(dib_enc_fused_bwd_kernel<true, true, 8>, smem, d.grid, m, Q, st, 32 * 9)
+                : launch_fused(dib_enc_fused_bwd_kernel<true, false, 8>, smem, d.grid, m, Q, st, 32 * 9);
   // 8 epilogue warps.  The 16-warp instantiation (<.., 16>, 32 columns per thread) was measured slower on B200
   // (0.498 vs 0.467 ms at C0): 17 warps cap the kernel at 96 registers and the spills outweigh the extra latency hiding.
   return relu ? launch_fused(dib_enc_fused_bwd_kernel<false, true, 8>, smem, d.grid, m, Q, st, 32 * 9)

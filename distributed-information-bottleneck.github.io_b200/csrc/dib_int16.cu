@@ -9,6 +9,7 @@
 //     own weight/bias gradients -- one pass over the last hidden activation.
 // Gradient operands are scaled by the power-of-two loss scale S (see dib_enc_fused.cu) to stay inside fp16 range.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "dib_common.cuh"
@@ -25,8 +26,8 @@ constexpr int kBarOff = kStages * kStageBytes;
 constexpr int kSmemTotal = kBarOff + 128 + 1024;
 
 struct Int16Args {
-  float* out32; __half* out16; int ldc;       // WGRAD partial base (fp32) | FWD/DGRAD output (fp16)
-  const __half* X; int ldx;                   // DGRAD: activation whose act' gates the gradient (or null)
+  float* out32; uint16_t* out16; int ldc;       // WGRAD partial base (fp32) | FWD/DGRAD output (fp16)
+  const uint16_t* X; int ldx;                   // DGRAD: activation whose act' gates the gradient (or null)
   const float* bias;                          // FWD
   float* dbias;                               // DGRAD: column sums of the produced gradient per 128-row tile [tiles_r][C] (or null)
   int M, T, C, R, act;
@@ -34,20 +35,23 @@ struct Int16Args {
   int nsplit, rows_per_split; long long split_stride;
 };
 
+template <bool BF16>
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  if constexpr (BF16) asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+template <bool BF16>
 __device__ __forceinline__ void unpack_h2(uint32_t u, float& a, float& b) {
-  const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
-  a = f.x; b = f.y;
+  if constexpr (BF16) { a = __uint_as_float(u << 16); b = __uint_as_float(u & 0xffff0000u); }
+  else { const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u)); a = f.x; b = f.y; }
 }
 
 // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the shared-memory stage ring runs across tiles and the
 // fp32 accumulator is double-buffered in TMEM (2 x 128 columns), so the epilogue of tile i overlaps the mainloop of
 // tile i+1.  Warp roles: 0 TMA producer | 1 MMA issuer (+ TMEM owner) | 2..5 epilogue.
-template <int MODE>
+template <int MODE, bool BF16>
 __global__ void __launch_bounds__(192, 2)
 dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Int16Args a) {
   constexpr bool A_MN = (MODE == DIB_GEMM_WGRAD), B_MN = (MODE != DIB_GEMM_DGRAD);
@@ -113,7 +117,7 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(0u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBN);
+      constexpr uint32_t idesc = umma_idesc(BF16 ? 1u : 0u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBN);
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         int r0, c0, split, t_begin, nk;
@@ -167,8 +171,8 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
               *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * a.out_scale, __uint_as_float(v[j + 1]) * a.out_scale,
                                                                 __uint_as_float(v[j + 2]) * a.out_scale, __uint_as_float(v[j + 3]) * a.out_scale);
           } else {
-            __half* dst = a.out16 + (long long)r * a.ldc + c;
-            const __half* xs = (MODE == DIB_GEMM_DGRAD && a.X) ? a.X + (long long)r * a.ldx + c : nullptr;
+            uint16_t* dst = a.out16 + (long long)r * a.ldc + c;
+            const uint16_t* xs = (MODE == DIB_GEMM_DGRAD && a.X) ? a.X + (long long)r * a.ldx + c : nullptr;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float f[8];
@@ -185,12 +189,12 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   float h0, h1;
-                  unpack_h2(xw[k], h0, h1);
+                  unpack_h2<BF16>(xw[k], h0, h1);
                   f[2 * k] *= dib_act_grad(a.act, h0, a.alpha);
                   f[2 * k + 1] *= dib_act_grad(a.act, h1, a.alpha);
                 }
               }
-              *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+              *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2<BF16>(f[0], f[1]), pack_h2<BF16>(f[2], f[3]), pack_h2<BF16>(f[4], f[5]), pack_h2<BF16>(f[6], f[7]));
               if constexpr (MODE == DIB_GEMM_DGRAD) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[j + k] = __float_as_uint(f[k]);     // keep the gated fp32 values for the column sums
@@ -272,11 +276,11 @@ dib_int16_colsum_kernel(const __half* __restrict__ dz, int ld, int M, int C, int
 // ----------------------------------------------------------------------------------------------------
 constexpr int kHeadMaxOut = 16, kHeadWarps = 8;
 
-template <int KPT, int OUT, int ROWS>   // hidden units per lane (K / 32); bound of the output width; rows in flight per warp
+template <int KPT, int OUT, int ROWS, bool BF16>   // hidden units per lane (K / 32); bound of the output width; rows in flight per warp
 __global__ void __launch_bounds__(kHeadWarps * 32)
-dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float* __restrict__ Wc, const float* __restrict__ bc,
+dib_int16_head_kernel(const uint16_t* __restrict__ g, int ldg, int K, const float* __restrict__ Wc, const float* __restrict__ bc,
                       int out_dim, int out_act, int hid_act, float alpha, int loss, const float* __restrict__ y, long long n,
-                      float inv_batch, float gscale, __half* __restrict__ dg, int lddg, float* __restrict__ user_pred,
+                      float inv_batch, float gscale, uint16_t* __restrict__ dg, int lddg, float* __restrict__ user_pred,
                       float* __restrict__ wpart, int wpart_stride, float* __restrict__ loss_part, float* __restrict__ acc_part) {
   __shared__ float red[kHeadWarps][KPT * 32];
   __shared__ float sred[kHeadWarps];
@@ -314,8 +318,8 @@ dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float*
 #pragma unroll
       for (int i = 0; i < KPT; i += 8) {
         const uint4 v = hv[rr][i / 8];
-        unpack_h2(v.x, h[i], h[i + 1]); unpack_h2(v.y, h[i + 2], h[i + 3]);
-        unpack_h2(v.z, h[i + 4], h[i + 5]); unpack_h2(v.w, h[i + 6], h[i + 7]);
+        unpack_h2<BF16>(v.x, h[i], h[i + 1]); unpack_h2<BF16>(v.y, h[i + 2], h[i + 3]);
+        unpack_h2<BF16>(v.z, h[i + 4], h[i + 5]); unpack_h2<BF16>(v.w, h[i + 6], h[i + 7]);
       }
       float z[OUT], dz[OUT];
 #pragma unroll
@@ -369,11 +373,11 @@ dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float*
           d[i] = s * gscale * dib_act_grad(hid_act, h[i], alpha);
           dbh[i] += d[i];
         }
-        __half* dst = dg + row * lddg + lane * KPT;
+        uint16_t* dst = dg + row * lddg + lane * KPT;
 #pragma unroll
         for (int i = 0; i < KPT; i += 8)
-          *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_h2(d[i], d[i + 1]), pack_h2(d[i + 2], d[i + 3]),
-                                                          pack_h2(d[i + 4], d[i + 5]), pack_h2(d[i + 6], d[i + 7]));
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_h2<BF16>(d[i], d[i + 1]), pack_h2<BF16>(d[i + 2], d[i + 3]),
+                                                          pack_h2<BF16>(d[i + 4], d[i + 5]), pack_h2<BF16>(d[i + 6], d[i + 7]));
       }
     }
   }
@@ -430,9 +434,13 @@ dib_int16_head_kernel(const __half* __restrict__ g, int ldg, int K, const float*
   if (threadIdx.x == 0) { float s = 0.f; for (int ww = 0; ww < kHeadWarps; ++ww) s += sred[ww]; acc_part[blockIdx.x] = s; }
 }
 
-__global__ void dib_f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+template <bool BF16>
+__global__ void dib_f32_to_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __float2half_rn(src[i]);
+  if (i < n) {
+    if constexpr (BF16) { const __nv_bfloat16 b = __float2bfloat16_rn(src[i]); dst[i] = *reinterpret_cast<const uint16_t*>(&b); }
+    else { const __half b = __float2half_rn(src[i]); dst[i] = *reinterpret_cast<const uint16_t*>(&b); }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -449,26 +457,26 @@ EncodeTiledFn encode_fn3() {
   return fn;
 }
 // K-major: [rows x ld] fp16, box 64 cols x brows
-bool map_k(CUtensorMap* m, const __half* base, long long cols, long long rows, long long ld, int brows) {
+bool map_k(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld, int brows) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)brows}, es[2] = {1, 1};
-  return encode_fn3()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, es,
+  return encode_fn3()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // MN-major: [krows x ld] fp16 whose contiguous dim is M/N -> (64, krow, panel), box 64 x 64 x npanels => smem [panel][krow][128 B]
-bool map_mn(CUtensorMap* m, const __half* base, long long cols, long long krows, long long ld, int npanels) {
+bool map_mn(CUtensorMap* m, const void* base, long long cols, long long krows, long long ld, int npanels) {
   cuuint64_t dims[3] = {64, (cuuint64_t)krows, (cuuint64_t)(cols / 64)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
   cuuint32_t box[3] = {64, (cuuint32_t)kBK, (cuuint32_t)npanels}, es[3] = {1, 1, 1};
-  return encode_fn3()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, es,
+  return encode_fn3()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int g_num_sms16 = 0;
-template <int MODE>
+template <int MODE, bool BF16>
 cudaError_t launch16(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Args& a, dim3 tiles, cudaStream_t st) {
   if (!g_num_sms16) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms16, cudaDevAttrMultiProcessorCount, dev); }
   const long long nt = (long long)tiles.x * tiles.y * tiles.z;
@@ -476,62 +484,66 @@ cudaError_t launch16(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Ar
   dim3 grid((unsigned)(nt < 2ll * g_num_sms16 ? nt : 2ll * g_num_sms16));
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(dib_int16_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    cudaError_t e = cudaFuncSetAttribute(dib_int16_gemm_kernel<MODE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dib_int16_gemm_kernel<MODE><<<grid, 192, kSmemTotal, st>>>(mA, mB, a);
+  dib_int16_gemm_kernel<MODE, BF16><<<grid, 192, kSmemTotal, st>>>(mA, mB, a);
   dib_note_launch();
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, cudaStream_t st) {
+cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, int bf16, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  dib_f32_to_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, static_cast<__half*>(dst16), n);
+  if (bf16) dib_f32_to_16_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, static_cast<uint16_t*>(dst16), n);
+  else dib_f32_to_16_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, static_cast<uint16_t*>(dst16), n);
   dib_note_launch();
   return cudaGetLastError();
 }
 
 // g_out[M x N] = act(g_in[M x K] W16[K x N] + bias)
 cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const float* bias, void* g_out, int ld_out, int M,
-                          int K, int N, int act, float alpha, cudaStream_t st) {
+                          int K, int N, int act, float alpha, int bf16, cudaStream_t st) {
   if (!encode_fn3()) return cudaErrorNotSupported;
   CUtensorMap mA, mB;
-  if (!map_k(&mA, static_cast<const __half*>(g_in), K, M, ld_in, kBM) || !map_mn(&mB, static_cast<const __half*>(w16), N, K, N, kBN / 64))
+  if (!map_k(&mA, g_in, K, M, ld_in, kBM) || !map_mn(&mB, w16, N, K, N, kBN / 64))
     return cudaErrorInvalidValue;
   Int16Args a{};
-  a.out16 = static_cast<__half*>(g_out); a.ldc = ld_out; a.bias = bias; a.M = M; a.T = K; a.C = N; a.act = act; a.alpha = alpha;
+  a.out16 = static_cast<uint16_t*>(g_out); a.ldc = ld_out; a.bias = bias; a.M = M; a.T = K; a.C = N; a.act = act; a.alpha = alpha;
   a.out_scale = 1.f; a.nsplit = 1;
-  return launch16<DIB_GEMM_FWD>(mA, mB, a, dim3(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(N, kBN), 1), st);
+  const dim3 tiles(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(N, kBN), 1);
+  return bf16 ? launch16<DIB_GEMM_FWD, true>(mA, mB, a, tiles, st) : launch16<DIB_GEMM_FWD, false>(mA, mB, a, tiles, st);
 }
 
 // dz_in[M x K] = (dz[M x N] W16[K x N]^T) * act'(g_in[M x K])      (g_in may be null: no activation, e.g. d_emb)
 cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const void* g_in, int ld_g, void* dz_in, int ld_out,
-                            int M, int K, int N, int act, float alpha, float* colsum_part, cudaStream_t st) {
+                            int M, int K, int N, int act, float alpha, float* colsum_part, int bf16, cudaStream_t st) {
   if (!encode_fn3()) return cudaErrorNotSupported;
   CUtensorMap mA, mB;
-  if (!map_k(&mA, static_cast<const __half*>(dz), N, M, ld_dz, kBM) || !map_k(&mB, static_cast<const __half*>(w16), N, K, N, kBN))
+  if (!map_k(&mA, dz, N, M, ld_dz, kBM) || !map_k(&mB, w16, N, K, N, kBN))
     return cudaErrorInvalidValue;
   Int16Args a{};
-  a.out16 = static_cast<__half*>(dz_in); a.ldc = ld_out; a.X = static_cast<const __half*>(g_in); a.ldx = ld_g;
+  a.out16 = static_cast<uint16_t*>(dz_in); a.ldc = ld_out; a.X = static_cast<const uint16_t*>(g_in); a.ldx = ld_g;
   a.M = M; a.T = N; a.C = K; a.act = act; a.alpha = alpha; a.out_scale = 1.f; a.nsplit = 1; a.dbias = colsum_part;
-  return launch16<DIB_GEMM_DGRAD>(mA, mB, a, dim3(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(K, kBN), 1), st);
+  const dim3 tiles(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(K, kBN), 1);
+  return bf16 ? launch16<DIB_GEMM_DGRAD, true>(mA, mB, a, tiles, st) : launch16<DIB_GEMM_DGRAD, false>(mA, mB, a, tiles, st);
 }
 
 // dW[K x N] (fp32 split partials, * out_scale) = g_in[M x K]^T dz[M x N];  db = colsum dz
 cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
-                            int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, cudaStream_t st) {
+                            int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, int bf16, cudaStream_t st) {
   if (!encode_fn3()) return cudaErrorNotSupported;
   CUtensorMap mA, mB;
-  if (!map_mn(&mA, static_cast<const __half*>(g_in), K, M, ld_g, kBM / 64) || !map_mn(&mB, static_cast<const __half*>(dz), N, M, ld_dz, kBN / 64))
+  if (!map_mn(&mA, g_in, K, M, ld_g, kBM / 64) || !map_mn(&mB, dz, N, M, ld_dz, kBN / 64))
     return cudaErrorInvalidValue;
   Int16Args a{};
   a.out32 = dW_part; a.ldc = N; a.dbias = nullptr; a.M = M; a.T = 0; a.C = N; a.R = K; a.out_scale = out_scale;
   a.nsplit = nsplit; a.rows_per_split = rows_per_split; a.split_stride = split_stride;
   (void)db_part;   // bias gradients come from the kernel that PRODUCES dz (dgrad epilogue / output head), not from here
-  return launch16<DIB_GEMM_WGRAD>(mA, mB, a, dim3(DIB_CEIL_DIV(N, kBN), DIB_CEIL_DIV(K, kBM), nsplit), st);
+  const dim3 tiles(DIB_CEIL_DIV(N, kBN), DIB_CEIL_DIV(K, kBM), nsplit);
+  return bf16 ? launch16<DIB_GEMM_WGRAD, true>(mA, mB, a, tiles, st) : launch16<DIB_GEMM_WGRAD, false>(mA, mB, a, tiles, st);
 }
 
 int dib_int16_head_blocks(int num_sms) { return num_sms * 2; }
@@ -539,18 +551,20 @@ int dib_int16_head_blocks(int num_sms) { return num_sms * 2; }
 cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const float* bc, int out_dim, int out_act, int hid_act,
                            float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,
                            float* user_pred, float* wpart, int wpart_stride, float* loss_part, float* acc_part, int nblocks,
-                           cudaStream_t st) {
+                           int bf16, cudaStream_t st) {
   if (out_dim > kHeadMaxOut || out_dim < 1 || K != 256) return cudaErrorInvalidValue;
-#define DIB_HEAD(OUT)                                                                                                   \
-  dib_int16_head_kernel<8, OUT, (OUT <= 2 ? 4 : 1)><<<nblocks, kHeadWarps * 32, 0, st>>>(static_cast<const __half*>(g), ldg, K, Wc, bc, out_dim,      \
-      out_act, hid_act, alpha, loss, y, n, inv_batch, gscale, static_cast<__half*>(dg), lddg, user_pred, wpart, wpart_stride, \
+#define DIB_HEAD_T(OUT, BF)                                                                                             \
+  dib_int16_head_kernel<8, OUT, (OUT <= 2 ? 4 : 1), BF><<<nblocks, kHeadWarps * 32, 0, st>>>(static_cast<const uint16_t*>(g), ldg, K, Wc, bc, out_dim,  \
+      out_act, hid_act, alpha, loss, y, n, inv_batch, gscale, static_cast<uint16_t*>(dg), lddg, user_pred, wpart, wpart_stride, \
       loss_part, acc_part)
+#define DIB_HEAD(OUT) do { if (bf16) DIB_HEAD_T(OUT, true); else DIB_HEAD_T(OUT, false); } while (0)
   if (out_dim == 1) DIB_HEAD(1);
   else if (out_dim == 2) DIB_HEAD(2);
   else if (out_dim <= 4) DIB_HEAD(4);
   else if (out_dim <= 8) DIB_HEAD(8);
   else DIB_HEAD(16);
 #undef DIB_HEAD
+#undef DIB_HEAD_T
   dib_note_launch();
   return cudaGetLastError();
 }

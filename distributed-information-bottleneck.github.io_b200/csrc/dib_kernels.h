@@ -119,21 +119,21 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
                                    cudaStream_t st);
 
 // ---- 16-bit integration network path (dib_int16.cu) ----
-cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, cudaStream_t st);
+cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, int bf16, cudaStream_t st);
 cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const float* bias, void* g_out, int ld_out, int M,
-                          int K, int N, int act, float alpha, cudaStream_t st);
+                          int K, int N, int act, float alpha, int bf16, cudaStream_t st);
 // colsum_part (nullable): [ceil(M/128)][K] per-row-tile column sums of dz_in = bias-gradient partials of the layer below
 cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const void* g_in, int ld_g, void* dz_in, int ld_out,
-                            int M, int K, int N, int act, float alpha, float* colsum_part, cudaStream_t st);
+                            int M, int K, int N, int act, float alpha, float* colsum_part, int bf16, cudaStream_t st);
 cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int nrows, int64_t count, float scale, float* out,
                                    cudaStream_t st);
 cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
-                            int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, cudaStream_t st);
+                            int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, int bf16, cudaStream_t st);
 int dib_int16_head_blocks(int num_sms);
 cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const float* bc, int out_dim, int out_act, int hid_act,
                            float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,
                            float* user_pred, float* wpart, int wpart_stride, float* loss_part, float* acc_part, int nblocks,
-                           cudaStream_t st);
+                           int bf16, cudaStream_t st);
 
 cudaError_t dib_launch_mi_sandwich(const float* mu_logvar, int64_t n, int E, const float* eps, uint64_t seed, uint32_t step,
                                    float* row_scratch, float* out2, cudaStream_t st);

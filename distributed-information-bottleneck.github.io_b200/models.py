@@ -74,6 +74,22 @@ class _Beta:
     def __array__(self, dtype=None, copy=None):
         return np.asarray(self._host, dtype=dtype)
 
+    # arithmetic the reference's drivers do with the variable: ``kl_loss / model.beta`` (train.py:214),
+    # ``self.beta * tensor`` (models.py:118), ``beta * 2.0`` -- delegate to the float32 host value
+    def _other(self, o):
+        return o.to(torch.float32) if isinstance(o, torch.Tensor) else o
+
+    def __mul__(self, o): return float(self._host) * self._other(o)
+    __rmul__ = __mul__
+    def __truediv__(self, o): return float(self._host) / self._other(o)
+    def __rtruediv__(self, o): return self._other(o) / float(self._host)
+    def __add__(self, o): return float(self._host) + self._other(o)
+    __radd__ = __add__
+    def __sub__(self, o): return float(self._host) - self._other(o)
+    def __rsub__(self, o): return self._other(o) - float(self._host)
+    def __neg__(self): return -float(self._host)
+    def __repr__(self): return f"<beta {float(self._host)!r}>"
+
 
 class _Network:
     """A view of one Dense stack inside the flat parameter buffer (model.feature_encoders[i] /
@@ -133,7 +149,8 @@ class DistributedIBNet:
     (models.py:26-123; ``dropout_rate``/``training`` from nb-radial cell 5).
 
     Extra keyword-only arguments (not in the reference): ``device``, ``seed`` (weight init + noise stream),
-    ``precision`` ('fp32' exact-FMA parity path | 'tf32' | 'bf16' tensor-core paths), ``process_group``
+    ``precision`` ('fp32' exact-FMA parity path | 'tf32' kind::tf32 GEMMs | 'fp16' / 'bf16' fused 16-bit-operand
+    tcgen05 kernels with fp32 accumulation; ``model.kernel_info()`` says what a handle actually runs), ``process_group``
     (data-parallel group; defaults to the WORLD group when torch.distributed is initialised), ``leaky_alpha``.
     """
 
@@ -155,6 +172,8 @@ class DistributedIBNet:
             raise NotImplementedError("dropout_rate > 0 (nb-radial only, default 0) is not implemented")
         if activation_fn not in _lib.ACTIVATIONS or output_activation_fn not in _lib.ACTIVATIONS:
             raise ValueError(f"unsupported activation {activation_fn!r}/{output_activation_fn!r}")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
         self.feature_dimensionalities = [int(d) for d in feature_dimensionalities]
         self.number_features = len(self.feature_dimensionalities)
         self.feature_encoder_architecture = [int(h) for h in feature_encoder_architecture]
@@ -191,6 +210,7 @@ class DistributedIBNet:
             self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._epoch_acc = torch.zeros(self.number_features + 4, dtype=torch.float32, device=self.device)
         self._train_step_count = 0
+        self._inference_calls = 0          # fresh noise per un-seeded inference call (tf.random.normal, models.py:108)
         self.optimizer = None
         self.compiled_metrics_names = []
         self.losses = []
@@ -251,6 +271,15 @@ class DistributedIBNet:
             self._workspace = None
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             assert self._workspace.data_ptr() % 256 == 0
+
+    def kernel_info(self, batch_hint=1):
+        """What the library runs for this model: precision, kernel families, operand / accumulator types."""
+        with torch.cuda.device(self.device):
+            self._ensure_handle(max(int(batch_hint), 1))
+            buf = ctypes.create_string_buffer(512)
+            if self._lib.dib_model_info(self._handle, buf, len(buf)) < 0:
+                raise _lib.DibError(self._lib.dib_last_error().decode())
+        return buf.value.decode()
 
     def _release_handle(self):
         if getattr(self, "_handle", None) is not None:
@@ -455,14 +484,23 @@ class DistributedIBNet:
         return logs
 
     # ------------------------------------------------------------------ Keras-like public surface
-    def __call__(self, inputs, training=None, eps=None, step=None):
+    def _inference_step(self):
+        """Philox 'step' word of an un-seeded inference call: bit 31 marks inference (training steps count from 0),
+        bit 30 separates it from the validation passes of fit, the low bits count calls -- every call draws fresh
+        noise like tf.random.normal at models.py:108 does."""
+        self._inference_calls += 1
+        return (3 << 30) | (self._inference_calls & 0x3FFFFFFF)
+
+    def __call__(self, inputs, training=None, eps=None, step=None, sample_offset=0):
         """models.py:96-123.  Returns the prediction; ``model.losses`` then holds [beta * sum_i KL_i] and
-        ``model.metrics_values`` the KL{i}/beta metrics, as add_loss/add_metric leave them in the reference."""
+        ``model.metrics_values`` the KL{i}/beta metrics, as add_loss/add_metric leave them in the reference.
+        Noise: explicit ``eps`` [n, F, E], or Philox keyed by ``step`` (reproducible), or -- default -- a fresh draw
+        on every call."""
         with torch.cuda.device(self.device):
             x = self._to_device(inputs, sum(self.feature_dimensionalities))
             e = self._to_device(eps) if eps is not None else None
-            st = self._train_step_count if step is None else step
-            pred, _, stats = self._forward(x, None, e, st, 0)
+            st = self._inference_step() if step is None else step
+            pred, _, stats = self._forward(x, None, e, st, sample_offset)
             n = x.shape[0]
             kl = stats[:self.number_features] / max(n, 1)
             self.losses = [self.beta._dev[0] * kl.sum()]
@@ -474,7 +512,10 @@ class DistributedIBNet:
 
     def compile(self, optimizer='adam', loss=None, metrics=None, **_):
         """train.py:138-142."""
-        self.optimizer = optimizers.get(optimizer) if not isinstance(optimizer, Adam) else optimizer
+        new_opt = optimizers.get(optimizer) if not isinstance(optimizer, Adam) else optimizer
+        if new_opt is not self.optimizer:        # a fresh Keras optimizer has fresh slots and iteration count
+            self._m.zero_(); self._v.zero_(); self._step_dev.zero_()
+        self.optimizer = new_opt
         self._loss_kind = resolve_loss(loss)
         self.compiled_metrics_names = []
         for m in (metrics or []):
@@ -600,9 +641,9 @@ class DistributedIBNet:
                 logs = self._read_epoch_logs()
                 if xv is not None:
                     logs.update(self._evaluate_into_logs(xv, yv, batch_size, epoch, world, rank))
-                if verbose not in (False, 0, 'auto') and rank == 0:
+                if verbose not in (False, 0) and rank == 0:          # 'auto' -> 1 like Keras outside notebooks
                     print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(
-                        f"{k}: {v:.4g}" for k, v in logs.items() if not k.lstrip('val_').startswith('KL')))
+                        f"{k}: {v:.4g}" for k, v in logs.items() if not k.removeprefix('val_').startswith('KL')))
                 for cb in cbs:
                     cb.on_epoch_end(epoch, logs)
                 if self.stop_training:
@@ -628,17 +669,20 @@ class DistributedIBNet:
         with torch.cuda.device(self.device):
             world, rank = parallel.world_and_rank(self.process_group)
             D = sum(self.feature_dimensionalities)
+            self._inference_calls += 1           # a fresh noise draw per evaluate() call
             logs = self._evaluate_into_logs(self._to_device(x, D), self._to_device(y, self._y_cols()), int(batch_size),
-                                            0, world, rank)
+                                            (1 << 29) | (self._inference_calls & 0x1FFFFFFF), world, rank)
         logs = {k[len("val_"):]: v for k, v in logs.items()}
         return logs if return_dict else [logs["loss"]] + [logs[m] for m in self.compiled_metrics_names]
 
     def predict(self, x, batch_size=32, **_):
         outs = []
         n = len(x)
+        st = self._inference_step()              # one noise stream per predict(); rows keyed by their global index
         for b0 in range(0, n, int(batch_size)):
-            outs.append(np.asarray(self(x[b0:b0 + int(batch_size)], training=False)) if not isinstance(x, torch.Tensor)
-                        else self(x[b0:b0 + int(batch_size)], training=False))
+            xb = x[b0:b0 + int(batch_size)]
+            o = self(xb, training=False, step=st, sample_offset=b0)
+            outs.append(o if isinstance(x, torch.Tensor) else np.asarray(o))
         return torch.cat(outs) if isinstance(x, torch.Tensor) else np.concatenate(outs)
 
 

@@ -54,9 +54,17 @@ enum dib_loss {
   DIB_LOSS_EXTERNAL = 3
 };
 
-/* arithmetic of the dense contractions. FP32 = CUDA-core FMA (parity path).  The tensor-core modes
- * use tcgen05.mma with fp32 accumulation in TMEM; everything else (PE, KL, exp, loss, Adam) stays fp32. */
-enum dib_precision { DIB_PREC_FP32 = 0, DIB_PREC_TF32 = 1, DIB_PREC_BF16 = 2 };
+/* arithmetic of the dense contractions; everything else (PE, exp, KL, loss, Adam, reductions) is fp32 in every mode
+ * and all tensor-core modes accumulate in fp32 (TMEM).
+ *   FP32: CUDA-core FMA -- the exact parity path (the reference's tf.keras fp32 graph on a CPU).
+ *   TF32: tcgen05.mma kind::tf32 on fp32 storage (10-bit mantissa, 8-bit exponent operands, rounded not truncated):
+ *         what stock TensorFlow does to an fp32 model on a tensor-core GPU.  Unfused grouped GEMMs.
+ *   FP16: tcgen05.mma kind::f16 on fp16 operands (10-bit mantissa like TF32 but a 5-bit exponent: |value| <= 65504,
+ *         saturating conversions, gradients carried under a power-of-two loss scale) -- the fused per-feature encoder
+ *         kernels and the 16-bit integration path; shapes outside their envelope run on the TF32 kernels.
+ *   BF16: the same fused kernels on bf16 operands (7-bit mantissa, fp32's exponent range).
+ * dib_model_info() reports which kernel family a handle actually selected. */
+enum dib_precision { DIB_PREC_FP32 = 0, DIB_PREC_TF32 = 1, DIB_PREC_BF16 = 2, DIB_PREC_FP16 = 3 };
 
 /* Mirrors the constructor of models.DistributedIBNet (models.py:56-66). */
 typedef struct dib_config {
@@ -209,6 +217,11 @@ const char* dib_last_error(void);
 
 /* "sm_100a" etc: the architecture the kernels were compiled for, and the ABI version. */
 const char* dib_build_info(void);
+
+/* one line describing what THIS handle runs, e.g.
+ * "precision=fp16 encoders=fused-tcgen05-f16 integration=int16-tcgen05-f16 operands=fp16 accumulate=fp32".
+ * Returns the number of bytes written (excluding the terminator), negative on error. */
+int32_t dib_model_info(const dib_model* h, char* out, size_t out_bytes);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,12 @@
-"""GPU (B200): the TF32 tensor-core path (tcgen05.mma, fp32 accumulation) against the float64 oracle and the
-exact-fp32 CUDA path.  Stated tolerance: TF32 keeps 10 mantissa bits per operand (relative rounding 2^-11 ~ 4.9e-4);
-with fp32 accumulation over K <= 512 terms of mixed sign the observed max-norm relative error of activations and
-gradients stays below 5e-3, which is the bound asserted here (the fp32 path is held to 5e-5 in test_gpu_parity)."""
+"""GPU (B200): the tensor-core modes (tcgen05.mma, fp32 accumulation in TMEM) against the float64 oracle and the
+exact-fp32 CUDA path.
+  'fp16' -- fused per-feature encoder kernels + 16-bit integration path, fp16 operands (10 explicit mantissa bits,
+            relative rounding 2^-11 ~ 4.9e-4, 5-bit exponent);
+  'tf32' -- kind::tf32 grouped GEMMs on fp32 storage (same mantissa, 8-bit exponent);
+  'bf16' -- the fused kernels on bf16 operands (7 explicit mantissa bits, relative rounding 2^-8 ~ 3.9e-3).
+Stated tolerance: with fp32 accumulation over K <= 512 terms of mixed sign the max-norm relative error of activations
+and gradients stays below 5e-3 for the 11-bit-significand modes and below 4e-2 for bf16 (8x the rounding unit), which
+are the bounds asserted here (the fp32 path is held to 5e-5 in test_gpu_parity)."""
 import numpy as np
 import pytest
 import torch
@@ -11,13 +16,28 @@ from tests.test_gpu_parity import LOSS_OF, build_model, load_case, make_labels, 
 
 pytestmark = pytest.mark.gpu
 TOL = 5e-3
+TOLS = {"fp16": 5e-3, "tf32": 5e-3, "bf16": 4e-2}
 
 
+def test_kernel_info_names_what_runs():
+    """The label a handle reports is the arithmetic it runs: C0 in 'fp16' selects the fused f16 kernels, 'tf32' never
+    does, an off-envelope shape in 'fp16' falls back to the tf32 kernels and says so."""
+    c0 = O.DIBConfig([1] * 16, [128, 128], [256, 256], 1)
+    assert "encoders=fused-tcgen05-f16 integration=int16-tcgen05-f16 operands=fp16" in build_model(c0, precision="fp16").kernel_info()
+    assert "encoders=fused-tcgen05-bf16 integration=int16-tcgen05-bf16 operands=bf16" in build_model(c0, precision="bf16").kernel_info()
+    assert "encoders=grouped-tcgen05-tf32 integration=tcgen05-tf32 operands=tf32" in build_model(c0, precision="tf32").kernel_info()
+    assert "simt-fp32" in build_model(c0, precision="fp32").kernel_info()
+    odd = O.DIBConfig([1] * 4, [64, 64], [128], 1)
+    assert "encoders=grouped-tcgen05-tf32" in build_model(odd, precision="fp16").kernel_info()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "tf32", "bf16"])
 @pytest.mark.parametrize("name", ["c0_small", "radial_like", "pendulum_like", "odd_shapes"])
-def test_tf32_forward_and_gradients_vs_oracle(golden_dir, name):
+def test_tc_forward_and_gradients_vs_oracle(golden_dir, name, prec):
+    TOL = TOLS[prec]
     cfg, z = load_case(golden_dir, name)
     loss_name, loss = LOSS_OF[name]
-    m = build_model(cfg, precision="tf32", loss=loss_name)
+    m = build_model(cfg, precision=prec, loss=loss_name)
     m.set_flat_weights(z["params"])
     beta = float(z["beta"])
     m.beta.assign(beta)
@@ -35,11 +55,12 @@ def test_tf32_forward_and_gradients_vs_oracle(golden_dir, name):
     off = 0
     for s in cfg.param_shapes():
         n = int(np.prod(s))
-        assert rel_err(g[off:off + n], g_ref[off:off + n]) < (0.1 if z["x"].shape[0] >= 64 else 0.35), (off, s)
+        assert rel_err(g[off:off + n], g_ref[off:off + n]) < (0.1 if z["x"].shape[0] >= 64 else 0.35) * (TOL / 5e-3) ** 0.5, (off, s)
         off += n
 
 
-def test_tf32_matches_fp32_path_multi_split_batch():
+@pytest.mark.parametrize("tc", ["fp16", "tf32", "bf16"])
+def test_tc_matches_fp32_path_multi_split_batch(tc):
     """4096 rows -> 16 deterministic batch splits in the weight-gradient kernels; ragged tail (4096+77)."""
     cfg = O.DIBConfig([1] * 16, [128, 128], [256, 256], 1)
     rng = np.random.default_rng(0)
@@ -48,7 +69,7 @@ def test_tf32_matches_fp32_path_multi_split_batch():
         x = rng.standard_normal((B, 16)).astype(np.float32)
         y = (x[:, 0] * x[:, 1] > 0).astype(np.float32)[:, None]
         out = {}
-        for prec in ("fp32", "tf32"):
+        for prec in ("fp32", tc):
             m = build_model(cfg, precision=prec)
             m.set_flat_weights(p)
             m.beta.assign(0.01)
@@ -56,14 +77,15 @@ def test_tf32_matches_fp32_path_multi_split_batch():
             g2, st2 = m.compute_gradients(x, y, step=1)
             assert torch.equal(g, g2) and torch.equal(st, st2)          # deterministic
             out[prec] = (g.cpu().numpy(), st.cpu().numpy())
-        assert rel_err(out["tf32"][0], out["fp32"][0]) < TOL
-        np.testing.assert_allclose(out["tf32"][1], out["fp32"][1], rtol=TOL)
+        assert rel_err(out[tc][0], out["fp32"][0]) < TOLS[tc]
+        np.testing.assert_allclose(out[tc][1], out["fp32"][1], rtol=TOLS[tc])
 
 
-def test_tf32_training_reduces_loss():
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_tc_training_reduces_loss(prec):
     import dib_b200
     x, y = O.boolean_circuit_truth_table()
-    m = dib_b200.DistributedIBNet([1] * 10, [128, 128], [256, 256], 1, precision="tf32", seed=3)
+    m = dib_b200.DistributedIBNet([1] * 10, [128, 128], [256, 256], 1, precision=prec, seed=3)
     m.compile(optimizer=dib_b200.Adam(1e-3), loss=dib_b200.losses.BinaryCrossentropy(from_logits=True), metrics=["accuracy"])
     h = m.fit(x, y, epochs=30, batch_size=256, callbacks=[dib_b200.InfoBottleneckAnnealingCallback(1e-4, 1e-3, 30, 1)]).history
     assert h["loss"][-1] < 0.6 * h["loss"][0] and h["accuracy"][-1] > 0.85
@@ -85,8 +107,8 @@ def test_fused_encoder_kernels_match_unfused_and_fp32(shape):
         x = rng.standard_normal((B, D)).astype(np.float32)
         y = (x[:, 0] * x[:, 1] > 0).astype(np.float32)[:, None] if out == 1 else rng.standard_normal((B, out)).astype(np.float32)
         res = {}
-        for tag, prec, unfused in (("fp32", "fp32", 0), ("tc_unfused", "tf32", 1), ("tc_fused_int32", "tf32", 2),
-                                   ("tc_fused", "tf32", 0)):
+        for tag, prec, unfused in (("fp32", "fp32", 0), ("tc_unfused", "tf32", 0), ("tc_fused_int32", "fp16", 2),
+                                   ("tc_fused", "fp16", 0)):
             m = build_model(cfg, precision=prec, loss=loss_name)
             m.debug_force_unfused(unfused)
             m.set_flat_weights(p)
