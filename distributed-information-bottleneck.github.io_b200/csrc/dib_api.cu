@@ -426,6 +426,12 @@ int dib_debug_force_unfused(dib_model* h, int32_t on) {
   return 0;
 }
 
+// kernel-variant switch for A/B measurements: key 0 = fused encoder backward kernel (1 = single chain, 2 = two chains)
+int dib_debug_set_variant(int32_t key, int32_t value) {
+  if (key == 0) { dib_enc_bwd_set_version(value); return 0; }
+  return fail("dib_debug_set_variant: unknown key");
+}
+
 int dib_profile_enable(dib_model* h, int32_t on) {
   if (!h) return fail("null model handle");
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

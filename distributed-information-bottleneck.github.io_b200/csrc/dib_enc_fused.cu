@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "dib_common.cuh"
 #include "dib_kernels.h"
@@ -85,6 +86,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return r;
 }
 
+// same with relu fused into the conversion (F2FP.RELU): max(x, 0) costs no instruction of its own
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+  uint32_t r;
+  if constexpr (BF16) asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -107,20 +117,33 @@ __device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, uint32_t tile, 
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < CH; j += 8) {
-      float f[8];
+      if constexpr (RELU) {
+        st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * CH + j),
+                     pack2_relu<BF16>(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                     pack2_relu<BF16>(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
+                     pack2_relu<BF16>(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
+                     pack2_relu<BF16>(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+      } else {
+        float f[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float z = __uint_as_float(v[j + k]);
-        f[k] = RELU ? fmaxf(z, 0.f) : dib_act(act, z, alpha);
+        for (int k = 0; k < 8; ++k) f[k] = dib_act(act, __uint_as_float(v[j + k]), alpha);
+        st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * CH + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
+                     pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
       }
-      st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * CH + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
-                   pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
     }
   }
 }
 
 // first-layer operand row: [x_0..x_{d-1}, sin(2x).., sin(4x).., ..., 1, 0...] (models.py:22-23 + the ones column
 // that carries every layer's bias through the bias-carrier matrices).  xv = the row's (prefetched) feature values.
+// sin for the positional encoding: reduce to one period in units of turns, then the SFU (sin.approx of an argument in
+// [-pi, pi] is good to ~1e-6 absolute; the reduction adds |arg| * 6e-8) -- no local-memory slow path like sinf's, and far
+// below the 16-bit operand rounding (5e-4 relative) that follows.
+__device__ __forceinline__ float dib_sin_pe(float a) {
+  float t = a * 0.15915494309189535f;
+  t -= rintf(t);
+  return __sinf(6.283185307179586f * t);
+}
 constexpr int kMaxFeatDim = 3;     // d * nfreq + 1 <= 16 and nfreq >= 1
 __device__ __forceinline__ void load_x(const float* xrow, int d, float (&xv)[kMaxFeatDim]) {
 #pragma unroll
@@ -140,7 +163,7 @@ __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, bool
       float xj = xv[0];
 #pragma unroll
       for (int q = 1; q < kMaxFeatDim; ++q) if (j == q) xj = xv[q];
-      v = blk == 0 ? xj : sinf((float)(1 << blk) * xj);
+      v = blk == 0 ? xj : dib_sin_pe((float)(1 << blk) * xj);
     } else if (col == w_in) {
       v = valid ? 1.f : 0.f;          // rows past the batch end contribute nothing
     }
@@ -742,6 +765,405 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
   if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
 }
 
+// ====================================================================================================
+// backward, version 2: the per-tile chain of version 1 (five MMA <-> epilogue round trips, one tile in flight) is cut
+// into two chains that run CONCURRENTLY on consecutive tiles, each with its own MMA-issuing thread, its own epilogue
+// warps and its own TMEM region:
+//   chain A (tile i)  : x -> [pe|1] -> D0 -> h1 -> D1 -> h2 -> D2 = (mu|logvar) -> d(mu|logvar) = dO      [8 warps]
+//   chain B (tile i-1): G2 = dO W2^T -> dz2 = G2*act'(h2) -> G1 = dz2 W1^T -> dz1 = G1*act'(h1); all wgrad MMAs [4 warps]
+// so the tile time is max(A, B) instead of A + B and two sets of warps keep the issue slots busy.  What makes two
+// tiles fit: dz2 / dz1 are written IN PLACE over h2 / h1 (their last reader, the dW2 / dW1 MMA, has retired by then),
+// so a tile needs h1 + h2 = 64 KB and two of them plus three 4 KB [pe|1] operands, one dO tile and the 58 KB of
+// weights are 214 KB.
+// TMEM: [0,128) chain A (D0, D1, D2) | [128,256) chain B (G2, G1) | [256,496) weight-gradient accumulators (as v1).
+// Warps: 0 MMA issuer A (+ weight TMA) | 1 MMA issuer B | 2 TMEM owner | 3 idle | 4..11 chain-A epilogue | 12..15 chain B.
+// ====================================================================================================
+constexpr int kV2OffDO = kOffA0;                       // 58 KB: [128 x 64] one panel (db2 reads 16 KB past it: A0s + h1)
+constexpr int kV2OffA0 = kV2OffDO + kPanel;            // THREE [pe|1] operands, 4 KB each (tile i + 1's is staged while tile i - 1 may
+                                                       // still be in chain B: a third buffer keeps chain A from waiting on it)
+constexpr int kV2OffH1 = kV2OffA0 + 3 * (2 * TM * 16); // 86 KB, 1024-aligned; h1[0], h1[1]
+constexpr int kV2OffH2 = kV2OffH1 + 2 * (2 * kPanel);  // h2[0], h2[1]
+constexpr int kV2OffBar = kV2OffH2 + 2 * (2 * kPanel); // 210 KB
+static_assert(kV2OffH1 % 1024 == 0 && kV2OffDO % 1024 == 0, "operand tiles must be 1024-byte aligned");
+constexpr int kV2Threads = 16 * 32;
+
+// gradient * act'(h) IN PLACE: the 128-byte row chunk of h is read, the gated 16-bit gradient is written back to the
+// same address (same thread), NC columns starting at col0.
+template <bool BF16, bool RELU, int NC>
+__device__ __forceinline__ void dgrad_inplace(uint32_t taddr, uint32_t tile, int r, int col0, int act, float alpha) {
+  constexpr int CH = 32;
+#pragma unroll
+  for (int hh = 0; hh < NC / CH; ++hh) {
+    uint32_t v[CH];
+    tmem_ld_32x32b_x32(taddr + col0 + hh * CH, v);
+    uint32_t hv[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ld_shared_v4(tile_chunk_addr(tile, r, col0 + hh * CH + j * 8), hv[j]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float g0 = __uint_as_float(v[j * 8 + 2 * k]), g1 = __uint_as_float(v[j * 8 + 2 * k + 1]);
+        if constexpr (RELU) {
+          o[k] = relu_gate2<BF16>(pack2<BF16>(g0, g1), hv[j][k]);
+        } else {
+          float h0, h1;
+          unpack2<BF16>(hv[j][k], h0, h1);
+          o[k] = pack2<BF16>(g0 * dib_act_grad(act, h0, alpha), g1 * dib_act_grad(act, h1, alpha));
+        }
+      }
+      st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * CH + j * 8), o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <bool BF16, bool RELU>
+__global__ void __launch_bounds__(kV2Threads, 1)
+dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFusedBwdParams Q) {
+  const EncFusedParams& P = Q.f;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t bar = sb + kV2OffBar;
+  const uint32_t bar_w = bar, bar_a0 = bar + 8, bar_d0 = bar + 16, bar_h1 = bar + 24, bar_d1 = bar + 32,
+                 bar_h2 = bar + 40, bar_d2 = bar + 48, bar_do = bar + 56, bar_dofree = bar + 64, bar_g2 = bar + 72,
+                 bar_dz2 = bar + 80, bar_g1 = bar + 88, bar_dw1 = bar + 96, bar_dz1 = bar + 104, bar_wg0 = bar + 112 /* [2] */,
+                 tmem_slot = bar + 128;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kV2OffBar + 128);
+  constexpr int kEA = 8, kEB = 4;     // epilogue warps of chain A / chain B
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, c = blockIdx.x, F = P.F;
+  const int ntiles = (int)((P.n + TM - 1) / TM);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.w0); tma_prefetch_desc(&maps.w1); tma_prefetch_desc(&maps.w2);
+    tma_prefetch_desc(&maps.b1); tma_prefetch_desc(&maps.b2);
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a0, kEA); mbar_init(bar_h1, kEA); mbar_init(bar_h2, kEA); mbar_init(bar_do, kEA);
+    mbar_init(bar_dz2, kEB); mbar_init(bar_dz1, kEB);
+    mbar_init(bar_d0, 1); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_dofree, 1); mbar_init(bar_g2, 1);
+    mbar_init(bar_g1, 1); mbar_init(bar_dw1, 1); mbar_init(bar_wg0, 1); mbar_init(bar_wg0 + 8, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot_g;
+  const uint32_t tR0 = tmem, tR1 = tmem + 128, tWG1 = tmem + 256, tWG2 = tmem + 384, tWG0 = tmem + 448, tWB1 = tmem + 464, tWB2 = tmem + 480;
+
+  int f_first, f_step, nslots, slot;
+  if (G >= F) { f_first = c % F; f_step = F * G; slot = c / F; nslots = (G - f_first + F - 1) / F; }
+  else { f_first = c; f_step = G; slot = 0; nslots = 1; }
+
+  constexpr uint32_t fmt = BF16 ? 1u : 0u;
+  constexpr uint32_t id_kk_128 = umma_idesc(fmt, 0, 0, HID);
+  constexpr uint32_t id_mm_128 = umma_idesc(fmt, 1, 1, HID), id_mm_64 = umma_idesc(fmt, 1, 1, EO),
+                     id_mm_16 = umma_idesc(fmt, 1, 1, 16);
+  uint32_t it = 0, fit = 0;          // running tile / feature counters of this CTA (barrier phases)
+  const float S = Q.gscale, invS = 1.f / Q.gscale;
+  auto a0_of = [&](uint32_t i) { return sb + kV2OffA0 + (i % 3u) * (2 * TM * 16); };
+  auto h1_of = [&](uint32_t i) { return sb + kV2OffH1 + (i & 1) * (2 * kPanel); };
+  auto h2_of = [&](uint32_t i) { return sb + kV2OffH2 + (i & 1) * (2 * kPanel); };
+  const uint32_t sDO = sb + kV2OffDO;
+
+  // Each role runs its own copy of the feature loop INSIDE its branch, behind a setmaxnreg that rebalances the register
+  // file between the warpgroups (launched with 128 per thread; per scheduler: 1 control warp x 56 + 2 chain-A warps x 168
+  // + 1 chain-B warp x 112 = 504 <= 512).  ptxas allocates each branch against its own budget only if the branches do not
+  // merge before the kernel's trivial tail.
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    for (int f = f_first; f < F; f += f_step, ++fit) {
+      const int ntl = slot < ntiles ? (ntiles - slot + nslots - 1) / nslots : 0;   // tiles of this (feature, CTA)
+      const bool any_tiles = ntl > 0; (void)any_tiles;
+      if (warp == 0) {
+      // ================= MMA issuer A: the forward recompute chain
+      if (lane == 0) {
+        load_weights(sb, maps, bar_w, f);
+        mbar_wait_backoff(bar_w, fit & 1);
+        for (int k = 0; k < ntl; ++k) {
+          const uint32_t i = it + k, ph = i & 1;
+          const uint32_t a0 = a0_of(i);
+          mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
+          issue_layer0<BF16>(sb, tR0, a0); umma_commit(bar_d0);
+          mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
+          issue_layer1<BF16>(sb, tR0, h1_of(i), a0); umma_commit(bar_d1);
+          mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
+          issue_layer2<BF16>(sb, tR0, h2_of(i), a0); umma_commit(bar_d2);
+        }
+      }
+      __syncwarp();
+      } else if (warp == 1) {
+      // ================= MMA issuer B: dgrad + every weight-gradient MMA
+      if (lane == 0) {
+        mbar_wait_backoff(bar_w, fit & 1);
+        for (int k = 0; k < ntl; ++k) {
+          const uint32_t i = it + k, ph = i & 1;
+          const uint32_t a0 = a0_of(i), h1 = h1_of(i), h2 = h2_of(i);
+          const bool first = k == 0;
+          // ---- layer 2 backward: G2 = dO W2^T ; dW2 += h2^T dO ; db2 += dO^T [pe|1]
+          mbar_wait_backoff(bar_do, ph); tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16<BF16>(tR1, umma_smem_desc(sDO + kk * 32, 16, 1024), umma_smem_desc(sb + kOffW2 + kk * 32, 16, 1024),
+                           id_kk_128, kk > 0 ? 1u : 0u);
+          umma_commit(bar_g2);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWG2, umma_smem_desc(h2 + kk * 2048, kPanel, 1024), umma_smem_desc(sDO + kk * 2048, kPanel, 1024),
+                           id_mm_64, (first && kk == 0) ? 0u : 1u);
+          // M = 128 is formed by dO (64 columns) and the 16 KB that follow it in shared memory (the [pe|1] operands and
+          // the start of h1[0]): TMEM lanes 64..127 of this accumulator are never read.
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWB2, umma_smem_desc(sDO + kk * 2048, kPanel, 1024),
+                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
+          umma_commit(bar_dofree);          // dO is free again; h2 may be overwritten by dz2
+          // ---- layer 1 backward: G1 = dz2 W1^T ; dW1 += h1^T dz2 ; db1 += dz2^T [pe|1]      (dz2 lives in the h2 buffer)
+          mbar_wait_backoff(bar_dz2, ph); tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tR1, umma_smem_desc(h2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
+                           umma_smem_desc(sb + kOffW1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024), id_kk_128, kk > 0 ? 1u : 0u);
+          umma_commit(bar_g1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWG1, umma_smem_desc(h1 + kk * 2048, kPanel, 1024), umma_smem_desc(h2 + kk * 2048, kPanel, 1024),
+                           id_mm_128, (first && kk == 0) ? 0u : 1u);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWB1, umma_smem_desc(h2 + kk * 2048, kPanel, 1024),
+                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
+          umma_commit(bar_dw1);             // h1 may be overwritten by dz1
+          // ---- layer 0 backward: [dW0;db0]^T += dz1^T [pe|1]      (dz1 lives in the h1 buffer)
+          mbar_wait_backoff(bar_dz1, ph); tc_fence_after_sync();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16<BF16>(tWG0, umma_smem_desc(h1 + kk * 2048, kPanel, 1024),
+                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
+          umma_commit(bar_wg0 + 8 * (i & 1));   // buffer set (i & 1) is free for tile i + 2
+        }
+      }
+      __syncwarp();
+      }
+      it += (uint32_t)ntl;
+      // accumulators flushed, every MMA retired: the next feature may reload the weights (all 16 warps meet here)
+      asm volatile("bar.sync 0, %0;" ::"n"(kV2Threads) : "memory");
+      tc_fence_after_sync();
+    }
+  } else if (warp < 4 + kEA) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    for (int f = f_first; f < F; f += f_step, ++fit) {
+      const int ntl = slot < ntiles ? (ntiles - slot + nslots - 1) / nslots : 0;   // tiles of this (feature, CTA)
+      const bool any_tiles = ntl > 0; (void)any_tiles;
+      {
+      // ================= chain A epilogue warps: 4 TMEM lane quarters x 2 column halves
+      const int ew = warp - 4, q = warp & 3, csel = ew >> 2;
+      const int et = ew * 32 + lane;
+      const int r = q * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      const int d = P.fdim[f], xo = P.x_off[f];
+      const float bs = Q.beta_dev[0] * Q.inv_batch * S;
+      const int ar = et & (TM - 1), khalf = et >> 7;          // [pe|1] operand: (row, k-half) staged by this thread
+      float xv[kMaxFeatDim];
+      if (any_tiles) {                                        // operand of the feature's first tile (both buffer sets are drained)
+        const long long grow0 = (long long)slot * TM + ar;
+        load_x(grow0 < P.n ? P.x + grow0 * P.ldx + xo : nullptr, d, xv);
+        write_a0_row<BF16>(a0_of(it), ar, khalf, grow0 < P.n, xv, d, P.nfreq);
+        DIB_EPI_SIGNAL(bar_a0);
+      }
+      for (int k = 0; k < ntl; ++k) {
+        const uint32_t i = it + k, ph = i & 1;
+        const int t = slot + k * nslots;
+        const long long row0 = (long long)t * TM;
+        const long long grow = row0 + r;
+        const bool valid = grow < P.n;
+        const bool has_next = k + 1 < ntl;
+        const long long grow_n = (long long)(t + nslots) * TM + ar;
+        // prefetch this thread's 16 embedding dims of the upstream gradient and the next tile's x
+        uint4 dpre[2];
+        if (Q.d_emb16) {
+          const uint16_t* src = Q.d_emb16 + (valid ? grow : 0) * Q.ldd16 + f * 32 + csel * 16;
+          dpre[0] = *reinterpret_cast<const uint4*>(src); dpre[1] = *reinterpret_cast<const uint4*>(src + 8);
+        }
+        if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv);
+        const float* ep = (P.eps && valid) ? P.eps + (grow * F + f) * 32 + csel * 16 : P.eps;
+        uint32_t nz16[8];            // this thread's 16 noise values, packed 16-bit (they multiply a 16-bit gradient)
+        // buffer set (i & 1) was last used by tile i - 2: all of its MMAs (chain B commits last) have retired
+        if (i >= 2) { mbar_wait(bar_wg0 + 8 * (i & 1), ((i >> 1) - 1) & 1); }
+        mbar_wait(bar_d0, ph); tc_fence_after_sync();
+        epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, h1_of(i), r, csel * 64, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_h1);
+        {                                                                                           // while layer 1 runs
+          float nrm[8];
+          noise8(ep, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, csel * 16, valid, nrm);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nz16[j] = pack2<BF16>(nrm[2 * j], nrm[2 * j + 1]);
+        }
+        mbar_wait(bar_d1, ph); tc_fence_after_sync();
+        epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, h2_of(i), r, csel * 64, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_h2);
+        {                                                                                           // while layer 2 runs
+          float nrm[8];
+          noise8(ep ? ep + 8 : nullptr, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, csel * 16 + 8, valid, nrm);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nz16[4 + j] = pack2<BF16>(nrm[2 * j], nrm[2 * j + 1]);
+        }
+        if (has_next)        // stage the next tile's [pe|1] operand: buffer (i + 1) % 3 was last read by tile i - 2 (retired, see above)
+          write_a0_row<BF16>(a0_of(i + 1), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
+        // ---- (mu, logvar) -> d(mu), d(logvar) -> dO tile, 8 embedding dims at a time.  The dO buffer is single: wait
+        // until the previous tile's dO has been consumed.  After the LAST TMEM load chain A's region is free for the
+        // next tile's layer 0, which then runs under the second half of this stage.
+        mbar_wait(bar_d2, ph); tc_fence_after_sync();
+        if (i >= 1) { mbar_wait(bar_dofree, (i - 1) & 1); }
+        {
+          const float* du = Q.d_emb ? Q.d_emb + (valid ? grow : 0) * Q.ldd + f * 32 + csel * 16 : nullptr;
+          const bool du16 = Q.d_emb16 != nullptr;
+          const uint32_t do_row = sDO + r * 128;
+          const int r7 = r & 7;
+#pragma unroll
+          for (int e8 = 0; e8 < 16; e8 += 8) {
+            uint32_t vm[8], vl[8];
+            tmem_ld_32x32b_x8(tR0 + lane_addr + csel * 16 + e8, vm);
+            tmem_ld_32x32b_x8(tR0 + lane_addr + 32 + csel * 16 + e8, vl);
+            tmem_ld_wait();
+            if (e8 == 8) {
+              if (has_next) { DIB_EPI_SIGNAL(bar_a0); }
+              else { tc_fence_before_sync(); }
+            }
+            float dm[8], dl[8];
+#pragma unroll
+            for (int e0 = 0; e0 < 8; e0 += 4) {
+              float g[4], nz[4];
+              if (du16) {
+                const uint4 gq = dpre[e8 >> 3];
+                uint32_t w0 = e0 == 0 ? gq.x : gq.z, w1 = e0 == 0 ? gq.y : gq.w;
+                unpack2<BF16>(w0, g[0], g[1]); unpack2<BF16>(w1, g[2], g[3]);
+              } else {
+                const float4 g4 = *reinterpret_cast<const float4*>(du + e8 + e0);
+                g[0] = g4.x * S; g[1] = g4.y * S; g[2] = g4.z * S; g[3] = g4.w * S;
+              }
+              unpack2<BF16>(nz16[(e8 + e0) >> 1], nz[0], nz[1]); unpack2<BF16>(nz16[((e8 + e0) >> 1) + 1], nz[2], nz[3]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
+                const float sg = __expf(0.5f * lv);
+                const float gs = g[j];
+                dm[e0 + j] = valid ? fmaf(bs, mu, gs) : 0.f;
+                dl[e0 + j] = valid ? fmaf(gs * nz[j], 0.5f * sg, bs * 0.5f * (sg * sg - 1.f)) : 0.f;
+              }
+            }
+            const int cm = (csel * 16 + e8) >> 3, cl = (32 + csel * 16 + e8) >> 3;       // 16-byte chunk indices
+            st_shared_v4(do_row + ((cm ^ r7) << 4), pack2<BF16>(dm[0], dm[1]), pack2<BF16>(dm[2], dm[3]),
+                         pack2<BF16>(dm[4], dm[5]), pack2<BF16>(dm[6], dm[7]));
+            st_shared_v4(do_row + ((cl ^ r7) << 4), pack2<BF16>(dl[0], dl[1]), pack2<BF16>(dl[2], dl[3]),
+                         pack2<BF16>(dl[4], dl[5]), pack2<BF16>(dl[6], dl[7]));
+          }
+        }
+        DIB_EPI_SIGNAL(bar_do);
+      }
+      // every MMA of this feature has retired (chain B's last commit) before the accumulators are read back
+      if (any_tiles) { const uint32_t il = it + ntl - 1; mbar_wait(bar_wg0 + 8 * (il & 1), (il >> 1) & 1); tc_fence_after_sync(); }
+      // ---- flush dW1[h1 = r][h2 cols csel*64 ..] (scaled back by 1/S)
+      {
+        float* part = Q.part + (long long)slot * Q.split_stride;
+        float* dst = part + Q.w1_off[f] + (long long)r * HID + csel * 64;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          if (any_tiles) { tmem_ld_32x32b_x32(tWG1 + lane_addr + csel * 64 + hh * 32, v); tmem_ld_wait(); }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + hh * 32 + j) = any_tiles
+                ? make_float4(__uint_as_float(v[j]) * invS, __uint_as_float(v[j + 1]) * invS,
+                              __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS)
+                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      tc_fence_before_sync();
+      }
+      it += (uint32_t)ntl;
+      // accumulators flushed, every MMA retired: the next feature may reload the weights (all 16 warps meet here)
+      asm volatile("bar.sync 0, %0;" ::"n"(kV2Threads) : "memory");
+      tc_fence_after_sync();
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    for (int f = f_first; f < F; f += f_step, ++fit) {
+      const int ntl = slot < ntiles ? (ntiles - slot + nslots - 1) / nslots : 0;   // tiles of this (feature, CTA)
+      const bool any_tiles = ntl > 0; (void)any_tiles;
+      {
+      // ================= chain B epilogue warps: one full row (128 columns) per thread
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      const int d = P.fdim[f];
+      for (int k = 0; k < ntl; ++k) {
+        const uint32_t i = it + k, ph = i & 1;
+        // ---- dz2 = G2 * act'(h2), in place over h2 (its last reader, the dW2 MMA, has retired: bar_dofree)
+        mbar_wait(bar_g2, ph); mbar_wait(bar_dofree, ph); tc_fence_after_sync();
+        dgrad_inplace<BF16, RELU, HID>(tR1 + lane_addr, h2_of(i), r, 0, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_dz2);
+        // ---- dz1 = G1 * act'(h1), in place over h1 (dW1 has retired: bar_dw1)
+        mbar_wait(bar_g1, ph); mbar_wait(bar_dw1, ph); tc_fence_after_sync();
+        dgrad_inplace<BF16, RELU, HID>(tR1 + lane_addr, h1_of(i), r, 0, P.act, P.alpha);
+        DIB_EPI_SIGNAL(bar_dz1);
+      }
+      if (any_tiles) { const uint32_t il = it + ntl - 1; mbar_wait(bar_wg0 + 8 * (il & 1), (il >> 1) & 1); tc_fence_after_sync(); }
+      // ---- flush dW2, [dW0;db0], db1, db2
+      float* part = Q.part + (long long)slot * Q.split_stride;
+      const int w_in = d * P.nfreq;
+      float* dst2 = part + Q.w2_off[f] + (long long)r * EO;                        // dW2[h2 = r][0..64)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        if (any_tiles) { tmem_ld_32x32b_x32(tWG2 + lane_addr + hh * 32, v); tmem_ld_wait(); }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst2 + hh * 32 + j) = any_tiles
+              ? make_float4(__uint_as_float(v[j]) * invS, __uint_as_float(v[j + 1]) * invS,
+                            __uint_as_float(v[j + 2]) * invS, __uint_as_float(v[j + 3]) * invS)
+              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      {
+        // dW0[k][h1 = r] (k < w_in), db0[r] = column w_in of dW0p^T; db1[h2 = r] = column w_in of dz2^T [pe|1]
+        uint32_t v0[16], v1[16];
+        if (any_tiles) { tmem_ld_32x32b_x16(tWG0 + lane_addr, v0); tmem_ld_32x32b_x16(tWB1 + lane_addr, v1); tmem_ld_wait(); }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float val = any_tiles ? __uint_as_float(v0[k]) * invS : 0.f;
+          if (k < w_in) part[Q.w0_off[f] + (long long)k * HID + r] = val;
+          else if (k == w_in) part[Q.b0_off[f] + r] = val;
+        }
+        float b1v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (k == w_in) b1v = any_tiles ? __uint_as_float(v1[k]) * invS : 0.f;
+        part[P.b1_off[f] + r] = b1v;
+        if (r < EO) {                                     // db2[o = r]: lanes 0..63 of the db2 accumulator
+          uint32_t v2[16];
+          if (any_tiles) { tmem_ld_32x32b_x16(tWB2 + lane_addr, v2); tmem_ld_wait(); }
+          float b2v = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) if (k == w_in) b2v = any_tiles ? __uint_as_float(v2[k]) * invS : 0.f;
+          part[P.b2_off[f] + r] = b2v;
+        }
+      }
+      tc_fence_before_sync();
+          }
+      it += (uint32_t)ntl;
+      // accumulators flushed, every MMA retired: the next feature may reload the weights (all 16 warps meet here)
+      asm volatile("bar.sync 0, %0;" ::"n"(kV2Threads) : "memory");
+      tc_fence_after_sync();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // fp32 master parameters -> packed 16-bit per-feature weights [W0p | W1 | W2 | Bb1 | Bb2]
 // (bias of layer 0 folded into W0p row w_in; b1 / b2 in row w_in of the bias carriers)
@@ -832,6 +1254,14 @@ cudaError_t launch_fused(K kern, int smem, int grid, const WeightMaps& m, const 
 
 }  // namespace
 
+// which backward kernel runs: 2 (default) or 1 (the single-chain kernel of round 1), DIB_ENC_BWD=1|2 in the environment
+static int g_enc_bwd_version = 0;
+int dib_enc_bwd_version() {
+  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '1') ? 1 : 2; }
+  return g_enc_bwd_version;
+}
+void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = v == 1 ? 1 : 2; }
+
 size_t dib_enc_fused_pack_bytes(int F) { return (size_t)F * kPackElems * 2; }
 int dib_enc_fused_fwd_ctas_per_sm() { return 2; }
 
@@ -873,8 +1303,15 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
   Q.d_emb = b.d_emb; Q.ldd = b.ldd; Q.beta_dev = b.beta_dev; Q.inv_batch = b.inv_batch; Q.gscale = b.gscale;
   Q.part = b.part; Q.split_stride = b.split_stride;
   Q.w0_off = d.w0_off; Q.b0_off = d.b0_off; Q.w1_off = d.w1_off; Q.w2_off = d.w2_off;
-  constexpr int smem = kOffBwdEnd + 256 + 1024;
   const bool relu = d.act == DIB_ACT_RELU;
+  if (dib_enc_bwd_version() == 2) {          // two chains on consecutive tiles (default)
+    constexpr int smem2 = kV2OffBar + 256 + 1024;
+    if (d.bf16) return relu ? launch_fused(dib_enc_fused_bwd2_kernel<true, true>, smem2, d.grid, m, Q, st, kV2Threads)
+                            : launch_fused(dib_enc_fused_bwd2_kernel<true, false>, smem2, d.grid, m, Q, st, kV2Threads);
+    return relu ? launch_fused(dib_enc_fused_bwd2_kernel<false, true>, smem2, d.grid, m, Q, st, kV2Threads)
+                : launch_fused(dib_enc_fused_bwd2_kernel<false, false>, smem2, d.grid, m, Q, st, kV2Threads);
+  }
+  constexpr int smem = kOffBwdEnd + 256 + 1024;
   if (d.bf16)    // bf16 operands end to end (7-bit mantissa gradients: the usual bf16-training trade, BASELINE config 4)
     return relu ? launch_fused(dib_enc_fused_bwd_kernel<true, true, 8>, smem, d.grid, m, Q, st, 32 * 9)
                 : launch_fused(dib_enc_fused_bwd_kernel<true, false, 8>, smem, d.grid, m, Q, st, 32 * 9);

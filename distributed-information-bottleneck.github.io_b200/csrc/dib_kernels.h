@@ -104,6 +104,8 @@ struct DibEncFusedIO {
   float* kl_part; int kl_stride;
   void* emb16 = nullptr; int ldemb16 = 0;   // optional fp16 copy of emb (16-bit integration path)
 };
+int dib_enc_bwd_version();
+void dib_enc_bwd_set_version(int v);
 size_t dib_enc_fused_pack_bytes(int F);
 int dib_enc_fused_fwd_ctas_per_sm();
 cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, cudaStream_t st);

@@ -212,6 +212,10 @@ int dib_debug_gemm_tc(int32_t mode, const float* A, int32_t lda, const float* B,
 /* bring-up switch (bit mask): 1 = unfused encoder kernels, 2 = integration network on fp32-storage TF32 kernels. */
 int dib_debug_force_unfused(dib_model* h, int32_t on);
 
+/* process-wide kernel-variant switch for A/B measurements.  key 0: fused encoder backward kernel, value 1 = the
+ * single-chain kernel of round 1, 2 = two chains on consecutive tiles (default; also DIB_ENC_BWD=1|2 in the environment). */
+int dib_debug_set_variant(int32_t key, int32_t value);
+
 /* text of the last error raised on this thread ("" if none). */
 const char* dib_last_error(void);
 
