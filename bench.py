@@ -387,9 +387,10 @@ def main():
         for i in range(args.warmup):
             device_step(i)
         barrier()
-        launches0 = int(lib.dib_launch_count())
+        count = lambda: int(lib.dib_launch_count()) + int(getattr(model, "_replayed_launches", 0))   # eager + graph-replayed kernels
+        launches0 = count()
         blk_ms, total_s, nblk = timed_blocks(device_step, args.steps, min_seconds)
-        launches = int(lib.dib_launch_count()) - launches0
+        launches = count() - launches0
         res = {"ms_per_step": blk_ms / args.steps, "timed_region_s": total_s, "blocks": nblk, "launches": launches,
                "launches_per_step": launches / (nblk * args.steps), "xs_d": xs_d, "ys_d": ys_d}
         res["value"] = PB * world / (res["ms_per_step"] * 1e-3)

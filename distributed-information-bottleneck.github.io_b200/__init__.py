@@ -7,9 +7,11 @@ backed by hand-written sm_100a CUDA kernels behind the C ABI of include/dib_b200
 from . import ctw, keras_compat, models, parallel, utils                              # noqa: F401
 from .keras_compat import Adam, Callback, History, losses, optimizers           # noqa: F401
 from .models import (DistributedIBNet, InfoBottleneckAnnealingCallback, PositionalEncoding,   # noqa: F401
-                     SaveCompressionMatricesCallback, StashEmbeddingsCallback, InfoPerFeatureCallback)
+                     SaveCompressionMatricesCallback, StashEmbeddingsCallback, InfoPerFeatureCallback,
+                     SimpleEncoder, SharedParticleEncoder)
 from ._lib import DibError, library_path                                         # noqa: F401
 
 __all__ = ["DistributedIBNet", "PositionalEncoding", "InfoBottleneckAnnealingCallback",
-           "SaveCompressionMatricesCallback", "StashEmbeddingsCallback", "InfoPerFeatureCallback", "Adam", "optimizers", "losses",
+           "SaveCompressionMatricesCallback", "StashEmbeddingsCallback", "InfoPerFeatureCallback", "SimpleEncoder",
+           "SharedParticleEncoder", "Adam", "optimizers", "losses",
            "Callback", "History", "models", "utils", "parallel", "keras_compat", "DibError", "library_path"]

@@ -6,10 +6,11 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uin
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ACTIVATIONS = {None: 0, "linear": 0, "relu": 1, "tanh": 2, "leaky_relu": 3, "sigmoid": 4, "elu": 5}
 LOSSES = {"bce_logits": 0, "sparse_ce_logits": 1, "mse": 2, "external": 3}
+ENCODER_KINDS = {"mlp": 0, "simple": 1}
 # 'fp16' / 'bf16': fused 16-bit-operand tcgen05 kernels (fp32 accumulate); 'tf32': kind::tf32 GEMMs on fp32 storage;
 # 'fp32': exact CUDA-core FMA parity path.  See enum dib_precision in include/dib_b200.h.
 PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
@@ -34,6 +35,10 @@ class DibConfig(ctypes.Structure):
         ("loss", c_int32),
         ("precision", c_int32),
         ("max_batch", c_int64),
+        ("logvar_offset", c_float),
+        ("kl_loss_exponent", c_float),
+        ("kl_loss_scale", c_float),
+        ("encoder_kind", c_int32),
     ]
 
 
@@ -50,9 +55,17 @@ SIGNATURES = {
     "dib_encode_feature": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "dib_train_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p,
                                  c_uint64, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dib_train_step_phased": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p,
+                                        c_uint64, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "dib_set_noise_step_device": (c_int32, [c_void_p, c_void_p]),
     "dib_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float,
                                 c_float, c_float, c_void_p]),
     "dib_metrics_update": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "dib_metrics_update_ex": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p]),
+    "dib_encoders_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_uint64, c_uint32, c_uint64, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
+    "dib_encoders_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p, c_uint64,
+                                        c_uint32, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dib_bhattacharyya": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "dib_pairwise_gaussian": (c_int32, [c_int32, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                         c_void_p]),

@@ -80,6 +80,12 @@ struct dib_model {
   int head_stride = 0, dbpart_stride = 0;
   std::vector<long long> g16_off, dg16_off, w16_off;   // [1..Li], [1..Li], [0..Li-1]
   int head_blocks = 0, lossacc_cap = 0;
+  // custom-step variants
+  float lv_off = 0.f, kl_exp = 1.f, kl_scale = 1.f;
+  const uint32_t* step_dev = nullptr;  // optional device-resident addend of the Philox step word (dib_set_noise_step_device)
+  bool simple = false;                 // nb-bool SimpleEncoder: two (1,1) constants per feature
+  int* d_xoff = nullptr;               // device copy of x_off (simple-encoder kernels)
+  long long beta_eff_off = 0;          // one float in the workspace: d(beta*scale*KL^p)/dKL
   // optional per-launch-group timing with CUDA events on the caller's stream (dib_profile_*)
   bool profiling = false;
   struct ProfRec { std::string label; cudaEvent_t a, b; };
@@ -159,6 +165,7 @@ void plan(dib_model* h) {
     h->dbpart_stride = wmax;                             // dgrad-epilogue column sums: [row tile][width]
     h->dbpart_off = take(c, (long long)DIB_CEIL_DIV(B, 128ll) * wmax);
   }
+  h->beta_eff_off = take(c, 64);
   h->wshadow_off = take(c, h->Pp);      // TF32-rounded copy of the parameters (tensor-core mode B operands)
   h->pack_off = take(c, (long long)(dib_enc_fused_pack_bytes(h->F) + 3) / 4);
   h->ws_floats = c;
@@ -178,7 +185,7 @@ void build_problems(dib_model* h, std::vector<DibGemmProblem>& v) {
     const Buf& b = j == L ? h->d_out : h->d_enc[j + 1];
     off = b.off + f * b.feat_stride; ld = b.ld;
   };
-  for (int j = 0; j <= L; ++j) {
+  for (int j = 0; j <= L && !h->simple; ++j) {
     h->enc_fwd[j] = (int)v.size();
     for (int f = 0; f < F; ++f) {
       DibGemmProblem p = zero();
@@ -192,7 +199,7 @@ void build_problems(dib_model* h, std::vector<DibGemmProblem>& v) {
       v.push_back(p);
     }
   }
-  for (int j = 1; j <= L; ++j) {
+  for (int j = 1; j <= L && !h->simple; ++j) {
     h->enc_dgrad[j] = (int)v.size();
     for (int f = 0; f < F; ++f) {
       DibGemmProblem p = zero();
@@ -204,7 +211,7 @@ void build_problems(dib_model* h, std::vector<DibGemmProblem>& v) {
       v.push_back(p);
     }
   }
-  for (int j = 0; j <= L; ++j) {
+  for (int j = 0; j <= L && !h->simple; ++j) {
     h->enc_wgrad[j] = (int)v.size();
     for (int f = 0; f < F; ++f) {
       DibGemmProblem p = zero();
@@ -264,6 +271,8 @@ struct Ctx {
   float* ws;
   cudaStream_t st;
   int n;
+  bool dev_step = false;     // dib_train_step only: add *h->step_dev to the Philox step word (dib_set_noise_step_device)
+  const uint32_t* step_dev() const { return dev_step ? h->step_dev : nullptr; }
 };
 
 void prof_begin(const Ctx& c, const char* label, int j = -1) {
@@ -315,9 +324,11 @@ int check_call(const dib_model* h, const void* params, const void* x, int64_t n,
 }
 
 // PE -> encoder layers (all features) -> reparam/KL -> integration layers -> loss/metrics
+int encode_all(const Ctx& c, const float* x, int ldx, int rnd, const int* row_index, int64_t n_src);
+
 int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, uint64_t seed, uint32_t step,
                 uint64_t sample_offset, float inv_batch, bool training, float* user_pred, float* user_emb,
-                float* out_stats) {
+                float* out_stats, bool enc_only = false) {
   dib_model* h = c.h;
   const int rnd = is_tc(h) ? 1 : 0;
   const bool fast_path = h->fused_ok && rnd && (!training || h->fused_bwd_ok) && !h->force_unfused && h->int16_ok && !h->force_int32;
@@ -333,6 +344,7 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
     const int ntiles = (int)DIB_CEIL_DIV((long long)c.n, 128ll);
     long long want = (long long)h->F * ntiles;
     DibEncFusedDesc d = h->fdesc;
+    d.logvar_offset = h->lv_off;
     const long long cap = (long long)h->num_sms * dib_enc_fused_fwd_ctas_per_sm();
     d.grid = (int)(want < cap ? want : cap);
     nblk_kl = DIB_CEIL_DIV(d.grid, h->F);
@@ -342,14 +354,20 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
     prof_end(c);
     DibEncFusedIO io;
     io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = c.n;
-    io.eps = eps; io.seed = seed; io.step = step; io.sample_offset = sample_offset;
+    io.eps = eps; io.seed = seed; io.step = step; io.step_dev = c.step_dev(); io.sample_offset = sample_offset;
     io.emb = c.ws + h->emb.off; io.ldemb = h->emb.ld; io.user_emb = user_emb;
     io.kl_part = c.ws + h->kl_part_off; io.kl_stride = h->kl_stride;
-    const bool i16 = h->int16_ok && !h->force_int32;
+    const bool i16 = h->int16_ok && !h->force_int32 && !enc_only;
     if (i16) { io.emb = nullptr; io.emb16 = c.ws + h->emb16_off; io.ldemb16 = h->F * h->E; }
+    if (enc_only) io.emb = nullptr;      // the caller's network consumes user_emb; nothing downstream reads the workspace copy
     prof_begin(c, "enc_fused_fwd");
     DIB_CUDA_OK(dib_enc_fused_forward(d, io, c.st));
     prof_end(c);
+    if (enc_only) {
+      DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->kl_stride, nblk_kl, c.ws + h->loss_part_off,
+                                            c.ws + h->acc_part_off, 0, h->F, c.n, 0, out_stats, c.st));
+      return 0;
+    }
     if (i16) {
       const int bf = h->precision == DIB_PREC_BF16 ? 1 : 0;
       // ---------------- integration network on 16-bit activations + fused output head
@@ -377,21 +395,19 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
       return 0;
     }
   } else {
-  prof_begin(c, "pe");
-  DIB_CUDA_OK(dib_launch_pe(x, h->D, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, c.n, rnd, c.st));
-  prof_end(c);
-  for (int j = 0; j <= h->L; ++j) {
-    prof_begin(c, "enc_fwd_l", j);
-    if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j], h->F, enc_fan_out(h, j), 0, 1, 0)) return 1;
-    prof_end(c);
-  }
+  if (encode_all(c, x, h->D, rnd, nullptr, 0)) return 1;
   DibReparamArgs ra;
   ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
-  ra.eps = eps; ra.seed = seed; ra.step = step; ra.sample_offset = sample_offset;
+  ra.eps = eps; ra.seed = seed; ra.step = step; ra.step_dev = c.step_dev(); ra.sample_offset = sample_offset;
   ra.F = h->F; ra.E = h->E; ra.n = c.n; ra.round_out = rnd;
   prof_begin(c, "reparam_kl_fwd");
   DIB_CUDA_OK(dib_launch_reparam_fwd(ra, c.ws + h->emb.off, h->emb.ld, user_emb, c.ws + h->kl_part_off, h->kl_stride, c.st));
   prof_end(c);
+  if (enc_only) {
+    DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->kl_stride, nblk_kl, c.ws + h->loss_part_off,
+                                          c.ws + h->acc_part_off, 0, h->F, c.n, 0, out_stats, c.st));
+    return 0;
+  }
   }
   for (int j = 0; j <= h->Li; ++j) {
     prof_begin(c, "int_fwd_l", j);
@@ -406,6 +422,42 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
   DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->kl_stride, nblk_kl, c.ws + h->loss_part_off,
                                         c.ws + h->acc_part_off, nblk, h->F, c.n, y != nullptr, out_stats, c.st));
   prof_end(c);
+  return 0;
+}
+
+// every feature encoder on n rows of x (deterministic part: mu | logvar incl. the offset) into the enc_out workspace
+// buffer: positional encoding + grouped GEMMs (models.py:72-78,106), or nb-bool's SimpleEncoder constants
+int encode_all(const Ctx& c, const float* x, int ldx, int rnd, const int* row_index, int64_t n_src) {
+  dib_model* h = c.h;
+  if (h->simple) {
+    prof_begin(c, "simple_enc_fwd");
+    DIB_CUDA_OK(dib_launch_simple_enc_fwd(x, ldx, h->d_xoff, c.params, c.ws + h->enc_out.off, h->enc_out.feat_stride,
+                                          h->enc_out.ld, h->F, h->E, c.n, -1, 0, row_index, n_src, c.st));
+    prof_end(c);
+  } else {
+    prof_begin(c, "pe");
+    DIB_CUDA_OK(dib_launch_pe(x, ldx, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, c.n, rnd, c.st,
+                              row_index, row_index ? h->d_col_feat : nullptr, n_src));
+    prof_end(c);
+    for (int j = 0; j <= h->L; ++j) {
+      prof_begin(c, "enc_fwd_l", j);
+      if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j], h->F, enc_fan_out(h, j), 0, 1, 0)) return 1;
+      prof_end(c);
+    }
+  }
+  DIB_CUDA_OK(dib_launch_add_logvar_offset(c.ws + h->enc_out.off, h->enc_out.feat_stride, h->enc_out.ld, h->F, h->E, c.n,
+                                           h->lv_off, -1, c.st));
+  return 0;
+}
+
+// weight for the per-sample KL gradients: beta itself (models.py:118) or d(beta*scale*KL^p)/dKL (nb-chaos cell 10)
+int ib_weight(const Ctx& c, const float* beta_dev, const float* stats, float inv_global_batch, const float** out) {
+  dib_model* h = c.h;
+  *out = beta_dev;
+  if (h->kl_exp == 1.f && h->kl_scale == 1.f) return 0;
+  float* be = c.ws + h->beta_eff_off;
+  DIB_CUDA_OK(dib_launch_beta_eff(stats, h->F, inv_global_batch, beta_dev, h->kl_exp, h->kl_scale, be, c.st));
+  *out = be;
   return 0;
 }
 
@@ -531,10 +583,18 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   h->act = cfg->activation_fn; h->out_act = cfg->output_activation_fn; h->loss = cfg->loss;
   h->precision = cfg->precision; h->use_pe = cfg->use_positional_encoding ? 1 : 0;
   h->alpha = cfg->leaky_relu_alpha; h->maxB = cfg->max_batch;
+  h->lv_off = cfg->logvar_offset;
+  h->kl_exp = cfg->kl_loss_exponent == 0.f ? 1.f : cfg->kl_loss_exponent;
+  h->kl_scale = cfg->kl_loss_scale == 0.f ? 1.f : cfg->kl_loss_scale;
+  h->simple = cfg->encoder_kind == DIB_ENCODER_SIMPLE;
+  if (cfg->encoder_kind != DIB_ENCODER_MLP && cfg->encoder_kind != DIB_ENCODER_SIMPLE) { delete h; return fail("dib_create: unknown encoder_kind"); }
+  if (!(h->kl_exp > 0.f)) { delete h; return fail("dib_create: kl_loss_exponent must be > 0"); }
+  if (h->simple) { h->L = 0; h->use_pe = 0; }
   // models.py:70: frequencies 2**arange(1, n) -> n-1 sinusoid blocks after the identity block
   h->nfreq = h->use_pe ? (cfg->number_positional_encoding_frequencies > 1 ? cfg->number_positional_encoding_frequencies : 1) : 1;
   h->fdims.assign(cfg->feature_dimensionalities, cfg->feature_dimensionalities + h->F);
   h->enc_arch.assign(cfg->feature_encoder_architecture, cfg->feature_encoder_architecture + h->L);
+  if (h->simple) for (int d : h->fdims) if (d != h->E) { delete h; return fail("dib_create: SimpleEncoder needs d_i == feature_embedding_dimension"); }
   h->int_arch.assign(cfg->integration_network_architecture, cfg->integration_network_architecture + h->Li);
   for (int d : h->fdims) if (d < 1) { delete h; return fail("dib_create: feature dimensionality < 1"); }
   for (int d : h->enc_arch) if (d < 1) { delete h; return fail("dib_create: encoder width < 1"); }
@@ -563,11 +623,17 @@ int dib_create(const dib_config* cfg, dib_model** out) {
     const long long o = off; off += (long long)(rows ? rows : 1) * cols; return o;
   };
   h->encW.assign(h->F, {}); h->encB.assign(h->F, {});
-  for (int f = 0; f < h->F; ++f)
+  for (int f = 0; f < h->F; ++f) {
+    if (h->simple) {                       // nb-bool cell 4: mu_scaling (1,1), logvar (1,1)
+      h->encW[f].push_back(add_var(1, 1));
+      h->encB[f].push_back(add_var(1, 1));
+      continue;
+    }
     for (int j = 0; j <= h->L; ++j) {
       h->encW[f].push_back(add_var(enc_fan_in(h, f, j), enc_fan_out(h, j)));
       h->encB[f].push_back(add_var(0, enc_fan_out(h, j)));
     }
+  }
   for (int j = 0; j <= h->Li; ++j) {
     h->intW.push_back(add_var(int_fan_in(h, j), int_fan_out(h, j)));
     h->intB.push_back(add_var(0, int_fan_out(h, j)));
@@ -588,6 +654,8 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->d_col_src, col_src.size() * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_col_freq, col_freq.size() * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_col_feat, col_feat.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_xoff, h->x_off.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_xoff, h->x_off.data(), h->x_off.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_probs, probs.data(), probs.size() * sizeof(DibGemmProblem), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_col_src, col_src.data(), col_src.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_col_freq, col_freq.data(), col_freq.size() * sizeof(int), cudaMemcpyHostToDevice);
@@ -642,6 +710,7 @@ void dib_destroy(dib_model* h) {
   if (h->d_col_src) cudaFree(h->d_col_src);
   if (h->d_col_freq) cudaFree(h->d_col_freq);
   if (h->d_col_feat) cudaFree(h->d_col_feat);
+  if (h->d_xoff) cudaFree(h->d_xoff);
   if (h->d_fused_tables) cudaFree(h->d_fused_tables);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
@@ -682,43 +751,71 @@ int dib_encode_feature(dib_model* h, const float* params, int32_t feature, const
   Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
   const int f = feature, wpad = DIB_ROUND_UP(h->w_in[f], 4);
   const int rnd = is_tc(h) ? 1 : 0;
-  if (rnd) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
-  DIB_CUDA_OK(dib_launch_pe(x_i, h->fdims[f], h->x_off[f], h->d_col_src, h->d_col_freq, h->pe_off[f], h->pe_off[f] + wpad,
-                            c.ws + h->pe.off, h->ldpe, 0, n, rnd, c.st));
-  for (int j = 0; j <= h->L; ++j)
-    if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j] + f, 1, enc_fan_out(h, j), 0, 1, 0)) return 1;
+  if (h->simple) {
+    DIB_CUDA_OK(dib_launch_simple_enc_fwd(x_i, h->fdims[f], h->d_xoff, c.params, c.ws + h->enc_out.off, h->enc_out.feat_stride,
+                                          h->enc_out.ld, h->F, h->E, n, f, 1, nullptr, 0, c.st));
+  } else {
+    if (rnd) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
+    DIB_CUDA_OK(dib_launch_pe(x_i, h->fdims[f], h->x_off[f], h->d_col_src, h->d_col_freq, h->pe_off[f], h->pe_off[f] + wpad,
+                              c.ws + h->pe.off, h->ldpe, 0, n, rnd, c.st));
+    for (int j = 0; j <= h->L; ++j)
+      if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j] + f, 1, enc_fan_out(h, j), 0, 1, 0)) return 1;
+  }
+  DIB_CUDA_OK(dib_launch_add_logvar_offset(c.ws + h->enc_out.off, h->enc_out.feat_stride, h->enc_out.ld, h->F, h->E, n,
+                                           h->lv_off, f, c.st));
   DIB_CUDA_OK(dib_launch_copy2d(c.ws + h->enc_out.off + f * h->enc_out.feat_stride, h->enc_out.ld, out_mu_logvar,
                                 2 * h->E, 2 * h->E, n, c.st));
   return 0;
 }
 
-int dib_train_step(dib_model* h, const float* params, const float* x, const float* y, int64_t n, const float* beta_dev,
-                   float inv_global_batch, const float* eps, uint64_t seed, uint32_t step, uint64_t sample_offset,
-                   float* grads_flat, float* out_stats, void* workspace, void* stream) {
+// phases: 1 = forward + compiled loss + integration-network backward (grads_flat[first integration parameter ..) final),
+//         2 = encoder backward (grads_flat[0 .. first integration parameter) final); 3 = both (= dib_train_step).
+// Phase 2 relies on the workspace exactly as phase 1 left it (same x, eps / seed / step, n).
+int dib_train_step_phased(dib_model* h, const float* params, const float* x, const float* y, int64_t n, const float* beta_dev,
+                          float inv_global_batch, const float* eps, uint64_t seed, uint32_t step, uint64_t sample_offset,
+                          float* grads_flat, float* out_stats, void* workspace, int32_t phases, void* stream) {
   if (check_call(h, params, x, n, workspace)) return 1;
   if ((!y && n > 0) || !beta_dev || !grads_flat || !out_stats)
     return fail("dib_train_step: y, beta_dev, grads_flat and out_stats are required");
+  if (phases < 1 || phases > 3) return fail("dib_train_step_phased: phases must be 1, 2 or 3");
+  const bool phA = (phases & 1) != 0, phB = (phases & 2) != 0;
   Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
+  c.dev_step = true;
+  const long long p_enc = h->intW[0];                // encoder parameters occupy [0, p_enc)
   if (n == 0) {
-    DIB_CUDA_OK(cudaMemsetAsync(grads_flat, 0, sizeof(float) * h->P, c.st));
-    DIB_CUDA_OK(cudaMemsetAsync(out_stats, 0, sizeof(float) * (h->F + 3), c.st));
+    if (phB) DIB_CUDA_OK(cudaMemsetAsync(grads_flat, 0, sizeof(float) * p_enc, c.st));
+    if (phA) {
+      DIB_CUDA_OK(cudaMemsetAsync(grads_flat + p_enc, 0, sizeof(float) * (h->P - p_enc), c.st));
+      DIB_CUDA_OK(cudaMemsetAsync(out_stats, 0, sizeof(float) * (h->F + 3), c.st));
+    }
     return 0;
   }
-  if (run_forward(c, x, y, eps, seed, step, sample_offset, inv_global_batch, true, nullptr, nullptr, out_stats)) return 1;
+  const bool nonlinear = h->kl_exp != 1.f || h->kl_scale != 1.f;
+  if (phA) {
+    if (run_forward(c, x, y, eps, seed, step, sample_offset, inv_global_batch, true, nullptr, nullptr, out_stats)) return 1;
+    const float* bw = nullptr;
+    if (ib_weight(c, beta_dev, out_stats, inv_global_batch, &bw)) return 1;
+  }
+  // weight of the per-sample KL gradients in the encoder backward: beta, or d(beta*scale*KL^p)/dKL left in the workspace by phase 1
+  const float* beta_w = nonlinear ? c.ws + h->beta_eff_off : beta_dev;
 
   // deterministic split of the batch for the weight gradients
   long long rps = DIB_CEIL_DIV((long long)n, (long long)kMaxSplits);
   if (rps < 256) rps = 256;
   rps = DIB_ROUND_UP(rps, 32);
   const int nsplit = (int)DIB_CEIL_DIV((long long)n, rps);
+  float* part = c.ws + h->part_off;
 
   const bool fused_enc = h->fused_ok && h->fused_bwd_ok && !h->force_unfused;
-  if (fused_enc && h->int16_ok && !h->force_int32) {
+  const bool i16 = fused_enc && h->int16_ok && !h->force_int32;
+  const float gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
+
+  // ---------------------------------------------------------------- phase 1: integration network backward
+  if (phA && i16) {
     const int bf = h->precision == DIB_PREC_BF16 ? 1 : 0;
-    const float gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
-    float* part = c.ws + h->part_off;
     const int Kh = h->int_arch[h->Li - 1];
     const int row_tiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
+    const long long p_head = h->intW[h->Li];
     // bias gradient of the last hidden layer: column sums of dg accumulated by the output head
     DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off + (long long)Kh * h->out + h->out, h->head_stride, h->head_blocks, Kh,
                                        1.f / gscale, grads_flat + h->intB[h->Li - 1], c.st));
@@ -737,81 +834,70 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
         DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->dbpart_off, K, row_tiles, K, 1.f / gscale, grads_flat + h->intB[j - 1], c.st));
       prof_end(c);
     }
-    const int ntiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
-    const long long want = (long long)h->F * ntiles;
-    DibEncFusedDesc d = h->fdesc;
-    d.grid = (int)(want < h->num_sms ? want : h->num_sms);
-    const int slots_max = DIB_CEIL_DIV(d.grid, h->F), slots_min = d.grid / h->F;
-    const long long p_enc = h->intW[0], p_head = h->intW[h->Li];
-    for (int srow = slots_min; srow < slots_max; ++srow)
-      DIB_CUDA_OK(cudaMemsetAsync(part + (long long)srow * h->Pp, 0, sizeof(float) * (size_t)p_enc, c.st));
-    DibEncFusedIO io;
-    io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = n;
-    io.eps = eps; io.seed = seed; io.step = step; io.sample_offset = sample_offset;
-    io.emb = nullptr; io.ldemb = 0; io.user_emb = nullptr; io.kl_part = nullptr; io.kl_stride = 0;
-    DibEncFusedBwdIO b;
-    b.d_emb = nullptr; b.ldd = 0; b.d_emb16 = c.ws + h->demb16_off; b.ldd16 = h->F * h->E;
-    b.beta_dev = beta_dev; b.inv_batch = inv_global_batch; b.gscale = gscale; b.part = part; b.split_stride = h->Pp;
-    prof_begin(c, "enc_fused_bwd");
-    DIB_CUDA_OK(dib_enc_fused_backward(d, io, b, c.st));
-    prof_end(c);
-    prof_begin(c, "wgrad_split_reduce");
-    DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, slots_max, p_enc, grads_flat, c.st));
+    prof_begin(c, "int_split_reduce");
     for (int j = 0; j < h->Li; ++j)     // hidden-layer kernels: batch-split partials (their biases were reduced above)
       DIB_CUDA_OK(dib_launch_reduce_partials(part + h->intW[j], h->Pp, nsplit, (long long)int_fan_in(h, j) * int_fan_out(h, j),
                                              grads_flat + h->intW[j], c.st));
     DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off, h->head_stride, h->head_blocks, h->P - p_head, 1.f, grads_flat + p_head, c.st));
     prof_end(c);
-    return 0;
-  }
-  // integration network backward (GradientTape through models.py:122)
-  for (int j = h->Li; j >= 0; --j) {
-    prof_begin(c, "int_wgrad_l", j);
-    if (gemm(c, DIB_GEMM_WGRAD, h->int_wgrad[j], 1, int_fan_out(h, j), int_fan_in(h, j), nsplit, (int)rps)) return 1;
+  } else if (phA) {
+    // integration network backward (GradientTape through models.py:122)
+    for (int j = h->Li; j >= 0; --j) {
+      prof_begin(c, "int_wgrad_l", j);
+      if (gemm(c, DIB_GEMM_WGRAD, h->int_wgrad[j], 1, int_fan_out(h, j), int_fan_in(h, j), nsplit, (int)rps)) return 1;
+      prof_end(c);
+      prof_begin(c, "int_dgrad_l", j);
+      if (gemm(c, DIB_GEMM_DGRAD, h->int_dgrad[j], 1, int_fan_in(h, j), 0, 1, 0)) return 1;
+      prof_end(c);
+    }
+    prof_begin(c, "int_split_reduce");
+    DIB_CUDA_OK(dib_launch_reduce_partials(part + p_enc, h->Pp, nsplit, h->P - p_enc, grads_flat + p_enc, c.st));
     prof_end(c);
-    prof_begin(c, "int_dgrad_l", j);
-    if (gemm(c, DIB_GEMM_DGRAD, h->int_dgrad[j], 1, int_fan_in(h, j), 0, 1, 0)) return 1;
-    prof_end(c);
   }
-  const bool fused = h->fused_ok && h->fused_bwd_ok && !h->force_unfused;
-  if (fused) {
+  if (!phB) return 0;
+
+  // ---------------------------------------------------------------- phase 2: encoder backward
+  if (fused_enc) {
     const int ntiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
     const long long want = (long long)h->F * ntiles;
     DibEncFusedDesc d = h->fdesc;
     d.grid = (int)(want < h->num_sms ? want : h->num_sms);
     const int slots_max = DIB_CEIL_DIV(d.grid, h->F), slots_min = d.grid / h->F;
-    const long long p_enc = h->intW[0];              // encoder parameters occupy [0, p_enc)
-    float* part = c.ws + h->part_off;
     // features served by one CTA fewer leave their last slot unwritten: zero it (ENCODER range only -- the
     // integration network's batch-split partials live in the same rows beyond p_enc)
     for (int srow = slots_min; srow < slots_max; ++srow)
       DIB_CUDA_OK(cudaMemsetAsync(part + (long long)srow * h->Pp, 0, sizeof(float) * (size_t)p_enc, c.st));
     DibEncFusedIO io;
     io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = n;
-    io.eps = eps; io.seed = seed; io.step = step; io.sample_offset = sample_offset;
+    io.eps = eps; io.seed = seed; io.step = step; io.step_dev = c.step_dev(); io.sample_offset = sample_offset;
     io.emb = nullptr; io.ldemb = 0; io.user_emb = nullptr; io.kl_part = nullptr; io.kl_stride = 0;
     DibEncFusedBwdIO b;
-    b.d_emb = c.ws + h->d_emb.off; b.ldd = h->d_emb.ld; b.beta_dev = beta_dev; b.inv_batch = inv_global_batch;
-    b.gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
-    b.part = part; b.split_stride = h->Pp;
+    if (i16) { b.d_emb = nullptr; b.ldd = 0; b.d_emb16 = c.ws + h->demb16_off; b.ldd16 = h->F * h->E; }
+    else { b.d_emb = c.ws + h->d_emb.off; b.ldd = h->d_emb.ld; }
+    b.beta_dev = beta_w; b.inv_batch = inv_global_batch; b.gscale = gscale; b.part = part; b.split_stride = h->Pp;
     prof_begin(c, "enc_fused_bwd");
     DIB_CUDA_OK(dib_enc_fused_backward(d, io, b, c.st));
     prof_end(c);
-    prof_begin(c, "wgrad_split_reduce");
+    prof_begin(c, "enc_split_reduce");
     DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, slots_max, p_enc, grads_flat, c.st));
-    DIB_CUDA_OK(dib_launch_reduce_partials(part + p_enc, h->Pp, nsplit, h->P - p_enc, grads_flat + p_enc, c.st));
     prof_end(c);
     return 0;
   }
   DibReparamArgs ra;
   ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
-  ra.eps = eps; ra.seed = seed; ra.step = step; ra.sample_offset = sample_offset;
+  ra.eps = eps; ra.seed = seed; ra.step = step; ra.step_dev = c.step_dev(); ra.sample_offset = sample_offset;
   ra.F = h->F; ra.E = h->E; ra.n = n; ra.round_out = is_tc(h) ? 1 : 0;
   prof_begin(c, "reparam_kl_bwd");
-  DIB_CUDA_OK(dib_launch_reparam_bwd(ra, c.ws + h->d_emb.off, h->d_emb.ld, beta_dev, inv_global_batch,
+  DIB_CUDA_OK(dib_launch_reparam_bwd(ra, c.ws + h->d_emb.off, h->d_emb.ld, beta_w, inv_global_batch,
                                      c.ws + h->d_out.off, c.st));
   prof_end(c);
-  for (int j = h->L; j >= 0; --j) {
+  if (h->simple) {
+    prof_begin(c, "simple_enc_wgrad");
+    DIB_CUDA_OK(dib_launch_simple_enc_wgrad(x, h->D, h->d_xoff, c.ws + h->d_out.off, h->d_out.feat_stride, h->d_out.ld, h->F, h->E,
+                                            n, nsplit, (int)rps, part, h->Pp, c.st));
+    prof_end(c);
+  }
+  for (int j = h->L; j >= 0 && !h->simple; --j) {
     prof_begin(c, "enc_wgrad_l", j);
     if (gemm(c, DIB_GEMM_WGRAD, h->enc_wgrad[j], h->F, enc_fan_out(h, j), h->enc_maxK[j], nsplit, (int)rps)) return 1;
     prof_end(c);
@@ -821,9 +907,24 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
       prof_end(c);
     }
   }
-  prof_begin(c, "wgrad_split_reduce");
-  DIB_CUDA_OK(dib_launch_reduce_partials(c.ws + h->part_off, h->Pp, nsplit, h->P, grads_flat, c.st));
+  prof_begin(c, "enc_split_reduce");
+  DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, nsplit, p_enc, grads_flat, c.st));
   prof_end(c);
+  return 0;
+}
+
+int dib_train_step(dib_model* h, const float* params, const float* x, const float* y, int64_t n, const float* beta_dev,
+                   float inv_global_batch, const float* eps, uint64_t seed, uint32_t step, uint64_t sample_offset,
+                   float* grads_flat, float* out_stats, void* workspace, void* stream) {
+  return dib_train_step_phased(h, params, x, y, n, beta_dev, inv_global_batch, eps, seed, step, sample_offset, grads_flat,
+                               out_stats, workspace, 3, stream);
+}
+
+// Philox 'step' word from device memory (CUDA-Graph replay: a captured launch cannot carry a fresh by-value step):
+// when set, every forward / train-step call uses step + *step_dev.  The caller owns and advances the counter.
+int dib_set_noise_step_device(dib_model* h, const uint32_t* step_dev) {
+  if (!h) return fail("null model handle");
+  h->step_dev = step_dev;
   return 0;
 }
 
@@ -836,9 +937,84 @@ int dib_adam_step(float* params, const float* grads, float* m, float* v, int64_t
   return 0;
 }
 
-int dib_metrics_update(const float* stats, const float* beta_dev, float* acc, int32_t number_features, void* stream) {
+int dib_metrics_update_ex(const float* stats, const float* beta_dev, float* acc, int32_t number_features,
+                          float kl_loss_exponent, float kl_loss_scale, void* stream) {
   if (!stats || !beta_dev || !acc || number_features < 1) return fail("dib_metrics_update: bad arguments");
-  DIB_CUDA_OK(dib_launch_metrics_update(stats, beta_dev, acc, number_features, static_cast<cudaStream_t>(stream)));
+  DIB_CUDA_OK(dib_launch_metrics_update(stats, beta_dev, acc, number_features, kl_loss_exponent == 0.f ? 1.f : kl_loss_exponent,
+                                        kl_loss_scale == 0.f ? 1.f : kl_loss_scale, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int dib_metrics_update(const float* stats, const float* beta_dev, float* acc, int32_t number_features, void* stream) {
+  return dib_metrics_update_ex(stats, beta_dev, acc, number_features, 1.f, 1.f, stream);
+}
+
+int dib_encoders_forward(dib_model* h, const float* params, const float* x, int64_t n, const float* eps, uint64_t seed,
+                         uint32_t step, uint64_t sample_offset, float* out_emb, float* out_stats, void* workspace, void* stream) {
+  if (check_call(h, params, x, n, workspace)) return 1;
+  if (!out_emb || !out_stats) return fail("dib_encoders_forward: out_emb and out_stats are required");
+  Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
+  if (n == 0) { DIB_CUDA_OK(cudaMemsetAsync(out_stats, 0, sizeof(float) * (h->F + 3), c.st)); return 0; }
+  return run_forward(c, x, nullptr, eps, seed, step, sample_offset, 0.f, false, nullptr, out_emb, out_stats, true);
+}
+
+int dib_encoders_backward(dib_model* h, const float* params, const float* x, const float* d_emb, int64_t n,
+                          const float* beta_dev, float inv_global_batch, const float* eps, uint64_t seed, uint32_t step,
+                          uint64_t sample_offset, float* grads_flat, float* out_stats, void* workspace, void* stream) {
+  if (check_call(h, params, x, n, workspace)) return 1;
+  if ((!d_emb && n > 0) || !beta_dev || !grads_flat || !out_stats)
+    return fail("dib_encoders_backward: d_emb, beta_dev, grads_flat and out_stats are required");
+  Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
+  DIB_CUDA_OK(cudaMemsetAsync(grads_flat, 0, sizeof(float) * h->P, c.st));
+  if (n == 0) { DIB_CUDA_OK(cudaMemsetAsync(out_stats, 0, sizeof(float) * (h->F + 3), c.st)); return 0; }
+  // the forward is recomputed here (training mode keeps what the backward needs); user_emb is not needed again
+  if (run_forward(c, x, nullptr, eps, seed, step, sample_offset, inv_global_batch, true, nullptr, nullptr, out_stats, true)) return 1;
+  const float* bw = beta_dev;
+  if (ib_weight(c, beta_dev, out_stats, inv_global_batch, &bw)) return 1;
+  long long rps = DIB_CEIL_DIV((long long)n, (long long)kMaxSplits);
+  if (rps < 256) rps = 256;
+  rps = DIB_ROUND_UP(rps, 32);
+  const int nsplit = (int)DIB_CEIL_DIV((long long)n, rps);
+  const long long p_enc = h->intW[0];
+  const int FE = h->F * h->E;
+  const bool fused = h->fused_ok && h->fused_bwd_ok && !h->force_unfused;
+  float* part = c.ws + h->part_off;
+  if (fused) {
+    const int ntiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
+    const long long want = (long long)h->F * ntiles;
+    DibEncFusedDesc d = h->fdesc;
+    d.logvar_offset = h->lv_off;
+    d.grid = (int)(want < h->num_sms ? want : h->num_sms);
+    const int slots_max = DIB_CEIL_DIV(d.grid, h->F), slots_min = d.grid / h->F;
+    for (int srow = slots_min; srow < slots_max; ++srow)
+      DIB_CUDA_OK(cudaMemsetAsync(part + (long long)srow * h->Pp, 0, sizeof(float) * (size_t)p_enc, c.st));
+    DibEncFusedIO io;
+    io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = n;
+    io.eps = eps; io.seed = seed; io.step = step; io.step_dev = c.step_dev(); io.sample_offset = sample_offset;
+    io.emb = nullptr; io.ldemb = 0; io.user_emb = nullptr; io.kl_part = nullptr; io.kl_stride = 0;
+    DibEncFusedBwdIO b;
+    b.d_emb = d_emb; b.ldd = FE; b.beta_dev = bw; b.inv_batch = inv_global_batch;
+    b.gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
+    b.part = part; b.split_stride = h->Pp;
+    DIB_CUDA_OK(dib_enc_fused_backward(d, io, b, c.st));
+    DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, slots_max, p_enc, grads_flat, c.st));
+    return 0;
+  }
+  DibReparamArgs ra;
+  ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
+  ra.eps = eps; ra.seed = seed; ra.step = step; ra.step_dev = c.step_dev(); ra.sample_offset = sample_offset;
+  ra.F = h->F; ra.E = h->E; ra.n = n; ra.round_out = is_tc(h) ? 1 : 0;
+  DIB_CUDA_OK(dib_launch_reparam_bwd(ra, d_emb, FE, bw, inv_global_batch, c.ws + h->d_out.off, c.st));
+  if (h->simple) {
+    DIB_CUDA_OK(dib_launch_simple_enc_wgrad(x, h->D, h->d_xoff, c.ws + h->d_out.off, h->d_out.feat_stride, h->d_out.ld, h->F, h->E,
+                                            n, nsplit, (int)rps, part, h->Pp, c.st));
+  } else {
+    for (int j = h->L; j >= 0; --j) {
+      if (gemm(c, DIB_GEMM_WGRAD, h->enc_wgrad[j], h->F, enc_fan_out(h, j), h->enc_maxK[j], nsplit, (int)rps)) return 1;
+      if (j >= 1 && gemm(c, DIB_GEMM_DGRAD, h->enc_dgrad[j], h->F, h->enc_arch[j - 1], 0, 1, 0)) return 1;
+    }
+  }
+  DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, nsplit, p_enc, grads_flat, c.st));
   return 0;
 }
 
@@ -900,10 +1076,7 @@ int dib_compression_matrices(dib_model* h, const float* params, const float* x, 
   const int rnd = is_tc(h) ? 1 : 0;
   if (rnd) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
   // all F encoders as ONE grouped problem per layer (the reference loops over features in Python, visualization.py:14-35)
-  DIB_CUDA_OK(dib_launch_pe(x, h->D, 0, h->d_col_src, h->d_col_freq, 0, h->ldpe, c.ws + h->pe.off, h->ldpe, 0, n, rnd, c.st,
-                            row_index, h->d_col_feat, n_total));
-  for (int j = 0; j <= h->L; ++j)
-    if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j], h->F, enc_fan_out(h, j), 0, 1, 0)) return 1;
+  if (encode_all(c, x, h->D, rnd, row_index, n_total)) return 1;
   const float* eo = c.ws + h->enc_out.off;
   if (out_mu_logvar)
     for (int f = 0; f < h->F; ++f)

@@ -67,7 +67,7 @@ dib_reparam_fwd_kernel(DibReparamArgs a, float* __restrict__ emb, int ldemb, flo
     const float* ep = a.eps ? a.eps + (row * a.F + f) * E : nullptr;
     for (int e0 = 0; e0 < E; e0 += 4) {
       float nrm[4];
-      if (!ep) dib_philox_normal4(a.seed, a.step, a.sample_offset + (uint64_t)row, (uint32_t)f, (uint32_t)(e0 >> 2), nrm);
+      if (!ep) dib_philox_normal4(a.seed, a.step + (a.step_dev ? a.step_dev[0] : 0u), a.sample_offset + (uint64_t)row, (uint32_t)f, (uint32_t)(e0 >> 2), nrm);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int e = e0 + j;
@@ -103,7 +103,7 @@ dib_reparam_bwd_kernel(DibReparamArgs a, const float* __restrict__ d_emb, int ld
   const float* ep = a.eps ? a.eps + (row * a.F + f) * E : nullptr;
   for (int e0 = 0; e0 < E; e0 += 4) {
     float nrm[4];
-    if (!ep) dib_philox_normal4(a.seed, a.step, a.sample_offset + (uint64_t)row, (uint32_t)f, (uint32_t)(e0 >> 2), nrm);
+    if (!ep) dib_philox_normal4(a.seed, a.step + (a.step_dev ? a.step_dev[0] : 0u), a.sample_offset + (uint64_t)row, (uint32_t)f, (uint32_t)(e0 >> 2), nrm);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int e = e0 + j;
@@ -328,7 +328,7 @@ __global__ void dib_pairwise_gauss_kernel(int mode, const float* __restrict__ ml
 
 // Keras Mean-metric aggregation over the batches of an epoch (see dib_metrics_update in dib_b200.h).
 __global__ void dib_metrics_update_kernel(const float* __restrict__ stats, const float* __restrict__ beta_dev,
-                                          float* __restrict__ acc, int F) {
+                                          float* __restrict__ acc, int F, float kl_exponent, float kl_scale) {
   __shared__ float red[8];
   const float n = stats[F + 2];
   float v = 0.f;
@@ -339,7 +339,9 @@ __global__ void dib_metrics_update_kernel(const float* __restrict__ stats, const
   }
   const float klsum = block_sum_256(v, red);
   if (threadIdx.x == 0 && n > 0.f) {
-    acc[F] += stats[F] + beta_dev[0] * klsum;
+    // models.py:118 beta * sum KL (sample-weighted: n * batch mean), or nb-chaos' beta * L * KL^p
+    acc[F] += stats[F] + (kl_exponent == 1.f ? beta_dev[0] * kl_scale * klsum
+                                            : n * beta_dev[0] * kl_scale * powf(klsum / n, kl_exponent));
     acc[F + 1] += stats[F + 1];
     acc[F + 2] += n;
     acc[F + 3] += 1.f;
@@ -508,8 +510,9 @@ cudaError_t dib_launch_pairwise_gauss(int mode, const float* ml1, int64_t ld1, i
   return cudaGetLastError();
 }
 
-cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st) {
-  dib_metrics_update_kernel<<<1, 256, 0, st>>>(stats, beta_dev, acc, F);
+cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, float kl_exponent,
+                                      float kl_scale, cudaStream_t st) {
+  dib_metrics_update_kernel<<<1, 256, 0, st>>>(stats, beta_dev, acc, F, kl_exponent, kl_scale);
   dib_note_launch();
   return cudaGetLastError();
 }
@@ -535,6 +538,112 @@ cudaError_t dib_launch_mi_sandwich(const float* mu_logvar, int64_t n, int E, con
   dib_mi_rows_kernel<<<(unsigned)n, 256, E * sizeof(float), st>>>(mu_logvar, (int)n, E, eps, seed, step, row_scratch);
   dib_note_launch();
   dib_mi_mean_kernel<<<1, 256, 0, st>>>(row_scratch, (int)n, out2);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+
+// ================================================================================================
+// custom-step variants of the front end
+// ================================================================================================
+namespace {
+
+__global__ void dib_add_logvar_offset_kernel(float* __restrict__ enc_out, long long feat_stride, int ldo, int F, int E,
+                                             long long n, float offset, int feature) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = feature >= 0 ? 1 : F;
+  if (idx >= n * E * nf) return;
+  const int e = (int)(idx % E);
+  const long long row = (idx / E) % n;
+  const int f = feature >= 0 ? feature : (int)(idx / ((long long)E * n));
+  enc_out[(long long)f * feat_stride + row * ldo + E + e] += offset;
+}
+
+// nb-bool cell 4: call(inputs) = concat([inputs * mu_scaling, ones_like(inputs) * logvar], -1)
+__global__ void dib_simple_enc_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ x_off,
+                                          const float* __restrict__ params, float* __restrict__ enc_out, long long feat_stride,
+                                          int ldo, int F, int E, long long n, int feature, int x_is_feature_only,
+                                          const int* __restrict__ row_index, long long n_src) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = feature >= 0 ? 1 : F;
+  if (idx >= n * E * nf) return;
+  const int e = (int)(idx % E);
+  const long long row = (idx / E) % n;
+  const int f = feature >= 0 ? feature : (int)(idx / ((long long)E * n));
+  long long srow = row;
+  if (row_index) { srow = row_index[(long long)f * n + row]; srow = srow < 0 ? 0 : (srow >= n_src ? n_src - 1 : srow); }
+  const float xv = x[srow * ldx + (x_is_feature_only ? 0 : x_off[f]) + e];
+  float* o = enc_out + (long long)f * feat_stride + row * ldo;
+  o[e] = xv * params[2 * f];
+  o[E + e] = params[2 * f + 1];
+  if (e == 0) for (int c = 2 * E; c < ldo; ++c) o[c] = 0.f;
+}
+
+// grid (F, nsplit): deterministic block sums of d_mu * x and d_logvar over one batch slice
+__global__ void __launch_bounds__(256)
+dib_simple_enc_wgrad_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ x_off, const float* __restrict__ d_out,
+                            long long feat_stride, int ldo, int E, long long n, int rows_per_split, float* __restrict__ part,
+                            long long split_stride) {
+  __shared__ float red[8];
+  const int f = blockIdx.x, split = blockIdx.y;
+  const long long r0 = (long long)split * rows_per_split, r1 = min(n, r0 + rows_per_split);
+  float gm = 0.f, gl = 0.f;
+  for (long long row = r0 + threadIdx.x; row < r1; row += blockDim.x) {
+    const float* dq = d_out + (long long)f * feat_stride + row * ldo;
+    const float* xr = x + row * ldx + x_off[f];
+    for (int e = 0; e < E; ++e) { gm = fmaf(dq[e], xr[e], gm); gl += dq[E + e]; }
+  }
+  const float sm = block_sum_256(gm, red);
+  const float sl = block_sum_256(gl, red);
+  if (threadIdx.x == 0) {
+    part[(long long)split * split_stride + 2 * f] = sm;
+    part[(long long)split * split_stride + 2 * f + 1] = sl;
+  }
+}
+
+__global__ void dib_beta_eff_kernel(const float* __restrict__ stats, int F, float inv_global_batch, const float* __restrict__ beta_dev,
+                                    float exponent, float scale, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float kl = 0.f;
+  for (int i = 0; i < F; ++i) kl += stats[i];
+  kl *= inv_global_batch;
+  out[0] = beta_dev[0] * scale * (exponent == 1.f ? 1.f : exponent * powf(kl, exponent - 1.f));
+}
+
+}  // namespace
+
+cudaError_t dib_launch_add_logvar_offset(float* enc_out, long long feat_stride, int ldo, int F, int E, int64_t n, float offset,
+                                         int feature, cudaStream_t st) {
+  const long long total = (long long)n * E * (feature >= 0 ? 1 : F);
+  if (total <= 0 || offset == 0.f) return cudaSuccess;
+  dib_add_logvar_offset_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(enc_out, feat_stride, ldo, F, E, n, offset, feature);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_simple_enc_fwd(const float* x, int ldx, const int* x_off_dev, const float* params, float* enc_out,
+                                      long long feat_stride, int ldo, int F, int E, int64_t n, int feature, int x_is_feature_only,
+                                      const int* row_index, int64_t n_src, cudaStream_t st) {
+  const long long total = (long long)n * E * (feature >= 0 ? 1 : F);
+  if (total <= 0) return cudaSuccess;
+  dib_simple_enc_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, ldx, x_off_dev, params, enc_out, feat_stride, ldo,
+                                                                             F, E, n, feature, x_is_feature_only, row_index, n_src);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_simple_enc_wgrad(const float* x, int ldx, const int* x_off_dev, const float* d_out, long long feat_stride,
+                                        int ldo, int F, int E, int64_t n, int nsplit, int rows_per_split, float* part,
+                                        long long split_stride, cudaStream_t st) {
+  dib_simple_enc_wgrad_kernel<<<dim3(F, nsplit), 256, 0, st>>>(x, ldx, x_off_dev, d_out, feat_stride, ldo, E, n, rows_per_split,
+                                                               part, split_stride);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_beta_eff(const float* stats, int F, float inv_global_batch, const float* beta_dev, float exponent,
+                                float scale, float* beta_eff_dev, cudaStream_t st) {
+  dib_beta_eff_kernel<<<1, 32, 0, st>>>(stats, F, inv_global_batch, beta_dev, exponent, scale, beta_eff_dev);
   dib_note_launch();
   return cudaGetLastError();
 }

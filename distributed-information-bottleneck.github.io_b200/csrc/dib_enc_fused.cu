@@ -70,6 +70,7 @@ struct EncFusedParams {
   const long long* b1_off; const long long* b2_off;   // [F] offsets of b1, b2 in params
   const float* eps;                        // [n, F, E] or null -> Philox
   unsigned long long seed; unsigned int step; unsigned long long sample_offset;
+  const unsigned int* step_dev;            // optional device addend of `step` (CUDA-Graph replay)
   float* emb; int ldemb; float* user_emb;  // outputs (forward); emb may be null when emb16 is given
   uint16_t* emb16; int ldemb16;            // 16-bit (fp16 / bf16) copy of emb for the 16-bit integration path (or null)
   float* kl_part; int kl_stride;           // [F][kl_stride] per-(feature, slot) KL partial sums
@@ -263,6 +264,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, c = blockIdx.x, F = P.F;
   const int ntiles = (int)((P.n + TM - 1) / TM);
+  const unsigned int nstep = P.step + (P.step_dev ? P.step_dev[0] : 0u);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.w0); tma_prefetch_desc(&maps.w1); tma_prefetch_desc(&maps.w2);
@@ -337,11 +339,11 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
           DIB_EPI_SIGNAL(bar_a0);
         }
-        noise8(ep, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, hsel * 16, valid, nrmA);   // while layer 1 runs
+        noise8(ep, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, hsel * 16, valid, nrmA);   // while layer 1 runs
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h2);
-        noise8(ep ? ep + 8 : nullptr, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, hsel * 16 + 8, valid, nrmB);   // while layer 2 runs
+        noise8(ep ? ep + 8 : nullptr, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, hsel * 16 + 8, valid, nrmB);   // while layer 2 runs
         // ---- (mu, logvar) -> reparameterise, KL, emb   (16 embedding dims per thread)
         mbar_wait(bar_d2, ph); tc_fence_after_sync();
         {
@@ -490,6 +492,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, c = blockIdx.x, F = P.F;
   const int ntiles = (int)((P.n + TM - 1) / TM);
+  const unsigned int nstep = P.step + (P.step_dev ? P.step_dev[0] : 0u);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.w0); tma_prefetch_desc(&maps.w1); tma_prefetch_desc(&maps.w2);
@@ -636,7 +639,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         mbar_wait(bar_d0, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU, NC>(tR0 + lane_addr, h1buf, r, csel * NC, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h1);
-        noise8(ep, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, csel * ND, valid,
+        noise8(ep, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, csel * ND, valid,
                *reinterpret_cast<float(*)[8]>(&nrm[0]));                                                  // while layer 1 runs
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
         // the previous tile's weight-gradient MMAs read H2 (dz1), DO, DZ2 and the other A0 buffer: retired from here on
@@ -648,7 +651,7 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           DIB_EPI_SIGNAL(bar_a0);
         }
         if constexpr (ND == 16)
-          noise8(ep ? ep + 8 : nullptr, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, csel * ND + 8, valid,
+          noise8(ep ? ep + 8 : nullptr, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, csel * ND + 8, valid,
                  *reinterpret_cast<float(*)[8]>(&nrm[ND - 8]));                                           // while layer 2 runs
         // ---- (mu, logvar) -> d(mu), d(logvar) -> DO tile   (8 embedding dims at a time to bound live registers)
         mbar_wait(bar_d2, ph); tc_fence_after_sync();
@@ -837,6 +840,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, c = blockIdx.x, F = P.F;
   const int ntiles = (int)((P.n + TM - 1) / TM);
+  const unsigned int nstep = P.step + (P.step_dev ? P.step_dev[0] : 0u);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.w0); tma_prefetch_desc(&maps.w1); tma_prefetch_desc(&maps.w2);
@@ -999,7 +1003,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
         DIB_EPI_SIGNAL(bar_h1);
         {                                                                                           // while layer 1 runs
           float nrm[8];
-          noise8(ep, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, csel * 16, valid, nrm);
+          noise8(ep, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, csel * 16, valid, nrm);
 #pragma unroll
           for (int j = 0; j < 4; ++j) nz16[j] = pack2<BF16>(nrm[2 * j], nrm[2 * j + 1]);
         }
@@ -1008,7 +1012,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
         DIB_EPI_SIGNAL(bar_h2);
         {                                                                                           // while layer 2 runs
           float nrm[8];
-          noise8(ep ? ep + 8 : nullptr, P.seed, P.step, P.sample_offset + (unsigned long long)grow, f, csel * 16 + 8, valid, nrm);
+          noise8(ep ? ep + 8 : nullptr, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, csel * 16 + 8, valid, nrm);
 #pragma unroll
           for (int j = 0; j < 4; ++j) nz16[4 + j] = pack2<BF16>(nrm[2 * j], nrm[2 * j + 1]);
         }
@@ -1173,7 +1177,7 @@ __global__ void dib_enc_pack_weights_kernel(const float* __restrict__ params, co
                                             const long long* __restrict__ b0_off, const long long* __restrict__ w1_off,
                                             const long long* __restrict__ b1_off, const long long* __restrict__ w2_off,
                                             const long long* __restrict__ b2_off, const int* __restrict__ fdim, int nfreq,
-                                            uint16_t* __restrict__ out) {
+                                            float logvar_offset, uint16_t* __restrict__ out) {
   const int f = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kPackElems) return;
@@ -1192,7 +1196,7 @@ __global__ void dib_enc_pack_weights_kernel(const float* __restrict__ params, co
   } else {
     i -= kB1Elems;
     const int k = i / EO, n = i - k * EO;
-    v = k == w_in ? params[b2_off[f] + n] : 0.f;
+    v = k == w_in ? params[b2_off[f] + n] + (n >= EO / 2 ? logvar_offset : 0.f) : 0.f;
   }
   uint16_t h;
   if constexpr (BF16) { __nv_bfloat16 b = __float2bfloat16_rn(v); h = *reinterpret_cast<uint16_t*>(&b); }
@@ -1237,7 +1241,7 @@ bool make_all_maps(WeightMaps* m, const void* packed, int F, bool bf16) {
 
 void fill_params(EncFusedParams& P, const DibEncFusedDesc& d, const DibEncFusedIO& io) {
   P.x = io.x; P.ldx = io.ldx; P.x_off = d.x_off; P.fdim = d.fdim; P.nfreq = d.nfreq; P.params = io.params;
-  P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step;
+  P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step; P.step_dev = io.step_dev;
   P.sample_offset = io.sample_offset; P.emb = io.emb; P.ldemb = io.ldemb; P.user_emb = io.user_emb;
   P.kl_part = io.kl_part; P.kl_stride = io.kl_stride; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha;
   P.round_emb = 1; P.emb16 = static_cast<uint16_t*>(io.emb16); P.ldemb16 = io.ldemb16;
@@ -1254,13 +1258,14 @@ cudaError_t launch_fused(K kern, int smem, int grid, const WeightMaps& m, const 
 
 }  // namespace
 
-// which backward kernel runs: 2 (default) or 1 (the single-chain kernel of round 1), DIB_ENC_BWD=1|2 in the environment
+// which backward kernel runs: 1 (the single-chain kernel) or 2 (two chains on consecutive tiles); DIB_ENC_BWD=1|2 in the
+// environment or dib_debug_set_variant(0, v)
 static int g_enc_bwd_version = 0;
 int dib_enc_bwd_version() {
-  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '1') ? 1 : 2; }
+  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '2') ? 2 : 1; }
   return g_enc_bwd_version;
 }
-void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = v == 1 ? 1 : 2; }
+void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = v == 2 ? 2 : 1; }
 
 size_t dib_enc_fused_pack_bytes(int F) { return (size_t)F * kPackElems * 2; }
 int dib_enc_fused_fwd_ctas_per_sm() { return 2; }
@@ -1269,10 +1274,10 @@ cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, vo
   dim3 grid(DIB_CEIL_DIV(kPackElems, 256), d.F);
   if (d.bf16)
     dib_enc_pack_weights_kernel<true><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.b1_off, d.w2_off,
-                                                           d.b2_off, d.fdim, d.nfreq, static_cast<uint16_t*>(packed));
+                                                           d.b2_off, d.fdim, d.nfreq, d.logvar_offset, static_cast<uint16_t*>(packed));
   else
     dib_enc_pack_weights_kernel<false><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.b1_off, d.w2_off,
-                                                            d.b2_off, d.fdim, d.nfreq, static_cast<uint16_t*>(packed));
+                                                            d.b2_off, d.fdim, d.nfreq, d.logvar_offset, static_cast<uint16_t*>(packed));
   dib_note_launch();
   return cudaGetLastError();
 }

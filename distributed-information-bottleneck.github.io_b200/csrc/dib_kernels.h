@@ -44,6 +44,7 @@ struct DibReparamArgs {
   int ldo;
   const float* eps;        // [n, F, E] or nullptr -> Philox
   uint64_t seed; uint32_t step; uint64_t sample_offset;
+  const uint32_t* step_dev = nullptr;   // optional device addend of `step` (CUDA-Graph replay)
   int F, E;
   int64_t n;
   int round_out = 0;
@@ -86,12 +87,30 @@ cudaError_t dib_launch_similarity(int kind, const float* e1, int64_t n, const fl
 cudaError_t dib_launch_infonce_head(int kind, const float* e1, const float* e2, int64_t n, int d, float temperature,
                                     float* scratch, float* out_loss, float* d_e1, float* d_e2, cudaStream_t st);
 
-cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, cudaStream_t st);
+cudaError_t dib_launch_metrics_update(const float* stats, const float* beta_dev, float* acc, int F, float kl_exponent,
+                                      float kl_scale, cudaStream_t st);
+
+// ---- custom-step variants ----
+// enc_out[f][row][E + e] += offset  (nb-particle cell 8: logvar offset), all features or only `feature` (>= 0)
+cudaError_t dib_launch_add_logvar_offset(float* enc_out, long long feat_stride, int ldo, int F, int E, int64_t n, float offset,
+                                         int feature, cudaStream_t st);
+// nb-bool cell 4 SimpleEncoder forward: enc_out[f][row] = (x[row, x_off[f] + e] * mu_scaling_f | logvar_f), e < E
+cudaError_t dib_launch_simple_enc_fwd(const float* x, int ldx, const int* x_off_dev, const float* params, float* enc_out,
+                                      long long feat_stride, int ldo, int F, int E, int64_t n, int feature, int x_is_feature_only,
+                                      const int* row_index, int64_t n_src, cudaStream_t st);
+// its weight gradients: part[split][2f] = sum_rows sum_e d_mu * x, part[split][2f+1] = sum_rows sum_e d_logvar
+cudaError_t dib_launch_simple_enc_wgrad(const float* x, int ldx, const int* x_off_dev, const float* d_out, long long feat_stride,
+                                        int ldo, int F, int E, int64_t n, int nsplit, int rows_per_split, float* part,
+                                        long long split_stride, cudaStream_t st);
+// beta_eff = beta * scale * p * (sum_i stats[i] * inv_global_batch)^(p-1)   (d(beta*scale*KL^p)/dKL; p = 1: beta * scale)
+cudaError_t dib_launch_beta_eff(const float* stats, int F, float inv_global_batch, const float* beta_dev, float exponent,
+                                float scale, float* beta_eff_dev, cudaStream_t st);
 
 // ---- fused per-feature encoder kernels (dib_enc_fused.cu): x -> emb / KL without touching HBM in between ----
 struct DibEncFusedDesc {        // static per model; all pointers are DEVICE arrays of length F
   int F = 0, nfreq = 1, act = 0, bf16 = 0, grid = 0;
   float alpha = 0.2f;
+  float logvar_offset = 0.f;      // folded into the logvar half of the b2 bias carrier when the weights are packed
   const int* x_off = nullptr; const int* fdim = nullptr;
   const long long* w0_off = nullptr; const long long* b0_off = nullptr; const long long* w1_off = nullptr;
   const long long* b1_off = nullptr; const long long* w2_off = nullptr; const long long* b2_off = nullptr;
@@ -100,6 +119,7 @@ struct DibEncFusedIO {
   const float* params; const void* packed;      // fp32 masters, packed 16-bit weights (dib_enc_fused_pack)
   const float* x; int ldx; int64_t n;
   const float* eps; uint64_t seed; uint32_t step; uint64_t sample_offset;
+  const uint32_t* step_dev = nullptr;       // optional device addend of `step` (CUDA-Graph replay)
   float* emb; int ldemb; float* user_emb;
   float* kl_part; int kl_stride;
   void* emb16 = nullptr; int ldemb16 = 0;   // optional fp16 copy of emb (16-bit integration path)

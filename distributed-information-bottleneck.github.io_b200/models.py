@@ -148,6 +148,14 @@ class DistributedIBNet:
     """Distributed IB model where each feature is passed through its own probabilistic encoder MLP
     (models.py:26-123; ``dropout_rate``/``training`` from nb-radial cell 5).
 
+    Custom-step variants of the same front end (keyword-only):
+      ``feature_encoder_architecture='simple'`` -- nb-bool cell 4's SimpleEncoder for every feature (two trainable (1,1)
+        constants mu_scaling = 1, logvar = -3; needs d_i == feature_embedding_dimension, no positional encoding);
+      ``logvar_offset`` -- constant added to every encoder's log-variance (nb-particle cell 8, -3 there);
+      ``kl_loss_exponent`` / ``kl_loss_scale`` -- nonlinear IB ``beta * scale * (sum_i KL_i) ** exponent`` (nb-chaos cell 10);
+      ``model.encode`` / ``model.encoder_gradients`` -- encoder-only steps for a caller-owned downstream network
+        (nb-particle's shared particle encoder + set transformer: see :class:`SharedParticleEncoder`).
+
     Extra keyword-only arguments (not in the reference): ``device``, ``seed`` (weight init + noise stream),
     ``precision`` ('fp32' exact-FMA parity path | 'tf32' kind::tf32 GEMMs | 'fp16' / 'bf16' fused 16-bit-operand
     tcgen05 kernels with fp32 accumulation; ``model.kernel_info()`` says what a handle actually runs), ``process_group``
@@ -166,7 +174,8 @@ class DistributedIBNet:
                  output_activation_fn: Optional[str] = None,
                  dropout_rate: float = 0.,
                  *, device=None, seed: int = 0, precision: str = 'fp32', process_group=None,
-                 leaky_alpha: float = 0.2):
+                 leaky_alpha: float = 0.2, logvar_offset: float = 0., kl_loss_exponent: float = 1.,
+                 kl_loss_scale: float = 1.):
         _require_cuda()
         if dropout_rate and dropout_rate > 0:
             raise NotImplementedError("dropout_rate > 0 (nb-radial only, default 0) is not implemented")
@@ -176,6 +185,14 @@ class DistributedIBNet:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
         self.feature_dimensionalities = [int(d) for d in feature_dimensionalities]
         self.number_features = len(self.feature_dimensionalities)
+        self.encoder_kind = "simple" if isinstance(feature_encoder_architecture, str) else "mlp"
+        if self.encoder_kind == "simple":
+            if feature_encoder_architecture != "simple":
+                raise ValueError("feature_encoder_architecture must be a list of widths or 'simple'")
+            feature_encoder_architecture, use_positional_encoding = [], False
+        self.logvar_offset = float(logvar_offset)
+        self.kl_loss_exponent = float(kl_loss_exponent)
+        self.kl_loss_scale = float(kl_loss_scale)
         self.feature_encoder_architecture = [int(h) for h in feature_encoder_architecture]
         self.integration_network_architecture = [int(h) for h in integration_network_architecture]
         self.output_dimensionality = int(output_dimensionality)
@@ -210,16 +227,29 @@ class DistributedIBNet:
             self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._epoch_acc = torch.zeros(self.number_features + 4, dtype=torch.float32, device=self.device)
         self._train_step_count = 0
+        # ---- CUDA-graph replay of the train step (launch-bound small batches; fewer host calls per step at any size)
+        env = os.environ.get("DIB_CUDA_GRAPH", "auto").lower()
+        self.use_cuda_graph = env not in ("0", "off", "false", "no")
+        self._graphs = {}                  # (n, global_batch, sample_offset, world) -> captured step
+        self._graph_seen = {}              # eager executions per key before capture (lazy one-time setup must be done)
+        self._graph_failed = False
+        self._noise_step_dev = None        # int32 device mirror of _train_step_count (Philox step word inside graphs)
+        self._step_dev_active = False
+        self._step_dev_dirty = False       # _train_step_count moved outside a graph replay: refill the device mirror
+        self._replayed_launches = 0        # kernels launched by graph replays (dib_launch_count only sees eager launches)
+        self._side_stream = None
+        self.overlap_allreduce = os.environ.get("DIB_OVERLAP_ALLREDUCE", "1") not in ("0", "off", "false", "no")
         self._inference_calls = 0          # fresh noise per un-seeded inference call (tf.random.normal, models.py:108)
         self.optimizer = None
         self.compiled_metrics_names = []
         self.losses = []
         self.metrics_values = {}
-        n_enc_vars = 2 * (len(self.feature_encoder_architecture) + 1)
+        n_enc_vars = 2 if self.encoder_kind == "simple" else 2 * (len(self.feature_encoder_architecture) + 1)
         self.feature_encoders = [                                            # models.py:79
             _FeatureEncoder(self, i, range(i * n_enc_vars, (i + 1) * n_enc_vars)) for i in range(self.number_features)]
         self.integration_network = _IntegrationNetwork(                      # models.py:84
             self, range(self.number_features * n_enc_vars, len(self._var_off)))
+        self._p_enc = int(self._var_off[self.number_features * n_enc_vars])  # first integration-network parameter
 
     # ------------------------------------------------------------------ library handle / buffers
     def _config(self, max_batch):
@@ -238,7 +268,9 @@ class DistributedIBNet:
             activation_fn=_lib.ACTIVATIONS[self.activation_fn], leaky_relu_alpha=self.leaky_alpha,
             feature_embedding_dimension=self.feature_embedding_dimension,
             output_activation_fn=_lib.ACTIVATIONS[self.output_activation_fn],
-            loss=_lib.LOSSES[self._loss_kind], precision=_lib.PRECISIONS[self.precision], max_batch=int(max_batch))
+            loss=_lib.LOSSES[self._loss_kind], precision=_lib.PRECISIONS[self.precision], max_batch=int(max_batch),
+            logvar_offset=self.logvar_offset, kl_loss_exponent=self.kl_loss_exponent, kl_loss_scale=self.kl_loss_scale,
+            encoder_kind=_lib.ENCODER_KINDS[self.encoder_kind])
 
     def _query_layout(self):
         with torch.cuda.device(self.device):
@@ -265,6 +297,8 @@ class DistributedIBNet:
             cfg = self._config(max_batch)
             _lib.check(self._lib.dib_create(ctypes.byref(cfg), ctypes.byref(h)))
             self._handle, self._handle_key, self._max_batch = h, key, max_batch
+            self._graphs.clear(); self._graph_seen.clear()       # captured launches point into the old workspace
+            self._step_dev_active = False
             if getattr(self, "_force_unfused", 0):
                 _lib.check(self._lib.dib_debug_force_unfused(h, int(self._force_unfused)))
             nbytes = int(self._lib.dib_workspace_bytes(h))
@@ -303,8 +337,11 @@ class DistributedIBNet:
         g = torch.Generator(device="cpu")
         g.manual_seed(self.seed)
         flat = torch.zeros(self._P, dtype=torch.float32)
-        for off, r, c in zip(self._var_off, self._var_rows, self._var_cols):
-            if r > 0:
+        n_simple = 2 * self.number_features if self.encoder_kind == "simple" else 0
+        for k, (off, r, c) in enumerate(zip(self._var_off, self._var_rows, self._var_cols)):
+            if k < n_simple:                 # nb-bool cell 4: mu_scaling = ones, logvar = -3 * ones
+                flat[off] = 1.0 if k % 2 == 0 else -3.0
+            elif r > 0:
                 lim = math.sqrt(6.0 / (r + c))
                 flat[off:off + r * c] = (torch.rand(r * c, generator=g) * 2 - 1) * lim
         self._params.copy_(flat)
@@ -407,17 +444,30 @@ class DistributedIBNet:
                                                           opt("dist"), opt("comp"), _lib.ptr(self._workspace), _stream()))
         return out
 
-    def _backward(self, x, y, global_batch, eps=None, sample_offset=0, step=None):
-        """dib_train_step: forward + reverse mode into self._gradstats = [grads (P) || stats (F+3)]."""
+    def _set_device_step(self, on):
+        """Philox step word from the device mirror of _train_step_count (graph replay) or by value (everything else)."""
+        if on == self._step_dev_active and self._handle is not None and not (on and self._step_dev_dirty):
+            return
+        if on:
+            self._step_dev_dirty = False
+            if self._noise_step_dev is None:
+                self._noise_step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._noise_step_dev.fill_(int(self._train_step_count) & 0x7FFFFFFF)
+        _lib.check(self._lib.dib_set_noise_step_device(self._handle, _lib.ptr(self._noise_step_dev) if on else None))
+        self._step_dev_active = on
+
+    def _backward(self, x, y, global_batch, eps=None, sample_offset=0, step=None, phases=3, device_step=False):
+        """dib_train_step[_phased]: forward + reverse mode into self._gradstats = [grads (P) || stats (F+3)]."""
         n = x.shape[0]
         self._ensure_handle(n)
         P = self._P
-        st = self._train_step_count if step is None else step
-        _lib.check(self._lib.dib_train_step(
+        self._set_device_step(device_step)
+        st = 0 if device_step else (self._train_step_count if step is None else step)
+        _lib.check(self._lib.dib_train_step_phased(
             self._handle, _lib.ptr(self._params), _lib.ptr(x), _lib.ptr(y), n, _lib.ptr(self.beta._dev),
             1.0 / float(global_batch), _lib.ptr(eps), self.noise_seed, int(st) & 0xFFFFFFFF,
             int(sample_offset), _lib.ptr(self._gradstats), _lib.ptr(self._gradstats[P:]), _lib.ptr(self._workspace),
-            _stream()))
+            int(phases), _stream()))
 
     def apply_gradients(self, flat_grads):
         """optimizer.apply_gradients(zip(grads, model.trainable_variables)) of the custom loops (train.py:217-219,
@@ -432,16 +482,122 @@ class DistributedIBNet:
                 _lib.ptr(self._params), _lib.ptr(g), _lib.ptr(self._m), _lib.ptr(self._v), self._P,
                 _lib.ptr(self._lr_dev), _lib.ptr(self._step_dev), opt.beta_1, opt.beta_2, opt.epsilon, _stream()))
         self._train_step_count += 1
+        self._step_dev_dirty = True
 
-    def _train_step(self, x, y, global_batch, eps=None, sample_offset=0):
-        """backward, all-reduce over the data-parallel group (one flat collective: grads || stats), Keras-Adam."""
-        P = self._P
-        self._backward(x, y, global_batch, eps, sample_offset)
-        parallel.allreduce_sum_(self._gradstats, self.process_group)
+    def _adam(self):
         opt = self.optimizer
         _lib.check(self._lib.dib_adam_step(
-            _lib.ptr(self._params), _lib.ptr(self._gradstats), _lib.ptr(self._m), _lib.ptr(self._v), P,
+            _lib.ptr(self._params), _lib.ptr(self._gradstats), _lib.ptr(self._m), _lib.ptr(self._v), self._P,
             _lib.ptr(self._lr_dev), _lib.ptr(self._step_dev), opt.beta_1, opt.beta_2, opt.epsilon, _stream()))
+
+    def _reduce_overlapped(self, world, run_phase1, run_phase2):
+        """The data-parallel exchange in two buckets: [integration grads || stats] is all-reduced on a side stream while
+        the encoder backward (phase 2) runs; [encoder grads] follows on the compute stream.  One process per GPU, NCCL."""
+        pe = self._p_enc
+        run_phase1()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        side, main = self._side_stream, torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            work = parallel.allreduce_sum_async(self._gradstats[pe:], self.process_group)
+        run_phase2()
+        parallel.allreduce_sum_(self._gradstats[:pe], self.process_group)
+        if work is not None:
+            work.wait()                      # the compute stream waits for bucket 1 (no host sync)
+        main.wait_stream(side)
+
+    def _train_step(self, x, y, global_batch, eps=None, sample_offset=0):
+        """backward, all-reduce over the data-parallel group, Keras-Adam.  Replayed from CUDA graphs once a
+        (batch size, offset) combination has run eagerly twice; the all-reduce is split into two buckets so that the
+        first overlaps the encoder backward."""
+        P = self._P
+        world, _ = parallel.world_and_rank(self.process_group)
+        key = (int(x.shape[0]), int(global_batch), int(sample_offset), world)
+        if self.use_cuda_graph and not self._graph_failed and eps is None and x.shape[0] > 0:
+            g = self._graphs.get(key)
+            if g is None and self._graph_seen.get(key, 0) >= 2:
+                g = self._capture_step(key)
+            if g is not None:
+                return self._replay_step(g, x, y, world)
+            self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+        if world > 1 and self.overlap_allreduce:
+            self._reduce_overlapped(world, lambda: self._backward(x, y, global_batch, eps, sample_offset, phases=1),
+                                    lambda: self._backward(x, y, global_batch, eps, sample_offset, phases=2))
+        else:
+            self._backward(x, y, global_batch, eps, sample_offset)
+            parallel.allreduce_sum_(self._gradstats, self.process_group)
+        self._adam()
+        self._train_step_count += 1
+        self._step_dev_dirty = True
+        return self._gradstats[P:]
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the step
+    def _capture_step(self, key):
+        """Capture the step for one (n, global_batch, sample_offset, world) into CUDA graphs.  Single GPU: ONE graph
+        (forward + backward + Adam + noise-step increment).  Data parallel: three graphs (phase 1 | phase 2 | Adam) with the
+        NCCL all-reduces issued eagerly between them.  Inputs are copied into static buffers before each replay; beta,
+        learning rate, the Adam step and the Philox step are device scalars, so nothing by-value changes between replays."""
+        n, global_batch, sample_offset, world = key
+        D = sum(self.feature_dimensionalities)
+        yc = self._y_cols()
+        try:
+            with torch.cuda.device(self.device):
+                gx = torch.zeros(n, D, dtype=torch.float32, device=self.device)
+                gy = torch.zeros((n, yc) if yc > 0 else (n,), dtype=torch.float32, device=self.device)
+                self._ensure_handle(n)
+                self._set_device_step(True)
+                torch.cuda.synchronize(self.device)
+                keep = [t.clone() for t in (self._params, self._m, self._v, self._step_dev, self._noise_step_dev)]
+                graphs = []
+                launches0 = int(self._lib.dib_launch_count())
+
+                def cap(fn):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fn()
+                    graphs.append(g)
+
+                def tail():
+                    self._adam()
+                    self._noise_step_dev.add_(1)
+
+                if world == 1:
+                    cap(lambda: (self._backward(gx, gy, global_batch, None, sample_offset, device_step=True), tail()))
+                else:
+                    cap(lambda: self._backward(gx, gy, global_batch, None, sample_offset, phases=1, device_step=True))
+                    cap(lambda: self._backward(gx, gy, global_batch, None, sample_offset, phases=2, device_step=True))
+                    cap(tail)
+                torch.cuda.synchronize(self.device)
+                # capture does not execute, but be safe against any eager side effect: restore the optimizer state
+                for t, k in zip((self._params, self._m, self._v, self._step_dev, self._noise_step_dev), keep):
+                    t.copy_(k)
+        except Exception as e:       # noqa: BLE001 -- an unsupported capture falls back to eager launches, loudly
+            import warnings
+            warnings.warn(f"CUDA-graph capture of the train step failed ({e!r}); continuing with eager launches")
+            self._graph_failed = True
+            self._set_device_step(False)
+            return None
+        g = dict(graphs=graphs, x=gx, y=gy, launches=int(self._lib.dib_launch_count()) - launches0)
+        self._graphs[key] = g
+        return g
+
+    def _replay_step(self, g, x, y, world):
+        P = self._P
+        if not self._step_dev_active or self._step_dev_dirty:
+            self._set_device_step(True)
+        self._replayed_launches += g["launches"]
+        g["x"].copy_(x.reshape(g["x"].shape), non_blocking=True)
+        g["y"].copy_(y.reshape(g["y"].shape), non_blocking=True)
+        if world == 1:
+            g["graphs"][0].replay()
+        elif self.overlap_allreduce:
+            self._reduce_overlapped(world, g["graphs"][0].replay, g["graphs"][1].replay)
+            g["graphs"][2].replay()
+        else:
+            g["graphs"][0].replay(); g["graphs"][1].replay()
+            parallel.allreduce_sum_(self._gradstats, self.process_group)
+            g["graphs"][2].replay()
         self._train_step_count += 1
         return self._gradstats[P:]
 
@@ -454,6 +610,43 @@ class DistributedIBNet:
             e = self._to_device(eps) if eps is not None else None
             self._backward(xd, yd, global_batch or max(xd.shape[0], 1), e, sample_offset, step)
             return self._gradstats[:self._P].clone(), self._gradstats[self._P:].clone()
+
+    # ------------------------------------------------------------------ encoder-only custom steps
+    def encode(self, x, eps=None, step=None, sample_offset=0):
+        """Every feature encoder + reparameterisation, without the integration network (nb-particle cell 8's
+        ``particle_encoder`` front end): returns (emb [n, F*E] = mu + exp(logvar/2) eps, KL_i batch means [F]) as device
+        tensors.  Noise as in ``__call__``: explicit ``eps``, Philox keyed by ``step``, or a fresh draw."""
+        with torch.cuda.device(self.device):
+            xd = self._to_device(x, sum(self.feature_dimensionalities))
+            e = self._to_device(eps) if eps is not None else None
+            n = xd.shape[0]
+            self._ensure_handle(n)
+            st = self._inference_step() if step is None else step
+            emb = torch.empty(n, self.number_features * self.feature_embedding_dimension, dtype=torch.float32, device=self.device)
+            stats = torch.empty(self.number_features + 3, dtype=torch.float32, device=self.device)
+            _lib.check(self._lib.dib_encoders_forward(
+                self._handle, _lib.ptr(self._params), _lib.ptr(xd), n, _lib.ptr(e), self.noise_seed, int(st) & 0xFFFFFFFF,
+                int(sample_offset), _lib.ptr(emb), _lib.ptr(stats), _lib.ptr(self._workspace), _stream()))
+            return emb, stats[:self.number_features] / max(n, 1)
+
+    def encoder_gradients(self, x, d_emb, global_batch=None, eps=None, step=None, sample_offset=0):
+        """Reverse mode of :meth:`encode` for a caller-owned downstream network: ``d_emb`` [n, F*E] is d(caller's loss)/d(emb)
+        (already carrying the caller's batch scaling); the IB term beta * scale * (sum KL)^p, with KL means over
+        ``global_batch`` rows (default n), is added here.  Returns (flat gradient [P] -- integration entries are zero --,
+        statistics vector).  Pass the same ``eps`` / ``step`` as the ``encode`` call it differentiates."""
+        with torch.cuda.device(self.device):
+            xd = self._to_device(x, sum(self.feature_dimensionalities))
+            gd = self._to_device(d_emb, self.number_features * self.feature_embedding_dimension)
+            e = self._to_device(eps) if eps is not None else None
+            n = xd.shape[0]
+            self._ensure_handle(n)
+            st = self._train_step_count if step is None else step
+            P = self._P
+            _lib.check(self._lib.dib_encoders_backward(
+                self._handle, _lib.ptr(self._params), _lib.ptr(xd), _lib.ptr(gd), n, _lib.ptr(self.beta._dev),
+                1.0 / float(global_batch or max(n, 1)), _lib.ptr(e), self.noise_seed, int(st) & 0xFFFFFFFF, int(sample_offset),
+                _lib.ptr(self._gradstats), _lib.ptr(self._gradstats[P:]), _lib.ptr(self._workspace), _stream()))
+            return self._gradstats[:P].clone(), self._gradstats[P:].clone()
 
     def debug_force_unfused(self, on=True, batch_hint=1):
         """Bring-up switch: keep the tensor-core mode on the unfused kernels (fused-vs-unfused comparisons)."""
@@ -468,8 +661,8 @@ class DistributedIBNet:
         return torch.randperm(n, generator=gen, device=self.device)
 
     def _metrics_update(self, stats):
-        _lib.check(self._lib.dib_metrics_update(_lib.ptr(stats), _lib.ptr(self.beta._dev), _lib.ptr(self._epoch_acc),
-                                                self.number_features, _stream()))
+        _lib.check(self._lib.dib_metrics_update_ex(_lib.ptr(stats), _lib.ptr(self.beta._dev), _lib.ptr(self._epoch_acc),
+                                                   self.number_features, self.kl_loss_exponent, self.kl_loss_scale, _stream()))
 
     def _read_epoch_logs(self, prefix=""):
         F = self.number_features
@@ -503,7 +696,7 @@ class DistributedIBNet:
             pred, _, stats = self._forward(x, None, e, st, sample_offset)
             n = x.shape[0]
             kl = stats[:self.number_features] / max(n, 1)
-            self.losses = [self.beta._dev[0] * kl.sum()]
+            self.losses = [self.beta._dev[0] * self.kl_loss_scale * kl.sum() ** self.kl_loss_exponent]
             self._last_kl = kl
             self.metrics_values = {"beta": self.beta.value()}
         return _as_numpy_like(inputs, pred)
@@ -703,7 +896,9 @@ class PendingBatchResult:
                 s = self._dev.detach().cpu().numpy().astype(np.float64)
             F = self._m.number_features
             nn = max(s[F + 2], 1.0)
-            out = {"loss": float((s[F] + self._beta * s[:F].sum()) / nn), "accuracy": float(s[F + 1] / nn)}
+            m = self._m
+            ib = self._beta * m.kl_loss_scale * (s[:F].sum() / nn) ** m.kl_loss_exponent      # models.py:118 / nb-chaos
+            out = {"loss": float(s[F] / nn + ib), "accuracy": float(s[F + 1] / nn)}
             for i in range(F):
                 out[f"KL{i}"] = float(s[i] / nn)
             self._out = out
@@ -831,3 +1026,69 @@ class InfoPerFeatureCallback(Callback):
                                                       number_evaluation_batches=self.number_evaluation_batches,
                                                       seed=self.seed + epoch)
             self.bounds.append([float(lo_up[0]), float(lo_up[1])])
+
+
+class SimpleEncoder:
+    """nb-bool cell 4: "Simple encoder for a binary-valued variable.  With two trainable constants, mu and logvar, this
+    encoder maps +1/-1 to a normal distribution with mean +mu/-mu and log variance of logvar."  Stand-alone callable with
+    the reference's surface (``mu_scaling``, ``logvar``, ``call``); to TRAIN a bank of them with the fused step build
+    ``DistributedIBNet(feature_dimensionalities, 'simple', integration_arch, out, feature_embedding_dimension=1)``."""
+
+    def __init__(self):
+        self.mu_scaling = np.ones((1, 1), np.float32)
+        self.logvar = -3.0 * np.ones((1, 1), np.float32)
+
+    def build(self, input_shape=None):
+        return
+
+    def __call__(self, inputs):
+        t = torch.as_tensor(inputs, dtype=torch.float32)
+        out = torch.cat([t * float(self.mu_scaling[0, 0]), torch.ones_like(t) * float(self.logvar[0, 0])], -1)
+        return _as_numpy_like(inputs, out)
+
+    call = __call__
+
+    @property
+    def trainable_variables(self):
+        return [self.mu_scaling, self.logvar]
+
+
+class SharedParticleEncoder:
+    """nb-particle cell 8's front end: ONE encoder MLP (positional encoding -> Dense stack -> (mu, logvar)) applied with
+    shared weights to every particle of every neighbourhood, logvar offset (-3 there), KL summed over embedding dims AND
+    particles and averaged over the batch -- i.e. a one-feature DistributedIBNet on B*particles rows whose KL means are
+    taken over B.  The downstream network (the notebook's set transformer) is the caller's: ``encode`` returns
+    [B, particles, E] embeddings, ``gradients`` takes d(loss)/d(embeddings) back."""
+
+    def __init__(self, particle_feature_dimensions, particle_encoder_arch_spec, bottleneck_dimension=32,
+                 number_positional_encoding_frequencies=5, activation_fn='leaky_relu', leaky_alpha=0.1,
+                 logvar_initialization=-3., **kw):
+        self.net = DistributedIBNet([int(particle_feature_dimensions)], list(particle_encoder_arch_spec), [], 1,
+                                    use_positional_encoding=number_positional_encoding_frequencies > 1,
+                                    number_positional_encoding_frequencies=number_positional_encoding_frequencies,
+                                    activation_fn=activation_fn, feature_embedding_dimension=bottleneck_dimension,
+                                    leaky_alpha=leaky_alpha, logvar_offset=logvar_initialization, **kw)
+        self.net.compile(optimizer='adam', loss='external')
+        self.beta = self.net.beta
+        self.d = int(particle_feature_dimensions)
+        self.E = int(bottleneck_dimension)
+
+    def encode(self, batch_inp, eps=None, step=None):
+        """batch_inp [B, particles, d] -> (embs_reparam [B, particles, E], kl = mean_B sum_{particles, E})."""
+        t = torch.as_tensor(batch_inp, dtype=torch.float32)
+        B, Np = t.shape[0], t.shape[1]
+        e = None if eps is None else torch.as_tensor(eps, dtype=torch.float32).reshape(B * Np, 1, self.E)
+        emb, kl_rows = self.net.encode(t.reshape(B * Np, self.d), eps=e, step=step)
+        return emb.reshape(B, Np, self.E), kl_rows[0] * Np
+
+    def gradients(self, batch_inp, d_embs, eps=None, step=None):
+        """Flat encoder gradient of (caller's loss + beta * kl) given d(caller's loss)/d(embs_reparam) [B, particles, E]."""
+        t = torch.as_tensor(batch_inp, dtype=torch.float32)
+        B, Np = t.shape[0], t.shape[1]
+        e = None if eps is None else torch.as_tensor(eps, dtype=torch.float32).reshape(B * Np, 1, self.E)
+        g, _ = self.net.encoder_gradients(t.reshape(B * Np, self.d), torch.as_tensor(d_embs).reshape(B * Np, self.E),
+                                          global_batch=B, eps=e, step=step)
+        return g
+
+    def apply_gradients(self, flat_grads):
+        self.net.apply_gradients(flat_grads)

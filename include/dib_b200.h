@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DIB_ABI_VERSION 1
+#define DIB_ABI_VERSION 2
 
 /* activation_fn strings accepted by tf.keras.layers.Dense in the reference's call sites
  * (train.py:37 'relu', nb-radial 'tanh', nb-bool LeakyReLU, None). */
@@ -66,6 +66,11 @@ enum dib_loss {
  * dib_model_info() reports which kernel family a handle actually selected. */
 enum dib_precision { DIB_PREC_FP32 = 0, DIB_PREC_TF32 = 1, DIB_PREC_BF16 = 2, DIB_PREC_FP16 = 3 };
 
+/* feature encoders: the per-feature MLP of models.py:72-78, or nb-bool cell 4's SimpleEncoder -- two trainable (1,1)
+ * constants per feature, output concat([x * mu_scaling, ones_like(x) * logvar]) (needs d_i == E, no positional encoding;
+ * flat parameter order per feature: mu_scaling, logvar; feature_encoder_architecture is ignored). */
+enum dib_encoder_kind { DIB_ENCODER_MLP = 0, DIB_ENCODER_SIMPLE = 1 };
+
 /* Mirrors the constructor of models.DistributedIBNet (models.py:56-66). */
 typedef struct dib_config {
   int32_t abi_version;               /* DIB_ABI_VERSION */
@@ -85,6 +90,12 @@ typedef struct dib_config {
   int32_t loss;                      /* enum dib_loss (model.compile(loss=...), train.py:138-142) */
   int32_t precision;                 /* enum dib_precision */
   int64_t max_batch;                 /* largest n any call will pass (sizes the workspace) */
+  /* ---- custom-step variants of the same front end (NEXT ROW f3); zero-initialised fields give models.py ---- */
+  float   logvar_offset;             /* constant added to every encoder's log-variance before sampling / KL / any output
+                                        (nb-particle cell 8: embs_logvars + logvar_initialization, -3 there) */
+  float   kl_loss_exponent;          /* nonlinear IB (nb-chaos cell 10): loss_IB = beta * kl_loss_scale * (sum_i KL_i)^exponent; */
+  float   kl_loss_scale;             /*   0 or 1 / 0 or 1 = the linear beta * sum_i KL_i of models.py:118 */
+  int32_t encoder_kind;              /* enum dib_encoder_kind */
 } dib_config;
 
 typedef struct dib_model dib_model;
@@ -129,6 +140,37 @@ int dib_train_step(dib_model* h, const float* params, const float* x, const floa
                    const float* eps, uint64_t seed, uint32_t step, uint64_t sample_offset,
                    float* grads_flat, float* out_stats, void* workspace, void* stream);
 
+/* NEXT ROW f3 -- encoder-only custom steps (nb-particle cell 8: a shared particle encoder feeding the caller's own
+ * network, e.g. a set transformer; nb-chaos cell 10): the model's integration network is not used.
+ *   dib_encoders_forward : x [n, sum d_i] -> out_emb [n, F*E] (u = mu + exp(logvar/2) eps) and out_stats (KL sums; loss = acc = 0).
+ *   dib_encoders_backward: recomputes that forward, then reverse mode from d_emb [n, F*E] = d(caller's loss)/d(emb)
+ *     (already carrying the caller's batch scaling) plus the IB term d(beta * scale * (sum KL)^p)/d(params) with KL means
+ *     over inv_global_batch; grads_flat [P]: encoder entries written, integration-network entries zeroed.
+ * A shared-weight encoder over a particle axis is F = 1 on n = B * particles rows with inv_global_batch = 1/B (KL summed
+ * over particles, averaged over the batch). */
+int dib_encoders_forward(dib_model* h, const float* params, const float* x, int64_t n, const float* eps, uint64_t seed,
+                         uint32_t step, uint64_t sample_offset, float* out_emb, float* out_stats, void* workspace, void* stream);
+int dib_encoders_backward(dib_model* h, const float* params, const float* x, const float* d_emb, int64_t n,
+                          const float* beta_dev, float inv_global_batch, const float* eps, uint64_t seed, uint32_t step,
+                          uint64_t sample_offset, float* grads_flat, float* out_stats, void* workspace, void* stream);
+
+/* dib_train_step in two halves, for overlapping the data-parallel collective with the encoder backward:
+ *   phases = 1: forward + compiled loss + integration-network backward -> grads_flat[first integration parameter, P) and
+ *               out_stats are final (bucket 1 can be all-reduced while phase 2 runs);
+ *   phases = 2: encoder backward -> grads_flat[0, first integration parameter) final.  Same arguments as the phase-1 call;
+ *   phases = 3: both (== dib_train_step).
+ * The first integration parameter is offsets[v] of variable v = number_features * (encoder variables per feature). */
+int dib_train_step_phased(dib_model* h, const float* params, const float* x, const float* y, int64_t n,
+                          const float* beta_dev, float inv_global_batch,
+                          const float* eps, uint64_t seed, uint32_t step, uint64_t sample_offset,
+                          float* grads_flat, float* out_stats, void* workspace, int32_t phases, void* stream);
+
+/* CUDA-Graph replay: a captured launch cannot carry a fresh by-value `step`, so the Philox step word may come from device
+ * memory: when step_dev != NULL every later dib_train_step[_phased] call of this handle uses step + *step_dev (dib_forward
+ * and the encoder-only entry points keep the by-value step).  The caller owns the counter and advances it (on the stream)
+ * between steps.  NULL restores the by-value behaviour. */
+int dib_set_noise_step_device(dib_model* h, const uint32_t* step_dev);
+
 /* tf.keras.optimizers.Adam dense update over the flat buffer (train.py:128-129, nb-radial Adam(lr)):
  *   t = *step_dev + 1 (the kernel increments *step_dev);  lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
  *   m += (1-b1)(g-m); v += (1-b2)(g^2-v); w -= lr_t*m/(sqrt(v)+eps)   (eps outside the bias correction). */
@@ -143,6 +185,9 @@ int dib_adam_step(float* params, const float* grads, float* m, float* v, int64_t
  *   acc[F+2]   += n ;  acc[F+3] += 1      (samples, batches)
  * stats is the (all-reduced) vector written by dib_train_step / dib_forward; acc has F+4 floats. */
 int dib_metrics_update(const float* stats, const float* beta_dev, float* acc, int32_t number_features, void* stream);
+/* the same with the nonlinear IB term: acc[F] += stats[F] + n * beta * kl_loss_scale * (sum_i stats[i] / n)^kl_loss_exponent */
+int dib_metrics_update_ex(const float* stats, const float* beta_dev, float* acc, int32_t number_features,
+                          float kl_loss_exponent, float kl_loss_scale, void* stream);
 
 /* utils.bhattacharyya_dist_mat (utils.py:177-212) followed by exp(-D) (visualization.py:34):
  * mu_logvar [n, 2E] -> out_dist [n, n] (may be NULL) and out_compression [n, n] (may be NULL). */

@@ -81,6 +81,17 @@ class DIBConfig:
     feature_embedding_dimension: int = 32
     output_activation_fn: Optional[str] = None
     leaky_alpha: float = 0.2
+    # ---- custom-step variants of the same front end ----
+    # logvar_offset: constant added to every encoder's log-variance output before sampling and KL
+    #   (nb-particle cell 8: `embs_logvars = embs_logvars + logvar_initialization`, -3 there)
+    logvar_offset: float = 0.0
+    # nonlinear IB: loss_IB = beta * kl_loss_scale * (sum_i KL_i) ** kl_loss_exponent
+    #   (nb-chaos cell 10: `loss = beta_var * number_states * kl ** kl_loss_exponent`); (1, 1) = models.py:118
+    kl_loss_exponent: float = 1.0
+    kl_loss_scale: float = 1.0
+    # 'mlp' (models.py:72-78) or 'simple': nb-bool cell 4 SimpleEncoder -- two trainable (1,1) constants per feature,
+    #   output concat([x * mu_scaling, ones_like(x) * logvar]); needs d_i == feature_embedding_dimension
+    encoder_kind: str = "mlp"
 
     @property
     def number_features(self):
@@ -109,6 +120,9 @@ class DIBConfig:
         Keras-oriented [in, out] (tf.keras.layers.Dense)."""
         shapes = []
         for i in range(self.number_features):
+            if self.encoder_kind == "simple":
+                shapes += [(1, 1), (1, 1)]                      # mu_scaling, logvar (nb-bool cell 4)
+                continue
             d = self.encoder_layer_dims(i)
             for k in range(len(d) - 1):
                 shapes += [(d[k], d[k + 1]), (d[k + 1],)]
@@ -125,8 +139,11 @@ def glorot_uniform_params(cfg: DIBConfig, rng: np.random.Generator, dtype=np.flo
     """[KERAS] Dense default init: kernel glorot_uniform (limit sqrt(6/(fan_in+fan_out))), bias zeros.
     The RNG stream is ours (numpy Generator); Keras' own stream is irreproducible without TF."""
     out = []
-    for s in cfg.param_shapes():
-        if len(s) == 2:
+    n_simple = 2 * cfg.number_features if cfg.encoder_kind == "simple" else 0
+    for idx, s in enumerate(cfg.param_shapes()):
+        if idx < n_simple:                                       # nb-bool cell 4: mu_scaling = 1, logvar = -3
+            out.append(np.full(1, 1.0 if idx % 2 == 0 else -3.0, dtype=dtype))
+        elif len(s) == 2:
             lim = math.sqrt(6.0 / (s[0] + s[1]))
             out.append(rng.uniform(-lim, lim, size=s).astype(dtype).ravel())
         else:
@@ -143,7 +160,7 @@ def unflatten(cfg: DIBConfig, flat: np.ndarray):
         off += n
     assert off == flat.size
     it = iter(views)
-    n_enc_layers = len(cfg.feature_encoder_architecture) + 1
+    n_enc_layers = 1 if cfg.encoder_kind == "simple" else len(cfg.feature_encoder_architecture) + 1
     encoders = [[(next(it), next(it)) for _ in range(n_enc_layers)] for _ in range(cfg.number_features)]
     n_int_layers = len(cfg.integration_network_architecture) + 1
     integration = [(next(it), next(it)) for _ in range(n_int_layers)]
@@ -241,8 +258,13 @@ def forward(cfg: DIBConfig, flat_params, x, eps, beta, y=None, loss=None, keep=F
     xs = split_features(cfg, x)
     embs, kls, enc_cache = [], [], []
     for i in range(cfg.number_features):
-        o, acts = encoder_forward(cfg, encoders[i], xs[i], keep=True)
-        mu, lv = o[:, :E], o[:, E:]                                   # models.py:106 tf.split(.,2,-1)
+        if cfg.encoder_kind == "simple":                              # nb-bool cell 4: concat([x*mu_scaling, 1*logvar])
+            ms, lvc = encoders[i][0]
+            assert xs[i].shape[1] == E, "SimpleEncoder needs d_i == feature_embedding_dimension"
+            o, acts = np.concatenate([xs[i] * ms, np.ones_like(xs[i]) * lvc], axis=-1), [xs[i]]
+        else:
+            o, acts = encoder_forward(cfg, encoders[i], xs[i], keep=True)
+        mu, lv = o[:, :E], o[:, E:] + cfg.logvar_offset               # models.py:106 tf.split(.,2,-1); nb-particle offset
         u = mu + np.exp(lv / 2.0) * eps[:, i, :]                      # models.py:108
         kl = (0.5 * (mu ** 2 + np.exp(lv) - lv - 1.0)).sum(axis=-1).mean()   # models.py:111-112
         embs.append(u)
@@ -264,26 +286,41 @@ def forward(cfg: DIBConfig, flat_params, x, eps, beta, y=None, loss=None, keep=F
                         loss=float("nan"), acc_sum=float("nan"))
     if y is not None and loss != "external":
         res.task_loss = float(task_loss_per_sample(loss, pred, y).mean())
-        res.loss = res.task_loss + float(beta) * float(kls.sum())     # models.py:118
+        res.loss = res.task_loss + ib_loss(cfg, beta, kls)            # models.py:118 / nb-chaos nonlinear IB
         res.acc_sum = accuracy_count(loss, pred, y)
     if keep:
         res.cache = dict(enc=enc_cache, int_acts=int_acts, encoders=encoders, integration=integration)
     return res
 
 
-def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.float64, batch_for_mean=None):
+def ib_loss(cfg: DIBConfig, beta, kls):
+    """beta * sum_i KL_i (models.py:118), or the nonlinear IB beta * L * KL**p of nb-chaos cell 10."""
+    return float(beta) * cfg.kl_loss_scale * float(np.sum(kls)) ** cfg.kl_loss_exponent
+
+
+def effective_beta(cfg: DIBConfig, beta, kls):
+    """d(ib_loss)/d(sum KL): the weight the per-sample KL gradients carry in reverse mode."""
+    p = cfg.kl_loss_exponent
+    return float(beta) * cfg.kl_loss_scale * (1.0 if p == 1.0 else p * float(np.sum(kls)) ** (p - 1.0))
+
+
+def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.float64, batch_for_mean=None, d_emb=None):
     """Reverse mode through forward() (what GradientTape does inside Keras' train_step).
     Returns (flat grads of mean-loss, ForwardResult).  ``batch_for_mean`` lets a shard of a larger
     global batch produce its additive share (grads scale 1/B_global)."""
     fr = forward(cfg, flat_params, x, eps, beta, y=y, loss=loss, keep=True, dtype=dtype)
     B = x.shape[0] if batch_for_mean is None else batch_for_mean
+    beta = effective_beta(cfg, beta, fr.kl_per_feature * (x.shape[0] / B))   # KL means are over the GLOBAL batch
     E = cfg.feature_embedding_dimension
     c = fr.cache
     eps = np.asarray(eps, dtype=dtype)
     # integration network backward
     int_acts, integration = c["int_acts"], c["integration"]
     # loss == "external": y is the caller's d(task loss)/d(pred), already batch-scaled (custom GradientTape loops)
-    dz = np.asarray(y, dtype=dtype).reshape(fr.pred.shape) if loss == "external" else task_loss_grad(loss, fr.pred, y) / B
+    if d_emb is not None:
+        dz = np.zeros_like(fr.pred)           # encoder-only step: the integration network is not part of the caller's graph
+    else:
+        dz = np.asarray(y, dtype=dtype).reshape(fr.pred.shape) if loss == "external" else task_loss_grad(loss, fr.pred, y) / B
     dz = dz * act_grad_from_output(cfg.output_activation_fn, int_acts[-1], cfg.leaky_alpha)
     int_grads = [None] * len(integration)
     for k in reversed(range(len(integration))):
@@ -292,7 +329,11 @@ def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.flo
         dh = dz @ W.T
         if k > 0:
             dz = dh * act_grad_from_output(cfg.activation_fn, int_acts[k], cfg.leaky_alpha)
-    d_emb = dh
+    if d_emb is not None:     # encoder-only custom steps (nb-particle cell 8): the caller's network produced d loss / d emb
+        d_emb = np.asarray(d_emb, dtype=dtype).reshape(fr.emb.shape)
+        int_grads = [(np.zeros_like(W), np.zeros_like(b)) for W, b in integration]
+    else:
+        d_emb = dh
     enc_grads = []
     for i in range(cfg.number_features):
         acts, mu, lv = c["enc"][i]
@@ -302,6 +343,9 @@ def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.flo
         dmu = du + beta * mu / B
         dlv = du * eps[:, i, :] * 0.5 * sig + beta * 0.5 * (np.exp(lv) - 1.0) / B
         dz = np.concatenate([dmu, dlv], axis=-1)
+        if cfg.encoder_kind == "simple":
+            enc_grads.append([(np.sum(dmu * acts[0]).reshape(1, 1), np.sum(dlv).reshape(1, 1))])
+            continue
         g = [None] * len(layers)
         for k in reversed(range(len(layers))):
             W, _ = layers[k]

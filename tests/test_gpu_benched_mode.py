@@ -226,3 +226,37 @@ def test_two_gpu_fit_equals_one_gpu_fit(tmp_path, prec):
             assert rel_err(b[k], a[k]) < 2e-4
         else:
             np.testing.assert_allclose(b[k], a[k], rtol=2e-4, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_cuda_graph_replay_and_phased_step_are_bit_identical_to_eager(prec):
+    """(i) `fit` with the step replayed from CUDA graphs (device-resident Philox / Adam step counters) reproduces the
+    eager-launch history and weights bit for bit; (ii) dib_train_step_phased(1) + (2) == dib_train_step."""
+    import dib_b200
+    x, y, cfg = _fit_case()
+    res = {}
+    for graph in (False, True):
+        m = build_model(cfg, precision=prec, lr=1e-3, seed=4)
+        m.use_cuda_graph = graph
+        m.noise_seed = 7
+        h = m.fit(x, y, epochs=3, batch_size=200, shuffle=True, verbose=False, validation_data=(x[:256], y[:256]),
+                  callbacks=[dib_b200.InfoBottleneckAnnealingCallback(1e-3, 1e-1, 1, 2)]).history
+        if graph:
+            assert len(m._graphs) >= 1 and m._replayed_launches > 0 and not m._graph_failed      # the graphs really replayed
+        res[graph] = (h, m.get_flat_weights())
+    assert set(res[True][0]) == set(res[False][0])
+    for k in res[False][0]:
+        np.testing.assert_array_equal(np.asarray(res[True][0][k]), np.asarray(res[False][0][k]), err_msg=k)
+    np.testing.assert_array_equal(res[True][1], res[False][1])
+    # (ii) phases
+    m = build_model(cfg, precision=prec, seed=4)
+    m.beta.assign(0.05)
+    with torch.cuda.device(m.device):
+        xd, yd = m._to_device(x[:300], 10), m._to_device(y[:300], 1)
+        m._backward(xd, yd, 300, step=3)
+        full = m._gradstats.clone()
+        m._gradstats.zero_()
+        m._backward(xd, yd, 300, step=3, phases=1)
+        assert torch.equal(m._gradstats[m._p_enc:], full[m._p_enc:]) and float(m._gradstats[:m._p_enc].abs().sum()) == 0
+        m._backward(xd, yd, 300, step=3, phases=2)
+        assert torch.equal(m._gradstats, full)

@@ -399,3 +399,89 @@ def test_infonce_custom_loop_trains():
         m.apply_gradients(g)
         losses.append(loss.item())
     assert losses[0] > 0.9 * 2 * np.log(n) * 0.5 and np.mean(losses[-5:]) < 0.8 * np.mean(losses[:5])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# next row f3 (continued): SimpleEncoder bank, shared particle encoder with logvar offset, nonlinear IB
+# ---------------------------------------------------------------------------------------------------------
+def test_simple_encoder_bank_matches_notebook_golden_and_oracle(golden_dir):
+    """nb-bool cell 4/6: 10 SimpleEncoders (2 constants each, E = 1) + [256]*3 leaky-relu predictor.  Forward against the
+    golden produced by executing the notebook's own SimpleEncoder class; one train step against the oracle."""
+    import dib_b200
+    z = np.load(os.path.join(golden_dir, "ref_simple_encoder.npz"))
+    cfg = O.DIBConfig([1] * 10, [], [256, 256, 256], 1, use_positional_encoding=False, feature_embedding_dimension=1,
+                      activation_fn="leaky_relu", encoder_kind="simple")
+    m = dib_b200.DistributedIBNet([1] * 10, "simple", [256, 256, 256], 1, activation_fn="leaky_relu",
+                                  feature_embedding_dimension=1, seed=3)
+    m.compile(optimizer=dib_b200.Adam(1e-3), loss=dib_b200.losses.BinaryCrossentropy(from_logits=True), metrics=["accuracy"])
+    p0 = m.get_flat_weights()
+    assert np.all(p0[0:20:2] == 1.0) and np.all(p0[1:20:2] == -3.0) and m.count_params() == cfg.param_count()
+    p = p0.copy()
+    p[:20] = z["enc_params"]
+    m.set_flat_weights(p)
+    for i in range(10):                                                       # a15 contract on the notebook's own class output
+        np.testing.assert_allclose(np.asarray(m.feature_encoders[i](z["x"][:, i:i + 1])), z[f"enc{i}"], rtol=1e-6, atol=1e-7)
+    emb, kl = m.encode(z["x"], eps=z["eps"])
+    np.testing.assert_allclose(emb.cpu().numpy(), z["emb"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(kl.cpu().numpy(), z["kl"], rtol=2e-6)
+    y = (z["x"][:, :1] * z["x"][:, 1:2] > 0).astype(np.float32)
+    m.beta.assign(0.05)
+    g, st = m.compute_gradients(z["x"], y, eps=z["eps"])
+    g_ref, fr = O.train_grads(cfg, p, z["x"], y, z["eps"], 0.05, O.LOSS_BCE_LOGITS)
+    assert rel_err(g.cpu().numpy(), g_ref) < 5e-5
+    assert rel_err(g.cpu().numpy()[:20], g_ref[:20]) < 1e-4                   # the 20 encoder constants themselves
+    out = m.train_on_batch(z["x"], y)                                         # per-step beta + Adam on the flat buffer
+    assert np.isfinite(out["loss"])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("tf32", 5e-3)])
+def test_shared_particle_encoder_with_logvar_offset(precision, tol):
+    """nb-particle cell 8: one encoder shared by 50 particles (12 -> PE(60) -> 128 -> 128 -> 64, LeakyReLU(0.1)),
+    logvar offset -3, KL summed over particles and dims, averaged over the batch; the downstream network is the caller's
+    (a fixed random readout here).  Embeddings, KL and encoder gradients against the oracle."""
+    import dib_b200
+    rng = np.random.default_rng(2)
+    B, Np, d, E = 8, 50, 12, 32
+    enc = dib_b200.SharedParticleEncoder(d, [128, 128], E, seed=5, precision=precision)
+    cfg = O.DIBConfig([d], [128, 128], [], 1, activation_fn="leaky_relu", leaky_alpha=0.1, feature_embedding_dimension=E,
+                      logvar_offset=-3.0)
+    p = enc.net.get_flat_weights()
+    x = rng.standard_normal((B, Np, d)).astype(np.float32)
+    eps = rng.standard_normal((B, Np, E)).astype(np.float32)
+    enc.beta.assign(2e-1)
+    embs, kl = enc.encode(x, eps=eps)
+    fr = O.forward(cfg, p, x.reshape(B * Np, d), eps.reshape(B * Np, 1, E), 0.2)
+    assert rel_err(embs.cpu().numpy().reshape(B * Np, E), fr.emb) < tol
+    np.testing.assert_allclose(float(kl), fr.kl_per_feature[0] * Np, rtol=10 * tol)
+    R = rng.standard_normal((B, Np, E)).astype(np.float32) / (B * Np)          # d loss / d embs of loss = sum(embs * R)
+    g = enc.gradients(x, R, eps=eps).cpu().numpy()
+    g_ref, _ = O.train_grads(cfg, p, x.reshape(B * Np, d), None, eps.reshape(B * Np, 1, E), 0.2, "external",
+                             batch_for_mean=B, d_emb=R.reshape(B * Np, E))
+    nenc = g_ref.size - (E * 1 + 1)
+    assert rel_err(g[:nenc], g_ref[:nenc]) < (tol if precision == "fp32" else 4 * tol)      # 400 rows only in the tc mode
+    assert np.all(g[nenc:] == 0)
+    enc.apply_gradients(g)
+
+
+def test_nonlinear_ib_weighting_matches_oracle():
+    """nb-chaos cell 10: loss_IB = beta * number_states * KL ** 2 through the fused train step: gradients, reported loss."""
+    import dib_b200
+    rng = np.random.default_rng(4)
+    cfg = O.DIBConfig([2], [128, 128], [64], 3, number_positional_encoding_frequencies=4, activation_fn="leaky_relu",
+                      feature_embedding_dimension=8, kl_loss_exponent=2.0, kl_loss_scale=12.0)
+    m = dib_b200.DistributedIBNet([2], [128, 128], [64], 3, number_positional_encoding_frequencies=4, activation_fn="leaky_relu",
+                                  feature_embedding_dimension=8, kl_loss_exponent=2.0, kl_loss_scale=12.0, seed=6)
+    m.compile(optimizer=dib_b200.Adam(3e-4), loss="mse")
+    B = 300
+    x = rng.standard_normal((B, 2)).astype(np.float32)
+    y = rng.standard_normal((B, 3)).astype(np.float32)
+    eps = rng.standard_normal((B, 1, 8)).astype(np.float32)
+    p = m.get_flat_weights()
+    m.beta.assign(0.7)
+    g, st = m.compute_gradients(x, y, eps=eps)
+    g_ref, fr = O.train_grads(cfg, p, x, y, eps, 0.7, O.LOSS_MSE)
+    assert rel_err(g.cpu().numpy(), g_ref) < 5e-5
+    pred = m(x, eps=eps)
+    np.testing.assert_allclose(float(m.losses[0]), O.ib_loss(cfg, 0.7, fr.kl_per_feature), rtol=2e-5)
+    out = m.train_on_batch(x, y)
+    assert np.isfinite(out["loss"])

@@ -270,3 +270,58 @@ def test_mi_sandwich_matches_reference_code_and_closed_forms(golden_dir):
     lo, up = O.mi_sandwich_batch(mu, np.zeros((bs, 2)), rng.standard_normal((bs, 2)))
     np.testing.assert_allclose(lo, np.log(k), atol=1e-6)
     assert up >= lo - 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# custom-step variants: SimpleEncoder bank, logvar offset, nonlinear IB, encoder-only reverse mode
+# ------------------------------------------------------------------------------------------------
+def test_simple_encoder_oracle_matches_notebook_golden(golden_dir):
+    """tests/golden/ref_simple_encoder.npz comes from exec'ing nb-bool cell 4 (class SimpleEncoder) and the per-gate forward
+    lines of its cell 6 verbatim (tests/golden/make_f3_golden.py)."""
+    z = np.load(os.path.join(golden_dir, "ref_simple_encoder.npz"))
+    cfg = O.DIBConfig([1] * 10, [], [256, 256, 256], 1, use_positional_encoding=False, feature_embedding_dimension=1,
+                      activation_fn="leaky_relu", encoder_kind="simple")
+    assert cfg.param_count() == 20 + (10 * 256 + 256) + 2 * (256 * 256 + 256) + 256 + 1
+    p = O.glorot_uniform_params(cfg, np.random.default_rng(0), dtype=np.float64)
+    assert np.all(p[0:20:2] == 1.0) and np.all(p[1:20:2] == -3.0)            # nb-bool cell 4 initial values
+    p[:20] = z["enc_params"]
+    fr = O.forward(cfg, p, z["x"], z["eps"], 0.1)
+    np.testing.assert_allclose(fr.emb, z["emb"], rtol=1e-12)
+    np.testing.assert_allclose(fr.kl_per_feature, z["kl"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("variant", ["simple", "offset_nonlinear", "encoder_only"])
+def test_variant_gradients_match_finite_differences(variant):
+    rng = np.random.default_rng(0)
+    d_emb = None
+    if variant == "simple":
+        cfg = O.DIBConfig([1] * 3, [], [8], 1, use_positional_encoding=False, feature_embedding_dimension=1,
+                          encoder_kind="simple", activation_fn="leaky_relu")
+    else:
+        cfg = O.DIBConfig([2, 1], [6], [5], 2, feature_embedding_dimension=3, logvar_offset=-3.0, kl_loss_exponent=2.0,
+                          kl_loss_scale=12.0, activation_fn="tanh")
+    p = O.glorot_uniform_params(cfg, rng, dtype=np.float64)
+    p = p + 0.01 * rng.standard_normal(p.size)
+    B, D = 7, sum(cfg.feature_dimensionalities)
+    x = rng.standard_normal((B, D))
+    y = rng.standard_normal((B, cfg.output_dimensionality))
+    eps = rng.standard_normal((B, cfg.number_features, cfg.feature_embedding_dimension))
+    if variant == "encoder_only":                                             # caller's loss = sum(emb * R)
+        R = rng.standard_normal((B, cfg.number_features * cfg.feature_embedding_dimension))
+        d_emb = R
+        f = lambda q: float((O.forward(cfg, q, x, eps, 0.3).emb * R).sum()) + O.ib_loss(cfg, 0.3, O.forward(cfg, q, x, eps, 0.3).kl_per_feature)
+        g, _ = O.train_grads(cfg, p, x, None, eps, 0.3, "external", d_emb=d_emb)
+    else:
+        f = lambda q: O.forward(cfg, q, x, eps, 0.3, y=y, loss=O.LOSS_MSE).loss
+        g, _ = O.train_grads(cfg, p, x, y, eps, 0.3, O.LOSS_MSE)
+    num = np.zeros_like(p)
+    for i in range(p.size):
+        dlt = np.zeros_like(p)
+        dlt[i] = 1e-6
+        num[i] = (f(p + dlt) - f(p - dlt)) / 2e-6
+    n_enc = sum(int(np.prod(s)) for s in cfg.param_shapes()[:-2 * (len(cfg.integration_network_architecture) + 1)])
+    if variant == "encoder_only":
+        assert np.all(g[n_enc:] == 0)
+        np.testing.assert_allclose(g[:n_enc], num[:n_enc], rtol=1e-5, atol=1e-7)
+    else:
+        np.testing.assert_allclose(g, num, rtol=1e-5, atol=1e-7)
