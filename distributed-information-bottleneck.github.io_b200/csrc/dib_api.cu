@@ -540,7 +540,7 @@ int dib_debug_gemm_tc(int32_t mode, const float* A, int32_t lda, const float* B,
 const char* dib_last_error(void) { return g_last_error.c_str(); }
 
 const char* dib_build_info(void) {
-  return "dib_b200 abi=1 arch=sm_100a paths=fp32-simt,tf32-tcgen05,fp16-fused-tcgen05,bf16-fused-tcgen05";
+  return "dib_b200 abi=2 arch=sm_100a paths=fp32-simt,tf32-tcgen05,fp16-fused-tcgen05,bf16-fused-tcgen05";
 }
 
 int32_t dib_model_info(const dib_model* h, char* out, size_t out_bytes) {
@@ -575,7 +575,7 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   if (cfg->activation_fn < 0 || cfg->activation_fn > DIB_ACT_ELU || cfg->output_activation_fn < 0 ||
       cfg->output_activation_fn > DIB_ACT_ELU)
     return fail("dib_create: unknown activation");
-  if (cfg->loss < 0 || cfg->loss > DIB_LOSS_EXTERNAL) return fail("dib_create: unknown loss");
+  if (cfg->loss < 0 || cfg->loss > DIB_LOSS_BCE_PROBS) return fail("dib_create: unknown loss");
   dib_model* h = new (std::nothrow) dib_model();
   if (!h) return fail("dib_create: out of host memory");
   h->F = cfg->number_features; h->L = cfg->number_encoder_layers; h->Li = cfg->number_integration_layers;
@@ -937,6 +937,40 @@ int dib_adam_step(float* params, const float* grads, float* m, float* v, int64_t
   return 0;
 }
 
+int dib_optimizer_step(int32_t kind, float* params, const float* grads, float* slot1, float* slot2, int64_t count,
+                       const float* lr_dev, int32_t* step_dev, float hyper0, float hyper1, float hyper2, void* stream) {
+  if (kind < 0 || kind > 1 || !params || !grads || !lr_dev || !step_dev || count < 0 || (kind == 1 && (!slot1 || !slot2)) ||
+      (kind == 0 && hyper0 != 0.f && !slot1))
+    return fail("dib_optimizer_step: bad arguments");
+  DIB_CUDA_OK(dib_launch_optimizer(kind, params, grads, slot1, slot2, count, lr_dev, step_dev, hyper0, hyper1, hyper2,
+                                   static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int dib_integration_forward(dib_model* h, const float* params, const float* emb, int64_t n, float* out_pred,
+                            void* workspace, void* stream) {
+  if (check_call(h, params, emb, n, workspace)) return 1;
+  if (!out_pred) return fail("dib_integration_forward: null output");
+  if (n == 0) return 0;
+  Ctx c{h, params, static_cast<float*>(workspace), static_cast<cudaStream_t>(stream), (int)n};
+  const int FE = h->F * h->E;
+  if (is_tc(h)) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
+  DIB_CUDA_OK(dib_launch_copy2d(emb, FE, c.ws + h->emb.off, h->emb.ld, FE, n, c.st));
+  if (h->emb.ld > FE)          // zero the padded operand columns
+    DIB_CUDA_OK(cudaMemset2DAsync(c.ws + h->emb.off + FE, sizeof(float) * h->emb.ld, 0, sizeof(float) * (h->emb.ld - FE), (size_t)n, c.st));
+  for (int j = 0; j <= h->Li; ++j)
+    if (gemm(c, DIB_GEMM_FWD, h->int_fwd[j], 1, int_fan_out(h, j), 0, 1, 0)) return 1;
+  DIB_CUDA_OK(dib_launch_copy2d(c.ws + h->pred.off, h->pred.ld, out_pred, h->out, h->out, n, c.st));
+  return 0;
+}
+
+int dib_positional_encoding(const float* x, int64_t n, int32_t d, int32_t number_frequencies, float* out, void* stream) {
+  if ((!x || !out) && n > 0) return fail("dib_positional_encoding: null pointer");
+  if (n < 0 || d < 1 || number_frequencies < 1 || number_frequencies > 31) return fail("dib_positional_encoding: bad sizes");
+  DIB_CUDA_OK(dib_launch_pe_plain(x, n, d, number_frequencies, out, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int dib_metrics_update_ex(const float* stats, const float* beta_dev, float* acc, int32_t number_features,
                           float kl_loss_exponent, float kl_loss_scale, void* stream) {
   if (!stats || !beta_dev || !acc || number_features < 1) return fail("dib_metrics_update: bad arguments");
@@ -1024,6 +1058,17 @@ int dib_mi_sandwich_bounds(const float* mu_logvar, int64_t n, int32_t embedding_
     return fail("dib_mi_sandwich_bounds: bad arguments");
   DIB_CUDA_OK(dib_launch_mi_sandwich(mu_logvar, n, embedding_dimension, eps, seed, step, row_scratch, out_lower_upper,
                                      static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int dib_mi_sandwich_bounds_batched(const float* mu_logvar, int32_t groups, int64_t n, int32_t embedding_dimension, const float* eps,
+                                   uint64_t seed, int32_t batches_per_feature, double* row_scratch, double* out_lower_upper,
+                                   void* stream) {
+  if (!mu_logvar || !row_scratch || !out_lower_upper || groups < 1 || groups > 65535 || n < 1 || n > 0x7fffffffll ||
+      embedding_dimension < 1 || embedding_dimension > 64 || batches_per_feature < 1)
+    return fail("dib_mi_sandwich_bounds_batched: bad arguments (1 <= groups <= 65535, 1 <= E <= 64)");
+  DIB_CUDA_OK(dib_launch_mi_sandwich_batched(mu_logvar, groups, n, embedding_dimension, eps, seed, batches_per_feature,
+                                             row_scratch, out_lower_upper, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -165,6 +165,10 @@ dib_loss_kernel(int loss, int out_act, float alpha, const float* __restrict__ pr
           if (loss == DIB_LOSS_BCE_LOGITS) {
             l += fmaxf(zz, 0.f) - zz * t + log1pf(expf(-fabsf(zz)));
             g = 1.f / (1.f + expf(-zz)) - t;
+          } else if (loss == DIB_LOSS_BCE_PROBS) {          // keras.backend.binary_crossentropy on probabilities
+            const float ep = 1e-7f, pc = fminf(fmaxf(zz, ep), 1.f - ep);
+            l -= t * logf(pc + ep) + (1.f - t) * logf(1.f - pc + ep);
+            g = (zz > ep && zz < 1.f - ep) ? -t / (pc + ep) + (1.f - t) / (1.f - pc + ep) : 0.f;
           } else {
             const float d = zz - t;
             l += d * d;
@@ -644,6 +648,178 @@ cudaError_t dib_launch_simple_enc_wgrad(const float* x, int ldx, const int* x_of
 cudaError_t dib_launch_beta_eff(const float* stats, int F, float inv_global_batch, const float* beta_dev, float exponent,
                                 float scale, float* beta_eff_dev, cudaStream_t st) {
   dib_beta_eff_kernel<<<1, 32, 0, st>>>(stats, F, inv_global_batch, beta_dev, exponent, scale, beta_eff_dev);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+// ================================================================================================
+// next row f1, batched: utils.estimate_mi_sandwich_bounds (utils.py:10-73) for G = features x evaluation batches groups of
+// n encoder outputs in ONE launch, accumulated in float64 like the reference (utils.py:40-41 casts to float64).
+//   log p(u_i | x_j) = -1/2 sum_e (u_ie - mu_je)^2 exp(-lv_je) - 1/2 sum_e lv_je - E/2 log(2 pi)
+//   lower = mean_i [ lp_ii - (logsumexp_j lp_ij - log n) ],  upper = the same without the diagonal term in the sum.
+// One thread per row i (u_i in a conflict-free shared-memory column), the (mu_j, exp(-lv_j), c_j) of 16 columns j staged
+// per step in shared memory (broadcast reads), one online logsumexp per row.  grid = (ceil(n / 128), G).
+// ================================================================================================
+namespace {
+
+constexpr int kMiRows = 128, kMiTJ = 16, kMiMaxE = 64;
+
+__global__ void __launch_bounds__(kMiRows)
+dib_mi_batched_kernel(const float* __restrict__ ml, int n, int E, const float* __restrict__ eps, unsigned long long seed,
+                      int batches_per_feature, double* __restrict__ row_out) {
+  extern __shared__ double sm[];                 // [kMiTJ][E] mu | [kMiTJ][E] inverse variance | [kMiTJ] c_j | [E][kMiRows] u
+  double* s_mu = sm; double* s_iv = sm + kMiTJ * E; double* s_c = sm + 2 * kMiTJ * E;
+  double* u = sm + 2 * kMiTJ * E + kMiTJ + threadIdx.x;          // u[e] lives at u[e * kMiRows]
+  const int g = blockIdx.y, tid = threadIdx.x;
+  const int i = blockIdx.x * kMiRows + tid;
+  const bool live = i < n;
+  const float* mlg = ml + (long long)g * n * 2 * E;
+  const int f = g / batches_per_feature, b = g % batches_per_feature;
+  const unsigned long long gseed = (seed << 8) + (unsigned long long)f;      // the per-feature stream of the looped API
+  if (live) {
+    const float* mi = mlg + (long long)i * 2 * E;
+#pragma unroll 4
+    for (int e0 = 0; e0 < E; e0 += 4) {
+      float nrm[4];
+      if (!eps) dib_philox_normal4(gseed, (unsigned)b, (unsigned long long)i, 0u, (unsigned)(e0 >> 2), nrm);
+      for (int k = 0; k < 4 && e0 + k < E; ++k) {
+        const int e = e0 + k;
+        const double z = eps ? (double)eps[((long long)g * n + i) * E + e] : (double)nrm[k];
+        u[e * kMiRows] = (double)mi[e] + exp(0.5 * (double)mi[E + e]) * z;    // utils.py:43-45, in float64
+      }
+    }
+  }
+  const double cst = -0.5 * (double)E * 1.8378770664093454836;                // -E/2 log(2 pi)
+  double m = -1e300, s_all = 0.0, s_off = 0.0, diag = 0.0;
+  for (int j0 = 0; j0 < n; j0 += kMiTJ) {
+    __syncthreads();
+    for (int t = tid; t < kMiTJ * E; t += kMiRows) {
+      const int jj = t / E, e = t - jj * E, j = j0 + jj;
+      if (j < n) { s_mu[t] = (double)mlg[(long long)j * 2 * E + e]; s_iv[t] = exp(-(double)mlg[(long long)j * 2 * E + E + e]); }
+    }
+    if (tid < kMiTJ && j0 + tid < n) {
+      double sl = 0.0;
+      for (int e = 0; e < E; ++e) sl += (double)mlg[(long long)(j0 + tid) * 2 * E + E + e];
+      s_c[tid] = -0.5 * sl + cst;
+    }
+    __syncthreads();
+    if (!live) continue;
+    const int jn = min(kMiTJ, n - j0);
+    for (int jj = 0; jj < jn; ++jj) {
+      double q = 0.0;
+#pragma unroll 8
+      for (int e = 0; e < E; ++e) { const double d = u[e * kMiRows] - s_mu[jj * E + e]; q = fma(d * d, s_iv[jj * E + e], q); }
+      const double lp = -0.5 * q + s_c[jj];
+      if (lp > m) { const double r = exp(m - lp); s_all *= r; s_off *= r; m = lp; }
+      const double ex = exp(lp - m);
+      s_all += ex;
+      if (j0 + jj == i) diag = lp; else s_off += ex;
+    }
+  }
+  if (live) {
+    const double logn = log((double)n);
+    double* o = row_out + ((long long)g * n + i) * 2;
+    o[0] = diag - (m + log(s_all) - logn);                                    // InfoNCE term       (utils.py:59-61)
+    o[1] = diag - (m + log(s_off) - logn);                                    // leave-one-out term (utils.py:63-64; still / bs)
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dib_mi_batched_mean_kernel(const double* __restrict__ row_out, int n, double* __restrict__ out) {
+  __shared__ double red[2][8];
+  const int g = blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { a += row_out[((long long)g * n + i) * 2]; b += row_out[((long long)g * n + i) * 2 + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sa = 0.0, sb2 = 0.0;
+    for (int w = 0; w < 8; ++w) { sa += red[0][w]; sb2 += red[1][w]; }
+    out[2 * g] = sa / n; out[2 * g + 1] = sb2 / n;
+  }
+}
+
+}  // namespace
+
+cudaError_t dib_launch_mi_sandwich_batched(const float* mu_logvar, int groups, int64_t n, int E, const float* eps, uint64_t seed,
+                                           int batches_per_feature, double* row_scratch, double* out, cudaStream_t st) {
+  if (n <= 0 || groups <= 0) return cudaSuccess;
+  if (E > kMiMaxE) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(2 * kMiTJ * E + kMiTJ + kMiRows * E) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dib_mi_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((2 * kMiTJ * kMiMaxE + kMiTJ + kMiRows * kMiMaxE) * sizeof(double)));
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dib_mi_batched_kernel<<<dim3((unsigned)((n + kMiRows - 1) / kMiRows), groups), kMiRows, smem, st>>>(
+      mu_logvar, (int)n, E, eps, seed, batches_per_feature < 1 ? 1 : batches_per_feature, row_scratch);
+  dib_note_launch();
+  dib_mi_batched_mean_kernel<<<groups, 256, 0, st>>>(row_scratch, (int)n, out);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+
+// ================================================================================================
+// the other Keras optimizers (train.py:41,128 tf.keras.optimizers.get(name)) and the stand-alone positional encoding
+// ================================================================================================
+namespace {
+
+__global__ void dib_sgd_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ v, long long count,
+                               const float* __restrict__ lr_dev, float momentum, int nesterov) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float lr = lr_dev[0], gi = g[i];
+  if (momentum == 0.f) { w[i] -= lr * gi; return; }
+  const float vi = momentum * v[i] - lr * gi;
+  v[i] = vi;
+  w[i] += nesterov ? momentum * vi - lr * gi : vi;
+}
+
+__global__ void dib_rmsprop_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ ms, float* __restrict__ mom,
+                                   long long count, const float* __restrict__ lr_dev, float rho, float momentum, float eps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float lr = lr_dev[0], gi = g[i];
+  const float m2 = rho * ms[i] + (1.f - rho) * gi * gi;
+  ms[i] = m2;
+  const float mo = momentum * mom[i] + lr * gi / sqrtf(m2 + eps);
+  mom[i] = mo;
+  w[i] -= mo;
+}
+
+__global__ void dib_pe_plain_kernel(const float* __restrict__ x, long long n, int d, int nfreq, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = d * nfreq;
+  if (idx >= n * W) return;
+  const long long row = idx / W;
+  const int col = (int)(idx - row * W), blk = col / d, k = col - blk * d;
+  const float xv = x[row * d + k];
+  out[idx] = blk == 0 ? xv : sinf((float)(1 << blk) * xv);
+}
+
+}  // namespace
+
+cudaError_t dib_launch_optimizer(int kind, float* params, const float* grads, float* s1, float* s2, int64_t count,
+                                 const float* lr_dev, int32_t* step_dev, float h0, float h1, float h2, cudaStream_t st) {
+  if (count > 0) {
+    if (kind == 0) dib_sgd_kernel<<<nblocks(count, 256), 256, 0, st>>>(params, grads, s1, count, lr_dev, h0, h1 != 0.f);
+    else dib_rmsprop_kernel<<<nblocks(count, 256), 256, 0, st>>>(params, grads, s1, s2, count, lr_dev, h0, h1, h2);
+    dib_note_launch();
+  }
+  dib_inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t dib_launch_pe_plain(const float* x, int64_t n, int d, int nfreq, float* out, cudaStream_t st) {
+  const long long total = (long long)n * d * nfreq;
+  if (total <= 0) return cudaSuccess;
+  dib_pe_plain_kernel<<<nblocks(total, 256), 256, 0, st>>>(x, n, d, nfreq, out);
   dib_note_launch();
   return cudaGetLastError();
 }

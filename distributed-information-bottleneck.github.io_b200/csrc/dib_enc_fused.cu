@@ -1258,14 +1258,14 @@ cudaError_t launch_fused(K kern, int smem, int grid, const WeightMaps& m, const 
 
 }  // namespace
 
-// which backward kernel runs: 1 (the single-chain kernel) or 2 (two chains on consecutive tiles); DIB_ENC_BWD=1|2 in the
-// environment or dib_debug_set_variant(0, v)
+// which backward kernel runs: 2 (default: two chains on consecutive tiles, 0.329 ms at C0) or 1 (the single-chain kernel of
+// round 1, 0.438 ms); DIB_ENC_BWD=1|2 in the environment or dib_debug_set_variant(0, v)
 static int g_enc_bwd_version = 0;
 int dib_enc_bwd_version() {
-  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '2') ? 2 : 1; }
+  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '1') ? 1 : 2; }
   return g_enc_bwd_version;
 }
-void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = v == 2 ? 2 : 1; }
+void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = v == 1 ? 1 : 2; }
 
 size_t dib_enc_fused_pack_bytes(int F) { return (size_t)F * kPackElems * 2; }
 int dib_enc_fused_fwd_ctas_per_sm() { return 2; }

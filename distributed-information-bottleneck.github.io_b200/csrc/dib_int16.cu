@@ -350,7 +350,11 @@ dib_int16_head_kernel(const uint16_t* __restrict__ g, int ldg, int K, const floa
           for (int o = 0; o < OUT; ++o) if (o < out_dim) {
             const float t = y[row * out_dim + o];
             if (loss == DIB_LOSS_BCE_LOGITS) { l += fmaxf(z[o], 0.f) - z[o] * t + log1pf(expf(-fabsf(z[o]))); dz[o] = (1.f / (1.f + expf(-z[o])) - t) * inv_out; }
-            else { const float d = z[o] - t; l += d * d; dz[o] = 2.f * d * inv_out; }
+            else if (loss == DIB_LOSS_BCE_PROBS) {
+              const float ep = 1e-7f, pc = fminf(fmaxf(z[o], ep), 1.f - ep);
+              l -= t * logf(pc + ep) + (1.f - t) * logf(1.f - pc + ep);
+              dz[o] = (z[o] > ep && z[o] < 1.f - ep) ? (-t / (pc + ep) + (1.f - t) / (1.f - pc + ep)) * inv_out : 0.f;
+            } else { const float d = z[o] - t; l += d * d; dz[o] = 2.f * d * inv_out; }
             acc += ((z[o] > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f;
           }
           l *= inv_out; acc *= inv_out;

@@ -72,6 +72,10 @@ cudaError_t dib_launch_reduce_partials(const float* part, long long split_stride
 
 cudaError_t dib_launch_copy2d(const float* src, int lds, float* dst, int ldd, int cols, int64_t n, cudaStream_t st);
 
+cudaError_t dib_launch_optimizer(int kind, float* params, const float* grads, float* s1, float* s2, int64_t count,
+                                 const float* lr_dev, int32_t* step_dev, float h0, float h1, float h2, cudaStream_t st);
+cudaError_t dib_launch_pe_plain(const float* x, int64_t n, int d, int nfreq, float* out, cudaStream_t st);
+
 cudaError_t dib_launch_adam(float* params, const float* grads, float* m, float* v, int64_t count,
                             const float* lr_dev, int32_t* step_dev, float b1, float b2, float eps, cudaStream_t st);
 
@@ -159,3 +163,7 @@ cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const
 
 cudaError_t dib_launch_mi_sandwich(const float* mu_logvar, int64_t n, int E, const float* eps, uint64_t seed, uint32_t step,
                                    float* row_scratch, float* out2, cudaStream_t st);
+// G = features x batches groups of n rows in one launch, float64 accumulation; group g uses the noise stream
+// (seed << 8) + g / batches_per_feature at step g % batches_per_feature
+cudaError_t dib_launch_mi_sandwich_batched(const float* mu_logvar, int groups, int64_t n, int E, const float* eps, uint64_t seed,
+                                           int batches_per_feature, double* row_scratch, double* out, cudaStream_t st);

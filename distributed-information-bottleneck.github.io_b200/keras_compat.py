@@ -16,17 +16,51 @@ class Adam:
     lr = property(lambda self: self.learning_rate, lambda self, v: setattr(self, "learning_rate", v))
 
 
+class SGD:
+    """tf.keras.optimizers.SGD(learning_rate=0.01, momentum=0.0, nesterov=False):
+    v = momentum * v - lr * g;  w += momentum * v - lr * g if nesterov else v   (dib_optimizer_step kind 0)."""
+    kind = 0
+
+    def __init__(self, learning_rate=0.01, momentum=0.0, nesterov=False, name="SGD"):
+        self.learning_rate, self.momentum, self.nesterov, self.name = learning_rate, float(momentum), bool(nesterov), name
+
+    lr = property(lambda self: self.learning_rate, lambda self, v: setattr(self, "learning_rate", v))
+
+    def hyper(self):
+        return self.momentum, 1.0 if self.nesterov else 0.0, 0.0
+
+
+class RMSprop:
+    """tf.keras.optimizers.RMSprop(learning_rate=0.001, rho=0.9, momentum=0.0, epsilon=1e-7) (non-centered), TensorFlow's
+    ApplyRMSProp: ms = rho ms + (1-rho) g^2;  mom = momentum mom + lr g / sqrt(ms + eps);  w -= mom  (kind 1)."""
+    kind = 1
+
+    def __init__(self, learning_rate=0.001, rho=0.9, momentum=0.0, epsilon=1e-7, centered=False, name="RMSprop"):
+        if centered:
+            raise NotImplementedError("RMSprop(centered=True) is not implemented")
+        self.learning_rate, self.rho, self.momentum, self.epsilon, self.name = learning_rate, float(rho), float(momentum), float(epsilon), name
+
+    lr = property(lambda self: self.learning_rate, lambda self, v: setattr(self, "learning_rate", v))
+
+    def hyper(self):
+        return self.rho, self.momentum, self.epsilon
+
+
 class optimizers:
     Adam = Adam
+    SGD = SGD
+    RMSprop = RMSprop
 
     @staticmethod
     def get(identifier):
-        """tf.keras.optimizers.get('adam') as used at train.py:128."""
-        if isinstance(identifier, Adam):
+        """tf.keras.optimizers.get(name) as used at train.py:128 (the --optimizer flag, train.py:41)."""
+        if isinstance(identifier, (Adam, SGD, RMSprop)):
             return identifier
-        if isinstance(identifier, str) and identifier.lower() == "adam":
-            return Adam()
-        raise ValueError(f"only Adam is implemented by the B200 engine, got {identifier!r}")
+        if isinstance(identifier, str):
+            table = {"adam": Adam, "sgd": SGD, "rmsprop": RMSprop}
+            if identifier.lower() in table:
+                return table[identifier.lower()]()
+        raise ValueError(f"optimizer {identifier!r} is not implemented by the B200 engine (adam, sgd, rmsprop are)")
 
 
 class _Loss:
@@ -38,8 +72,10 @@ class _Loss:
 
 
 class BinaryCrossentropy(_Loss):
-    """data.py:65 / nb-radial: BinaryCrossentropy(from_logits=True)."""
+    """data.py:65 / nb-radial: BinaryCrossentropy(from_logits=True); from_logits=False (the Keras default) is the
+    clipped-probability form for models with output_activation_fn='sigmoid'."""
     kind = "bce_logits"
+    kind_probs = "bce_probs"
 
 
 class SparseCategoricalCrossentropy(_Loss):
@@ -63,15 +99,19 @@ class losses:
 def resolve_loss(loss):
     if isinstance(loss, _Loss):
         if not loss.from_logits:
+            if getattr(loss, "kind_probs", None):
+                return loss.kind_probs
             raise NotImplementedError(
-                "the fused loss kernels take logits (from_logits=True), as every reference call site does")
+                f"{type(loss).__name__}(from_logits=False) is not implemented: the reference's call sites pass logits")
         return loss.kind
     if isinstance(loss, str):
         key = loss.lower()
         if key in ("mse", "mean_squared_error"):
             return "mse"
-        if key in ("bce_logits", "sparse_ce_logits"):
+        if key in ("bce_logits", "sparse_ce_logits", "bce_probs"):
             return key
+        if key == "binary_crossentropy":               # the Keras string means from_logits=False
+            return "bce_probs"
         if key in ("external", "custom"):       # GradientTape-style loops: the caller owns the task loss
             return "external"
     raise ValueError(f"unsupported loss {loss!r}")

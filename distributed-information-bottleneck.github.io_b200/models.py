@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from . import parallel
-from .keras_compat import Adam, Callback, History, optimizers, resolve_loss
+from .keras_compat import Adam, RMSprop, SGD, Callback, History, optimizers, resolve_loss
 
 
 def _require_cuda():
@@ -45,8 +45,18 @@ class PositionalEncoding:
         self.frequencies = list(frequencies)
 
     def __call__(self, inputs):
-        t = torch.as_tensor(inputs)
-        return _as_numpy_like(inputs, torch.cat([t] + [torch.sin(f * t) for f in self.frequencies], -1))
+        freqs = [int(f) for f in self.frequencies]
+        if freqs != [2 ** k for k in range(1, len(freqs) + 1)]:
+            raise NotImplementedError("the library's positional encoding uses the reference's frequencies 2**arange(1, n)")
+        _require_cuda()
+        t = torch.as_tensor(inputs, dtype=torch.float32)
+        dev = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        x = t.to(dev).reshape(-1, t.shape[-1]).contiguous()
+        out = torch.empty(x.shape[0], x.shape[1] * (len(freqs) + 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().dib_positional_encoding(_lib.ptr(x), x.shape[0], x.shape[1], len(freqs) + 1, _lib.ptr(out),
+                                                           _stream()))
+        return _as_numpy_like(inputs, out.reshape(*t.shape[:-1], out.shape[-1]))
 
     call = __call__
 
@@ -123,25 +133,18 @@ class _FeatureEncoder(_Network):
 
 class _IntegrationNetwork(_Network):
     """model.integration_network (models.py:84).  Direct calls are rare (the fused step never materialises this
-    boundary); provided with plain torch ops over the weight views for completeness."""
+    boundary); they run dib_integration_forward on the model's precision path."""
 
     def __call__(self, emb, training=None):
         m = self._model
-        h = torch.as_tensor(emb, dtype=torch.float32, device=m.device)
-        ws = self.weights
-        n_layers = len(ws) // 2
-        for k in range(n_layers):
-            h = h @ ws[2 * k] + ws[2 * k + 1]
-            h = _torch_act(m.activation_fn if k < n_layers - 1 else m.output_activation_fn, h, m.leaky_alpha)
-        return _as_numpy_like(emb, h)
-
-
-def _torch_act(name, h, alpha):
-    if name in (None, "linear"):
-        return h
-    if name == "leaky_relu":
-        return torch.nn.functional.leaky_relu(h, alpha)
-    return getattr(torch, name)(h) if hasattr(torch, name) else getattr(torch.nn.functional, name)(h)
+        with torch.cuda.device(m.device):
+            e = m._to_device(emb, m.number_features * m.feature_embedding_dimension)
+            n = e.shape[0]
+            m._ensure_handle(n)
+            out = torch.empty(n, m.output_dimensionality, dtype=torch.float32, device=m.device)
+            _lib.check(m._lib.dib_integration_forward(m._handle, _lib.ptr(m._params), _lib.ptr(e), n, _lib.ptr(out),
+                                                      _lib.ptr(m._workspace), _stream()))
+        return _as_numpy_like(emb, out)
 
 
 class DistributedIBNet:
@@ -475,20 +478,28 @@ class DistributedIBNet:
         g = torch.as_tensor(flat_grads, dtype=torch.float32).to(self.device).contiguous()
         if g.numel() != self._P:
             raise ValueError(f"expected {self._P} gradient values, got {g.numel()}")
-        opt = self.optimizer
         self._sync_lr()
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.dib_adam_step(
-                _lib.ptr(self._params), _lib.ptr(g), _lib.ptr(self._m), _lib.ptr(self._v), self._P,
-                _lib.ptr(self._lr_dev), _lib.ptr(self._step_dev), opt.beta_1, opt.beta_2, opt.epsilon, _stream()))
+            self._optimizer_update(g)
         self._train_step_count += 1
         self._step_dev_dirty = True
 
-    def _adam(self):
+    def _optimizer_update(self, grads):
+        """One dense update of the flat parameter buffer by the compiled optimizer (Adam: dib_adam_step; SGD / RMSprop:
+        dib_optimizer_step); the two slot buffers are Adam's m / v, SGD's velocity, RMSprop's mean square / momentum."""
         opt = self.optimizer
-        _lib.check(self._lib.dib_adam_step(
-            _lib.ptr(self._params), _lib.ptr(self._gradstats), _lib.ptr(self._m), _lib.ptr(self._v), self._P,
-            _lib.ptr(self._lr_dev), _lib.ptr(self._step_dev), opt.beta_1, opt.beta_2, opt.epsilon, _stream()))
+        if isinstance(opt, Adam):
+            _lib.check(self._lib.dib_adam_step(
+                _lib.ptr(self._params), _lib.ptr(grads), _lib.ptr(self._m), _lib.ptr(self._v), self._P,
+                _lib.ptr(self._lr_dev), _lib.ptr(self._step_dev), opt.beta_1, opt.beta_2, opt.epsilon, _stream()))
+        else:
+            h0, h1, h2 = opt.hyper()
+            _lib.check(self._lib.dib_optimizer_step(
+                opt.kind, _lib.ptr(self._params), _lib.ptr(grads), _lib.ptr(self._m), _lib.ptr(self._v), self._P,
+                _lib.ptr(self._lr_dev), _lib.ptr(self._step_dev), h0, h1, h2, _stream()))
+
+    def _adam(self):
+        self._optimizer_update(self._gradstats)
 
     def _reduce_overlapped(self, world, run_phase1, run_phase2):
         """The data-parallel exchange in two buckets: [integration grads || stats] is all-reduced on a side stream while
@@ -705,7 +716,7 @@ class DistributedIBNet:
 
     def compile(self, optimizer='adam', loss=None, metrics=None, **_):
         """train.py:138-142."""
-        new_opt = optimizers.get(optimizer) if not isinstance(optimizer, Adam) else optimizer
+        new_opt = optimizers.get(optimizer)
         if new_opt is not self.optimizer:        # a fresh Keras optimizer has fresh slots and iteration count
             self._m.zero_(); self._v.zero_(); self._step_dev.zero_()
         self.optimizer = new_opt
@@ -1019,13 +1030,12 @@ class InfoPerFeatureCallback(Callback):
         m = self.model
         x = self.x_validation
         xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-        offs = np.cumsum([0] + list(m.feature_dimensionalities))
+        # all features x all evaluation batches in one grouped encoder pass + one float64 sandwich launch
+        lo_up = utils.estimate_mi_sandwich_bounds_all_features(m, xt, evaluation_batch_size=self.evaluation_batch_size,
+                                                               number_evaluation_batches=self.number_evaluation_batches,
+                                                               seed=self.seed + epoch)
         for i in range(m.number_features):
-            lo_up = utils.estimate_mi_sandwich_bounds(m.feature_encoders[i], xt[:, offs[i]:offs[i + 1]],
-                                                      evaluation_batch_size=self.evaluation_batch_size,
-                                                      number_evaluation_batches=self.number_evaluation_batches,
-                                                      seed=self.seed + epoch)
-            self.bounds.append([float(lo_up[0]), float(lo_up[1])])
+            self.bounds.append([float(lo_up[i, 0]), float(lo_up[i, 1])])
 
 
 class SimpleEncoder:

@@ -84,7 +84,7 @@ def mi_sandwich_batch(mu_logvar, eps=None, seed=0, step=0):
     out = torch.empty(2, dtype=torch.float32, device=dev)
     e = None if eps is None else _dev(eps, dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.dib_mi_sandwich_bounds(_lib.ptr(mu_logvar), n, E, _lib.ptr(e), int(seed), int(step) & 0xFFFFFFFF,
+        _lib.check(lib.dib_mi_sandwich_bounds(_lib.ptr(mu_logvar.contiguous()), n, E, _lib.ptr(e), int(seed), int(step) & 0xFFFFFFFF,
                                               _lib.ptr(scratch), _lib.ptr(out),
                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return out
@@ -113,6 +113,31 @@ def estimate_mi_sandwich_bounds(encoder, dataset, evaluation_batch_size=1024, nu
         o = model._encode_feature(encoder.index, x.index_select(0, idx))
         outs.append(mi_sandwich_batch(o, None, seed=(int(seed) << 8) + encoder.index, step=b))
     return torch.stack(outs).mean(0).double().cpu().numpy()
+
+
+def estimate_mi_sandwich_bounds_all_features(model, x, evaluation_batch_size=1024, number_evaluation_batches=8, seed=0):
+    """utils.py:10-73 for EVERY feature encoder of ``model`` at once (what InfoPerFeatureCallback, models.py:188-223, loops
+    over in Python): one grouped encoder forward on the gathered rows (dib_compression_matrices) and ONE launch of the
+    batched float64 sandwich kernel (dib_mi_sandwich_bounds_batched) over features x batches groups.  Row draws and noise
+    streams are those of the per-feature ``estimate_mi_sandwich_bounds`` calls with the same ``seed``.
+    ``x``: [N, sum d_i] rows (a ``(x, y)`` tuple is accepted).  Returns a float64 array [F, 2] = (lower, upper) in nats."""
+    if isinstance(x, (tuple, list)):
+        x = x[0]
+    lib = _lib.load()
+    xd = _dev(x, model.device)
+    N, F, E = xd.shape[0], model.number_features, model.feature_embedding_dimension
+    bs, nb = int(evaluation_batch_size), int(number_evaluation_batches)
+    gen = torch.Generator(device=model.device)
+    gen.manual_seed(int(seed))
+    idx = torch.cat([torch.randint(0, N, (bs,), generator=gen, device=model.device) for _ in range(nb)])
+    row_index = idx.to(torch.int32).unsqueeze(0).expand(F, -1).contiguous()
+    ml = model.compression_matrices(xd, row_index, want=("mu_logvar",))["mu_logvar"]          # [F, nb * bs, 2E]
+    scratch = torch.empty(F * nb * bs * 2, dtype=torch.float64, device=model.device)
+    out = torch.empty(F * nb, 2, dtype=torch.float64, device=model.device)
+    with torch.cuda.device(model.device):
+        _lib.check(lib.dib_mi_sandwich_bounds_batched(_lib.ptr(ml), F * nb, bs, E, None, int(seed), nb, _lib.ptr(scratch),
+                                                      _lib.ptr(out), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out.view(F, nb, 2).mean(1).cpu().numpy()
 
 
 SIMILARITY_TYPES = {"l2sq": 0, "l2": 1, "l1": 2, "linf": 3, "cosine": 4}

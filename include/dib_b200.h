@@ -51,7 +51,11 @@ enum dib_loss {
    * cell 7): the CALLER owns the task loss.  dib_forward returns the predictions; in dib_train_step the `y` argument
    * is reinterpreted as d(task loss)/d(predictions) [n, out], already carrying the caller's batch-mean scaling (it is
    * NOT multiplied by inv_global_batch; the beta*KL term still is).  Task-loss and accuracy statistics are 0. */
-  DIB_LOSS_EXTERNAL = 3
+  DIB_LOSS_EXTERNAL = 3,
+  /* tf.keras.losses.BinaryCrossentropy() on PROBABILITIES (from_logits=False, the Keras default; use with
+   * output_activation_fn = sigmoid): -[y log(p~ + eps) + (1-y) log(1 - p~ + eps)], p~ = clip(p, eps, 1-eps), eps = 1e-7
+   * (keras.backend.binary_crossentropy); the gradient is zero where p is clipped. */
+  DIB_LOSS_BCE_PROBS = 4
 };
 
 /* arithmetic of the dense contractions; everything else (PE, exp, KL, loss, Adam, reductions) is fp32 in every mode
@@ -178,6 +182,23 @@ int dib_adam_step(float* params, const float* grads, float* m, float* v, int64_t
                   const float* lr_dev, int32_t* step_dev, float beta_1, float beta_2, float epsilon,
                   void* stream);
 
+/* the other optimizers tf.keras.optimizers.get(name) hands out (train.py:41,128); same device scalars as dib_adam_step.
+ *   kind 0 SGD     : v = momentum * v - lr * g;  w += nesterov ? momentum * v - lr * g : v        (slot1 = v; slot2 unused)
+ *   kind 1 RMSprop : ms = rho * ms + (1-rho) g^2;  mom = momentum * mom + lr * g / sqrt(ms + eps);  w -= mom   (TF ApplyRMSProp;
+ *                    slot1 = ms, slot2 = mom)
+ * hyper = {momentum, nesterov(0/1), 0} for SGD, {rho, momentum, epsilon} for RMSprop.  *step_dev is incremented. */
+int dib_optimizer_step(int32_t kind, float* params, const float* grads, float* slot1, float* slot2, int64_t count,
+                       const float* lr_dev, int32_t* step_dev, float hyper0, float hyper1, float hyper2, void* stream);
+
+/* model.integration_network(emb) (models.py:84,122) as a stand-alone call: emb [n, F*E] -> out_pred [n, out] through the
+ * Dense stack with the output activation, on the model's precision path (fp32 FMA / tf32 tcgen05). */
+int dib_integration_forward(dib_model* h, const float* params, const float* emb, int64_t n, float* out_pred,
+                            void* workspace, void* stream);
+
+/* models.PositionalEncoding.call (models.py:12-23) as a stand-alone call: x [n, d] ->
+ * out [n, d * number_frequencies] = concat([x] + [sin(2^k x) for k = 1 .. number_frequencies-1], -1), block-major. */
+int dib_positional_encoding(const float* x, int64_t n, int32_t d, int32_t number_frequencies, float* out, void* stream);
+
 /* Keras metric aggregation of one batch (Model.fit's Mean metrics; add_metric at models.py:115,121):
  *   acc[0..F)  += stats[i]/n              (KL_i batch mean; history['KL{i}'] = acc[i]/acc[F+3])
  *   acc[F]     += stats[F] + beta*sum_i stats[i]   (sample-weighted total loss; history['loss'] = acc[F]/acc[F+2])
@@ -227,6 +248,16 @@ int dib_infonce_head(int32_t kind, const float* e1, const float* e2, int64_t n, 
  * output); eps [n, E] or NULL -> Philox(seed, step, row, feature 0, dim); row_scratch [2n] floats; out [2]. */
 int dib_mi_sandwich_bounds(const float* mu_logvar, int64_t n, int32_t embedding_dimension, const float* eps, uint64_t seed,
                            uint32_t step, float* row_scratch, float* out_lower_upper, void* stream);
+
+/* NEXT ROW f1, batched -- the whole of utils.estimate_mi_sandwich_bounds / InfoPerFeatureCallback (models.py:188-223) in one
+ * launch: `groups` = features x evaluation batches independent problems of n rows each, mu_logvar [groups, n, 2E] (the
+ * out_mu_logvar of dib_compression_matrices with n = batches * batch size rows per feature is exactly this layout),
+ * accumulated in float64 as the reference does (utils.py:40-41).  eps [groups, n, E] or NULL -> Philox keyed
+ * ((seed << 8) + g / batches_per_feature; step g % batches_per_feature; row; feature 0; dim), i.e. the streams of the
+ * per-feature, per-batch calls.  row_scratch: groups * n * 2 doubles; out: [groups, 2] doubles (lower, upper) in nats. */
+int dib_mi_sandwich_bounds_batched(const float* mu_logvar, int32_t groups, int64_t n, int32_t embedding_dimension,
+                                   const float* eps, uint64_t seed, int32_t batches_per_feature, double* row_scratch,
+                                   double* out_lower_upper, void* stream);
 
 /* NEXT ROW f4 -- ctw.estimate_entropy(seq, alphabet_size) (chaos/ctw.pyx:2-3 -> chaos/cppctw.cpp:163-171): infinite-depth
  * Context-Tree-Weighting entropy-rate estimate in bits/symbol.  HOST functions on HOST memory (the suffix-tree build is

@@ -27,6 +27,8 @@ import numpy as np
 LOSS_BCE_LOGITS = "bce_logits"          # tf.keras.losses.BinaryCrossentropy(from_logits=True)  data.py:65
 LOSS_SPARSE_CE_LOGITS = "sparse_ce_logits"  # SparseCategoricalCrossentropy(from_logits=True)   data.py:343
 LOSS_MSE = "mse"                        # regression targets (data.py:129 implies it)
+LOSS_BCE_PROBS = "bce_probs"            # [KERAS] BinaryCrossentropy() on probabilities (from_logits=False, the Keras default)
+_KERAS_EPS = 1e-7                       # keras.backend.epsilon()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -206,6 +208,10 @@ def task_loss_per_sample(loss, pred, y):
     if loss == LOSS_MSE:
         yy = y.reshape(pred.shape).astype(pred.dtype)
         return ((pred - yy) ** 2).mean(axis=-1)
+    if loss == LOSS_BCE_PROBS:      # keras.backend.binary_crossentropy: clip to [eps, 1-eps], then log(p + eps)
+        yy = y.reshape(pred.shape).astype(pred.dtype)
+        pc = np.clip(pred, _KERAS_EPS, 1.0 - _KERAS_EPS)
+        return (-(yy * np.log(pc + _KERAS_EPS) + (1.0 - yy) * np.log(1.0 - pc + _KERAS_EPS))).mean(axis=-1)
     raise ValueError(loss)
 
 
@@ -223,6 +229,11 @@ def task_loss_grad(loss, pred, y):
     if loss == LOSS_MSE:
         yy = y.reshape(pred.shape).astype(pred.dtype)
         return 2.0 * (pred - yy) / pred.shape[-1]
+    if loss == LOSS_BCE_PROBS:
+        yy = y.reshape(pred.shape).astype(pred.dtype)
+        pc = np.clip(pred, _KERAS_EPS, 1.0 - _KERAS_EPS)
+        g = -yy / (pc + _KERAS_EPS) + (1.0 - yy) / (1.0 - pc + _KERAS_EPS)
+        return np.where((pred > _KERAS_EPS) & (pred < 1.0 - _KERAS_EPS), g, 0.0) / pred.shape[-1]
     raise ValueError(loss)
 
 
@@ -383,6 +394,30 @@ def adam_step(params, grads, st: AdamState, lr, beta_1=0.9, beta_2=0.999, epsilo
     st.m += (grads - st.m) * (dt(1.0) - dt(beta_1))
     st.v += (grads * grads - st.v) * (dt(1.0) - dt(beta_2))
     params -= lr_t * st.m / (np.sqrt(st.v) + dt(epsilon))
+    return params
+
+
+def sgd_step(params, grads, velocity, lr, momentum=0.0, nesterov=False):
+    """[KERAS] tf.keras.optimizers.SGD: v = momentum*v - lr*g; w += momentum*v - lr*g (nesterov) or v."""
+    dt = params.dtype.type
+    if momentum == 0.0:
+        params -= dt(lr) * grads
+        return params
+    velocity *= dt(momentum)
+    velocity -= dt(lr) * grads
+    params += (dt(momentum) * velocity - dt(lr) * grads) if nesterov else velocity
+    return params
+
+
+def rmsprop_step(params, grads, ms, mom, lr, rho=0.9, momentum=0.0, epsilon=1e-7):
+    """[KERAS/TF] non-centered RMSprop as TensorFlow's ApplyRMSProp kernel computes it:
+    ms = rho*ms + (1-rho)*g^2; mom = momentum*mom + lr*g/sqrt(ms + eps); w -= mom."""
+    dt = params.dtype.type
+    ms *= dt(rho)
+    ms += (dt(1.0) - dt(rho)) * grads * grads
+    mom *= dt(momentum)
+    mom += dt(lr) * grads / np.sqrt(ms + dt(epsilon))
+    params -= mom
     return params
 
 

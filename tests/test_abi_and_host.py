@@ -79,8 +79,15 @@ def test_keras_compat_objects():
     assert resolve_loss(dib_b200.losses.BinaryCrossentropy(from_logits=True)) == "bce_logits"
     assert resolve_loss(dib_b200.losses.SparseCategoricalCrossentropy(from_logits=True)) == "sparse_ce_logits"
     assert resolve_loss("mse") == "mse"
+    assert resolve_loss(dib_b200.losses.BinaryCrossentropy()) == "bce_probs"        # Keras default from_logits=False
     with pytest.raises(NotImplementedError):
-        resolve_loss(dib_b200.losses.BinaryCrossentropy())
+        resolve_loss(dib_b200.losses.SparseCategoricalCrossentropy())
+    sgd = dib_b200.optimizers.get("sgd")
+    assert (sgd.learning_rate, sgd.momentum, sgd.nesterov) == (0.01, 0.0, False) and sgd.hyper() == (0.0, 0.0, 0.0)
+    rms = dib_b200.optimizers.get("RMSprop")
+    assert rms.hyper() == (0.9, 0.0, 1e-7) and dib_b200.optimizers.get(rms) is rms
+    with pytest.raises(ValueError):
+        dib_b200.optimizers.get("adagrad")
     h = dib_b200.History()
     h.on_epoch_end(0, {"loss": 1.0}); h.on_epoch_end(1, {"loss": 0.5})
     assert h.history == {"loss": [1.0, 0.5]}

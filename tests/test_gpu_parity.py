@@ -485,3 +485,97 @@ def test_nonlinear_ib_weighting_matches_oracle():
     np.testing.assert_allclose(float(m.losses[0]), O.ib_loss(cfg, 0.7, fr.kl_per_feature), rtol=2e-5)
     out = m.train_on_batch(x, y)
     assert np.isfinite(out["loss"])
+
+
+def test_mi_bounds_all_features_in_one_launch_matches_per_feature_loop_and_float64_oracle():
+    """next row f1, batched (dib_mi_sandwich_bounds_batched): all features x all evaluation batches in one launch against
+    (a) the per-feature / per-batch loop with the same row draws and noise streams, (b) the float64 oracle on the batched
+    kernel's own inputs with explicit noise."""
+    from dib_b200 import _lib, utils
+    import ctypes
+    cfg = O.DIBConfig([1, 2, 1], [64, 32], [32], 1, feature_embedding_dimension=8)
+    m = build_model(cfg, seed=3)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((3000, 4)).astype(np.float32)
+    got = utils.estimate_mi_sandwich_bounds_all_features(m, x, evaluation_batch_size=256, number_evaluation_batches=3, seed=11)
+    offs = [0, 1, 3, 4]
+    for i in range(3):
+        ref = utils.estimate_mi_sandwich_bounds(m.feature_encoders[i], x[:, offs[i]:offs[i + 1]], 256, 3, seed=11)
+        np.testing.assert_allclose(got[i], ref, rtol=2e-5, atol=2e-6)           # the looped path accumulates in fp32
+    assert got.dtype == np.float64 and np.all(got[:, 0] <= got[:, 1] + 1e-9)
+    # (b) explicit noise, float64 oracle
+    lib = _lib.load()
+    G, n, E = 5, 300, 8
+    mu, lv = rng.standard_normal((G, n, E)), rng.standard_normal((G, n, E)) * 0.5 - 1.0
+    eps = rng.standard_normal((G, n, E)).astype(np.float32)
+    dev = torch.device("cuda")
+    ml = torch.from_numpy(np.concatenate([mu, lv], -1)).float().to(dev).contiguous()
+    scratch = torch.empty(G * n * 2, dtype=torch.float64, device=dev)
+    out = torch.empty(G, 2, dtype=torch.float64, device=dev)
+    _lib.check(lib.dib_mi_sandwich_bounds_batched(_lib.ptr(ml), G, n, E, _lib.ptr(torch.from_numpy(eps).to(dev)), 0, 1,
+                                                  _lib.ptr(scratch), _lib.ptr(out),
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    for g in range(G):
+        ref = O.mi_sandwich_batch(mu[g].astype(np.float32), lv[g].astype(np.float32), eps[g].astype(np.float64))
+        np.testing.assert_allclose(out[g].cpu().numpy(), ref, rtol=1e-9, atol=1e-9)     # float64 on both sides
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "sgd_nesterov", "rmsprop", "rmsprop_momentum"])
+def test_other_keras_optimizers_match_oracle(opt_name):
+    """tf.keras.optimizers.get(name) beyond Adam (train.py:41,128): three steps through the public API against the
+    oracle's restatement of the Keras / TensorFlow update rules."""
+    import dib_b200
+    cfg = O.DIBConfig([1, 2], [16], [12], 1, feature_embedding_dimension=4)
+    rng = np.random.default_rng(9)
+    opt = {"sgd": dib_b200.SGD(0.05), "sgd_nesterov": dib_b200.SGD(0.05, momentum=0.9, nesterov=True),
+           "rmsprop": dib_b200.RMSprop(1e-2), "rmsprop_momentum": dib_b200.RMSprop(1e-2, rho=0.8, momentum=0.5)}[opt_name]
+    m = build_model(cfg, seed=1)
+    m.compile(optimizer=opt, loss="bce_logits", metrics=["accuracy"])
+    p = m.get_flat_weights().copy()
+    s1, s2 = np.zeros_like(p), np.zeros_like(p)
+    m.beta.assign(0.1)
+    for t in range(3):
+        x = rng.standard_normal((50, 3)).astype(np.float32)
+        y = (x[:, :1] > 0).astype(np.float32)
+        eps = philox.normal_noise(m.noise_seed, t, np.arange(50), 2, 4, dtype=np.float64)
+        g, _ = O.train_grads(cfg, p, x, y, eps, 0.1, O.LOSS_BCE_LOGITS)
+        g = g.astype(np.float32)
+        if opt_name.startswith("sgd"):
+            O.sgd_step(p, g, s1, 0.05, opt.momentum, opt.nesterov)
+        else:
+            O.rmsprop_step(p, g, s1, s2, 1e-2, opt.rho, opt.momentum, opt.epsilon)
+        m.train_on_batch(x, y)
+    assert rel_err(m.get_flat_weights(), p) < 2e-5
+
+
+def test_bce_on_probabilities_and_library_entry_points():
+    """BinaryCrossentropy() with the Keras default from_logits=False on a sigmoid-output model; and the stand-alone
+    model.integration_network(emb) / PositionalEncoding(freqs)(x) calls, which run in the library (no torch math)."""
+    import dib_b200
+    cfg = O.DIBConfig([1, 1, 2], [16, 8], [12, 10], 2, feature_embedding_dimension=4, output_activation_fn="sigmoid")
+    rng = np.random.default_rng(10)
+    m = build_model(cfg, seed=2)
+    m.compile(optimizer="adam", loss=dib_b200.losses.BinaryCrossentropy(), metrics=["accuracy"])
+    p = m.get_flat_weights()
+    B = 70
+    x = rng.standard_normal((B, 4)).astype(np.float32)
+    y = rng.integers(0, 2, size=(B, 2)).astype(np.float32)
+    eps = rng.standard_normal((B, 3, 4)).astype(np.float32)
+    m.beta.assign(0.2)
+    g, st = m.compute_gradients(x, y, eps=eps)
+    g_ref, fr = O.train_grads(cfg, p, x, y, eps, 0.2, O.LOSS_BCE_PROBS)
+    assert rel_err(g.cpu().numpy(), g_ref) < 5e-5
+    np.testing.assert_allclose(st.cpu().numpy()[3] / B, fr.task_loss, rtol=2e-5)
+    np.testing.assert_allclose(st.cpu().numpy()[4], fr.acc_sum, rtol=1e-6)
+    # integration network as a callable
+    emb = rng.standard_normal((33, 12)).astype(np.float32)
+    got = m.integration_network(emb)
+    _, integ = O.unflatten(cfg, p.astype(np.float64))
+    h = emb.astype(np.float64)
+    for k, (W, b) in enumerate(integ):
+        h = O.act_fwd(cfg.activation_fn if k < len(integ) - 1 else cfg.output_activation_fn, h @ W + b)
+    assert rel_err(got, h) < 2e-5
+    # positional encoding as a callable (models.py:12-23)
+    xs = rng.standard_normal((17, 3)).astype(np.float32)
+    pe = dib_b200.PositionalEncoding(2 ** np.arange(1, 5))(xs)
+    np.testing.assert_allclose(pe, O.positional_encoding(xs.astype(np.float64), [2, 4, 8, 16]), rtol=0, atol=2e-6)
