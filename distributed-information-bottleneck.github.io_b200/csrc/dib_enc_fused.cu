@@ -73,6 +73,8 @@ struct EncFusedParams {
   const unsigned int* step_dev;            // optional device addend of `step` (CUDA-Graph replay)
   float* emb; int ldemb; float* user_emb;  // outputs (forward); emb may be null when emb16 is given
   uint16_t* emb16; int ldemb16;            // 16-bit (fp16 / bf16) copy of emb for the 16-bit integration path (or null)
+  uint16_t* eps16;                         // [n, F*32] 16-bit copy of the Philox noise: written by the training forward, read by the
+                                           // two-chain backward instead of regenerating it (the gradient operands are 16-bit anyway)
   float* kl_part; int kl_stride;           // [F][kl_stride] per-(feature, slot) KL partial sums
   int F; long long n; int act; float alpha;
   int round_emb;
@@ -340,10 +342,16 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           DIB_EPI_SIGNAL(bar_a0);
         }
         noise8(ep, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, hsel * 16, valid, nrmA);   // while layer 1 runs
+        if (P.eps16 && valid)        // hand the noise to the backward kernel of this step (16-bit, like its gradient operands)
+          *reinterpret_cast<uint4*>(P.eps16 + (grow * F + f) * 32 + hsel * 16) =
+              make_uint4(pack2<BF16>(nrmA[0], nrmA[1]), pack2<BF16>(nrmA[2], nrmA[3]), pack2<BF16>(nrmA[4], nrmA[5]), pack2<BF16>(nrmA[6], nrmA[7]));
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h2);
         noise8(ep ? ep + 8 : nullptr, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, hsel * 16 + 8, valid, nrmB);   // while layer 2 runs
+        if (P.eps16 && valid)
+          *reinterpret_cast<uint4*>(P.eps16 + (grow * F + f) * 32 + hsel * 16 + 8) =
+              make_uint4(pack2<BF16>(nrmB[0], nrmB[1]), pack2<BF16>(nrmB[2], nrmB[3]), pack2<BF16>(nrmB[4], nrmB[5]), pack2<BF16>(nrmB[6], nrmB[7]));
         // ---- (mu, logvar) -> reparameterise, KL, emb   (16 embedding dims per thread)
         mbar_wait(bar_d2, ph); tc_fence_after_sync();
         {
@@ -822,7 +830,7 @@ __device__ __forceinline__ void dgrad_inplace(uint32_t taddr, uint32_t tile, int
   }
 }
 
-template <bool BF16, bool RELU>
+template <bool BF16, bool RELU, bool EPS16>
 __global__ void __launch_bounds__(kV2Threads, 1)
 dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFusedBwdParams Q) {
   const EncFusedParams& P = Q.f;
@@ -996,12 +1004,18 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
         if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv);
         const float* ep = (P.eps && valid) ? P.eps + (grow * F + f) * 32 + csel * 16 : P.eps;
         uint32_t nz16[8];            // this thread's 16 noise values, packed 16-bit (they multiply a 16-bit gradient)
+        constexpr bool have_eps16 = EPS16;
+        if constexpr (have_eps16) {            // written by this step's forward kernel: 32 B per thread instead of 4 Philox calls
+          const uint16_t* e16 = P.eps16 + ((valid ? grow : 0) * F + f) * 32 + csel * 16;
+          const uint4 q0 = *reinterpret_cast<const uint4*>(e16), q1 = *reinterpret_cast<const uint4*>(e16 + 8);
+          nz16[0] = q0.x; nz16[1] = q0.y; nz16[2] = q0.z; nz16[3] = q0.w; nz16[4] = q1.x; nz16[5] = q1.y; nz16[6] = q1.z; nz16[7] = q1.w;
+        }
         // buffer set (i & 1) was last used by tile i - 2: all of its MMAs (chain B commits last) have retired
         if (i >= 2) { mbar_wait(bar_wg0 + 8 * (i & 1), ((i >> 1) - 1) & 1); }
         mbar_wait(bar_d0, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, h1_of(i), r, csel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h1);
-        {                                                                                           // while layer 1 runs
+        if constexpr (!have_eps16) {                                                                // while layer 1 runs
           float nrm[8];
           noise8(ep, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, csel * 16, valid, nrm);
 #pragma unroll
@@ -1010,7 +1024,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, h2_of(i), r, csel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h2);
-        {                                                                                           // while layer 2 runs
+        if constexpr (!have_eps16) {                                                                // while layer 2 runs
           float nrm[8];
           noise8(ep ? ep + 8 : nullptr, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, csel * 16 + 8, valid, nrm);
 #pragma unroll
@@ -1244,7 +1258,7 @@ void fill_params(EncFusedParams& P, const DibEncFusedDesc& d, const DibEncFusedI
   P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step; P.step_dev = io.step_dev;
   P.sample_offset = io.sample_offset; P.emb = io.emb; P.ldemb = io.ldemb; P.user_emb = io.user_emb;
   P.kl_part = io.kl_part; P.kl_stride = io.kl_stride; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha;
-  P.round_emb = 1; P.emb16 = static_cast<uint16_t*>(io.emb16); P.ldemb16 = io.ldemb16;
+  P.round_emb = 1; P.emb16 = static_cast<uint16_t*>(io.emb16); P.ldemb16 = io.ldemb16; P.eps16 = static_cast<uint16_t*>(io.eps16);
 }
 
 template <typename K, typename A>
@@ -1311,10 +1325,12 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
   const bool relu = d.act == DIB_ACT_RELU;
   if (dib_enc_bwd_version() == 2) {          // two chains on consecutive tiles (default)
     constexpr int smem2 = kV2OffBar + 256 + 1024;
-    if (d.bf16) return relu ? launch_fused(dib_enc_fused_bwd2_kernel<true, true>, smem2, d.grid, m, Q, st, kV2Threads)
-                            : launch_fused(dib_enc_fused_bwd2_kernel<true, false>, smem2, d.grid, m, Q, st, kV2Threads);
-    return relu ? launch_fused(dib_enc_fused_bwd2_kernel<false, true>, smem2, d.grid, m, Q, st, kV2Threads)
-                : launch_fused(dib_enc_fused_bwd2_kernel<false, false>, smem2, d.grid, m, Q, st, kV2Threads);
+    const bool e16 = Q.f.eps16 != nullptr && Q.f.eps == nullptr;     // this step's forward left the noise in the workspace
+#define DIB_BWD2(BF, RL) (e16 ? launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, true>, smem2, d.grid, m, Q, st, kV2Threads) \
+                              : launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, false>, smem2, d.grid, m, Q, st, kV2Threads))
+    if (d.bf16) return relu ? DIB_BWD2(true, true) : DIB_BWD2(true, false);
+    return relu ? DIB_BWD2(false, true) : DIB_BWD2(false, false);
+#undef DIB_BWD2
   }
   constexpr int smem = kOffBwdEnd + 256 + 1024;
   if (d.bf16)    // bf16 operands end to end (7-bit mantissa gradients: the usual bf16-training trade, BASELINE config 4)

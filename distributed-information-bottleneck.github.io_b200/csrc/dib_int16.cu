@@ -11,10 +11,13 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "dib_common.cuh"
 #include "dib_kernels.h"
 #include "dib_sm100.cuh"
+
+int dib_int16_rb_enabled();
 
 namespace {
 
@@ -245,6 +248,193 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 2 * kBN); }
+}
+
+// ====================================================================================================
+// Resident-B variant for FWD / DGRAD (the B operand is a weight matrix): with M = 65 536 rows and 128-row tiles the old
+// kernel re-fetched the [K x 128] weight tile from L2 for every one of the 512 row tiles -- at ~20 B/clk of L2
+// bandwidth per SM that traffic (not the MMAs) set the kernel time (ncu: long_scoreboard 44-57 %).  Here each persistent
+// CTA owns ONE column tile, loads its [K x BN] slice of the weights once (<= 128 KB of shared memory) and streams only
+// the activation tiles through a deeper ring; BN = 256 (full output width of the hidden layers) reads A exactly once.
+// Warp roles as above: 0 TMA producer | 1 MMA issuer (+ TMEM owner) | 2..5 epilogue.
+// ====================================================================================================
+constexpr int kRbStages = 5;
+template <int BN> constexpr int rb_tmem_cols() { return 2 * BN; }
+
+template <int MODE, bool BF16, int BN>
+__global__ void __launch_bounds__(192, 1)
+dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Int16Args a, int nkb) {
+  static_assert(MODE != DIB_GEMM_WGRAD, "resident-B variant: FWD / DGRAD only");
+  constexpr bool B_MN = (MODE == DIB_GEMM_FWD);
+  constexpr int kBPanel = BN * 128;                    // bytes of one 64-deep k-block of the resident B slice
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t sB = sb, sA = sb + nkb * kBPanel;      // resident B | A ring
+  const int bar_off = nkb * kBPanel + kRbStages * kABytes;
+  const uint32_t bar_base = sb + bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kRbStages + s); };
+  auto tfull_bar = [&](int acc) { return bar_base + 8u * (2 * kRbStages + acc); };
+  auto tempty_bar = [&](int acc) { return bar_base + 8u * (2 * kRbStages + 2 + acc); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * kRbStages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kRbStages + 5);
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + bar_off + 8 * (2 * kRbStages + 5));
+
+  __shared__ float colsum_s[4][BN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = a.M, C = a.C;
+  const int tiles_r = DIB_CEIL_DIV(R, kBM), tiles_c = DIB_CEIL_DIV(C, BN);
+  // this CTA's fixed column tile and its row tiles: blockIdx.x = col + tiles_c * k  (gridDim.x is a multiple of tiles_c)
+  const int ctile = blockIdx.x % tiles_c, c0 = ctile * BN;
+  const int rfirst = blockIdx.x / tiles_c, rstep = gridDim.x / tiles_c;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
+    for (int s = 0; s < kRbStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int acc = 0; acc < 2; ++acc) { mbar_init(tfull_bar(acc), 1); mbar_init(tempty_bar(acc), 4); }
+    mbar_init(bfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, rb_tmem_cols<BN>()); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // the weight slice of this column tile, once
+      mbar_expect_tx(bfull_bar, (uint32_t)(nkb * kBPanel));
+      for (int k = 0; k < nkb; ++k) {
+        const uint32_t dst = sB + k * kBPanel;
+        // one box per k-block: FWD [BN/64 panels][64 k-rows][128 B] (MN-major), DGRAD [BN rows][128 B] (K-major)
+        if constexpr (B_MN) tma_load_3d(dst, &mapB, bfull_bar, 0, k * kBK, c0 / 64);
+        else                tma_load_2d(dst, &mapB, bfull_bar, k * kBK, c0);
+      }
+      uint32_t it = 0;
+      for (int rt = rfirst; rt < tiles_r; rt += rstep) {
+        for (int k = 0; k < nkb; ++k, ++it) {
+          const int s = it % kRbStages, ph = (it / kRbStages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), kABytes);
+          tma_load_2d(sA + s * kABytes, &mapA, full_bar(s), k * kBK, rt * kBM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BF16 ? 1u : 0u, 0u, B_MN ? 1u : 0u, BN);
+      mbar_wait(bfull_bar, 0);
+      tc_fence_after_sync();
+      uint32_t it = 0, lt = 0;
+      for (int rt = rfirst; rt < tiles_r; rt += rstep, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(tempty_bar(acc), ((lt >> 1) & 1) ^ 1);           // the epilogue has drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int k = 0; k < nkb; ++k, ++it) {
+          const int s = it % kRbStages, ph = (it / kRbStages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = sA + s * kABytes, b_addr = sB + k * kBPanel;
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk) {
+            // A K-major: 32 B inside the swizzle span.  B MN-major (FWD): 16 k-rows = 2048 B inside a [64 k x 64 n] panel,
+            // panels 8 KB apart; B K-major (DGRAD): rows = output columns, 128-row groups 16 KB apart handled by SBO = 1024.
+            const uint64_t adesc = umma_smem_desc(a_addr + kk * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t lt = 0;
+    for (int rt = rfirst; rt < tiles_r; rt += rstep, ++lt) {
+      const int acc = lt & 1, r0 = rt * kBM;
+      mbar_wait(tfull_bar(acc), (lt >> 1) & 1); tc_fence_after_sync();
+      const int r = r0 + q * 32 + lane;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+        tmem_ld_wait();
+        if (r < R && c0 + cc < C) {          // C is a multiple of 64: a 32-column chunk is entirely inside or outside
+          const int c = c0 + cc;
+          uint16_t* dst = a.out16 + (long long)r * a.ldc + c;
+          const uint16_t* xs = (MODE == DIB_GEMM_DGRAD && a.X) ? a.X + (long long)r * a.ldx + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j + k]);
+            if constexpr (MODE == DIB_GEMM_FWD) {
+              const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c + j), b1 = *reinterpret_cast<const float4*>(a.bias + c + j + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = dib_act(a.act, f[k] + bb[k], a.alpha);
+            } else if (xs) {
+              const uint4 xv = *reinterpret_cast<const uint4*>(xs + j);
+              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float h0, h1;
+                unpack_h2<BF16>(xw[k], h0, h1);
+                f[2 * k] *= dib_act_grad(a.act, h0, a.alpha);
+                f[2 * k + 1] *= dib_act_grad(a.act, h1, a.alpha);
+              }
+            }
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2<BF16>(f[0], f[1]), pack_h2<BF16>(f[2], f[3]), pack_h2<BF16>(f[4], f[5]), pack_h2<BF16>(f[6], f[7]));
+            if constexpr (MODE == DIB_GEMM_DGRAD) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[j + k] = __float_as_uint(f[k]);     // keep the gated fp32 values for the column sums
+            }
+          }
+        } else if constexpr (MODE == DIB_GEMM_DGRAD) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;                                  // rows / columns outside the matrix add nothing
+        }
+        if constexpr (MODE == DIB_GEMM_DGRAD) {
+          if (a.dbias) {
+            // bias gradient of the layer below = column sums of the gradient just produced (31-shuffle transpose-reduce)
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+              for (int i = 0; i < o; ++i) {
+                const bool up = (lane & o) != 0;
+                const float send = up ? w[i] : w[i + o], keep = up ? w[i + o] : w[i];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              }
+            }
+            colsum_s[q][cc + lane] = w[0];
+          }
+        }
+      }
+      if constexpr (MODE == DIB_GEMM_DGRAD) {
+        if (a.dbias) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int et = (warp - 2) * 32 + lane;
+          for (int cidx = et; cidx < BN; cidx += 128)
+            if (c0 + cidx < C)
+              a.dbias[(long long)rt * C + c0 + cidx] = (colsum_s[0][cidx] + colsum_s[1][cidx]) + (colsum_s[2][cidx] + colsum_s[3][cidx]);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, rb_tmem_cols<BN>()); }
 }
 
 // bias gradient of a hidden layer: column sums of the fp16 gradient over one batch slice -> fp32 split partial.
@@ -497,7 +687,44 @@ cudaError_t launch16(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Ar
   return cudaGetLastError();
 }
 
+// resident-B launch: grid = a multiple of the column-tile count, at most one CTA per SM
+template <int MODE, bool BF16, int BN>
+cudaError_t launch_rb(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Args& a, int nkb, cudaStream_t st) {
+  if (!g_num_sms16) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms16, cudaDevAttrMultiProcessorCount, dev); }
+  const int tiles_r = DIB_CEIL_DIV(a.M, kBM), tiles_c = DIB_CEIL_DIV(a.C, BN);
+  long long grid = (long long)tiles_r * tiles_c;
+  const long long cap = (long long)(g_num_sms16 / tiles_c) * tiles_c;
+  if (grid > cap) grid = cap;
+  if (grid <= 0) return cudaSuccess;
+  const int smem = nkb * BN * 128 + kRbStages * kABytes + 128 + 1024;
+  static int attr_smem = 0;
+  if (attr_smem < smem) {
+    cudaError_t e = cudaFuncSetAttribute(dib_int16_rb_kernel<MODE, BF16, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  dib_int16_rb_kernel<MODE, BF16, BN><<<(unsigned)grid, 192, smem, st>>>(mA, mB, a, nkb);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+// BN for the resident-B kernel (0 = not eligible): the weight slice [T x BN] 16-bit plus the A ring must fit in shared memory
+int rb_pick_bn(int T, int C) {
+  if (!dib_int16_rb_enabled() || T % kBK != 0 || C % 64 != 0) return 0;
+  const int nkb = T / kBK, budget = 227 * 1024 - (kRbStages * kABytes + 128 + 1024) - 4 * 256 * 4 - 1024;
+  if (C % 256 == 0 && nkb * 256 * 128 <= budget) return 256;
+  if (nkb * 128 * 128 <= budget) return 128;
+  return 0;
+}
+
 }  // namespace
+
+static int g_int16_rb = -1;
+int dib_int16_rb_enabled() {
+  if (g_int16_rb < 0) { const char* e = getenv("DIB_INT16_RB"); g_int16_rb = (e && e[0] == '0') ? 0 : 1; }
+  return g_int16_rb;
+}
+void dib_int16_rb_set(int on) { g_int16_rb = on ? 1 : 0; }
 
 cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, int bf16, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
@@ -517,6 +744,11 @@ cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const fl
   Int16Args a{};
   a.out16 = static_cast<uint16_t*>(g_out); a.ldc = ld_out; a.bias = bias; a.M = M; a.T = K; a.C = N; a.act = act; a.alpha = alpha;
   a.out_scale = 1.f; a.nsplit = 1;
+  if (const int bn = rb_pick_bn(K, N)) {          // weights resident in shared memory, activations streamed
+    if (!map_mn(&mB, w16, N, K, N, bn / 64)) return cudaErrorInvalidValue;
+    if (bn == 256) return bf16 ? launch_rb<DIB_GEMM_FWD, true, 256>(mA, mB, a, K / kBK, st) : launch_rb<DIB_GEMM_FWD, false, 256>(mA, mB, a, K / kBK, st);
+    return bf16 ? launch_rb<DIB_GEMM_FWD, true, 128>(mA, mB, a, K / kBK, st) : launch_rb<DIB_GEMM_FWD, false, 128>(mA, mB, a, K / kBK, st);
+  }
   const dim3 tiles(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(N, kBN), 1);
   return bf16 ? launch16<DIB_GEMM_FWD, true>(mA, mB, a, tiles, st) : launch16<DIB_GEMM_FWD, false>(mA, mB, a, tiles, st);
 }
@@ -531,6 +763,11 @@ cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const vo
   Int16Args a{};
   a.out16 = static_cast<uint16_t*>(dz_in); a.ldc = ld_out; a.X = static_cast<const uint16_t*>(g_in); a.ldx = ld_g;
   a.M = M; a.T = N; a.C = K; a.act = act; a.alpha = alpha; a.out_scale = 1.f; a.nsplit = 1; a.dbias = colsum_part;
+  if (const int bn = rb_pick_bn(N, K)) {          // W^T slice resident, dz streamed
+    if (!map_k(&mB, w16, N, K, N, bn)) return cudaErrorInvalidValue;
+    if (bn == 256) return bf16 ? launch_rb<DIB_GEMM_DGRAD, true, 256>(mA, mB, a, N / kBK, st) : launch_rb<DIB_GEMM_DGRAD, false, 256>(mA, mB, a, N / kBK, st);
+    return bf16 ? launch_rb<DIB_GEMM_DGRAD, true, 128>(mA, mB, a, N / kBK, st) : launch_rb<DIB_GEMM_DGRAD, false, 128>(mA, mB, a, N / kBK, st);
+  }
   const dim3 tiles(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(K, kBN), 1);
   return bf16 ? launch16<DIB_GEMM_DGRAD, true>(mA, mB, a, tiles, st) : launch16<DIB_GEMM_DGRAD, false>(mA, mB, a, tiles, st);
 }

@@ -127,6 +127,7 @@ struct DibEncFusedIO {
   float* emb; int ldemb; float* user_emb;
   float* kl_part; int kl_stride;
   void* emb16 = nullptr; int ldemb16 = 0;   // optional fp16 copy of emb (16-bit integration path)
+  void* eps16 = nullptr;                    // optional [n, F*32] 16-bit noise hand-off: forward writes, two-chain backward reads
 };
 int dib_enc_bwd_version();
 void dib_enc_bwd_set_version(int v);
@@ -156,6 +157,8 @@ cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int 
 cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
                             int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, int bf16, cudaStream_t st);
 int dib_int16_head_blocks(int num_sms);
+int dib_int16_rb_enabled();
+void dib_int16_rb_set(int on);
 cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const float* bc, int out_dim, int out_act, int hid_act,
                            float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,
                            float* user_pred, float* wpart, int wpart_stride, float* loss_part, float* acc_part, int nblocks,

@@ -126,3 +126,36 @@ def test_fused_encoder_kernels_match_unfused_and_fp32(shape):
                 n = int(np.prod(s))
                 assert rel_err(res[tag][1][off:off + n], res["fp32"][1][off:off + n]) < (10 * TOL if B >= 4096 else 0.15), (tag, B, off, s)
                 off += n
+
+
+@pytest.mark.parametrize("shape", ["c0", "radial3"])
+def test_int16_resident_weight_gemms_match_streamed_kernels_bitwise(shape):
+    """The integration FWD / DGRAD GEMMs with the weight slice resident in shared memory (BN = 128 / 256, one CTA per SM)
+    issue the same MMAs in the same order as the streamed-B kernels they replace: predictions, gradients and statistics
+    must be bit-identical, incl. a ragged last row tile."""
+    from dib_b200 import _lib
+    lib = _lib.load()
+    if shape == "c0":
+        cfg, D = O.DIBConfig([1] * 16, [128, 128], [256, 256], 1), 16
+    else:
+        cfg, D = O.DIBConfig([1] * 12, [128, 128], [256, 256, 256], 3, activation_fn="tanh", use_positional_encoding=False), 12
+    rng = np.random.default_rng(5)
+    p = O.glorot_uniform_params(cfg, rng)
+    p = p + (p == 0) * (0.05 * rng.standard_normal(p.size)).astype(np.float32)
+    B = 128 * 37 + 19
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    y = rng.standard_normal((B, cfg.output_dimensionality)).astype(np.float32)
+    res = {}
+    try:
+        for rb in (0, 1):
+            _lib.check(lib.dib_debug_set_variant(1, rb))
+            m = build_model(cfg, precision="fp16", loss="mse")
+            m.set_flat_weights(p)
+            m.beta.assign(0.02)
+            pred = m(x, step=2)
+            g, st = m.compute_gradients(x, y, step=2)
+            res[rb] = (np.asarray(pred), g.cpu().numpy(), st.cpu().numpy())
+    finally:
+        _lib.check(lib.dib_debug_set_variant(1, 1))
+    for a, b in zip(res[0], res[1]):
+        np.testing.assert_array_equal(a, b)

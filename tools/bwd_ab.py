@@ -10,9 +10,11 @@ from dib_b200 import _lib
 from oracle import dib_oracle as O
 
 variant = int(sys.argv[1])
+rb = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 lib = _lib.load()
 _lib.check(lib.dib_debug_set_variant(0, variant))
-out = {"variant": variant}
+_lib.check(lib.dib_debug_set_variant(1, rb))
+out = {"variant": variant, "int16_resident_b": rb}
 
 
 def model(cfgargs, prec, loss="bce_logits"):
