@@ -157,12 +157,12 @@ __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, bool
                                              int nfreq) {
   float f[8];
   const int w_in = d * nfreq;
+  int blk = (khalf * 8) / d, j = khalf * 8 - blk * d;      // one division per call; (blk, j) then advance with the column
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int col = khalf * 8 + k;
     float v = 0.f;
     if (col < w_in) {
-      const int blk = col / d, j = col - blk * d;
       float xj = xv[0];
 #pragma unroll
       for (int q = 1; q < kMaxFeatDim; ++q) if (j == q) xj = xv[q];
@@ -171,6 +171,7 @@ __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, bool
       v = valid ? 1.f : 0.f;          // rows past the batch end contribute nothing
     }
     f[k] = v;
+    if (++j == d) { j = 0; ++blk; }
   }
   st_shared_v4(a0 + khalf * (TM * 16) + r * 16, pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
                pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
@@ -370,7 +371,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
-                const float s = expf(0.5f * lv);
+                const float s = __expf(0.5f * lv);      // ex2.approx: relative error 2^-21, far inside the 16-bit operand rounding
                 u[j] = fmaf(s, e0 < 8 ? nrmA[e0 + j] : nrmB[e0 - 8 + j], mu);
                 kl_acc += 0.5f * (mu * mu + s * s - lv - 1.f);
               }
@@ -796,7 +797,7 @@ constexpr int kV2OffH1 = kV2OffA0 + 3 * (2 * TM * 16); // 86 KB, 1024-aligned; h
 constexpr int kV2OffH2 = kV2OffH1 + 2 * (2 * kPanel);  // h2[0], h2[1]
 constexpr int kV2OffBar = kV2OffH2 + 2 * (2 * kPanel); // 210 KB
 static_assert(kV2OffH1 % 1024 == 0 && kV2OffDO % 1024 == 0, "operand tiles must be 1024-byte aligned");
-constexpr int kV2Threads = 16 * 32;
+constexpr int kV2CtrlEA = 4 + 8;               // control warpgroup + chain-A epilogue warps; chain B adds EBW (4 or 8) warps
 
 // gradient * act'(h) IN PLACE: the 128-byte row chunk of h is read, the gated 16-bit gradient is written back to the
 // same address (same thread), NC columns starting at col0.
@@ -830,8 +831,8 @@ __device__ __forceinline__ void dgrad_inplace(uint32_t taddr, uint32_t tile, int
   }
 }
 
-template <bool BF16, bool RELU, bool EPS16>
-__global__ void __launch_bounds__(kV2Threads, 1)
+template <bool BF16, bool RELU, bool EPS16, int EBW>
+__global__ void __launch_bounds__(32 * (kV2CtrlEA + EBW), 1)
 dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFusedBwdParams Q) {
   const EncFusedParams& P = Q.f;
   extern __shared__ uint8_t smem_raw[];
@@ -843,7 +844,9 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
                  bar_dz2 = bar + 80, bar_g1 = bar + 88, bar_dw1 = bar + 96, bar_dz1 = bar + 104, bar_wg0 = bar + 112 /* [2] */,
                  tmem_slot = bar + 128;
   volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kV2OffBar + 128);
-  constexpr int kEA = 8, kEB = 4;     // epilogue warps of chain A / chain B
+  constexpr int kEA = 8, kEB = EBW;   // epilogue warps of chain A / chain B
+  constexpr int kV2Threads = 32 * (kV2CtrlEA + EBW);
+  static_assert(EBW == 4 || EBW == 8, "chain B: 4 warps (a full row per thread) or 8 (half a row)");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, c = blockIdx.x, F = P.F;
@@ -887,7 +890,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
   // + 1 chain-B warp x 112 = 504 <= 512).  ptxas allocates each branch against its own budget only if the branches do not
   // merge before the kernel's trivial tail.
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");     // per scheduler: 56 + 2 x 168 + 112 (EBW 4) | 56 + 2 x 128 + 2 x 96 (EBW 8) <= 512
     for (int f = f_first; f < F; f += f_step, ++fit) {
       const int ntl = slot < ntiles ? (ntiles - slot + nslots - 1) / nslots : 0;   // tiles of this (feature, CTA)
       const bool any_tiles = ntl > 0; (void)any_tiles;
@@ -967,7 +970,8 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
       tc_fence_after_sync();
     }
   } else if (warp < 4 + kEA) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    if constexpr (EBW == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     for (int f = f_first; f < F; f += f_step, ++fit) {
       const int ntl = slot < ntiles ? (ntiles - slot + nslots - 1) / nslots : 0;   // tiles of this (feature, CTA)
       const bool any_tiles = ntl > 0; (void)any_tiles;
@@ -1109,13 +1113,14 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
       tc_fence_after_sync();
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    if constexpr (EBW == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
     for (int f = f_first; f < F; f += f_step, ++fit) {
       const int ntl = slot < ntiles ? (ntiles - slot + nslots - 1) / nslots : 0;   // tiles of this (feature, CTA)
       const bool any_tiles = ntl > 0; (void)any_tiles;
       {
-      // ================= chain B epilogue warps: one full row (128 columns) per thread
-      const int q = warp & 3;
+      // ================= chain B epilogue warps: one full row (128 columns) per thread, or half a row with 8 warps
+      constexpr int NCB = HID * 4 / EBW;               // columns per thread
+      const int q = warp & 3, cselb = (warp - 4 - kEA) >> 2;
       const int r = q * 32 + lane;
       const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
       const int d = P.fdim[f];
@@ -1123,15 +1128,16 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
         const uint32_t i = it + k, ph = i & 1;
         // ---- dz2 = G2 * act'(h2), in place over h2 (its last reader, the dW2 MMA, has retired: bar_dofree)
         mbar_wait(bar_g2, ph); mbar_wait(bar_dofree, ph); tc_fence_after_sync();
-        dgrad_inplace<BF16, RELU, HID>(tR1 + lane_addr, h2_of(i), r, 0, P.act, P.alpha);
+        dgrad_inplace<BF16, RELU, NCB>(tR1 + lane_addr, h2_of(i), r, cselb * NCB, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_dz2);
         // ---- dz1 = G1 * act'(h1), in place over h1 (dW1 has retired: bar_dw1)
         mbar_wait(bar_g1, ph); mbar_wait(bar_dw1, ph); tc_fence_after_sync();
-        dgrad_inplace<BF16, RELU, HID>(tR1 + lane_addr, h1_of(i), r, 0, P.act, P.alpha);
+        dgrad_inplace<BF16, RELU, NCB>(tR1 + lane_addr, h1_of(i), r, cselb * NCB, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_dz1);
       }
       if (any_tiles) { const uint32_t il = it + ntl - 1; mbar_wait(bar_wg0 + 8 * (il & 1), (il >> 1) & 1); tc_fence_after_sync(); }
-      // ---- flush dW2, [dW0;db0], db1, db2
+      // ---- flush dW2, [dW0;db0], db1, db2 (cold path: the first four chain-B warps cover the 128 TMEM lanes)
+      if (cselb == 0) {
       float* part = Q.part + (long long)slot * Q.split_stride;
       const int w_in = d * P.nfreq;
       float* dst2 = part + Q.w2_off[f] + (long long)r * EO;                        // dW2[h2 = r][0..64)
@@ -1168,6 +1174,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
           for (int k = 0; k < 16; ++k) if (k == w_in) b2v = any_tiles ? __uint_as_float(v2[k]) * invS : 0.f;
           part[P.b2_off[f] + r] = b2v;
         }
+      }
       }
       tc_fence_before_sync();
           }
@@ -1276,10 +1283,10 @@ cudaError_t launch_fused(K kern, int smem, int grid, const WeightMaps& m, const 
 // round 1, 0.438 ms); DIB_ENC_BWD=1|2 in the environment or dib_debug_set_variant(0, v)
 static int g_enc_bwd_version = 0;
 int dib_enc_bwd_version() {
-  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '1') ? 1 : 2; }
+  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '1') ? 1 : ((e && e[0] == '3') ? 3 : 2); }
   return g_enc_bwd_version;
 }
-void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = v == 1 ? 1 : 2; }
+void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = (v == 1 || v == 3) ? v : 2; }
 
 size_t dib_enc_fused_pack_bytes(int F) { return (size_t)F * kPackElems * 2; }
 int dib_enc_fused_fwd_ctas_per_sm() { return 2; }
@@ -1323,11 +1330,15 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
   Q.part = b.part; Q.split_stride = b.split_stride;
   Q.w0_off = d.w0_off; Q.b0_off = d.b0_off; Q.w1_off = d.w1_off; Q.w2_off = d.w2_off;
   const bool relu = d.act == DIB_ACT_RELU;
-  if (dib_enc_bwd_version() == 2) {          // two chains on consecutive tiles (default)
+  if (dib_enc_bwd_version() >= 2) {          // two chains on consecutive tiles (2: default; 3: eight chain-B warps)
     constexpr int smem2 = kV2OffBar + 256 + 1024;
     const bool e16 = Q.f.eps16 != nullptr && Q.f.eps == nullptr;     // this step's forward left the noise in the workspace
-#define DIB_BWD2(BF, RL) (e16 ? launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, true>, smem2, d.grid, m, Q, st, kV2Threads) \
-                              : launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, false>, smem2, d.grid, m, Q, st, kV2Threads))
+    const bool eb8 = dib_enc_bwd_version() == 3;                     // 8 chain-B warps (half a row per thread) instead of 4
+#define DIB_BWD2(BF, RL)                                                                                                            \
+  (eb8 ? (e16 ? launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, true, 8>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 8))              \
+              : launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, false, 8>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 8)))            \
+       : (e16 ? launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, true, 4>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 4))              \
+              : launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, false, 4>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 4))))
     if (d.bf16) return relu ? DIB_BWD2(true, true) : DIB_BWD2(true, false);
     return relu ? DIB_BWD2(false, true) : DIB_BWD2(false, false);
 #undef DIB_BWD2

@@ -721,7 +721,10 @@ int rb_pick_bn(int T, int C) {
 
 static int g_int16_rb = -1;
 int dib_int16_rb_enabled() {
-  if (g_int16_rb < 0) { const char* e = getenv("DIB_INT16_RB"); g_int16_rb = (e && e[0] == '0') ? 0 : 1; }
+  // measured on B200 at C0 (profiles/r02_int16_resident_b_ab.json): slower than the streamed kernels (fwd 48 vs 37 / 32 us,
+  // dgrad_l1 99 vs 63 us) -- one CTA per SM halves the epilogue warps per SM and the epilogue, not the L2 re-reads of the
+  // weights, is what paces these GEMMs.  Kept selectable (DIB_INT16_RB=1, dib_debug_set_variant(1, 1)); default off.
+  if (g_int16_rb < 0) { const char* e = getenv("DIB_INT16_RB"); g_int16_rb = (e && e[0] == '1') ? 1 : 0; }
   return g_int16_rb;
 }
 void dib_int16_rb_set(int on) { g_int16_rb = on ? 1 : 0; }

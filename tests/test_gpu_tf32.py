@@ -156,6 +156,6 @@ def test_int16_resident_weight_gemms_match_streamed_kernels_bitwise(shape):
             g, st = m.compute_gradients(x, y, step=2)
             res[rb] = (np.asarray(pred), g.cpu().numpy(), st.cpu().numpy())
     finally:
-        _lib.check(lib.dib_debug_set_variant(1, 1))
+        _lib.check(lib.dib_debug_set_variant(1, 0))
     for a, b in zip(res[0], res[1]):
         np.testing.assert_array_equal(a, b)
