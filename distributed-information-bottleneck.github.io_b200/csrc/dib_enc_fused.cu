@@ -1283,10 +1283,10 @@ cudaError_t launch_fused(K kern, int smem, int grid, const WeightMaps& m, const 
 // round 1, 0.438 ms); DIB_ENC_BWD=1|2 in the environment or dib_debug_set_variant(0, v)
 static int g_enc_bwd_version = 0;
 int dib_enc_bwd_version() {
-  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '1') ? 1 : ((e && e[0] == '3') ? 3 : 2); }
+  if (!g_enc_bwd_version) { const char* e = getenv("DIB_ENC_BWD"); g_enc_bwd_version = (e && e[0] == '1') ? 1 : 2; }
   return g_enc_bwd_version;
 }
-void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = (v == 1 || v == 3) ? v : 2; }
+void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = v == 1 ? 1 : 2; }
 
 size_t dib_enc_fused_pack_bytes(int F) { return (size_t)F * kPackElems * 2; }
 int dib_enc_fused_fwd_ctas_per_sm() { return 2; }
@@ -1330,15 +1330,14 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
   Q.part = b.part; Q.split_stride = b.split_stride;
   Q.w0_off = d.w0_off; Q.b0_off = d.b0_off; Q.w1_off = d.w1_off; Q.w2_off = d.w2_off;
   const bool relu = d.act == DIB_ACT_RELU;
-  if (dib_enc_bwd_version() >= 2) {          // two chains on consecutive tiles (2: default; 3: eight chain-B warps)
+  if (dib_enc_bwd_version() >= 2) {          // two chains on consecutive tiles (default)
     constexpr int smem2 = kV2OffBar + 256 + 1024;
     const bool e16 = Q.f.eps16 != nullptr && Q.f.eps == nullptr;     // this step's forward left the noise in the workspace
-    const bool eb8 = dib_enc_bwd_version() == 3;                     // 8 chain-B warps (half a row per thread) instead of 4
+    // EBW = 8 (eight chain-B warps, half a row per thread, 640 threads) was built and HUNG on the B200 (round 2, run 4): not
+    // instantiated.  Measured with EBW = 4 at C0: 0.263 ms.
 #define DIB_BWD2(BF, RL)                                                                                                            \
-  (eb8 ? (e16 ? launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, true, 8>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 8))              \
-              : launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, false, 8>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 8)))            \
-       : (e16 ? launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, true, 4>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 4))              \
-              : launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, false, 4>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 4))))
+  (e16 ? launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, true, 4>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 4))                     \
+       : launch_fused(dib_enc_fused_bwd2_kernel<BF, RL, false, 4>, smem2, d.grid, m, Q, st, 32 * (kV2CtrlEA + 4)))
     if (d.bf16) return relu ? DIB_BWD2(true, true) : DIB_BWD2(true, false);
     return relu ? DIB_BWD2(false, true) : DIB_BWD2(false, false);
 #undef DIB_BWD2

@@ -290,7 +290,6 @@ int dib_debug_force_unfused(dib_model* h, int32_t on);
 
 /* process-wide kernel-variant switch for A/B measurements.  key 0: fused encoder backward kernel, value 1 = the
  * single-chain kernel of round 1, 2 = two chains on consecutive tiles (default; also DIB_ENC_BWD=1|2 in the environment).
- * 3 = the same with eight instead of four chain-B warps.
  * key 1: 16-bit integration FWD / DGRAD GEMMs, 1 = weight slice resident in shared memory, 0 = re-streamed per tile (default:
  * measured faster; also DIB_INT16_RB=0|1). */
 int dib_debug_set_variant(int32_t key, int32_t value);
