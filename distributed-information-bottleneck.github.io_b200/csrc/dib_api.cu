@@ -76,7 +76,7 @@ struct dib_model {
   int kl_stride = 0, num_sms = 148, part_rows = kMaxSplits;
   // 16-bit integration network path (dib_int16.cu); offsets are FLOAT offsets into the workspace
   bool int16_ok = false;
-  long long emb16_off = 0, demb16_off = 0, headpart_off = 0, dbpart_off = 0, eps16_off = 0;
+  long long emb16_off = 0, demb16_off = 0, headpart_off = 0, dbpart_off = 0, eps16_off = 0, a0g_off = 0;
   int head_stride = 0, dbpart_stride = 0;
   std::vector<long long> g16_off, dg16_off, w16_off;   // [1..Li], [1..Li], [0..Li-1]
   int head_blocks = 0, lossacc_cap = 0;
@@ -152,6 +152,7 @@ void plan(dib_model* h) {
     h->emb16_off = take(c, (B * FE + 1) / 2);
     h->demb16_off = take(c, (B * FE + 1) / 2);
     h->eps16_off = take(c, (B * FE + 1) / 2);      // the step's noise, 16-bit, from the forward to the backward kernel
+    h->a0g_off = take(c, B * h->F * 8);            // ... and its [pe|1] first-layer operand rows (16 x 16-bit per row and feature)
     h->g16_off.assign(h->Li + 1, 0); h->dg16_off.assign(h->Li + 1, 0); h->w16_off.assign(h->Li + 1, 0);
     for (int j = 1; j <= h->Li; ++j) {
       h->g16_off[j] = take(c, (B * h->int_arch[j - 1] + 1) / 2);
@@ -361,7 +362,7 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
     const bool i16 = h->int16_ok && !h->force_int32 && !enc_only;
     if (i16) { io.emb = nullptr; io.emb16 = c.ws + h->emb16_off; io.ldemb16 = h->F * h->E; }
     if (enc_only) io.emb = nullptr;      // the caller's network consumes user_emb; nothing downstream reads the workspace copy
-    if (training && !eps && dib_enc_bwd_version() >= 2) io.eps16 = c.ws + h->eps16_off;
+    if (training && !eps && dib_enc_bwd_version() >= 2) { io.eps16 = c.ws + h->eps16_off; io.a0g = c.ws + h->a0g_off; }
     prof_begin(c, "enc_fused_fwd");
     DIB_CUDA_OK(dib_enc_fused_forward(d, io, c.st));
     prof_end(c);
@@ -875,7 +876,7 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = n;
     io.eps = eps; io.seed = seed; io.step = step; io.step_dev = c.step_dev(); io.sample_offset = sample_offset;
     io.emb = nullptr; io.ldemb = 0; io.user_emb = nullptr; io.kl_part = nullptr; io.kl_stride = 0;
-    if (!eps && dib_enc_bwd_version() >= 2) io.eps16 = c.ws + h->eps16_off;      // written by this step's forward
+    if (!eps && dib_enc_bwd_version() >= 2) { io.eps16 = c.ws + h->eps16_off; io.a0g = c.ws + h->a0g_off; }   // written by this step's forward
     DibEncFusedBwdIO b;
     if (i16) { b.d_emb = nullptr; b.ldd = 0; b.d_emb16 = c.ws + h->demb16_off; b.ldd16 = h->F * h->E; }
     else { b.d_emb = c.ws + h->d_emb.off; b.ldd = h->d_emb.ld; }
@@ -1031,7 +1032,7 @@ int dib_encoders_backward(dib_model* h, const float* params, const float* x, con
     io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = n;
     io.eps = eps; io.seed = seed; io.step = step; io.step_dev = c.step_dev(); io.sample_offset = sample_offset;
     io.emb = nullptr; io.ldemb = 0; io.user_emb = nullptr; io.kl_part = nullptr; io.kl_stride = 0;
-    if (!eps && dib_enc_bwd_version() >= 2) io.eps16 = c.ws + h->eps16_off;      // written by this step's forward
+    if (!eps && dib_enc_bwd_version() >= 2) { io.eps16 = c.ws + h->eps16_off; io.a0g = c.ws + h->a0g_off; }   // written by this step's forward
     DibEncFusedBwdIO b;
     b.d_emb = d_emb; b.ldd = FE; b.beta_dev = bw; b.inv_batch = inv_global_batch;
     b.gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));

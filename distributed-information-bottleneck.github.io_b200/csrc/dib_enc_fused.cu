@@ -73,6 +73,8 @@ struct EncFusedParams {
   const unsigned int* step_dev;            // optional device addend of `step` (CUDA-Graph replay)
   float* emb; int ldemb; float* user_emb;  // outputs (forward); emb may be null when emb16 is given
   uint16_t* emb16; int ldemb16;            // 16-bit (fp16 / bf16) copy of emb for the 16-bit integration path (or null)
+  uint16_t* a0g;                           // [n, F, 16] 16-bit copy of the [pe|1] first-layer operand rows: written by the training
+                                           // forward, TMA-loaded by the two-chain backward instead of recomputing the encoding
   uint16_t* eps16;                         // [n, F*32] 16-bit copy of the Philox noise: written by the training forward, read by the
                                            // two-chain backward instead of regenerating it (the gradient operands are 16-bit anyway)
   float* kl_part; int kl_stride;           // [F][kl_stride] per-(feature, slot) KL partial sums
@@ -154,7 +156,7 @@ __device__ __forceinline__ void load_x(const float* xrow, int d, float (&xv)[kMa
 }
 template <bool BF16>
 __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, bool valid, const float (&xv)[kMaxFeatDim], int d,
-                                             int nfreq) {
+                                             int nfreq, uint16_t* gdst = nullptr) {
   float f[8];
   const int w_in = d * nfreq;
   int blk = (khalf * 8) / d, j = khalf * 8 - blk * d;      // one division per call; (blk, j) then advance with the column
@@ -173,8 +175,9 @@ __device__ __forceinline__ void write_a0_row(uint32_t a0, int r, int khalf, bool
     f[k] = v;
     if (++j == d) { j = 0; ++blk; }
   }
-  st_shared_v4(a0 + khalf * (TM * 16) + r * 16, pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
-               pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
+  const uint32_t p0 = pack2<BF16>(f[0], f[1]), p1 = pack2<BF16>(f[2], f[3]), p2 = pack2<BF16>(f[4], f[5]), p3 = pack2<BF16>(f[6], f[7]);
+  st_shared_v4(a0 + khalf * (TM * 16) + r * 16, p0, p1, p2, p3);
+  if (gdst) *reinterpret_cast<uint4*>(gdst) = make_uint4(p0, p1, p2, p3);       // hand-off to this step's backward kernel
 }
 
 // eps for embedding dims [dim0, dim0 + 8) of one row (dim0 a multiple of 8; eps_row points at dim0): explicit tensor or
@@ -199,7 +202,7 @@ __device__ __forceinline__ void noise8(const float* eps_row, unsigned long long 
   }
 }
 
-struct WeightMaps { CUtensorMap w0, w1, w2, b1, b2; };
+struct WeightMaps { CUtensorMap w0, w1, w2, b1, b2, a0lo, a0hi; };   // a0lo / a0hi: the two k-halves of the [pe|1] hand-off (bwd2)
 
 // one thread: stage a feature's packed weights (W0p, W1, W2, bias carriers) into shared memory
 __device__ __forceinline__ void load_weights(uint32_t sb, const WeightMaps& m, uint32_t bar, int f) {
@@ -322,7 +325,8 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
       if (slot < ntiles) {                                       // operand of the first tile
         const long long grow = (long long)slot * TM + ar;
         load_x(grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, xv);
-        write_a0_row<BF16>(sb + ((it & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow < P.n, xv, d, P.nfreq);
+        write_a0_row<BF16>(sb + ((it & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow < P.n, xv, d, P.nfreq,
+                           (P.a0g && grow < P.n) ? P.a0g + (grow * F + f) * 16 + khalf * 8 : nullptr);
         DIB_EPI_SIGNAL(bar_a0);
       }
       for (int t = slot; t < ntiles; t += nslots, ++it) {
@@ -339,7 +343,8 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h1);
         if (has_next) {      // stage the next tile's operand in the other A0 buffer: its layer-0 MMA then runs early
-          write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
+          write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq,
+                             (P.a0g && grow_n < P.n) ? P.a0g + (grow_n * F + f) * 16 + khalf * 8 : nullptr);
           DIB_EPI_SIGNAL(bar_a0);
         }
         noise8(ep, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, hsel * 16, valid, nrmA);   // while layer 1 runs
@@ -842,7 +847,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
   const uint32_t bar_w = bar, bar_a0 = bar + 8, bar_d0 = bar + 16, bar_h1 = bar + 24, bar_d1 = bar + 32,
                  bar_h2 = bar + 40, bar_d2 = bar + 48, bar_do = bar + 56, bar_dofree = bar + 64, bar_g2 = bar + 72,
                  bar_dz2 = bar + 80, bar_g1 = bar + 88, bar_dw1 = bar + 96, bar_dz1 = bar + 104, bar_wg0 = bar + 112 /* [2] */,
-                 tmem_slot = bar + 128;
+                 tmem_slot = bar + 128, bar_a0t = bar + 136;
   volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kV2OffBar + 128);
   constexpr int kEA = 8, kEB = EBW;   // epilogue warps of chain A / chain B
   constexpr int kV2Threads = 32 * (kV2CtrlEA + EBW);
@@ -861,6 +866,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
     mbar_init(bar_dz2, kEB); mbar_init(bar_dz1, kEB);
     mbar_init(bar_d0, 1); mbar_init(bar_d1, 1); mbar_init(bar_d2, 1); mbar_init(bar_dofree, 1); mbar_init(bar_g2, 1);
     mbar_init(bar_g1, 1); mbar_init(bar_dw1, 1); mbar_init(bar_wg0, 1); mbar_init(bar_wg0 + 8, 1);
+    mbar_init(bar_a0t, 1);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -898,13 +904,24 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
       // ================= MMA issuer A: the forward recompute chain
       if (lane == 0) {
         load_weights(sb, maps, bar_w, f);
+        // hand-off mode: the [pe|1] operand of a tile arrives by TMA from the forward kernel's copy (two 2 KB k-halves)
+        auto load_a0 = [&](uint32_t i, int k) {
+          const int row0 = (slot + k * nslots) * TM;
+          mbar_expect_tx(bar_a0t, 2 * TM * 16);
+          tma_load_3d(a0_of(i), &maps.a0lo, bar_a0t, 0, f, row0);
+          tma_load_3d(a0_of(i) + TM * 16, &maps.a0hi, bar_a0t, 0, f, row0);
+        };
+        if (EPS16 && ntl > 0) load_a0(it, 0);
         mbar_wait_backoff(bar_w, fit & 1);
         for (int k = 0; k < ntl; ++k) {
           const uint32_t i = it + k, ph = i & 1;
           const uint32_t a0 = a0_of(i);
+          if (EPS16) mbar_wait_backoff(bar_a0t, ph);
           mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
           issue_layer0<BF16>(sb, tR0, a0); umma_commit(bar_d0);
           mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
+          // chain A has started tile i, so tile i - 2 has retired and operand buffer (i + 1) % 3 is free
+          if (EPS16 && k + 1 < ntl) load_a0(i + 1, k + 1);
           issue_layer1<BF16>(sb, tR0, h1_of(i), a0); umma_commit(bar_d1);
           mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
           issue_layer2<BF16>(sb, tR0, h2_of(i), a0); umma_commit(bar_d2);
@@ -986,9 +1003,11 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
       const int ar = et & (TM - 1), khalf = et >> 7;          // [pe|1] operand: (row, k-half) staged by this thread
       float xv[kMaxFeatDim];
       if (any_tiles) {                                        // operand of the feature's first tile (both buffer sets are drained)
-        const long long grow0 = (long long)slot * TM + ar;
-        load_x(grow0 < P.n ? P.x + grow0 * P.ldx + xo : nullptr, d, xv);
-        write_a0_row<BF16>(a0_of(it), ar, khalf, grow0 < P.n, xv, d, P.nfreq);
+        if constexpr (!EPS16) {                               // (hand-off mode: issuer A loads it by TMA; the signal only frees R0)
+          const long long grow0 = (long long)slot * TM + ar;
+          load_x(grow0 < P.n ? P.x + grow0 * P.ldx + xo : nullptr, d, xv);
+          write_a0_row<BF16>(a0_of(it), ar, khalf, grow0 < P.n, xv, d, P.nfreq);
+        }
         DIB_EPI_SIGNAL(bar_a0);
       }
       for (int k = 0; k < ntl; ++k) {
@@ -1005,7 +1024,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
           const uint16_t* src = Q.d_emb16 + (valid ? grow : 0) * Q.ldd16 + f * 32 + csel * 16;
           dpre[0] = *reinterpret_cast<const uint4*>(src); dpre[1] = *reinterpret_cast<const uint4*>(src + 8);
         }
-        if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv);
+        if constexpr (!EPS16) { if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv); }
         const float* ep = (P.eps && valid) ? P.eps + (grow * F + f) * 32 + csel * 16 : P.eps;
         uint32_t nz16[8];            // this thread's 16 noise values, packed 16-bit (they multiply a 16-bit gradient)
         constexpr bool have_eps16 = EPS16;
@@ -1034,8 +1053,10 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
 #pragma unroll
           for (int j = 0; j < 4; ++j) nz16[4 + j] = pack2<BF16>(nrm[2 * j], nrm[2 * j + 1]);
         }
-        if (has_next)        // stage the next tile's [pe|1] operand: buffer (i + 1) % 3 was last read by tile i - 2 (retired, see above)
-          write_a0_row<BF16>(a0_of(i + 1), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
+        if constexpr (!EPS16) {
+          if (has_next)      // stage the next tile's [pe|1] operand: buffer (i + 1) % 3 was last read by tile i - 2 (retired, see above)
+            write_a0_row<BF16>(a0_of(i + 1), ar, khalf, grow_n < P.n, xv, d, P.nfreq);
+        }
         // ---- (mu, logvar) -> d(mu), d(logvar) -> dO tile, 8 embedding dims at a time.  The dO buffer is single: wait
         // until the previous tile's dO has been consumed.  After the LAST TMEM load chain A's region is free for the
         // next tile's layer 0, which then runs under the second half of this stage.
@@ -1260,12 +1281,29 @@ bool make_all_maps(WeightMaps* m, const void* packed, int F, bool bf16) {
          make_wmap(&m->b2, pk + kW0Elems + kW1Elems + kW2Elems + kB1Elems, EO, K0, F, bf16);
 }
 
+// [n, F, 16] 16-bit hand-off buffer -> per k-half a 3D map (8 elements, feature, row), box 8 x 1 x 128 rows: lands as the
+// unswizzled [128 rows][16 B] half of the first-layer operand; rows past n are zero-filled (their ones column included)
+bool make_a0_maps(WeightMaps* m, const void* a0g, long long n, int F, bool bf16) {
+  const uint16_t* base = static_cast<const uint16_t*>(a0g);
+  cuuint64_t dims[3] = {8, (cuuint64_t)F, (cuuint64_t)n};
+  cuuint64_t strides[2] = {32, (cuuint64_t)F * 32};
+  cuuint32_t box[3] = {8, 1, (cuuint32_t)TM};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  for (int half = 0; half < 2; ++half)
+    if (encode_fn2()(half ? &m->a0hi : &m->a0lo, dt, 3, const_cast<uint16_t*>(base + half * 8), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  return true;
+}
+
 void fill_params(EncFusedParams& P, const DibEncFusedDesc& d, const DibEncFusedIO& io) {
   P.x = io.x; P.ldx = io.ldx; P.x_off = d.x_off; P.fdim = d.fdim; P.nfreq = d.nfreq; P.params = io.params;
   P.b1_off = d.b1_off; P.b2_off = d.b2_off; P.eps = io.eps; P.seed = io.seed; P.step = io.step; P.step_dev = io.step_dev;
   P.sample_offset = io.sample_offset; P.emb = io.emb; P.ldemb = io.ldemb; P.user_emb = io.user_emb;
   P.kl_part = io.kl_part; P.kl_stride = io.kl_stride; P.F = d.F; P.n = io.n; P.act = d.act; P.alpha = d.alpha;
-  P.round_emb = 1; P.emb16 = static_cast<uint16_t*>(io.emb16); P.ldemb16 = io.ldemb16; P.eps16 = static_cast<uint16_t*>(io.eps16);
+  P.round_emb = 1; P.emb16 = static_cast<uint16_t*>(io.emb16); P.ldemb16 = io.ldemb16; P.eps16 = static_cast<uint16_t*>(io.eps16); P.a0g = static_cast<uint16_t*>(io.a0g);
 }
 
 template <typename K, typename A>
@@ -1332,7 +1370,9 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
   const bool relu = d.act == DIB_ACT_RELU;
   if (dib_enc_bwd_version() >= 2) {          // two chains on consecutive tiles (default)
     constexpr int smem2 = kV2OffBar + 256 + 1024;
-    const bool e16 = Q.f.eps16 != nullptr && Q.f.eps == nullptr;     // this step's forward left the noise in the workspace
+    // this step's forward left the noise and the [pe|1] operand rows in the workspace (16-bit hand-off buffers)
+    const bool e16 = Q.f.eps16 != nullptr && Q.f.a0g != nullptr && Q.f.eps == nullptr;
+    if (e16 && !make_a0_maps(&m, Q.f.a0g, io.n, d.F, d.bf16)) return cudaErrorInvalidValue;
     // EBW = 8 (eight chain-B warps, half a row per thread, 640 threads) was built and HUNG on the B200 (round 2, run 4): not
     // instantiated.  Measured with EBW = 4 at C0: 0.263 ms.
 #define DIB_BWD2(BF, RL)                                                                                                            \

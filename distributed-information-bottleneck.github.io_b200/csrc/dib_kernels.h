@@ -128,6 +128,7 @@ struct DibEncFusedIO {
   float* kl_part; int kl_stride;
   void* emb16 = nullptr; int ldemb16 = 0;   // optional fp16 copy of emb (16-bit integration path)
   void* eps16 = nullptr;                    // optional [n, F*32] 16-bit noise hand-off: forward writes, two-chain backward reads
+  void* a0g = nullptr;                      // optional [n, F, 16] 16-bit [pe|1] operand hand-off (same direction)
 };
 int dib_enc_bwd_version();
 void dib_enc_bwd_set_version(int v);
