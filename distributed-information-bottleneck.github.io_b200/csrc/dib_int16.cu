@@ -159,6 +159,24 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const int r = r0 + q * 32 + lane;
 #pragma unroll 1
       for (int cc = 0; cc < kBN; cc += 32) {
+        // the epilogue's own global operands (bias slice / the activation row that gates the gradient) are fetched BEFORE the
+        // TMEM load so that their latency hides under it (they sat behind tcgen05.wait::ld: 41 % of the FWD kernel's stall
+        // samples, profiles/r02_int16_ncu_full.txt)
+        const bool live = r < R && c0 + cc < C;
+        float4 bpre[8];
+        uint4 xpre[4];
+        if constexpr (MODE == DIB_GEMM_FWD) {
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bpre[j] = *reinterpret_cast<const float4*>(a.bias + c0 + cc + 4 * j);
+          }
+        }
+        if constexpr (MODE == DIB_GEMM_DGRAD) {
+          if (live && a.X) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xpre[j] = *reinterpret_cast<const uint4*>(a.X + (long long)r * a.ldx + c0 + cc + 8 * j);
+          }
+        }
         uint32_t v[32];
         if (nk > 0) { tmem_ld_32x32b_x32(tmem_base + acc * kBN + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v); tmem_ld_wait(); }
         else {
@@ -182,12 +200,12 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
               for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j + k]);
               if constexpr (MODE == DIB_GEMM_FWD) {
-                const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c + j), b1 = *reinterpret_cast<const float4*>(a.bias + c + j + 4);
+                const float4 b0 = bpre[j >> 2], b1 = bpre[(j >> 2) + 1];
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = dib_act(a.act, f[k] + bb[k], a.alpha);
               } else if (xs) {
-                const uint4 xv = *reinterpret_cast<const uint4*>(xs + j);
+                const uint4 xv = xpre[j >> 3];
                 const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -360,6 +378,21 @@ dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const int r = r0 + q * 32 + lane;
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
+        const bool live = r < R && c0 + cc < C;     // global operands of the epilogue first: their latency hides under the TMEM load
+        float4 bpre[8];
+        uint4 xpre[4];
+        if constexpr (MODE == DIB_GEMM_FWD) {
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bpre[j] = *reinterpret_cast<const float4*>(a.bias + c0 + cc + 4 * j);
+          }
+        }
+        if constexpr (MODE == DIB_GEMM_DGRAD) {
+          if (live && a.X) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xpre[j] = *reinterpret_cast<const uint4*>(a.X + (long long)r * a.ldx + c0 + cc + 8 * j);
+          }
+        }
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
         tmem_ld_wait();
@@ -373,12 +406,12 @@ dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j + k]);
             if constexpr (MODE == DIB_GEMM_FWD) {
-              const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c + j), b1 = *reinterpret_cast<const float4*>(a.bias + c + j + 4);
+              const float4 b0 = bpre[j >> 2], b1 = bpre[(j >> 2) + 1];
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
               for (int k = 0; k < 8; ++k) f[k] = dib_act(a.act, f[k] + bb[k], a.alpha);
             } else if (xs) {
-              const uint4 xv = *reinterpret_cast<const uint4*>(xs + j);
+              const uint4 xv = xpre[j >> 3];
               const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
