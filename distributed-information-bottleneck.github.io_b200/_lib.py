@@ -39,6 +39,7 @@ class DibConfig(ctypes.Structure):
         ("kl_loss_exponent", c_float),
         ("kl_loss_scale", c_float),
         ("encoder_kind", c_int32),
+        ("dropout_rate", c_float),
     ]
 
 

@@ -56,6 +56,8 @@ struct dib_model {
   long long ws_floats = 0;
   Buf pe, enc_out, emb, pred, d_pred, d_emb, d_out;
   std::vector<Buf> enc_act, d_enc;  // index 1..L  (output of layer j-1)
+  std::vector<Buf> enc_drop;        // index 1..L  (dropout_rate > 0: what layer j reads -- enc_act[j] after Keras Dropout)
+  float drop = 0.f;
   std::vector<Buf> int_act, d_int;  // index 1..Li
   long long part_off = 0, kl_part_off = 0, loss_part_off = 0, acc_part_off = 0, wshadow_off = 0;
   int nblk_max = 0;
@@ -126,6 +128,8 @@ void plan(dib_model* h) {
   h->enc_act.assign(h->L + 1, Buf());
   h->d_enc.assign(h->L + 1, Buf());
   for (int j = 1; j <= h->L; ++j) h->enc_act[j] = make_buf(c, B, h->enc_arch[j - 1], h->F);
+  h->enc_drop.assign(h->L + 1, Buf());
+  for (int j = 1; j <= h->L && h->drop > 0.f; ++j) h->enc_drop[j] = make_buf(c, B, h->enc_arch[j - 1], h->F);
   h->enc_out = make_buf(c, B, 2 * h->E, h->F);
   h->emb = make_buf(c, B, h->F * h->E, 1);
   h->int_act.assign(h->Li + 1, Buf());
@@ -179,9 +183,12 @@ void build_problems(dib_model* h, std::vector<DibGemmProblem>& v) {
   h->enc_fwd.assign(L + 1, -1); h->enc_dgrad.assign(L + 1, -1); h->enc_wgrad.assign(L + 1, -1);
   h->int_fwd.assign(Li + 1, -1); h->int_dgrad.assign(Li + 1, -1); h->int_wgrad.assign(Li + 1, -1);
   h->enc_maxK.assign(L + 1, 0);
-  auto encA = [&](int f, int j, long long& off, int& ld) {   // input of encoder layer j
+  auto encA = [&](int f, int j, long long& off, int& ld) {   // input of encoder layer j (after Dropout when there is one)
     if (j == 0) { off = h->pe.off + h->pe_off[f]; ld = h->ldpe; }
-    else { off = h->enc_act[j].off + f * h->enc_act[j].feat_stride; ld = h->enc_act[j].ld; }
+    else {
+      const Buf& b = h->drop > 0.f ? h->enc_drop[j] : h->enc_act[j];
+      off = b.off + f * b.feat_stride; ld = b.ld;
+    }
   };
   auto encDZ = [&](int f, int j, long long& off, int& ld) {  // grad wrt pre-activation output of layer j
     const Buf& b = j == L ? h->d_out : h->d_enc[j + 1];
@@ -326,7 +333,8 @@ int check_call(const dib_model* h, const void* params, const void* x, int64_t n,
 }
 
 // PE -> encoder layers (all features) -> reparam/KL -> integration layers -> loss/metrics
-int encode_all(const Ctx& c, const float* x, int ldx, int rnd, const int* row_index, int64_t n_src);
+struct NoiseKey { uint64_t seed; uint32_t step; uint64_t sample_offset; bool training; };
+int encode_all(const Ctx& c, const float* x, int ldx, int rnd, const int* row_index, int64_t n_src, const NoiseKey* key = nullptr);
 
 int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, uint64_t seed, uint32_t step,
                 uint64_t sample_offset, float inv_batch, bool training, float* user_pred, float* user_emb,
@@ -398,7 +406,8 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
       return 0;
     }
   } else {
-  if (encode_all(c, x, h->D, rnd, nullptr, 0)) return 1;
+  const NoiseKey nk{seed, step, sample_offset, training};
+  if (encode_all(c, x, h->D, rnd, nullptr, 0, &nk)) return 1;
   DibReparamArgs ra;
   ra.enc_out = c.ws + h->enc_out.off; ra.feat_stride = h->enc_out.feat_stride; ra.ldo = h->enc_out.ld;
   ra.eps = eps; ra.seed = seed; ra.step = step; ra.step_dev = c.step_dev(); ra.sample_offset = sample_offset;
@@ -430,7 +439,7 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
 
 // every feature encoder on n rows of x (deterministic part: mu | logvar incl. the offset) into the enc_out workspace
 // buffer: positional encoding + grouped GEMMs (models.py:72-78,106), or nb-bool's SimpleEncoder constants
-int encode_all(const Ctx& c, const float* x, int ldx, int rnd, const int* row_index, int64_t n_src) {
+int encode_all(const Ctx& c, const float* x, int ldx, int rnd, const int* row_index, int64_t n_src, const NoiseKey* key) {
   dib_model* h = c.h;
   if (h->simple) {
     prof_begin(c, "simple_enc_fwd");
@@ -445,6 +454,13 @@ int encode_all(const Ctx& c, const float* x, int ldx, int rnd, const int* row_in
     for (int j = 0; j <= h->L; ++j) {
       prof_begin(c, "enc_fwd_l", j);
       if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j], h->F, enc_fan_out(h, j), 0, 1, 0)) return 1;
+      if (j < h->L && h->drop > 0.f) {     // Keras Dropout after the hidden Dense (training) / identity copy (inference)
+        const bool tr = key && key->training;
+        DIB_CUDA_OK(dib_launch_dropout(c.ws + h->enc_act[j + 1].off, c.ws + h->enc_drop[j + 1].off, h->enc_act[j + 1].feat_stride,
+                                       h->enc_act[j + 1].ld, h->enc_arch[j], h->F, c.n, tr ? h->drop : 0.f, key ? key->seed : 0,
+                                       key ? key->step : 0, tr ? c.step_dev() : nullptr, key ? key->sample_offset : 0, j + 1, -1, 0,
+                                       rnd, c.st));
+      }
       prof_end(c);
     }
   }
@@ -592,6 +608,8 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   h->kl_exp = cfg->kl_loss_exponent == 0.f ? 1.f : cfg->kl_loss_exponent;
   h->kl_scale = cfg->kl_loss_scale == 0.f ? 1.f : cfg->kl_loss_scale;
   h->simple = cfg->encoder_kind == DIB_ENCODER_SIMPLE;
+  h->drop = cfg->dropout_rate;
+  if (!(h->drop >= 0.f && h->drop < 1.f)) { delete h; return fail("dib_create: dropout_rate must be in [0, 1)"); }
   if (cfg->encoder_kind != DIB_ENCODER_MLP && cfg->encoder_kind != DIB_ENCODER_SIMPLE) { delete h; return fail("dib_create: unknown encoder_kind"); }
   if (!(h->kl_exp > 0.f)) { delete h; return fail("dib_create: kl_loss_exponent must be > 0"); }
   if (h->simple) { h->L = 0; h->use_pe = 0; }
@@ -672,7 +690,7 @@ int dib_create(const dib_config* cfg, dib_model** out) {
   }
   // ---- fused encoder kernels: two hidden layers of 128, E = 32, first-layer fan-in (+ bias column) <= 16
   {
-    bool ok = want16(h) && h->L == 2 && h->enc_arch[0] == 128 && h->enc_arch[1] == 128 && h->E == 32;
+    bool ok = want16(h) && h->drop == 0.f && h->L == 2 && h->enc_arch[0] == 128 && h->enc_arch[1] == 128 && h->E == 32;
     for (int f = 0; ok && f < h->F; ++f) ok = h->w_in[f] + 1 <= 16;
     if (ok) {
       const int F = h->F;
@@ -763,8 +781,12 @@ int dib_encode_feature(dib_model* h, const float* params, int32_t feature, const
     if (rnd) DIB_CUDA_OK(dib_launch_round_copy(c.params, c.ws + h->wshadow_off, h->P, c.st));
     DIB_CUDA_OK(dib_launch_pe(x_i, h->fdims[f], h->x_off[f], h->d_col_src, h->d_col_freq, h->pe_off[f], h->pe_off[f] + wpad,
                               c.ws + h->pe.off, h->ldpe, 0, n, rnd, c.st));
-    for (int j = 0; j <= h->L; ++j)
+    for (int j = 0; j <= h->L; ++j) {
       if (gemm(c, DIB_GEMM_FWD, h->enc_fwd[j] + f, 1, enc_fan_out(h, j), 0, 1, 0)) return 1;
+      if (j < h->L && h->drop > 0.f)       // inference: Dropout is the identity
+        DIB_CUDA_OK(dib_launch_dropout(c.ws + h->enc_act[j + 1].off, c.ws + h->enc_drop[j + 1].off, h->enc_act[j + 1].feat_stride,
+                                       h->enc_act[j + 1].ld, h->enc_arch[j], h->F, n, 0.f, 0, 0, nullptr, 0, j + 1, f, 0, rnd, c.st));
+    }
   }
   DIB_CUDA_OK(dib_launch_add_logvar_offset(c.ws + h->enc_out.off, h->enc_out.feat_stride, h->enc_out.ld, h->F, h->E, n,
                                            h->lv_off, f, c.st));
@@ -910,6 +932,9 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     if (j >= 1) {
       prof_begin(c, "enc_dgrad_l", j);
       if (gemm(c, DIB_GEMM_DGRAD, h->enc_dgrad[j], h->F, h->enc_arch[j - 1], 0, 1, 0)) return 1;
+      if (h->drop > 0.f)                   // Dropout backward: the same keep mask, scaled
+        DIB_CUDA_OK(dib_launch_dropout(nullptr, c.ws + h->d_enc[j].off, h->d_enc[j].feat_stride, h->d_enc[j].ld, h->enc_arch[j - 1],
+                                       h->F, n, h->drop, seed, step, c.step_dev(), sample_offset, j, -1, 1, is_tc(h) ? 1 : 0, c.st));
       prof_end(c);
     }
   }
@@ -1053,6 +1078,9 @@ int dib_encoders_backward(dib_model* h, const float* params, const float* x, con
     for (int j = h->L; j >= 0; --j) {
       if (gemm(c, DIB_GEMM_WGRAD, h->enc_wgrad[j], h->F, enc_fan_out(h, j), h->enc_maxK[j], nsplit, (int)rps)) return 1;
       if (j >= 1 && gemm(c, DIB_GEMM_DGRAD, h->enc_dgrad[j], h->F, h->enc_arch[j - 1], 0, 1, 0)) return 1;
+      if (j >= 1 && h->drop > 0.f)
+        DIB_CUDA_OK(dib_launch_dropout(nullptr, c.ws + h->d_enc[j].off, h->d_enc[j].feat_stride, h->d_enc[j].ld, h->enc_arch[j - 1],
+                                       h->F, n, h->drop, seed, step, c.step_dev(), sample_offset, j, -1, 1, is_tc(h) ? 1 : 0, c.st));
     }
   }
   DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, nsplit, p_enc, grads_flat, c.st));

@@ -823,3 +823,54 @@ cudaError_t dib_launch_pe_plain(const float* x, int64_t n, int d, int nfreq, flo
   dib_note_launch();
   return cudaGetLastError();
 }
+
+
+// ================================================================================================
+// Keras Dropout on the hidden activations of the feature encoders (nb-radial cell 5), Philox-keyed
+// ================================================================================================
+namespace {
+
+__global__ void dib_dropout_kernel(const float* __restrict__ src, float* __restrict__ dst, long long feat_stride, int ld, int width,
+                                   int F, long long n, float rate, unsigned long long seed, unsigned int step,
+                                   const unsigned int* __restrict__ step_dev, unsigned long long sample_offset, int layer,
+                                   int feature, int backward, int round_out) {
+  const int nq = (width + 3) >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = feature >= 0 ? 1 : F;
+  if (idx >= n * nq * nf) return;
+  const int quad = (int)(idx % nq);
+  const long long row = (idx / nq) % n;
+  const int f = feature >= 0 ? feature : (int)(idx / ((long long)nq * n));
+  const long long base = (long long)f * feat_stride + row * ld + 4 * quad;
+  float keep[4] = {1.f, 1.f, 1.f, 1.f};
+  if (rate > 0.f) {
+    const unsigned long long sample = sample_offset + (unsigned long long)row;
+    uint32_t r[4];
+    dib_philox4x32_10((uint32_t)sample, (uint32_t)(sample >> 32) ^ ((uint32_t)f << 8),
+                      0x80000000u | ((uint32_t)layer << 24) | (uint32_t)quad, step + (step_dev ? step_dev[0] : 0u),
+                      (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const float inv_keep = 1.f / (1.f - rate);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) keep[k] = (((float)(r[k] >> 8) + 0.5f) * 5.9604644775390625e-08f >= rate) ? inv_keep : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (4 * quad + k < width) {
+      const float v = (backward ? dst[base + k] : src[base + k]) * keep[k];
+      dst[base + k] = dib_maybe_round(v, round_out);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t dib_launch_dropout(const float* src, float* dst, long long feat_stride, int ld, int width, int F, int64_t n, float rate,
+                               uint64_t seed, uint32_t step, const uint32_t* step_dev, uint64_t sample_offset, int layer,
+                               int feature, int backward, int round_out, cudaStream_t st) {
+  const long long total = (long long)n * ((width + 3) / 4) * (feature >= 0 ? 1 : F);
+  if (total <= 0) return cudaSuccess;
+  dib_dropout_kernel<<<nblocks(total, 256), 256, 0, st>>>(src, dst, feat_stride, ld, width, F, n, rate, seed, step, step_dev,
+                                                         sample_offset, layer, feature, backward, round_out);
+  dib_note_launch();
+  return cudaGetLastError();
+}

@@ -106,6 +106,14 @@ cudaError_t dib_launch_simple_enc_fwd(const float* x, int ldx, const int* x_off_
 cudaError_t dib_launch_simple_enc_wgrad(const float* x, int ldx, const int* x_off_dev, const float* d_out, long long feat_stride,
                                         int ldo, int F, int E, int64_t n, int nsplit, int rows_per_split, float* part,
                                         long long split_stride, cudaStream_t st);
+// Keras Dropout on the encoder activations [F][feat_stride] rows of ld floats, `width` live columns (nb-radial cell 5):
+//   backward == 0: dst = src * keep / (1 - rate)   (rate == 0: plain copy -- inference, where Dropout is the identity)
+//   backward == 1: dst *= keep / (1 - rate)         (src ignored)
+// keep from Philox (seed, step [+ *step_dev], sample_offset + row, feature, layer, column): oracle/philox.py :: dropout_keep
+cudaError_t dib_launch_dropout(const float* src, float* dst, long long feat_stride, int ld, int width, int F, int64_t n, float rate,
+                               uint64_t seed, uint32_t step, const uint32_t* step_dev, uint64_t sample_offset, int layer,
+                               int feature, int backward, int round_out, cudaStream_t st);
+
 // beta_eff = beta * scale * p * (sum_i stats[i] * inv_global_batch)^(p-1)   (d(beta*scale*KL^p)/dKL; p = 1: beta * scale)
 cudaError_t dib_launch_beta_eff(const float* stats, int F, float inv_global_batch, const float* beta_dev, float exponent,
                                 float scale, float* beta_eff_dev, cudaStream_t st);

@@ -180,8 +180,9 @@ class DistributedIBNet:
                  leaky_alpha: float = 0.2, logvar_offset: float = 0., kl_loss_exponent: float = 1.,
                  kl_loss_scale: float = 1.):
         _require_cuda()
-        if dropout_rate and dropout_rate > 0:
-            raise NotImplementedError("dropout_rate > 0 (nb-radial only, default 0) is not implemented")
+        if not (0.0 <= float(dropout_rate) < 1.0):
+            raise ValueError("dropout_rate must be in [0, 1)")
+        self.dropout_rate = float(dropout_rate)       # nb-radial cell 5: Dropout after every hidden encoder Dense (train steps only)
         if activation_fn not in _lib.ACTIVATIONS or output_activation_fn not in _lib.ACTIVATIONS:
             raise ValueError(f"unsupported activation {activation_fn!r}/{output_activation_fn!r}")
         if precision not in _lib.PRECISIONS:
@@ -276,7 +277,7 @@ class DistributedIBNet:
             output_activation_fn=_lib.ACTIVATIONS[self.output_activation_fn],
             loss=_lib.LOSSES[self._loss_kind], precision=_lib.PRECISIONS[self.precision], max_batch=int(max_batch),
             logvar_offset=self.logvar_offset, kl_loss_exponent=self.kl_loss_exponent, kl_loss_scale=self.kl_loss_scale,
-            encoder_kind=_lib.ENCODER_KINDS[self.encoder_kind])
+            encoder_kind=_lib.ENCODER_KINDS[self.encoder_kind], dropout_rate=self.dropout_rate)
 
     def _query_layout(self):
         with torch.cuda.device(self.device):

@@ -100,6 +100,9 @@ typedef struct dib_config {
   float   kl_loss_exponent;          /* nonlinear IB (nb-chaos cell 10): loss_IB = beta * kl_loss_scale * (sum_i KL_i)^exponent; */
   float   kl_loss_scale;             /*   0 or 1 / 0 or 1 = the linear beta * sum_i KL_i of models.py:118 */
   int32_t encoder_kind;              /* enum dib_encoder_kind */
+  float   dropout_rate;              /* nb-radial cell 5: tf.keras.layers.Dropout(rate) after every hidden Dense of the feature
+                                        encoders, active in dib_train_step only (Keras training=True); masks from the Philox
+                                        stream (oracle/philox.py :: dropout_keep).  Encoders then run on the unfused kernels. */
 } dib_config;
 
 typedef struct dib_model dib_model;

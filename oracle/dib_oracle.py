@@ -94,6 +94,8 @@ class DIBConfig:
     # 'mlp' (models.py:72-78) or 'simple': nb-bool cell 4 SimpleEncoder -- two trainable (1,1) constants per feature,
     #   output concat([x * mu_scaling, ones_like(x) * logvar]); needs d_i == feature_embedding_dimension
     encoder_kind: str = "mlp"
+    # nb-radial cell 5: tf.keras.layers.Dropout(dropout_rate) after every hidden Dense of the feature encoders (training only)
+    dropout_rate: float = 0.0
 
     @property
     def number_features(self):
@@ -184,15 +186,26 @@ def split_features(cfg: DIBConfig, x):
     return [x[:, offs[i]:offs[i + 1]] for i in range(cfg.number_features)]
 
 
-def encoder_forward(cfg: DIBConfig, layers, x_i, keep=False):
-    """models.py:72-78 Sequential: [PE] -> Dense(h,act)... -> Dense(2E) (linear).  a15 contract."""
+def encoder_forward(cfg: DIBConfig, layers, x_i, keep=False, drop=None):
+    """models.py:72-78 Sequential: [PE] -> Dense(h,act)... -> Dense(2E) (linear).  a15 contract.
+    ``drop(layer, shape)`` (training with dropout_rate > 0, nb-radial cell 5) returns the Keras Dropout scale mask
+    (0 or 1/(1-rate)) applied to the OUTPUT of hidden layer ``layer`` (1-based: the activation that feeds layer ``layer``).
+    With ``keep``: returns (out, acts, pres, masks) where acts[k] feeds layer k (after dropout), pres[k] is the same
+    activation before dropout (what act' is taken from), masks[k] the scale mask (None where there is none)."""
     h = positional_encoding(x_i, cfg.frequencies) if cfg.use_positional_encoding else x_i
-    acts = [h]
+    acts, pres, masks = [h], [h], [None]
     for k, (W, b) in enumerate(layers):
         z = h @ W + b
-        h = act_fwd(cfg.activation_fn, z, cfg.leaky_alpha) if k < len(layers) - 1 else z
+        if k < len(layers) - 1:
+            hh = act_fwd(cfg.activation_fn, z, cfg.leaky_alpha)
+            m = drop(k + 1, hh.shape) if drop is not None else None
+            h = hh * m if m is not None else hh
+            pres.append(hh); masks.append(m)
+        else:
+            h = z
+            pres.append(z); masks.append(None)
         acts.append(h)
-    return (h, acts) if keep else h
+    return (h, acts, pres, masks) if keep else h
 
 
 def task_loss_per_sample(loss, pred, y):
@@ -258,7 +271,15 @@ class ForwardResult:
     cache: dict = field(default_factory=dict)
 
 
-def forward(cfg: DIBConfig, flat_params, x, eps, beta, y=None, loss=None, keep=False, dtype=np.float64):
+def dropout_fn(cfg: DIBConfig, seed, step, sample_ids, feature, dtype=np.float64):
+    """The Philox-keyed Dropout masks of one feature encoder for a training step (see oracle/philox.py :: dropout_keep)."""
+    from . import philox
+    rate = np.float32(cfg.dropout_rate)
+    scale = dtype(1.0) / (dtype(1.0) - dtype(rate))
+    return lambda layer, shape: philox.dropout_keep(seed, step, sample_ids, feature, layer, shape[1], rate).astype(dtype) * scale
+
+
+def forward(cfg: DIBConfig, flat_params, x, eps, beta, y=None, loss=None, keep=False, dtype=np.float64, dropout=None):
     """models.py:96-123 with eps explicit: u = mu + exp(logvar/2)*eps  (== tf.random.normal(mean=mu,
     stddev=exp(logvar/2)), models.py:108).  eps: [B, F, E]."""
     p = np.asarray(flat_params, dtype=dtype)
@@ -274,13 +295,17 @@ def forward(cfg: DIBConfig, flat_params, x, eps, beta, y=None, loss=None, keep=F
             assert xs[i].shape[1] == E, "SimpleEncoder needs d_i == feature_embedding_dimension"
             o, acts = np.concatenate([xs[i] * ms, np.ones_like(xs[i]) * lvc], axis=-1), [xs[i]]
         else:
-            o, acts = encoder_forward(cfg, encoders[i], xs[i], keep=True)
+            # dropout = (seed, step, global sample ids) of a TRAINING step; None = inference (Keras: Dropout is the identity)
+            drop = dropout_fn(cfg, dropout[0], dropout[1], dropout[2], i, dtype) if (dropout is not None and cfg.dropout_rate > 0) else None
+            o, acts, pres, masks = encoder_forward(cfg, encoders[i], xs[i], keep=True, drop=drop)
         mu, lv = o[:, :E], o[:, E:] + cfg.logvar_offset               # models.py:106 tf.split(.,2,-1); nb-particle offset
         u = mu + np.exp(lv / 2.0) * eps[:, i, :]                      # models.py:108
         kl = (0.5 * (mu ** 2 + np.exp(lv) - lv - 1.0)).sum(axis=-1).mean()   # models.py:111-112
         embs.append(u)
         kls.append(kl)
-        enc_cache.append((acts, mu, lv))
+        if cfg.encoder_kind == "simple":
+            pres, masks = acts, [None] * len(acts)
+        enc_cache.append((acts, mu, lv, pres, masks))
     emb = np.concatenate(embs, axis=-1)                               # models.py:122
     h = emb
     int_acts = [h]
@@ -315,11 +340,12 @@ def effective_beta(cfg: DIBConfig, beta, kls):
     return float(beta) * cfg.kl_loss_scale * (1.0 if p == 1.0 else p * float(np.sum(kls)) ** (p - 1.0))
 
 
-def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.float64, batch_for_mean=None, d_emb=None):
+def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.float64, batch_for_mean=None, d_emb=None,
+                dropout=None):
     """Reverse mode through forward() (what GradientTape does inside Keras' train_step).
     Returns (flat grads of mean-loss, ForwardResult).  ``batch_for_mean`` lets a shard of a larger
     global batch produce its additive share (grads scale 1/B_global)."""
-    fr = forward(cfg, flat_params, x, eps, beta, y=y, loss=loss, keep=True, dtype=dtype)
+    fr = forward(cfg, flat_params, x, eps, beta, y=y, loss=loss, keep=True, dtype=dtype, dropout=dropout)
     B = x.shape[0] if batch_for_mean is None else batch_for_mean
     beta = effective_beta(cfg, beta, fr.kl_per_feature * (x.shape[0] / B))   # KL means are over the GLOBAL batch
     E = cfg.feature_embedding_dimension
@@ -347,7 +373,7 @@ def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.flo
         d_emb = dh
     enc_grads = []
     for i in range(cfg.number_features):
-        acts, mu, lv = c["enc"][i]
+        acts, mu, lv, pres, masks = c["enc"][i]
         layers = c["encoders"][i]
         du = d_emb[:, i * E:(i + 1) * E]
         sig = np.exp(lv / 2.0)
@@ -362,7 +388,10 @@ def train_grads(cfg: DIBConfig, flat_params, x, y, eps, beta, loss, dtype=np.flo
             W, _ = layers[k]
             g[k] = (acts[k].T @ dz, dz.sum(axis=0))
             if k > 0:
-                dz = (dz @ W.T) * act_grad_from_output(cfg.activation_fn, acts[k], cfg.leaky_alpha)
+                dh = dz @ W.T
+                if masks[k] is not None:
+                    dh = dh * masks[k]                               # Dropout backward: the same scale mask
+                dz = dh * act_grad_from_output(cfg.activation_fn, pres[k], cfg.leaky_alpha)
         enc_grads.append(g)
     flat = []
     for g in enc_grads:
@@ -432,7 +461,7 @@ def fit(cfg: DIBConfig, flat_params, x, y, *, loss, epochs, batch_size, lr,
         eps_fn: Callable[[int, np.ndarray], np.ndarray],
         perm_fn: Optional[Callable[[int, int], np.ndarray]] = None,
         beta_fn: Optional[Callable[[int], float]] = None,
-        validation_data=None, dtype=np.float64, adam_kwargs=None):
+        validation_data=None, dtype=np.float64, adam_kwargs=None, dropout_seed=None):
     """[KERAS] Model.fit epoch mechanics around the reference's call() (train.py:157-166):
       * per epoch: on_epoch_begin sets beta (models.py:147); indices shuffled (perm_fn(epoch, N));
         consecutive batches incl. a short last one;
@@ -464,7 +493,9 @@ def fit(cfg: DIBConfig, flat_params, x, y, *, loss, epochs, batch_size, lr,
         for b0 in range(0, N, batch_size):
             idx = perm[b0:b0 + batch_size]
             eps = eps_fn(step, np.arange(len(idx)))
-            g, fr = train_grads(cfg, p, x[idx], y[idx], eps, beta, loss, dtype=dtype)
+            # Dropout (nb-radial cell 5) is active in the training steps only; its masks share the step / row keying of the noise
+            drop = (dropout_seed, step, np.arange(len(idx))) if (dropout_seed is not None and cfg.dropout_rate > 0) else None
+            g, fr = train_grads(cfg, p, x[idx], y[idx], eps, beta, loss, dtype=dtype, dropout=drop)
             adam_step(p, g.astype(dtype), st, lr, **adam_kwargs)
             n = len(idx)
             sums["loss"] += fr.loss * n

@@ -79,3 +79,22 @@ def normal_noise(seed, step, sample_ids, num_features, embed_dim, dtype=np.float
     out[..., 2] = rb * np.cos(2.0 * np.pi * u3)
     out[..., 3] = rb * np.sin(2.0 * np.pi * u3)
     return out.reshape(n, num_features, 4 * q)[:, :, :embed_dim].astype(dtype)
+
+
+def dropout_keep(seed, step, sample_ids, feature, layer, width, rate):
+    """Keras Dropout keep-mask of one encoder activation [len(sample_ids), width] (nb-radial cell 5: Dropout(rate) after
+    every hidden Dense of the feature encoders), from the same counter-based generator as the noise so that the CUDA
+    kernels and this oracle agree and the result does not depend on the sharding:
+        counter = (sample_lo, sample_hi ^ (feature << 8), 0x80000000 | (layer << 24) | (column // 4), step)
+        u_k as above (k = column % 4);  keep = u_k >= rate   (probability 1 - rate)
+    Must match csrc/dib_elementwise.cu :: dib_dropout_kernel."""
+    sample_ids = np.asarray(sample_ids, dtype=np.uint64)
+    q = (width + 3) // 4
+    s_lo = (sample_ids & _MASK)[:, None]
+    s_hi = (sample_ids >> np.uint64(32))[:, None]
+    quad = np.arange(q, dtype=np.uint64)[None, :]
+    c1 = (s_hi ^ np.uint64(int(feature) << 8)) & _MASK
+    c2 = (np.uint64(0x80000000) | np.uint64(int(layer) << 24) | quad) & _MASK
+    r = philox4x32_10(s_lo, c1, c2, np.uint64(int(step) & 0xFFFFFFFF), int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+    u = np.stack([((rk >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -24) for rk in r], -1)
+    return (u.reshape(len(sample_ids), 4 * q)[:, :width] >= np.float32(rate))

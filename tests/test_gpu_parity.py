@@ -579,3 +579,32 @@ def test_bce_on_probabilities_and_library_entry_points():
     xs = rng.standard_normal((17, 3)).astype(np.float32)
     pe = dib_b200.PositionalEncoding(2 ** np.arange(1, 5))(xs)
     np.testing.assert_allclose(pe, O.positional_encoding(xs.astype(np.float64), [2, 4, 8, 16]), rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("tf32", 5e-3)])
+def test_dropout_in_feature_encoders_matches_oracle(precision, tol):
+    """nb-radial cell 5: `dropout_rate` puts a Keras Dropout after every hidden Dense of the feature encoders.  Train-step
+    gradients with the Philox-keyed masks against the oracle; inference (validation, model(x)) ignores dropout; `fit` runs."""
+    import dib_b200
+    cfg = O.DIBConfig([1] * 6, [128, 128], [256, 256, 256], 1, use_positional_encoding=False, activation_fn="tanh",
+                      dropout_rate=0.25)
+    rng = np.random.default_rng(12)
+    B = 640
+    x = rng.standard_normal((B, 6)).astype(np.float32)
+    y = (x[:, :1] * x[:, 1:2] > 0).astype(np.float32)
+    m = dib_b200.DistributedIBNet([1] * 6, [128, 128], [256, 256, 256], 1, use_positional_encoding=False, activation_fn="tanh",
+                                  dropout_rate=0.25, precision=precision, seed=5)
+    m.compile(optimizer=dib_b200.Adam(1e-4), loss=dib_b200.losses.BinaryCrossentropy(from_logits=True), metrics=["accuracy"])
+    m.noise_seed = 31
+    p = m.get_flat_weights()
+    m.beta.assign(0.01)
+    eps = philox.normal_noise(31, 4, np.arange(B), 6, 32, dtype=np.float64)
+    g, st = m.compute_gradients(x, y, step=4)
+    g_ref, fr = O.train_grads(cfg, p, x, y, eps, 0.01, O.LOSS_BCE_LOGITS, dropout=(31, 4, np.arange(B)))
+    assert rel_err(g.cpu().numpy(), g_ref) < tol
+    g_nodrop, _ = O.train_grads(cfg, p, x, y, eps, 0.01, O.LOSS_BCE_LOGITS)
+    assert rel_err(g_ref, g_nodrop) > 0.05                                   # the masks really change the step
+    pred = np.asarray(m(x, step=4))                                          # inference: Dropout is the identity
+    assert rel_err(pred, O.forward(cfg, p, x, eps, 0.01).pred) < tol
+    h = m.fit(x, y, epochs=2, batch_size=128, verbose=False, validation_data=(x[:128], y[:128])).history
+    assert np.isfinite(h["loss"]).all() and np.isfinite(h["val_loss"]).all()

@@ -325,3 +325,28 @@ def test_variant_gradients_match_finite_differences(variant):
         np.testing.assert_allclose(g[:n_enc], num[:n_enc], rtol=1e-5, atol=1e-7)
     else:
         np.testing.assert_allclose(g, num, rtol=1e-5, atol=1e-7)
+
+
+def test_dropout_oracle_gradients_and_mask_statistics():
+    """nb-radial cell 5 Dropout after every hidden encoder Dense: Philox-keyed masks keep a 1 - rate fraction, the
+    backward applies the same scale mask (finite differences), inference ignores it."""
+    rng = np.random.default_rng(0)
+    cfg = O.DIBConfig([2, 1], [6, 5], [5], 2, feature_embedding_dimension=3, activation_fn="tanh", dropout_rate=0.3)
+    p = O.glorot_uniform_params(cfg, rng, dtype=np.float64)
+    p = p + 0.01 * rng.standard_normal(p.size)
+    B = 9
+    x, y, eps = rng.standard_normal((B, 3)), rng.standard_normal((B, 2)), rng.standard_normal((B, 2, 3))
+    dr = (7, 3, np.arange(B) + 100)
+    g, _ = O.train_grads(cfg, p, x, y, eps, 0.3, O.LOSS_MSE, dropout=dr)
+    f = lambda q: O.forward(cfg, q, x, eps, 0.3, y=y, loss=O.LOSS_MSE, dropout=dr).loss
+    num = np.zeros_like(p)
+    for i in range(p.size):
+        d = np.zeros_like(p)
+        d[i] = 1e-6
+        num[i] = (f(p + d) - f(p - d)) / 2e-6
+    np.testing.assert_allclose(g, num, rtol=1e-5, atol=1e-7)
+    keep = philox.dropout_keep(7, 3, np.arange(20000), 1, 2, 8, 0.3)
+    assert abs(keep.mean() - 0.7) < 5e-3
+    assert not np.array_equal(keep, philox.dropout_keep(7, 4, np.arange(20000), 1, 2, 8, 0.3))      # a new mask every step
+    cfg0 = O.DIBConfig([2, 1], [6, 5], [5], 2, feature_embedding_dimension=3, activation_fn="tanh")
+    np.testing.assert_array_equal(O.forward(cfg, p, x, eps, 0.3).pred, O.forward(cfg0, p, x, eps, 0.3).pred)
