@@ -23,6 +23,19 @@ __device__ __forceinline__ float dib_act(int act, float z, float alpha) {
   }
 }
 
+// the same for the 16-bit-operand kernels, whose outputs are rounded to 11 / 8 significant bits anyway: tanh / sigmoid / elu on
+// the SFU approximations (tanh.approx: relative error ~2^-11; ex2 / rcp.approx ~2^-22) instead of the libm routines
+__device__ __forceinline__ float dib_act16(int act, float z, float alpha) {
+  switch (act) {
+    case DIB_ACT_RELU: return fmaxf(z, 0.f);
+    case DIB_ACT_TANH: { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z)); return t; }
+    case DIB_ACT_LEAKY_RELU: return z > 0.f ? z : alpha * z;
+    case DIB_ACT_SIGMOID: return __fdividef(1.f, 1.f + __expf(-z));
+    case DIB_ACT_ELU: return z > 0.f ? z : __expf(z) - 1.f;
+    default: return z;
+  }
+}
+
 __device__ __forceinline__ float dib_act_grad(int act, float h, float alpha) {
   switch (act) {
     case DIB_ACT_RELU: return h > 0.f ? 1.f : 0.f;

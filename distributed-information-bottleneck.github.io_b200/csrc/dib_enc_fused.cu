@@ -131,7 +131,7 @@ __device__ __forceinline__ void epilogue_to_tile(uint32_t taddr, uint32_t tile, 
       } else {
         float f[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = dib_act(act, __uint_as_float(v[j + k]), alpha);
+        for (int k = 0; k < 8; ++k) f[k] = dib_act16(act, __uint_as_float(v[j + k]), alpha);
         st_shared_v4(tile_chunk_addr(tile, r, col0 + hh * CH + j), pack2<BF16>(f[0], f[1]), pack2<BF16>(f[2], f[3]),
                      pack2<BF16>(f[4], f[5]), pack2<BF16>(f[6], f[7]));
       }
@@ -1067,6 +1067,12 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
           const bool du16 = Q.d_emb16 != nullptr;
           const uint32_t do_row = sDO + r * 128;
           const int r7 = r & 7;
+          // rows past the batch end contribute nothing: their upstream gradient and KL weight are zeroed once, here, instead of
+          // selecting per element.  With hs = sigma / 2 = exp2(lv * log2(e)/2 - 1):
+          //   d(mu)     = bs * mu + g
+          //   d(logvar) = g * eps * sigma/2 + bs/2 * (sigma^2 - 1) = (g * eps) * hs + ((2 bs * hs) * hs - bs/2)
+          const float bsv = valid ? bs : 0.f, gS = valid ? S : 0.f, bs2 = 2.f * bsv, hb = 0.5f * bsv;
+          if (!valid) { dpre[0] = make_uint4(0u, 0u, 0u, 0u); dpre[1] = make_uint4(0u, 0u, 0u, 0u); }
 #pragma unroll
           for (int e8 = 0; e8 < 16; e8 += 8) {
             uint32_t vm[8], vl[8];
@@ -1087,16 +1093,16 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
                 unpack2<BF16>(w0, g[0], g[1]); unpack2<BF16>(w1, g[2], g[3]);
               } else {
                 const float4 g4 = *reinterpret_cast<const float4*>(du + e8 + e0);
-                g[0] = g4.x * S; g[1] = g4.y * S; g[2] = g4.z * S; g[3] = g4.w * S;
+                g[0] = g4.x * gS; g[1] = g4.y * gS; g[2] = g4.z * gS; g[3] = g4.w * gS;
               }
               unpack2<BF16>(nz16[(e8 + e0) >> 1], nz[0], nz[1]); unpack2<BF16>(nz16[((e8 + e0) >> 1) + 1], nz[2], nz[3]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float mu = __uint_as_float(vm[e0 + j]), lv = __uint_as_float(vl[e0 + j]);
-                const float sg = __expf(0.5f * lv);
-                const float gs = g[j];
-                dm[e0 + j] = valid ? fmaf(bs, mu, gs) : 0.f;
-                dl[e0 + j] = valid ? fmaf(gs * nz[j], 0.5f * sg, bs * 0.5f * (sg * sg - 1.f)) : 0.f;
+                float hs;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(hs) : "f"(fmaf(lv, 0.72134752044448170f, -1.f)));
+                dm[e0 + j] = fmaf(bsv, mu, g[j]);
+                dl[e0 + j] = fmaf(g[j] * nz[j], hs, fmaf(bs2 * hs, hs, -hb));
               }
             }
             const int cm = (csel * 16 + e8) >> 3, cl = (32 + csel * 16 + e8) >> 3;       // 16-byte chunk indices

@@ -203,7 +203,7 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                 const float4 b0 = bpre[j >> 2], b1 = bpre[(j >> 2) + 1];
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                for (int k = 0; k < 8; ++k) f[k] = dib_act(a.act, f[k] + bb[k], a.alpha);
+                for (int k = 0; k < 8; ++k) f[k] = dib_act16(a.act, f[k] + bb[k], a.alpha);
               } else if (xs) {
                 const uint4 xv = xpre[j >> 3];
                 const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -409,7 +409,7 @@ dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               const float4 b0 = bpre[j >> 2], b1 = bpre[(j >> 2) + 1];
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int k = 0; k < 8; ++k) f[k] = dib_act(a.act, f[k] + bb[k], a.alpha);
+              for (int k = 0; k < 8; ++k) f[k] = dib_act16(a.act, f[k] + bb[k], a.alpha);
             } else if (xs) {
               const uint4 xv = xpre[j >> 3];
               const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
