@@ -502,6 +502,7 @@ int dib_debug_force_unfused(dib_model* h, int32_t on) {
 int dib_debug_set_variant(int32_t key, int32_t value) {
   if (key == 0) { dib_enc_bwd_set_version(value); return 0; }
   if (key == 1) { dib_int16_rb_set(value); return 0; }
+  if (key == 2) { dib_int16_head1_set(value); return 0; }
   return fail("dib_debug_set_variant: unknown key");
 }
 

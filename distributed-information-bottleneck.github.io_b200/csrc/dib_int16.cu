@@ -18,6 +18,7 @@
 #include "dib_sm100.cuh"
 
 int dib_int16_rb_enabled();
+int dib_int16_head1_enabled();
 
 namespace {
 
@@ -661,6 +662,140 @@ dib_int16_head_kernel(const uint16_t* __restrict__ g, int ldg, int K, const floa
   if (threadIdx.x == 0) { float s = 0.f; for (int ww = 0; ww < kHeadWarps; ++ww) s += sred[ww]; acc_part[blockIdx.x] = s; }
 }
 
+
+// ----------------------------------------------------------------------------------------------------
+// output head, single-output specialisation (C0, nb-radial: out = 1).  Same mapping as above (a warp per row, 8 hidden
+// units per lane) but 8 rows per pass: the eight row dot products are reduced with ONE transposing butterfly (9 shuffles
+// instead of 40), after which lane L holds the logit of row L & 7 and the loss / metric / d loss / d z arithmetic runs once
+// per pass, lane-parallel, instead of once per row on every lane (ncu: the generic kernel was issue-bound at 45 %).
+// ----------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(kHeadWarps * 32)
+dib_int16_head1_kernel(const uint16_t* __restrict__ g, int ldg, int K, const float* __restrict__ Wc, const float* __restrict__ bc,
+                       int out_act, int hid_act, float alpha, int loss, const float* __restrict__ y, long long n,
+                       float inv_batch, float gscale, uint16_t* __restrict__ dg, int lddg, float* __restrict__ user_pred,
+                       float* __restrict__ wpart, int wpart_stride, float* __restrict__ loss_part, float* __restrict__ acc_part) {
+  constexpr int KPT = 8, ROWS = 8;
+  __shared__ float red[kHeadWarps][KPT * 32];
+  __shared__ float sred[kHeadWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kHeadWarps + warp, nw = gridDim.x * kHeadWarps;
+  float w[KPT], dw[KPT], dbh[KPT];
+#pragma unroll
+  for (int i = 0; i < KPT; ++i) { w[i] = Wc[lane * KPT + i]; dw[i] = 0.f; dbh[i] = 0.f; }
+  const float bias = bc[0];
+  float db = 0.f, lsum = 0.f, asum = 0.f;
+  const bool train = dg != nullptr;
+  const int myr = lane & (ROWS - 1);
+
+  for (long long row0 = (long long)gw * ROWS; row0 < n; row0 += (long long)nw * ROWS) {
+    float h[ROWS][KPT], s[ROWS];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      const long long row = row0 + rr < n ? row0 + rr : n - 1;
+      const uint4 v = *reinterpret_cast<const uint4*>(g + row * ldg + lane * KPT);
+      unpack_h2<BF16>(v.x, h[rr][0], h[rr][1]); unpack_h2<BF16>(v.y, h[rr][2], h[rr][3]);
+      unpack_h2<BF16>(v.z, h[rr][4], h[rr][5]); unpack_h2<BF16>(v.w, h[rr][6], h[rr][7]);
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) a = fmaf(h[rr][i], w[i], a);
+      s[rr] = a;
+    }
+    // transposing butterfly: afterwards lane L holds the warp total of s[L & 7]
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const bool up = (lane & o) != 0;
+        const float send = up ? s[i] : s[i + o], keep = up ? s[i + o] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    float z = s[0];
+    z += __shfl_xor_sync(0xffffffffu, z, 8);
+    z += __shfl_xor_sync(0xffffffffu, z, 16);
+    // ---- lane L: compiled loss / metric / d loss / d z of row row0 + (L & 7)
+    const long long mrow = row0 + myr;
+    const bool live = mrow < n;
+    z = dib_act(out_act, z + bias, alpha);
+    float dz = 0.f;
+    if (live && y) {
+      const float t = y[mrow];
+      float l;
+      if (loss == DIB_LOSS_BCE_LOGITS) { l = fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z))); dz = 1.f / (1.f + expf(-z)) - t; }
+      else if (loss == DIB_LOSS_BCE_PROBS) {
+        const float ep = 1e-7f, pc = fminf(fmaxf(z, ep), 1.f - ep);
+        l = -(t * logf(pc + ep) + (1.f - t) * logf(1.f - pc + ep));
+        dz = (z > ep && z < 1.f - ep) ? -t / (pc + ep) + (1.f - t) / (1.f - pc + ep) : 0.f;
+      } else if (loss == DIB_LOSS_SPARSE_CE_LOGITS) { l = 0.f; dz = 0.f; }        // one class: the softmax is constant
+      else { const float d = z - t; l = d * d; dz = 2.f * d; }
+      const float acc = loss == DIB_LOSS_SPARSE_CE_LOGITS ? ((int)t == 0 ? 1.f : 0.f) : (((z > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f);
+      if (lane < ROWS) { lsum += l; asum += acc; }
+    }
+    if (user_pred && live && lane < ROWS) user_pred[mrow] = z;
+    if (train) {
+      dz = live ? dz * inv_batch * dib_act_grad(out_act, z, alpha) : 0.f;
+      if (lane < ROWS) db += dz;
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) {
+        const float dzr = __shfl_sync(0xffffffffu, dz, rr);
+        if (row0 + rr >= n) break;
+        const float ds = dzr * gscale;
+        float d[KPT];
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+          dw[i] = fmaf(h[rr][i], dzr, dw[i]);
+          d[i] = ds * w[i] * dib_act_grad(hid_act, h[rr][i], alpha);
+          dbh[i] += d[i];
+        }
+        *reinterpret_cast<uint4*>(dg + (row0 + rr) * lddg + lane * KPT) =
+            make_uint4(pack_h2<BF16>(d[0], d[1]), pack_h2<BF16>(d[2], d[3]), pack_h2<BF16>(d[4], d[5]), pack_h2<BF16>(d[6], d[7]));
+      }
+    }
+  }
+  // ---- per-block partials, fixed order over the block's warps (layout as the generic kernel: [dWc | dbc | colsum dg])
+  if (train) {
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) red[warp][lane * KPT + i] = dw[i];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) {
+        float a = 0.f;
+        for (int ww = 0; ww < kHeadWarps; ++ww) a += red[ww][lane * KPT + i];
+        wpart[(long long)blockIdx.x * wpart_stride + lane * KPT + i] = a;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) red[warp][lane * KPT + i] = dbh[i];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int i = 0; i < KPT; ++i) {
+        float a = 0.f;
+        for (int ww = 0; ww < kHeadWarps; ++ww) a += red[ww][lane * KPT + i];
+        wpart[(long long)blockIdx.x * wpart_stride + (long long)K + 1 + lane * KPT + i] = a;
+      }
+    }
+    __syncthreads();
+    db = dib_warp_sum(db);
+    if (lane == 0) sred[warp] = db;
+    __syncthreads();
+    if (threadIdx.x == 0) { float a = 0.f; for (int ww = 0; ww < kHeadWarps; ++ww) a += sred[ww]; wpart[(long long)blockIdx.x * wpart_stride + K] = a; }
+    __syncthreads();
+  }
+  lsum = dib_warp_sum(lsum);
+  if (lane == 0) sred[warp] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) { float a = 0.f; for (int ww = 0; ww < kHeadWarps; ++ww) a += sred[ww]; loss_part[blockIdx.x] = a; }
+  __syncthreads();
+  asum = dib_warp_sum(asum);
+  if (lane == 0) sred[warp] = asum;
+  __syncthreads();
+  if (threadIdx.x == 0) { float a = 0.f; for (int ww = 0; ww < kHeadWarps; ++ww) a += sred[ww]; acc_part[blockIdx.x] = a; }
+}
+
 template <bool BF16>
 __global__ void dib_f32_to_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -752,6 +887,10 @@ int rb_pick_bn(int T, int C) {
 
 }  // namespace
 
+static int g_int16_head1 = 1;           // single-output head: 8-rows-per-pass kernel (1, default) or the generic one (0)
+int dib_int16_head1_enabled() { return g_int16_head1; }
+void dib_int16_head1_set(int on) { g_int16_head1 = on ? 1 : 0; }
+
 static int g_int16_rb = -1;
 int dib_int16_rb_enabled() {
   // measured on B200 at C0 (profiles/r02_int16_resident_b_ab.json): slower than the streamed kernels (fwd 48 vs 37 / 32 us,
@@ -835,7 +974,12 @@ cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const
       out_act, hid_act, alpha, loss, y, n, inv_batch, gscale, static_cast<uint16_t*>(dg), lddg, user_pred, wpart, wpart_stride, \
       loss_part, acc_part)
 #define DIB_HEAD(OUT) do { if (bf16) DIB_HEAD_T(OUT, true); else DIB_HEAD_T(OUT, false); } while (0)
-  if (out_dim == 1) DIB_HEAD(1);
+  if (out_dim == 1 && dib_int16_head1_enabled()) {
+    if (bf16) dib_int16_head1_kernel<true><<<nblocks, kHeadWarps * 32, 0, st>>>(static_cast<const uint16_t*>(g), ldg, K, Wc, bc, out_act,
+        hid_act, alpha, loss, y, n, inv_batch, gscale, static_cast<uint16_t*>(dg), lddg, user_pred, wpart, wpart_stride, loss_part, acc_part);
+    else dib_int16_head1_kernel<false><<<nblocks, kHeadWarps * 32, 0, st>>>(static_cast<const uint16_t*>(g), ldg, K, Wc, bc, out_act,
+        hid_act, alpha, loss, y, n, inv_batch, gscale, static_cast<uint16_t*>(dg), lddg, user_pred, wpart, wpart_stride, loss_part, acc_part);
+  } else if (out_dim == 1) DIB_HEAD(1);
   else if (out_dim == 2) DIB_HEAD(2);
   else if (out_dim <= 4) DIB_HEAD(4);
   else if (out_dim <= 8) DIB_HEAD(8);

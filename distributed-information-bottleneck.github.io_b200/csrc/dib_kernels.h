@@ -168,6 +168,7 @@ cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_d
 int dib_int16_head_blocks(int num_sms);
 int dib_int16_rb_enabled();
 void dib_int16_rb_set(int on);
+void dib_int16_head1_set(int on);
 cudaError_t dib_int16_head(const void* g, int ldg, int K, const float* Wc, const float* bc, int out_dim, int out_act, int hid_act,
                            float alpha, int loss, const float* y, long long n, float inv_batch, float gscale, void* dg, int lddg,
                            float* user_pred, float* wpart, int wpart_stride, float* loss_part, float* acc_part, int nblocks,

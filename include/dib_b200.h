@@ -294,7 +294,9 @@ int dib_debug_force_unfused(dib_model* h, int32_t on);
 /* process-wide kernel-variant switch for A/B measurements.  key 0: fused encoder backward kernel, value 1 = the
  * single-chain kernel of round 1, 2 = two chains on consecutive tiles (default; also DIB_ENC_BWD=1|2 in the environment).
  * key 1: 16-bit integration FWD / DGRAD GEMMs, 1 = weight slice resident in shared memory, 0 = re-streamed per tile (default:
- * measured faster; also DIB_INT16_RB=0|1). */
+ * measured faster; also DIB_INT16_RB=0|1).
+ * key 2: fused output head for output_dimensionality == 1, 1 = eight rows per pass with a lane-parallel loss (default), 0 = the
+ * generic kernel. */
 int dib_debug_set_variant(int32_t key, int32_t value);
 
 /* text of the last error raised on this thread ("" if none). */

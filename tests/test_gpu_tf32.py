@@ -159,3 +159,35 @@ def test_int16_resident_weight_gemms_match_streamed_kernels_bitwise(shape):
         _lib.check(lib.dib_debug_set_variant(1, 0))
     for a, b in zip(res[0], res[1]):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("loss_name", ["bce_logits", "mse"])
+def test_single_output_head_kernel_matches_generic_head(loss_name):
+    """The out = 1 output-head kernel (8 rows per pass, transposing butterfly, lane-parallel loss) against the generic head:
+    same arithmetic per row, a different (still fixed) summation tree for the 256-term logit -> fp32 round-off only."""
+    from dib_b200 import _lib
+    lib = _lib.load()
+    cfg = O.DIBConfig([1] * 16, [128, 128], [256, 256], 1)
+    rng = np.random.default_rng(6)
+    p = O.glorot_uniform_params(cfg, rng)
+    p = p + (p == 0) * (0.05 * rng.standard_normal(p.size)).astype(np.float32)
+    B = 128 * 21 + 5
+    x = rng.standard_normal((B, 16)).astype(np.float32)
+    y = (x[:, :1] * x[:, 1:2] > 0).astype(np.float32) if loss_name == "bce_logits" else rng.standard_normal((B, 1)).astype(np.float32)
+    res = {}
+    try:
+        for v in (0, 1):
+            _lib.check(lib.dib_debug_set_variant(2, v))
+            m = build_model(cfg, precision="fp16", loss=loss_name)
+            m.set_flat_weights(p)
+            m.beta.assign(0.02)
+            pred = m(x, step=2)
+            g, st = m.compute_gradients(x, y, step=2)
+            g2, _ = m.compute_gradients(x, y, step=2)
+            assert torch.equal(g, g2)                                            # deterministic
+            res[v] = (np.asarray(pred), g.cpu().numpy(), st.cpu().numpy())
+    finally:
+        _lib.check(lib.dib_debug_set_variant(2, 1))
+    assert rel_err(res[1][0], res[0][0]) < 1e-5
+    assert rel_err(res[1][1], res[0][1]) < 2e-4          # the 16-bit rounding of dg can flip on a 1-ulp change of the logit
+    np.testing.assert_allclose(res[1][2], res[0][2], rtol=1e-5)
