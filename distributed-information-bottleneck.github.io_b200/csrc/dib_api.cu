@@ -82,6 +82,7 @@ struct dib_model {
   int head_stride = 0, dbpart_stride = 0;
   std::vector<long long> g16_off, dg16_off, w16_off;   // [1..Li], [1..Li], [0..Li-1]
   int head_blocks = 0, lossacc_cap = 0;
+  int head_used = 0;                // rows of the head partials the last forward wrote (fused tail kernel: its CTA count)
   // custom-step variants
   float lv_off = 0.f, kl_exp = 1.f, kl_scale = 1.f;
   const uint32_t* step_dev = nullptr;  // optional device-resident addend of the Philox step word (dib_set_noise_step_device)
@@ -386,15 +387,33 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
       for (int j = 0; j < h->Li; ++j)
         DIB_CUDA_OK(dib_int16_convert(c.params + h->intW[j], c.ws + h->w16_off[j], (long long)int_fan_in(h, j) * int_fan_out(h, j), bf, c.st));
       prof_end(c);
-      for (int j = 0; j < h->Li; ++j) {
+      const int Kh = h->int_arch[h->Li - 1];
+      const float gscale = training ? exp2f(ceilf(log2f(1.f / inv_batch))) : 1.f;
+      // single-output models: the last two hidden layers and the head run as ONE kernel (g2 stays on chip)
+      const bool fwd2 = h->Li >= 2 && dib_int16_fwd2_ok(int_fan_in(h, h->Li - 2), int_fan_out(h, h->Li - 2), int_fan_out(h, h->Li - 1), h->out);
+      const int n_plain = fwd2 ? h->Li - 2 : h->Li;
+      for (int j = 0; j < n_plain; ++j) {
         prof_begin(c, "int16_fwd_l", j);
         DIB_CUDA_OK(dib_int16_fwd(j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]), int_fan_in(h, j),
                                   c.ws + h->w16_off[j], c.params + h->intB[j], c.ws + h->g16_off[j + 1], int_fan_out(h, j), c.n,
                                   int_fan_in(h, j), int_fan_out(h, j), h->act, h->alpha, bf, c.st));
         prof_end(c);
       }
-      const int Kh = h->int_arch[h->Li - 1];
-      const float gscale = training ? exp2f(ceilf(log2f(1.f / inv_batch))) : 1.f;
+      if (fwd2) {
+        const int j0 = h->Li - 2, j1 = h->Li - 1;
+        prof_begin(c, "int16_fwd2_head");
+        DIB_CUDA_OK(dib_int16_fwd2_head(j0 == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j0]), int_fan_in(h, j0),
+                                        int_fan_in(h, j0), c.ws + h->w16_off[j0], c.params + h->intB[j0], c.ws + h->w16_off[j1],
+                                        c.params + h->intB[j1], c.ws + h->g16_off[j1], c.params + h->intW[h->Li], c.params + h->intB[h->Li],
+                                        h->act, h->out_act, h->alpha, h->loss, y, c.n, inv_batch, gscale,
+                                        training ? (void*)(c.ws + h->dg16_off[h->Li]) : nullptr, user_pred, c.ws + h->headpart_off,
+                                        h->head_stride, c.ws + h->loss_part_off, c.ws + h->acc_part_off, &h->head_used, bf, c.st));
+        DIB_CUDA_OK(dib_launch_finalize_stats(c.ws + h->kl_part_off, h->kl_stride, nblk_kl, c.ws + h->loss_part_off,
+                                              c.ws + h->acc_part_off, h->head_used, h->F, c.n, y != nullptr, out_stats, c.st));
+        prof_end(c);
+        return 0;
+      }
+      h->head_used = h->head_blocks;
       prof_begin(c, "int16_head_loss");
       DIB_CUDA_OK(dib_int16_head(c.ws + h->g16_off[h->Li], Kh, Kh, c.params + h->intW[h->Li], c.params + h->intB[h->Li], h->out,
                                  h->out_act, h->act, h->alpha, h->loss, y, c.n, inv_batch, gscale,
@@ -503,6 +522,8 @@ int dib_debug_set_variant(int32_t key, int32_t value) {
   if (key == 0) { dib_enc_bwd_set_version(value); return 0; }
   if (key == 1) { dib_int16_rb_set(value); return 0; }
   if (key == 2) { dib_int16_head1_set(value); return 0; }
+  if (key == 3) { dib_int16_fwd2_set(value); return 0; }
+  if (key == 4) { dib_int16_2sm_set(value); return 0; }
   return fail("dib_debug_set_variant: unknown key");
 }
 
@@ -845,7 +866,7 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     const int row_tiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
     const long long p_head = h->intW[h->Li];
     // bias gradient of the last hidden layer: column sums of dg accumulated by the output head
-    DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off + (long long)Kh * h->out + h->out, h->head_stride, h->head_blocks, Kh,
+    DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off + (long long)Kh * h->out + h->out, h->head_stride, h->head_used, Kh,
                                        1.f / gscale, grads_flat + h->intB[h->Li - 1], c.st));
     for (int j = h->Li - 1; j >= 0; --j) {
       const void* in_j = j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]);
@@ -866,7 +887,7 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     for (int j = 0; j < h->Li; ++j)     // hidden-layer kernels: batch-split partials (their biases were reduced above)
       DIB_CUDA_OK(dib_launch_reduce_partials(part + h->intW[j], h->Pp, nsplit, (long long)int_fan_in(h, j) * int_fan_out(h, j),
                                              grads_flat + h->intW[j], c.st));
-    DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off, h->head_stride, h->head_blocks, h->P - p_head, 1.f, grads_flat + p_head, c.st));
+    DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off, h->head_stride, h->head_used, h->P - p_head, 1.f, grads_flat + p_head, c.st));
     prof_end(c);
   } else if (phA) {
     // integration network backward (GradientTape through models.py:122)

@@ -218,28 +218,34 @@ __device__ __forceinline__ void load_weights(uint32_t sb, const WeightMaps& m, u
 }
 
 // the three forward contractions of one tile, each preceded by its bias-carrier step (issued by one thread)
-template <bool BF16>
+// W = true: called by a fully converged warp, one elected lane issues (operands stay in uniform registers, no waterfall loop)
+template <bool BF16, bool W>
+__device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (W) umma_f16_w(d_tmem, adesc, bdesc, idesc, accumulate);
+  else umma_f16<BF16>(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+template <bool BF16, bool W = false>
 __device__ __forceinline__ void issue_layer0(uint32_t sb, uint32_t tD, uint32_t a0) {
   constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, HID);
-  umma_f16<BF16>(tD, umma_smem_desc(a0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffW0, K0 * 128, 1024), id, 0u);
+  umma_issue<BF16, W>(tD, umma_desc16(a0 >> 4, TM * 16, 128, kLayoutNone), umma_desc16((sb >> 4) + ((kOffW0) >> 4), K0 * 128, 1024), id, 0u);
 }
-template <bool BF16>
+template <bool BF16, bool W = false>
 __device__ __forceinline__ void issue_layer1(uint32_t sb, uint32_t tD, uint32_t h1, uint32_t a0) {
   constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, HID);
-  umma_f16<BF16>(tD, umma_smem_desc(a0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffBb1, K0 * 128, 1024), id, 0u);
+  umma_issue<BF16, W>(tD, umma_desc16(a0 >> 4, TM * 16, 128, kLayoutNone), umma_desc16((sb >> 4) + ((kOffBb1) >> 4), K0 * 128, 1024), id, 0u);
 #pragma unroll
   for (int kk = 0; kk < HID / 16; ++kk)
-    umma_f16<BF16>(tD, umma_smem_desc(h1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
-                   umma_smem_desc(sb + kOffW1 + kk * 2048, kPanel, 1024), id, 1u);
+    umma_issue<BF16, W>(tD, umma_desc16((h1 >> 4) + (((kk >> 2) * kPanel + (kk & 3) * 32) >> 4), 16, 1024),
+                   umma_desc16((sb >> 4) + ((kOffW1 + kk * 2048) >> 4), kPanel, 1024), id, 1u);
 }
-template <bool BF16>
+template <bool BF16, bool W = false>
 __device__ __forceinline__ void issue_layer2(uint32_t sb, uint32_t tD, uint32_t h2, uint32_t a0) {
   constexpr uint32_t id = umma_idesc(BF16 ? 1u : 0u, 0, 1, EO);
-  umma_f16<BF16>(tD, umma_smem_desc(a0, TM * 16, 128, kLayoutNone), umma_smem_desc(sb + kOffBb2, K0 * 128, 1024), id, 0u);
+  umma_issue<BF16, W>(tD, umma_desc16(a0 >> 4, TM * 16, 128, kLayoutNone), umma_desc16((sb >> 4) + ((kOffBb2) >> 4), K0 * 128, 1024), id, 0u);
 #pragma unroll
   for (int kk = 0; kk < HID / 16; ++kk)
-    umma_f16<BF16>(tD, umma_smem_desc(h2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
-                   umma_smem_desc(sb + kOffW2 + kk * 2048, kPanel, 1024), id, 1u);
+    umma_issue<BF16, W>(tD, umma_desc16((h2 >> 4) + (((kk >> 2) * kPanel + (kk & 3) * 32) >> 4), 16, 1024),
+                   umma_desc16((sb >> 4) + ((kOffW2 + kk * 2048) >> 4), kPanel, 1024), id, 1u);
 }
 
 #define DIB_EPI_SIGNAL(bar)            \
@@ -295,22 +301,21 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
 
   for (int f = f_first; f < F; f += f_step, ++fit) {
     if (warp == 0) {
-      if (lane == 0) {
-        load_weights(sb, maps, bar_w, f);
-        mbar_wait_backoff(bar_w, fit & 1);
-        for (int t = slot; t < ntiles; t += nslots, ++it) {
-          const uint32_t ph = it & 1;
-          mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
-          const uint32_t a0 = sb + ((it & 1) ? kOffFwdA0b : kOffA0);
-          issue_layer0<BF16>(sb, tR0, a0); umma_commit(bar_d0);
-          mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
-          issue_layer1<BF16>(sb, tR0, hbuf, a0); umma_commit(bar_d1);
-          mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
-          issue_layer2<BF16>(sb, tR1, hbuf, a0); umma_commit(bar_d2);
-          if (t + nslots >= ntiles) mbar_wait_backoff(bar_d2, ph);   // drain before the next feature's weights land
-        }
-      } else {
-        for (int t = slot; t < ntiles; t += nslots) ++it;
+      // the whole warp walks the issue sequence (uniform control flow: descriptors and barrier addresses stay in uniform
+      // registers); one elected lane executes each tcgen05 instruction
+      if (lane == 0) load_weights(sb, maps, bar_w, f);
+      __syncwarp();
+      mbar_wait_backoff(bar_w, fit & 1);
+      for (int t = slot; t < ntiles; t += nslots, ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
+        const uint32_t a0 = sb + ((it & 1) ? kOffFwdA0b : kOffA0);
+        issue_layer0<BF16, true>(sb, tR0, a0); umma_commit_w(bar_d0);
+        mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
+        issue_layer1<BF16, true>(sb, tR0, hbuf, a0); umma_commit_w(bar_d1);
+        mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
+        issue_layer2<BF16, true>(sb, tR1, hbuf, a0); umma_commit_w(bar_d2);
+        if (t + nslots >= ntiles) mbar_wait_backoff(bar_d2, ph);   // drain before the next feature's weights land
       }
       __syncwarp();
     } else {
@@ -560,36 +565,36 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           mbar_wait_backoff(bar_do, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffDO + kk * 32, 16, 1024),
-                           umma_smem_desc(sb + kOffW2 + kk * 32, 16, 1024), id_kk_128, kk > 0 ? 1u : 0u);
+            umma_f16<BF16>(tR1, umma_desc16((sb >> 4) + ((kOffDO + kk * 32) >> 4), 16, 1024),
+                           umma_desc16((sb >> 4) + ((kOffW2 + kk * 32) >> 4), 16, 1024), id_kk_128, kk > 0 ? 1u : 0u);
           umma_commit(bar_g2);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWG2, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(sb + kOffDO + kk * 2048, kPanel, 1024), id_mm_64, (first && kk == 0) ? 0u : 1u);
+            umma_f16<BF16>(tWG2, umma_desc16((sb >> 4) + ((kOffH2 + kk * 2048) >> 4), kPanel, 1024),
+                           umma_desc16((sb >> 4) + ((kOffDO + kk * 2048) >> 4), kPanel, 1024), id_mm_64, (first && kk == 0) ? 0u : 1u);
           // db2 += dO^T [pe|1]: M = 128 is formed by dO (64 columns) and the panel that follows it in shared memory
           // (dz2, finite garbage at this point): TMEM lanes 64..127 of this accumulator are never read.
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWB2, umma_smem_desc(sb + kOffDO + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+            umma_f16<BF16>(tWB2, umma_desc16((sb >> 4) + ((kOffDO + kk * 2048) >> 4), kPanel, 1024),
+                           umma_desc16((a0 >> 4) + ((kk * 256) >> 4), 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           // ---- layer 1 backward: G1 = dz2 W1^T ; dW1 += h1^T dz2 ; db1 += dz2^T [pe|1]
           mbar_wait_backoff(bar_dz2, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tR1, umma_smem_desc(sb + kOffDZ2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
-                           umma_smem_desc(sb + kOffW1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024), id_kk_128,
+            umma_f16<BF16>(tR1, umma_desc16((sb >> 4) + ((kOffDZ2 + (kk >> 2) * kPanel + (kk & 3) * 32) >> 4), 16, 1024),
+                           umma_desc16((sb >> 4) + ((kOffW1 + (kk >> 2) * kPanel + (kk & 3) * 32) >> 4), 16, 1024), id_kk_128,
                            kk > 0 ? 1u : 0u);
           umma_commit(bar_g1);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWG1, umma_smem_desc(h1buf + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(sb + kOffDZ2 + kk * 2048, kPanel, 1024), id_mm_128, (first && kk == 0) ? 0u : 1u);
+            umma_f16<BF16>(tWG1, umma_desc16((h1buf >> 4) + ((kk * 2048) >> 4), kPanel, 1024),
+                           umma_desc16((sb >> 4) + ((kOffDZ2 + kk * 2048) >> 4), kPanel, 1024), id_mm_128, (first && kk == 0) ? 0u : 1u);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWB1, umma_smem_desc(sb + kOffDZ2 + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+            umma_f16<BF16>(tWB1, umma_desc16((sb >> 4) + ((kOffDZ2 + kk * 2048) >> 4), kPanel, 1024),
+                           umma_desc16((a0 >> 4) + ((kk * 256) >> 4), 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           // ---- the NEXT tile's layer 0 (its operand was staged long ago; R0 is free since this tile's h2 epilogue):
           // its first epilogue then follows this tile's last one without an MMA round trip in between
@@ -601,8 +606,8 @@ dib_enc_fused_bwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           mbar_wait_backoff(bar_dz1, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWG0, umma_smem_desc(sb + kOffH2 + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16,
+            umma_f16<BF16>(tWG0, umma_desc16((sb >> 4) + ((kOffH2 + kk * 2048) >> 4), kPanel, 1024),
+                           umma_desc16((a0 >> 4) + ((kk * 256) >> 4), 128, TM * 16, kLayoutNone), id_mm_16,
                            (first && kk == 0) ? 0u : 1u);
           umma_commit(bar_wg);
           if (t + nslots >= ntiles) mbar_wait_backoff(bar_wg, ph);
@@ -902,35 +907,41 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
       const bool any_tiles = ntl > 0; (void)any_tiles;
       if (warp == 0) {
       // ================= MMA issuer A: the forward recompute chain
-      if (lane == 0) {
-        load_weights(sb, maps, bar_w, f);
+      // (the whole warp walks the issue sequence -- uniform control flow keeps descriptors and barrier addresses in uniform
+      //  registers -- and one elected lane executes each tcgen05 instruction; TMA loads stay on lane 0)
+      {
+        if (lane == 0) load_weights(sb, maps, bar_w, f);
         // hand-off mode: the [pe|1] operand of a tile arrives by TMA from the forward kernel's copy (two 2 KB k-halves)
         auto load_a0 = [&](uint32_t i, int k) {
-          const int row0 = (slot + k * nslots) * TM;
-          mbar_expect_tx(bar_a0t, 2 * TM * 16);
-          tma_load_3d(a0_of(i), &maps.a0lo, bar_a0t, 0, f, row0);
-          tma_load_3d(a0_of(i) + TM * 16, &maps.a0hi, bar_a0t, 0, f, row0);
+          if (lane == 0) {
+            const int row0 = (slot + k * nslots) * TM;
+            mbar_expect_tx(bar_a0t, 2 * TM * 16);
+            tma_load_3d(a0_of(i), &maps.a0lo, bar_a0t, 0, f, row0);
+            tma_load_3d(a0_of(i) + TM * 16, &maps.a0hi, bar_a0t, 0, f, row0);
+          }
+          __syncwarp();
         };
         if (EPS16 && ntl > 0) load_a0(it, 0);
+        __syncwarp();
         mbar_wait_backoff(bar_w, fit & 1);
         for (int k = 0; k < ntl; ++k) {
           const uint32_t i = it + k, ph = i & 1;
           const uint32_t a0 = a0_of(i);
           if (EPS16) mbar_wait_backoff(bar_a0t, ph);
           mbar_wait_backoff(bar_a0, ph); tc_fence_after_sync();
-          issue_layer0<BF16>(sb, tR0, a0); umma_commit(bar_d0);
+          issue_layer0<BF16, true>(sb, tR0, a0); umma_commit_w(bar_d0);
           mbar_wait_backoff(bar_h1, ph); tc_fence_after_sync();
           // chain A has started tile i, so tile i - 2 has retired and operand buffer (i + 1) % 3 is free
           if (EPS16 && k + 1 < ntl) load_a0(i + 1, k + 1);
-          issue_layer1<BF16>(sb, tR0, h1_of(i), a0); umma_commit(bar_d1);
+          issue_layer1<BF16, true>(sb, tR0, h1_of(i), a0); umma_commit_w(bar_d1);
           mbar_wait_backoff(bar_h2, ph); tc_fence_after_sync();
-          issue_layer2<BF16>(sb, tR0, h2_of(i), a0); umma_commit(bar_d2);
+          issue_layer2<BF16, true>(sb, tR0, h2_of(i), a0); umma_commit_w(bar_d2);
         }
       }
       __syncwarp();
       } else if (warp == 1) {
       // ================= MMA issuer B: dgrad + every weight-gradient MMA
-      if (lane == 0) {
+      {                                     // whole warp, elected lane issues (see issuer A)
         mbar_wait_backoff(bar_w, fit & 1);
         for (int k = 0; k < ntl; ++k) {
           const uint32_t i = it + k, ph = i & 1;
@@ -940,43 +951,43 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
           mbar_wait_backoff(bar_do, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16<BF16>(tR1, umma_smem_desc(sDO + kk * 32, 16, 1024), umma_smem_desc(sb + kOffW2 + kk * 32, 16, 1024),
+            umma_f16_w(tR1, umma_desc16((sDO >> 4) + ((kk * 32) >> 4), 16, 1024), umma_desc16((sb >> 4) + ((kOffW2 + kk * 32) >> 4), 16, 1024),
                            id_kk_128, kk > 0 ? 1u : 0u);
-          umma_commit(bar_g2);
+          umma_commit_w(bar_g2);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWG2, umma_smem_desc(h2 + kk * 2048, kPanel, 1024), umma_smem_desc(sDO + kk * 2048, kPanel, 1024),
+            umma_f16_w(tWG2, umma_desc16((h2 >> 4) + ((kk * 2048) >> 4), kPanel, 1024), umma_desc16((sDO >> 4) + ((kk * 2048) >> 4), kPanel, 1024),
                            id_mm_64, (first && kk == 0) ? 0u : 1u);
           // M = 128 is formed by dO (64 columns) and the 16 KB that follow it in shared memory (the [pe|1] operands and
           // the start of h1[0]): TMEM lanes 64..127 of this accumulator are never read.
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWB2, umma_smem_desc(sDO + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
-          umma_commit(bar_dofree);          // dO is free again; h2 may be overwritten by dz2
+            umma_f16_w(tWB2, umma_desc16((sDO >> 4) + ((kk * 2048) >> 4), kPanel, 1024),
+                           umma_desc16((a0 >> 4) + ((kk * 256) >> 4), 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
+          umma_commit_w(bar_dofree);          // dO is free again; h2 may be overwritten by dz2
           // ---- layer 1 backward: G1 = dz2 W1^T ; dW1 += h1^T dz2 ; db1 += dz2^T [pe|1]      (dz2 lives in the h2 buffer)
           mbar_wait_backoff(bar_dz2, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tR1, umma_smem_desc(h2 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024),
-                           umma_smem_desc(sb + kOffW1 + (kk >> 2) * kPanel + (kk & 3) * 32, 16, 1024), id_kk_128, kk > 0 ? 1u : 0u);
-          umma_commit(bar_g1);
+            umma_f16_w(tR1, umma_desc16((h2 >> 4) + (((kk >> 2) * kPanel + (kk & 3) * 32) >> 4), 16, 1024),
+                           umma_desc16((sb >> 4) + ((kOffW1 + (kk >> 2) * kPanel + (kk & 3) * 32) >> 4), 16, 1024), id_kk_128, kk > 0 ? 1u : 0u);
+          umma_commit_w(bar_g1);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWG1, umma_smem_desc(h1 + kk * 2048, kPanel, 1024), umma_smem_desc(h2 + kk * 2048, kPanel, 1024),
+            umma_f16_w(tWG1, umma_desc16((h1 >> 4) + ((kk * 2048) >> 4), kPanel, 1024), umma_desc16((h2 >> 4) + ((kk * 2048) >> 4), kPanel, 1024),
                            id_mm_128, (first && kk == 0) ? 0u : 1u);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWB1, umma_smem_desc(h2 + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
-          umma_commit(bar_dw1);             // h1 may be overwritten by dz1
+            umma_f16_w(tWB1, umma_desc16((h2 >> 4) + ((kk * 2048) >> 4), kPanel, 1024),
+                           umma_desc16((a0 >> 4) + ((kk * 256) >> 4), 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
+          umma_commit_w(bar_dw1);             // h1 may be overwritten by dz1
           // ---- layer 0 backward: [dW0;db0]^T += dz1^T [pe|1]      (dz1 lives in the h1 buffer)
           mbar_wait_backoff(bar_dz1, ph); tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_f16<BF16>(tWG0, umma_smem_desc(h1 + kk * 2048, kPanel, 1024),
-                           umma_smem_desc(a0 + kk * 256, 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
-          umma_commit(bar_wg0 + 8 * (i & 1));   // buffer set (i & 1) is free for tile i + 2
+            umma_f16_w(tWG0, umma_desc16((h1 >> 4) + ((kk * 2048) >> 4), kPanel, 1024),
+                           umma_desc16((a0 >> 4) + ((kk * 256) >> 4), 128, TM * 16, kLayoutNone), id_mm_16, (first && kk == 0) ? 0u : 1u);
+          umma_commit_w(bar_wg0 + 8 * (i & 1));   // buffer set (i & 1) is free for tile i + 2
         }
       }
       __syncwarp();

@@ -19,6 +19,7 @@
 
 int dib_int16_rb_enabled();
 int dib_int16_head1_enabled();
+int dib_int16_2sm_enabled();
 
 namespace {
 
@@ -102,12 +103,11 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         int r0, c0, split, t_begin, nk;
         decode(tile, r0, c0, split, t_begin, nk);
-        for (int k = 0; k < nk; ++k, ++it) {
-          const int s = it % kStages, ph = (it / kStages) & 1;
+        for (int k = 0; k < nk; ++k) {
           mbar_wait(empty_bar(s), ph ^ 1);
           mbar_expect_tx(full_bar(s), kStageBytes);
           const uint32_t a_dst = sb + s * kStageBytes, b_dst = a_dst + kABytes;
@@ -116,13 +116,19 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           else                tma_load_2d(a_dst, &mapA, full_bar(s), t0, r0);
           if constexpr (B_MN) tma_load_3d(b_dst, &mapB, full_bar(s), 0, t0, c0 / 64);
           else                tma_load_2d(b_dst, &mapB, full_bar(s), t0, c0);
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                       // the whole warp runs the issue loop (uniform registers), one elected lane issues
       constexpr uint32_t idesc = umma_idesc(BF16 ? 1u : 0u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBN);
-      uint32_t it = 0, lt = 0;
+      // K-major: 32 B inside the swizzle span; MN-major (16-bit, SWIZZLE_128B): 16 k-rows = 2048 B, panels 8 KB apart.
+      // Only the start-address field of the descriptors moves (stage, 16-deep k step) -- see umma_desc_lo.
+      const uint32_t a_lo0 = umma_desc_lo(sb, A_MN ? kBK * 128 : 16), b_lo0 = umma_desc_lo(sb + kABytes, B_MN ? kBK * 128 : 16);
+      const uint32_t d_hi = umma_desc_hi(1024);
+      constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4, b_step = (B_MN ? 2048 : 32) >> 4, st_step = kStageBytes >> 4;
+      uint32_t s = 0, ph = 0, lt = 0;
       for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         int r0, c0, split, t_begin, nk;
         decode(tile, r0, c0, split, t_begin, nk);
@@ -131,21 +137,17 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         mbar_wait(tempty_bar(acc), ((lt >> 1) & 1) ^ 1);           // the epilogue has drained this accumulator
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * kBN;
-        for (int k = 0; k < nk; ++k, ++it) {
-          const int s = it % kStages, ph = (it / kStages) & 1;
+        for (int k = 0; k < nk; ++k) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after_sync();
-          const uint32_t a_addr = sb + s * kStageBytes, b_addr = a_addr + kABytes;
+          const uint32_t a_lo = a_lo0 + s * st_step, b_lo = b_lo0 + s * st_step;
 #pragma unroll
-          for (int kk = 0; kk < kBK / 16; ++kk) {
-            // K-major: 32 B inside the swizzle span; MN-major (16-bit, SWIZZLE_128B): 16 k-rows = 2048 B, panels 8 KB apart
-            const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(a_addr + kk * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + kk * 2048, kBK * 128, 1024) : umma_smem_desc(b_addr + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (k > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(s));
+          for (int kk = 0; kk < kBK / 16; ++kk)
+            umma_f16_w(d_tmem, umma_desc_join(a_lo + kk * a_step, d_hi), umma_desc_join(b_lo + kk * b_step, d_hi), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_w(empty_bar(s));
+          if (++s == kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull_bar(acc));
+        umma_commit_w(tfull_bar(acc));
         ++lt;
       }
     }
@@ -469,6 +471,240 @@ dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, rb_tmem_cols<BN>()); }
+}
+
+// 32 values per lane over the warp's 32 rows -> lane L holds the column-L total (31 shuffles, fixed order)
+__device__ __forceinline__ float warp_colsum32(float (&w)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const bool up = (lane & o) != 0;
+      const float send = up ? w[i] : w[i + o], keep = up ? w[i + o] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return w[0];
+}
+
+// ====================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): the streamed GEMMs above move 64 FLOP per byte of L2->SM traffic with their
+// 128 x 128 tiles and run AT the L2 fabric's rate (fwd_l0: 268 MB in 32 us = 8.4 TB/s, 540 TFLOP/s).  Here two CTAs on the
+// two SMs of a TPC share one 256 x 256 output tile: each loads its own 128 rows of A and HALF of the B tile (128 of the 256
+// columns), one thread of the even CTA issues M = 256 MMAs that read both shared memories, and each CTA's TMEM receives its
+// 128 rows of the fp32 accumulator -> 128 FLOP per byte, half the traffic.  One CTA per SM, 6-stage ring of 32 KB per CTA,
+// accumulator double-buffered (2 x 256 TMEM columns), eight epilogue warps (two column halves).
+// Warp roles: 0 TMA producer (both CTAs) | 1 TMEM owner (both), MMA issuer (even CTA) | 2..9 epilogue.
+// ====================================================================================================
+constexpr int k2BN = 256, k2Stages = 6;
+constexpr int k2StageBytes = kABytes + kBBytes;
+constexpr int k2BarOff = k2Stages * k2StageBytes;
+constexpr int k2SmemTotal = k2BarOff + 256 + 1024;
+
+template <int MODE, bool BF16>
+__global__ void __launch_bounds__(320, 1)
+dib_int16_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Int16Args a) {
+  constexpr bool A_MN = (MODE == DIB_GEMM_WGRAD), B_MN = (MODE != DIB_GEMM_DGRAD);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t bar_base = sb + k2BarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (k2Stages + s); };
+  auto tfull_bar = [&](int acc) { return bar_base + 8u * (2 * k2Stages + acc); };
+  auto tempty_bar = [&](int acc) { return bar_base + 8u * (2 * k2Stages + 2 + acc); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * k2Stages + 4);
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + k2BarOff + 8 * (2 * k2Stages + 4));
+
+  __shared__ float colsum_s[2][4][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int R = (MODE == DIB_GEMM_WGRAD) ? a.R : a.M, C = a.C;
+  const int tiles_rp = DIB_CEIL_DIV(R, 2 * kBM), tiles_c = DIB_CEIL_DIV(C, k2BN);
+  const int nsp = (MODE == DIB_GEMM_WGRAD) ? a.nsplit : 1;
+  const int ntile = tiles_rp * tiles_c * nsp;
+  const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
+    for (int s = 0; s < k2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int acc = 0; acc < 2; ++acc) { mbar_init(tfull_bar(acc), 1); mbar_init(tempty_bar(acc), 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem2_alloc(tmem_slot, 2 * k2BN); tmem2_relinquish(); }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  auto decode = [&](int tile, int& r0, int& c0, int& split, int& t_begin, int& nk) {
+    const int per = tiles_rp * tiles_c;
+    split = tile / per;
+    const int rem = tile - split * per;
+    r0 = (rem / tiles_c) * 2 * kBM + (int)rank * kBM; c0 = (rem % tiles_c) * k2BN;
+    int t_end;
+    if (MODE == DIB_GEMM_WGRAD) { t_begin = split * a.rows_per_split; t_end = min(a.M, t_begin + a.rows_per_split); }
+    else { t_begin = 0; t_end = a.T; }
+    nk = t_end > t_begin ? DIB_CEIL_DIV(t_end - t_begin, kBK) : 0;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      const uint32_t fl0 = mapa_shared(full_bar(0), 0);          // the even CTA's barriers count both CTAs' bytes
+      for (int tile = cl; tile < ntile; tile += ncl) {
+        int r0, c0, split, t_begin, nk;
+        decode(tile, r0, c0, split, t_begin, nk);
+        const int cb = c0 + (int)rank * kBN;                     // this CTA's half of the B tile
+        for (int k = 0; k < nk; ++k) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * k2StageBytes);
+          const uint32_t fl = fl0 + 8u * s;
+          const uint32_t a_dst = sb + s * k2StageBytes, b_dst = a_dst + kABytes;
+          const int t0 = t_begin + k * kBK;
+          if constexpr (A_MN) tma2_load_3d(a_dst, &mapA, fl, 0, t0, r0 / 64);
+          else                tma2_load_2d(a_dst, &mapA, fl, t0, r0);
+          if constexpr (B_MN) tma2_load_3d(b_dst, &mapB, fl, 0, t0, cb / 64);
+          else                tma2_load_2d(b_dst, &mapB, fl, t0, cb);
+          if (++s == k2Stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {                       // the whole warp runs the issue loop (uniform registers), one elected lane issues
+      constexpr uint32_t idesc = umma_idesc(BF16 ? 1u : 0u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, k2BN, 2 * kBM);
+      // descriptors: only the start-address field moves (stage, 16-deep k step) -- see umma_desc_lo
+      const uint32_t a_lo0 = umma_desc_lo(sb, A_MN ? kBK * 128 : 16), b_lo0 = umma_desc_lo(sb + kABytes, B_MN ? kBK * 128 : 16);
+      const uint32_t d_hi = umma_desc_hi(1024);
+      constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4, b_step = (B_MN ? 2048 : 32) >> 4, st_step = k2StageBytes >> 4;
+      uint32_t s = 0, ph = 0, lt = 0;
+      for (int tile = cl; tile < ntile; tile += ncl) {
+        int r0, c0, split, t_begin, nk;
+        decode(tile, r0, c0, split, t_begin, nk);
+        if (nk == 0) continue;
+        const int acc = lt & 1;
+        mbar_wait(tempty_bar(acc), ((lt >> 1) & 1) ^ 1);           // both CTAs' epilogues have drained this accumulator
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * k2BN;
+        for (int k = 0; k < nk; ++k) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_lo = a_lo0 + s * st_step, b_lo = b_lo0 + s * st_step;
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk)
+            umma2_f16_w(d_tmem, umma_desc_join(a_lo + kk * a_step, d_hi), umma_desc_join(b_lo + kk * b_step, d_hi), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          umma2_commit_w(empty_bar(s), 3);
+          if (++s == k2Stages) { s = 0; ph ^= 1; }
+        }
+        umma2_commit_w(tfull_bar(acc), 3);
+        ++lt;
+      }
+    }
+  } else {
+    const int wg = (warp - 2) >> 2, wq = (warp - 2) & 3, q = warp & 3;
+    const int wcol = wg * 128;
+    uint32_t lt = 0;
+    for (int tile = cl; tile < ntile; tile += ncl) {
+      int r0, c0, split, t_begin, nk;
+      decode(tile, r0, c0, split, t_begin, nk);
+      const int acc = lt & 1;
+      if (nk > 0) { mbar_wait(tfull_bar(acc), (lt >> 1) & 1); tc_fence_after_sync(); }
+      const int r = r0 + q * 32 + lane;
+#pragma unroll 1
+      for (int cc = wcol; cc < wcol + 128; cc += 32) {
+        const bool live = r < R && c0 + cc < C;
+        float4 bpre[8];
+        uint4 xpre[4];
+        if constexpr (MODE == DIB_GEMM_FWD) {
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bpre[j] = *reinterpret_cast<const float4*>(a.bias + c0 + cc + 4 * j);
+          }
+        }
+        if constexpr (MODE == DIB_GEMM_DGRAD) {
+          if (live && a.X) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xpre[j] = *reinterpret_cast<const uint4*>(a.X + (long long)r * a.ldx + c0 + cc + 8 * j);
+          }
+        }
+        uint32_t v[32];
+        if (nk > 0) { tmem_ld_32x32b_x32(tmem_base + acc * k2BN + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v); tmem_ld_wait(); }
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (live) {
+          const int c = c0 + cc;
+          if constexpr (MODE == DIB_GEMM_WGRAD) {
+            float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * a.out_scale, __uint_as_float(v[j + 1]) * a.out_scale,
+                                                                __uint_as_float(v[j + 2]) * a.out_scale, __uint_as_float(v[j + 3]) * a.out_scale);
+          } else {
+            uint16_t* dst = a.out16 + (long long)r * a.ldc + c;
+            const bool gate = (MODE == DIB_GEMM_DGRAD) && a.X != nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float f[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[j + k]);
+              if constexpr (MODE == DIB_GEMM_FWD) {
+                const float4 b0 = bpre[j >> 2], b1 = bpre[(j >> 2) + 1];
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = dib_act16(a.act, f[k] + bb[k], a.alpha);
+              } else if (gate) {
+                const uint4 xv = xpre[j >> 3];
+                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float h0, h1;
+                  unpack_h2<BF16>(xw[k], h0, h1);
+                  f[2 * k] *= dib_act_grad(a.act, h0, a.alpha);
+                  f[2 * k + 1] *= dib_act_grad(a.act, h1, a.alpha);
+                }
+              }
+              *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2<BF16>(f[0], f[1]), pack_h2<BF16>(f[2], f[3]), pack_h2<BF16>(f[4], f[5]), pack_h2<BF16>(f[6], f[7]));
+              if constexpr (MODE == DIB_GEMM_DGRAD) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[j + k] = __float_as_uint(f[k]);
+              }
+            }
+          }
+        } else if constexpr (MODE == DIB_GEMM_DGRAD) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if constexpr (MODE == DIB_GEMM_DGRAD) {
+          if (a.dbias) {
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
+            colsum_s[wg][wq][cc - wcol + lane] = warp_colsum32(w, lane);
+          }
+        }
+      }
+      if constexpr (MODE == DIB_GEMM_DGRAD) {
+        if (a.dbias) {
+          if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+          const int et = wq * 32 + lane;
+          if (r0 < R && c0 + wcol + et < C)
+            a.dbias[(long long)(r0 / kBM) * C + c0 + wcol + et] = (colsum_s[wg][0][et] + colsum_s[wg][1][et]) + (colsum_s[wg][2][et] + colsum_s[wg][3][et]);
+          if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+      }
+      if (nk > 0) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        ++lt;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) { tc_fence_after_sync(); tmem2_dealloc(tmem_base, 2 * k2BN); }
 }
 
 // bias gradient of a hidden layer: column sums of the fp16 gradient over one batch slice -> fp32 split partial.
@@ -796,6 +1032,280 @@ dib_int16_head1_kernel(const uint16_t* __restrict__ g, int ldg, int K, const flo
   if (threadIdx.x == 0) { float a = 0.f; for (int ww = 0; ww < kHeadWarps; ++ww) a += sred[ww]; acc_part[blockIdx.x] = a; }
 }
 
+// ====================================================================================================
+// Fused tail of the integration network for single-output models (C0, nb-radial): the last two hidden layers
+// (256 wide each) and the output head in ONE persistent kernel -- models.py:81-84,122 + the compiled loss.
+//   per 128-row tile:  L0  D0 = A W0   (A, W0 k-blocks streamed through a 3-stage TMA ring; N = 256, fp32 in TMEM cols 0..255)
+//                      e0  g1 = act(D0 + b0) -> 16-bit -> swizzled shared tile (= L1's A operand) and -> HBM (the backward needs it)
+//                      L1  D1 = g1 W1  (W1 k-blocks through the same ring; TMEM cols 256..511), started per 64-column chunk of g1
+//                      e1  g2 = act(D1 + b1) kept PACKED IN REGISTERS (64 per thread), logit = g2 . w + b, compiled loss / metric,
+//                          d loss / d logit, dg2 = dz w act'(g2) -> HBM, output-layer weight / bias gradients and the bias gradient
+//                          of the last hidden layer as per-CTA partials.
+// g2 never reaches HBM, the head's re-read of it (and its launch) disappears, and L0 of tile i+1 runs under e1 of tile i.
+// Warp roles: 0 TMA producer | 1 MMA issuer (+ TMEM owner) | 2..5 epilogue columns 0..127 | 6..9 epilogue columns 128..255.
+// ====================================================================================================
+constexpr int kF2N = 256, kF2Stages = 3;
+constexpr int kF2AB = kBM * 128, kF2BB = kF2N * 128, kF2Stage = kF2AB + kF2BB;      // 16 KB + 32 KB
+constexpr int kF2G1Off = kF2Stages * kF2Stage;
+constexpr int kF2BarOff = kF2G1Off + kBM * kF2N * 2;
+constexpr int kF2Smem = kF2BarOff + 256 + 1024;
+
+struct Fwd2Args {
+  const float *b0, *b1, *wout, *bout;
+  uint16_t* g1; int ldg1;             // out: first fused layer's activation [M x 256]
+  uint16_t* dg2; int lddg;            // out (training) or null: gradient w.r.t. the second fused layer's pre-activation, x gscale
+  const float* y; float* user_pred;
+  float* wpart; int wpart_stride; float *loss_part, *acc_part;
+  int M, nk0, act, out_act, loss;
+  float alpha, inv_batch, gscale;
+};
+
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ACT is a template parameter: with the activation switch inside the fully unrolled register-resident passes the kernel grew to
+// 14.5 K SASS instructions (232 KB, jump tables per element) and ran instruction-fetch bound (ncu: no_instructions 37 % of samples).
+template <bool BF16, int ACT>
+__global__ void __launch_bounds__(320, 1)
+dib_int16_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW0,
+                      const __grid_constant__ CUtensorMap mapW1, const Fwd2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t bar_base = sb + kF2BarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kF2Stages + s); };
+  const uint32_t d0_full = bar_base + 8u * (2 * kF2Stages), d1_full = d0_full + 8u, d1_empty = d0_full + 16u;
+  auto g1_ready = [&](int k) { return d0_full + 24u + 8u * k; };
+  const uint32_t tmem_slot = d0_full + 24u + 32u;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(sg + kF2BarOff + 8 * (2 * kF2Stages) + 56);
+
+  __shared__ __align__(16) float s_b0[kF2N], s_b1[kF2N], s_w[kF2N];
+  __shared__ float s_z[2][2][kBM];
+  __shared__ float s_col[2][2][4][128];
+  __shared__ float s_red[3][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = DIB_CEIL_DIV(a.M, kBM);
+
+  for (int i = threadIdx.x; i < kF2N; i += blockDim.x) { s_b0[i] = a.b0[i]; s_b1[i] = a.b1[i]; s_w[i] = a.wout[i]; }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapW0); tma_prefetch_desc(&mapW1);
+    for (int s = 0; s < kF2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(d0_full, 1); mbar_init(d1_full, 1); mbar_init(d1_empty, 8);
+    for (int k = 0; k < 4; ++k) mbar_init(g1_ready(k), 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const uint32_t g1s = sb + kF2G1Off;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        for (int k = 0; k < a.nk0; ++k) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), kF2Stage);
+          const uint32_t dst = sb + s * kF2Stage;
+          tma_load_2d(dst, &mapA, full_bar(s), k * kBK, tile * kBM);
+          tma_load_3d(dst + kF2AB, &mapW0, full_bar(s), 0, k * kBK, 0);
+          if (++s == kF2Stages) { s = 0; ph ^= 1; }
+        }
+        for (int k = 0; k < kF2N / kBK; ++k) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), kF2BB);
+          tma_load_3d(sb + s * kF2Stage + kF2AB, &mapW1, full_bar(s), 0, k * kBK, 0);
+          if (++s == kF2Stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {                                       // the whole warp runs the issue loop (uniform registers), one elected lane issues
+      constexpr uint32_t idesc = umma_idesc(BF16 ? 1u : 0u, 0u, 1u, kF2N);
+      // descriptors: only the start-address field moves (stage, 16-deep k step) -- see umma_desc_lo
+      const uint32_t a_lo0 = umma_desc_lo(sb, 16), b_lo0 = umma_desc_lo(sb + kF2AB, kBK * 128), g_lo0 = umma_desc_lo(g1s, 16);
+      const uint32_t d_hi = umma_desc_hi(1024);
+      constexpr uint32_t st_step = kF2Stage >> 4;
+      uint32_t s = 0, ph = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, ++lt) {
+        // L0 -> D0.  D0 was drained by e0 of the previous tile: L1 of that tile (already issued) waited for all g1 chunks.
+        for (int k = 0; k < a.nk0; ++k) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_lo = a_lo0 + s * st_step, b_lo = b_lo0 + s * st_step;
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk)
+            umma_f16_w(tmem_base, umma_desc_join(a_lo + kk * 2, d_hi), umma_desc_join(b_lo + kk * 128, d_hi), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_w(empty_bar(s));
+          if (++s == kF2Stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit_w(d0_full);
+        // L1 -> D1, k-block by k-block as e0 finishes the 64-column chunks of g1
+        mbar_wait(d1_empty, (lt & 1) ^ 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < kF2N / kBK; ++k) {
+          mbar_wait(g1_ready(k), lt & 1);
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_lo = g_lo0 + k * (kF2AB >> 4), b_lo = b_lo0 + s * st_step;
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk)
+            umma_f16_w(tmem_base + kF2N, umma_desc_join(a_lo + kk * 2, d_hi), umma_desc_join(b_lo + kk * 128, d_hi), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          umma_commit_w(empty_bar(s));
+          if (++s == kF2Stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit_w(d1_full);
+      }
+    }
+  } else {
+    const int wg = (warp - 2) >> 2, wq = (warp - 2) & 3, q = warp & 3;       // TMEM lane quarter = warp id % 4
+    const int colbase = wg * 128, rt = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const bool train = a.dg2 != nullptr;
+    const float bout = a.bout[0];
+    float acc_dw = 0.f, acc_dbh = 0.f, lsum = 0.f, asum = 0.f, dbo = 0.f;     // column accumulators: column colbase + wq * 32 + lane
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, ++lt) {
+      const long long row = (long long)tile * kBM + rt;
+      const bool live = row < a.M;
+      // ---------------- e0: g1 = act(D0 + b0)
+      mbar_wait(d0_full, lt & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int cc = colbase + 32 * j;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + (uint32_t)cc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+          const float4 ba = *reinterpret_cast<const float4*>(&s_b0[cc + g]), bb = *reinterpret_cast<const float4*>(&s_b0[cc + g + 4]);
+          const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = dib_act16(ACT, __uint_as_float(v[g + k]) + bv[k], a.alpha);
+          const uint32_t p0 = pack_h2<BF16>(f[0], f[1]), p1 = pack_h2<BF16>(f[2], f[3]), p2 = pack_h2<BF16>(f[4], f[5]), p3 = pack_h2<BF16>(f[6], f[7]);
+          const int c = cc + g;
+          st_shared_v4u(g1s + (c >> 6) * kF2AB + rt * 128 + ((((c & 63) >> 3) ^ (rt & 7)) << 4), p0, p1, p2, p3);
+          if (live) *reinterpret_cast<uint4*>(a.g1 + row * a.ldg1 + c) = make_uint4(p0, p1, p2, p3);
+        }
+        if (j & 1) {                       // a 64-column chunk of g1 (one k-block of L1) is complete for this warp's rows
+          fence_proxy_async_smem();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(g1_ready(wg * 2 + (j >> 1)));
+        }
+      }
+      // ---------------- e1, pass 1: g2 = act(D1 + b1) packed into registers, partial logit
+      mbar_wait(d1_full, lt & 1);
+      tc_fence_after_sync();
+      uint32_t g2p[64];
+      float zp = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cc = colbase + 32 * j;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + (uint32_t)(kF2N + cc), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 32; g += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(&s_b1[cc + g]), wv = *reinterpret_cast<const float4*>(&s_w[cc + g]);
+          const uint32_t pa = pack_h2<BF16>(dib_act16(ACT, __uint_as_float(v[g]) + bv.x, a.alpha), dib_act16(ACT, __uint_as_float(v[g + 1]) + bv.y, a.alpha));
+          const uint32_t pb = pack_h2<BF16>(dib_act16(ACT, __uint_as_float(v[g + 2]) + bv.z, a.alpha), dib_act16(ACT, __uint_as_float(v[g + 3]) + bv.w, a.alpha));
+          g2p[j * 16 + (g >> 1)] = pa; g2p[j * 16 + (g >> 1) + 1] = pb;
+          float h0, h1, h2, h3;
+          unpack_h2<BF16>(pa, h0, h1); unpack_h2<BF16>(pb, h2, h3);
+          zp = fmaf(h0, wv.x, zp); zp = fmaf(h1, wv.y, zp); zp = fmaf(h2, wv.z, zp); zp = fmaf(h3, wv.w, zp);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d1_empty);
+      // ---------------- logit, compiled loss / metric, d loss / d logit (both column halves compute it; half 0 accumulates)
+      s_z[lt & 1][wg][rt] = zp;
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      float z = dib_act(a.out_act, (s_z[lt & 1][0][rt] + s_z[lt & 1][1][rt]) + bout, a.alpha);
+      float dz = 0.f;
+      if (live && a.y) {
+        const float t = a.y[row];
+        float l;
+        if (a.loss == DIB_LOSS_BCE_LOGITS) { l = fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z))); dz = 1.f / (1.f + expf(-z)) - t; }
+        else if (a.loss == DIB_LOSS_BCE_PROBS) {
+          const float ep = 1e-7f, pc = fminf(fmaxf(z, ep), 1.f - ep);
+          l = -(t * logf(pc + ep) + (1.f - t) * logf(1.f - pc + ep));
+          dz = (z > ep && z < 1.f - ep) ? -t / (pc + ep) + (1.f - t) / (1.f - pc + ep) : 0.f;
+        } else if (a.loss == DIB_LOSS_SPARSE_CE_LOGITS) { l = 0.f; dz = 0.f; }        // one class: the softmax is constant
+        else { const float d = z - t; l = d * d; dz = 2.f * d; }
+        const float acc = a.loss == DIB_LOSS_SPARSE_CE_LOGITS ? ((int)t == 0 ? 1.f : 0.f) : (((z > 0.5f ? 1.f : 0.f) == t) ? 1.f : 0.f);
+        if (wg == 0) { lsum += l; asum += acc; }
+      }
+      if (a.user_pred && live && wg == 0) a.user_pred[row] = z;
+      if (train) {
+        const float dzs = live ? dz * a.inv_batch * dib_act_grad(a.out_act, z, a.alpha) : 0.f;
+        const float ds = dzs * a.gscale;
+        if (wg == 0) dbo += dzs;
+        // ---------------- e1, pass 2: dg2 = ds w act'(g2) -> HBM; column sums of g2 dz (output-layer dW) and of dg2 (bias gradient)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = colbase + 32 * j;
+          float wa[32], wb[32];
+#pragma unroll
+          for (int g = 0; g < 32; g += 8) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[cc + g]), w1 = *reinterpret_cast<const float4*>(&s_w[cc + g + 4]);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            float d[8];
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+              float h0, h1;
+              unpack_h2<BF16>(g2p[j * 16 + ((g + k) >> 1)], h0, h1);
+              wa[g + k] = h0 * dzs; wa[g + k + 1] = h1 * dzs;
+              d[k] = ds * wv[k] * dib_act_grad(ACT, h0, a.alpha);
+              d[k + 1] = ds * wv[k + 1] * dib_act_grad(ACT, h1, a.alpha);
+              wb[g + k] = d[k]; wb[g + k + 1] = d[k + 1];
+            }
+            if (live)
+              *reinterpret_cast<uint4*>(a.dg2 + row * a.lddg + cc + g) =
+                  make_uint4(pack_h2<BF16>(d[0], d[1]), pack_h2<BF16>(d[2], d[3]), pack_h2<BF16>(d[4], d[5]), pack_h2<BF16>(d[6], d[7]));
+          }
+          const float ca = warp_colsum32(wa, lane), cb = warp_colsum32(wb, lane);
+          s_col[wg][0][wq][32 * j + lane] = ca;
+          s_col[wg][1][wq][32 * j + lane] = cb;
+        }
+        // the four warps of this column half cover the tile's 128 rows: fixed-order combine into the thread-owned column
+        if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int t = wq * 32 + lane;
+        acc_dw += (s_col[wg][0][0][t] + s_col[wg][0][1][t]) + (s_col[wg][0][2][t] + s_col[wg][0][3][t]);
+        acc_dbh += (s_col[wg][1][0][t] + s_col[wg][1][1][t]) + (s_col[wg][1][2][t] + s_col[wg][1][3][t]);
+        if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+    }
+    // ---------------- per-CTA partials, layout of the head kernels: [dWc (K) | dbc (1) | column sums of dg2 (K)], loss, accuracy
+    const int t = colbase + wq * 32 + lane;
+    if (train) {
+      a.wpart[(long long)blockIdx.x * a.wpart_stride + t] = acc_dw;
+      a.wpart[(long long)blockIdx.x * a.wpart_stride + kF2N + 1 + t] = acc_dbh;
+    }
+    if (wg == 0) {
+      lsum = dib_warp_sum(lsum); asum = dib_warp_sum(asum); dbo = dib_warp_sum(dbo);
+      if (lane == 0) { s_red[0][wq] = lsum; s_red[1][wq] = asum; s_red[2][wq] = dbo; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (wq == 0 && lane == 0) {
+        a.loss_part[blockIdx.x] = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
+        a.acc_part[blockIdx.x] = (s_red[1][0] + s_red[1][1]) + (s_red[1][2] + s_red[1][3]);
+        if (train) a.wpart[(long long)blockIdx.x * a.wpart_stride + kF2N] = (s_red[2][0] + s_red[2][1]) + (s_red[2][2] + s_red[2][3]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
 template <bool BF16>
 __global__ void dib_f32_to_16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -876,6 +1386,31 @@ cudaError_t launch_rb(const CUtensorMap& mA, const CUtensorMap& mB, const Int16A
   return cudaGetLastError();
 }
 
+// CTA-pair launch: clusters of two CTAs (one per SM of a TPC), at most one cluster per SM pair
+template <int MODE, bool BF16>
+cudaError_t launch2(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Args& a, cudaStream_t st) {
+  if (!g_num_sms16) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms16, cudaDevAttrMultiProcessorCount, dev); }
+  const int R = (MODE == DIB_GEMM_WGRAD) ? a.R : a.M;
+  const long long nt = (long long)DIB_CEIL_DIV(R, 2 * kBM) * DIB_CEIL_DIV(a.C, k2BN) * ((MODE == DIB_GEMM_WGRAD) ? a.nsplit : 1);
+  if (nt <= 0) return cudaSuccess;
+  const long long ncl = nt < g_num_sms16 / 2 ? nt : g_num_sms16 / 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dib_int16_gemm2_kernel<MODE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemTotal);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * ncl)); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = k2SmemTotal; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, dib_int16_gemm2_kernel<MODE, BF16>, mA, mB, a);
+  dib_note_launch();
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 // BN for the resident-B kernel (0 = not eligible): the weight slice [T x BN] 16-bit plus the A ring must fit in shared memory
 int rb_pick_bn(int T, int C) {
   if (!dib_int16_rb_enabled() || T % kBK != 0 || C % 64 != 0) return 0;
@@ -890,6 +1425,13 @@ int rb_pick_bn(int T, int C) {
 static int g_int16_head1 = 1;           // single-output head: 8-rows-per-pass kernel (1, default) or the generic one (0)
 int dib_int16_head1_enabled() { return g_int16_head1; }
 void dib_int16_head1_set(int on) { g_int16_head1 = on ? 1 : 0; }
+
+static int g_int16_2sm = -1;             // CTA-pair (cta_group::2) GEMMs for output widths that are multiples of 256
+int dib_int16_2sm_enabled() {
+  if (g_int16_2sm < 0) { const char* e = getenv("DIB_INT16_2SM"); g_int16_2sm = (e && e[0] == '1') ? 1 : 0; }
+  return g_int16_2sm;
+}
+void dib_int16_2sm_set(int on) { g_int16_2sm = on ? 1 : 0; }
 
 static int g_int16_rb = -1;
 int dib_int16_rb_enabled() {
@@ -924,6 +1466,8 @@ cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const fl
     if (bn == 256) return bf16 ? launch_rb<DIB_GEMM_FWD, true, 256>(mA, mB, a, K / kBK, st) : launch_rb<DIB_GEMM_FWD, false, 256>(mA, mB, a, K / kBK, st);
     return bf16 ? launch_rb<DIB_GEMM_FWD, true, 128>(mA, mB, a, K / kBK, st) : launch_rb<DIB_GEMM_FWD, false, 128>(mA, mB, a, K / kBK, st);
   }
+  if (dib_int16_2sm_enabled() && N % k2BN == 0)
+    return bf16 ? launch2<DIB_GEMM_FWD, true>(mA, mB, a, st) : launch2<DIB_GEMM_FWD, false>(mA, mB, a, st);
   const dim3 tiles(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(N, kBN), 1);
   return bf16 ? launch16<DIB_GEMM_FWD, true>(mA, mB, a, tiles, st) : launch16<DIB_GEMM_FWD, false>(mA, mB, a, tiles, st);
 }
@@ -943,6 +1487,8 @@ cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const vo
     if (bn == 256) return bf16 ? launch_rb<DIB_GEMM_DGRAD, true, 256>(mA, mB, a, N / kBK, st) : launch_rb<DIB_GEMM_DGRAD, false, 256>(mA, mB, a, N / kBK, st);
     return bf16 ? launch_rb<DIB_GEMM_DGRAD, true, 128>(mA, mB, a, N / kBK, st) : launch_rb<DIB_GEMM_DGRAD, false, 128>(mA, mB, a, N / kBK, st);
   }
+  if (dib_int16_2sm_enabled() && K % k2BN == 0)
+    return bf16 ? launch2<DIB_GEMM_DGRAD, true>(mA, mB, a, st) : launch2<DIB_GEMM_DGRAD, false>(mA, mB, a, st);
   const dim3 tiles(DIB_CEIL_DIV(M, kBM), DIB_CEIL_DIV(K, kBN), 1);
   return bf16 ? launch16<DIB_GEMM_DGRAD, true>(mA, mB, a, tiles, st) : launch16<DIB_GEMM_DGRAD, false>(mA, mB, a, tiles, st);
 }
@@ -958,8 +1504,66 @@ cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_d
   a.out32 = dW_part; a.ldc = N; a.dbias = nullptr; a.M = M; a.T = 0; a.C = N; a.R = K; a.out_scale = out_scale;
   a.nsplit = nsplit; a.rows_per_split = rows_per_split; a.split_stride = split_stride;
   (void)db_part;   // bias gradients come from the kernel that PRODUCES dz (dgrad epilogue / output head), not from here
+  if (dib_int16_2sm_enabled() && N % k2BN == 0)
+    return bf16 ? launch2<DIB_GEMM_WGRAD, true>(mA, mB, a, st) : launch2<DIB_GEMM_WGRAD, false>(mA, mB, a, st);
   const dim3 tiles(DIB_CEIL_DIV(N, kBN), DIB_CEIL_DIV(K, kBM), nsplit);
   return bf16 ? launch16<DIB_GEMM_WGRAD, true>(mA, mB, a, tiles, st) : launch16<DIB_GEMM_WGRAD, false>(mA, mB, a, tiles, st);
+}
+
+static int g_int16_fwd2 = -1;            // fused [hidden, hidden, head] kernel for single-output models (1, default) or the separate kernels (0)
+int dib_int16_fwd2_enabled() {
+  if (g_int16_fwd2 < 0) { const char* e = getenv("DIB_INT16_FWD2"); g_int16_fwd2 = (e && e[0] == '0') ? 0 : 1; }
+  return g_int16_fwd2;
+}
+void dib_int16_fwd2_set(int on) { g_int16_fwd2 = on ? 1 : 0; }
+int dib_int16_fwd2_ok(int K0, int N1, int N2, int out_dim) {
+  return dib_int16_fwd2_enabled() && K0 % kBK == 0 && K0 >= kBK && N1 == kF2N && N2 == kF2N && out_dim == 1;
+}
+
+// g1 = act(g_in W0 + b0) -> HBM;  g2 = act(g1 W1 + b1) (on chip);  logit = g2 . wout + bout;  compiled loss / metric;
+// training (dg2 != null): dg2, per-CTA partials of the output layer's gradients and of the last hidden layer's bias gradient.
+// *nblocks = CTAs launched = rows of wpart / loss_part / acc_part written.
+cudaError_t dib_int16_fwd2_head(const void* g_in, int ld_in, int K0, const void* w16_0, const float* b0, const void* w16_1, const float* b1,
+                                void* g1, const float* wout, const float* bout, int act, int out_act, float alpha, int loss, const float* y,
+                                int M, float inv_batch, float gscale, void* dg2, float* user_pred, float* wpart, int wpart_stride,
+                                float* loss_part, float* acc_part, int* nblocks, int bf16, cudaStream_t st) {
+  if (!encode_fn3()) return cudaErrorNotSupported;
+  if (!g_num_sms16) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms16, cudaDevAttrMultiProcessorCount, dev); }
+  CUtensorMap mA, mW0, mW1;
+  if (!map_k(&mA, g_in, K0, M, ld_in, kBM) || !map_mn(&mW0, w16_0, kF2N, K0, kF2N, kF2N / 64) || !map_mn(&mW1, w16_1, kF2N, kF2N, kF2N, kF2N / 64))
+    return cudaErrorInvalidValue;
+  Fwd2Args a{};
+  a.b0 = b0; a.b1 = b1; a.wout = wout; a.bout = bout; a.g1 = static_cast<uint16_t*>(g1); a.ldg1 = kF2N;
+  a.dg2 = static_cast<uint16_t*>(dg2); a.lddg = kF2N; a.y = y; a.user_pred = user_pred; a.wpart = wpart; a.wpart_stride = wpart_stride;
+  a.loss_part = loss_part; a.acc_part = acc_part; a.M = M; a.nk0 = K0 / kBK; a.act = act; a.out_act = out_act; a.loss = loss;
+  a.alpha = alpha; a.inv_batch = inv_batch; a.gscale = gscale;
+  const int tiles = DIB_CEIL_DIV(M, kBM);
+  const int grid = tiles < g_num_sms16 ? tiles : g_num_sms16;
+  *nblocks = grid;
+  if (grid <= 0) return cudaSuccess;
+  cudaError_t e = cudaErrorInvalidValue;
+#define DIB_F2_LAUNCH(BF, ACT)                                                                                                       \
+  do {                                                                                                                               \
+    static bool attr = false;                                                                                                        \
+    e = attr ? cudaSuccess : cudaFuncSetAttribute(dib_int16_fwd2_kernel<BF, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Smem); \
+    if (e != cudaSuccess) return e;                                                                                                  \
+    attr = true;                                                                                                                     \
+    dib_int16_fwd2_kernel<BF, ACT><<<grid, 320, kF2Smem, st>>>(mA, mW0, mW1, a);                                                      \
+  } while (0)
+#define DIB_F2_ACT(ACT) do { if (bf16) DIB_F2_LAUNCH(true, ACT); else DIB_F2_LAUNCH(false, ACT); } while (0)
+  switch (act) {
+    case DIB_ACT_LINEAR: DIB_F2_ACT(DIB_ACT_LINEAR); break;
+    case DIB_ACT_RELU: DIB_F2_ACT(DIB_ACT_RELU); break;
+    case DIB_ACT_TANH: DIB_F2_ACT(DIB_ACT_TANH); break;
+    case DIB_ACT_LEAKY_RELU: DIB_F2_ACT(DIB_ACT_LEAKY_RELU); break;
+    case DIB_ACT_SIGMOID: DIB_F2_ACT(DIB_ACT_SIGMOID); break;
+    case DIB_ACT_ELU: DIB_F2_ACT(DIB_ACT_ELU); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef DIB_F2_ACT
+#undef DIB_F2_LAUNCH
+  dib_note_launch();
+  return cudaGetLastError();
 }
 
 int dib_int16_head_blocks(int num_sms) { return num_sms * 2; }

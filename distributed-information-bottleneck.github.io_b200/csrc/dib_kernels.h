@@ -166,6 +166,15 @@ cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int 
 cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
                             int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, int bf16, cudaStream_t st);
 int dib_int16_head_blocks(int num_sms);
+int dib_int16_2sm_enabled();
+void dib_int16_2sm_set(int on);
+int dib_int16_fwd2_enabled();
+void dib_int16_fwd2_set(int on);
+int dib_int16_fwd2_ok(int K0, int N1, int N2, int out_dim);
+cudaError_t dib_int16_fwd2_head(const void* g_in, int ld_in, int K0, const void* w16_0, const float* b0, const void* w16_1, const float* b1,
+                                void* g1, const float* wout, const float* bout, int act, int out_act, float alpha, int loss, const float* y,
+                                int M, float inv_batch, float gscale, void* dg2, float* user_pred, float* wpart, int wpart_stride,
+                                float* loss_part, float* acc_part, int* nblocks, int bf16, cudaStream_t st);
 int dib_int16_rb_enabled();
 void dib_int16_rb_set(int on);
 void dib_int16_head1_set(int on);

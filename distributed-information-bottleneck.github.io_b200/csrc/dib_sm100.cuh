@@ -129,6 +129,96 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------ CTA pair (cta_group::2)
+// Two CTAs of a cluster (same TPC) execute ONE tcgen05.mma with M = 256: each CTA holds its 128 rows of A, HALF of B (N / 2) in its
+// own shared memory and its 128 rows of the accumulator in its own TMEM.  Only the even CTA issues MMAs; both issue TMA loads
+// that signal the even CTA's mbarrier (CUTLASS SM100_TMA_2SM_LOAD / SM100_MMA_F16BF16_2x1SM_SS / umma_arrive_multicast_2x1SM).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {            // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of THIS CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {      // arrive on a (possibly remote) mbarrier
+  // relaxed: the only thing the waiter consumes is TMEM that tcgen05.wait::ld has already finished reading -- a release here would
+  // also wait for this warp's outstanding global stores (MEMBAR + ERRBAR: 12 % of the CTA-pair kernel's stall samples)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the bytes are counted on `cluster_bar` (the even CTA's barrier)
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const void* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const void* map, uint32_t cluster_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem2_alloc(uint32_t smem_dst, uint32_t ncols) {   // the same warp id in BOTH CTAs of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem2_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (instruction descriptor built with m = 256); issued by one thread of the even CTA
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in every CTA of `cta_mask` when all MMAs issued so far have completed
+__device__ __forceinline__ void umma2_commit(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+
+// ---- warp-uniform issue: the WHOLE warp runs the issue loop (uniform control flow lets ptxas keep descriptors, barrier
+// addresses and loop state in uniform registers) and one elected lane executes the instruction.  With `if (lane == 0)` around the
+// loop every tcgen05 operand went through an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~15 instructions per MMA).
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma2_f16_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_w(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(cta_mask) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, sm_100 version bit.
 //   K-major  operand tile [rows x 128 B]: 8-row groups of 1024 B;  SBO = 1024 (next 8 rows), LBO unused (=16 B).
@@ -149,6 +239,25 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)layout_type << 61;
   return d;
 }
+
+// the same from an address in 16-byte units: `(base >> 4) + constant` folds to ONE add per descriptor in an unrolled issue sequence
+// (the byte-address form costs add + shift + mask + or for each of the two descriptors of every MMA; a lone issuing thread then
+// issues MMAs more slowly than the tensor pipe retires them)
+__device__ __forceinline__ uint64_t umma_desc16(uint32_t addr16, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = kLayoutSw128) {
+  const uint32_t lo = addr16 + (((lbo_bytes >> 4) & 0x3FFF) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+// The same descriptor split in two words for issue loops: only the 14-bit start-address field (bits 0..13 of the low word, units
+// of 16 bytes) changes between the MMAs of a kernel, so a loop advances `lo` by (byte offset >> 4) and keeps `hi` -- a single
+// issuing thread otherwise spends more time rebuilding 64-bit descriptors than the tensor pipe spends on the MMA.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout_type = kLayoutSw128) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor), dense, fp32 accumulate, M = 128.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32;  a_mn / b_mn: 1 = MN-major operand

@@ -296,7 +296,9 @@ int dib_debug_force_unfused(dib_model* h, int32_t on);
  * key 1: 16-bit integration FWD / DGRAD GEMMs, 1 = weight slice resident in shared memory, 0 = re-streamed per tile (default:
  * measured faster; also DIB_INT16_RB=0|1).
  * key 2: fused output head for output_dimensionality == 1, 1 = eight rows per pass with a lane-parallel loss (default), 0 = the
- * generic kernel. */
+ * generic kernel.
+ * key 3: single-output models whose last two hidden integration layers are 256 wide, 1 = those layers + the head + the loss as one
+ * kernel (default; also DIB_INT16_FWD2=0|1), 0 = one kernel per layer and the head kernel of key 2. */
 int dib_debug_set_variant(int32_t key, int32_t value);
 
 /* text of the last error raised on this thread ("" if none). */

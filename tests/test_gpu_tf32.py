@@ -191,3 +191,75 @@ def test_single_output_head_kernel_matches_generic_head(loss_name):
     assert rel_err(res[1][0], res[0][0]) < 1e-5
     assert rel_err(res[1][1], res[0][1]) < 2e-4          # the 16-bit rounding of dg can flip on a 1-ulp change of the logit
     np.testing.assert_allclose(res[1][2], res[0][2], rtol=1e-5)
+
+
+@pytest.mark.parametrize("precision,act,loss_name,integ", [("fp16", "relu", "bce_logits", [256, 256]), ("bf16", "tanh", "mse", [256, 256]),
+                                                        ("fp16", "tanh", "bce_logits", [128, 256, 256])])
+def test_fused_integration_tail_matches_per_layer_kernels(precision, act, loss_name, integ):
+    """The fused [hidden 256, hidden 256, head, loss] kernel (dib_int16_fwd2_kernel) against the per-layer GEMM kernels + head:
+    the same 16-bit roundings of g1 / g2 / dg2, fp32 round-off differences only in the 256-term logit and the partial sums.
+    Ragged last tile, a non-power-of-two number of tiles, a deeper integration network (one plain layer before the fused tail)."""
+    from dib_b200 import _lib
+    lib = _lib.load()
+    cfg = O.DIBConfig([1] * 16, [128, 128], integ, 1, activation_fn=act)
+    rng = np.random.default_rng(16)
+    p = O.glorot_uniform_params(cfg, rng)
+    p = p + (p == 0) * (0.05 * rng.standard_normal(p.size)).astype(np.float32)
+    res = {}
+    try:
+        for B in (128 * 3 + 17, 128 * 160 + 77):
+            x = rng.standard_normal((B, 16)).astype(np.float32)
+            y = (x[:, :1] * x[:, 1:2] > 0).astype(np.float32) if loss_name == "bce_logits" else rng.standard_normal((B, 1)).astype(np.float32)
+            for v in (0, 1):
+                _lib.check(lib.dib_debug_set_variant(3, v))
+                m = build_model(cfg, precision=precision, loss=loss_name)
+                m.set_flat_weights(p)
+                m.beta.assign(0.02)
+                pred = m(x, step=2)
+                g, st = m.compute_gradients(x, y, step=2)
+                g2, _ = m.compute_gradients(x, y, step=2)
+                assert torch.equal(g, g2)                                            # deterministic
+                assert torch.isfinite(g).all()
+                res[v] = (np.asarray(pred), g.cpu().numpy(), st.cpu().numpy())
+            assert rel_err(res[1][0], res[0][0]) < 1e-5
+            assert rel_err(res[1][1], res[0][1]) < 2e-4      # a 1-ulp change of the logit can flip a 16-bit rounding of dg2
+            np.testing.assert_allclose(res[1][2], res[0][2], rtol=1e-5)
+    finally:
+        _lib.check(lib.dib_debug_set_variant(3, 1))
+
+
+@pytest.mark.parametrize("precision,act,integ,fwd2", [("fp16", "relu", [256, 256], 0), ("fp16", "relu", [256, 256], 1),
+                                                     ("bf16", "tanh", [256, 256, 256], 0)])
+def test_cta_pair_gemms_match_single_cta_gemms(precision, act, integ, fwd2):
+    """The cta_group::2 GEMM kernel (256 x 256 tile per CTA pair, M = 256 MMAs, B halves in the two shared memories) against the
+    single-CTA 128 x 128 kernels for FWD / DGRAD (+ column sums) / WGRAD: identical k order per output element -> same results up to
+    fp32 accumulation details.  Ragged batches: an odd number of 128-row tiles (the pair's second CTA works on an empty tile)."""
+    from dib_b200 import _lib
+    lib = _lib.load()
+    cfg = O.DIBConfig([1] * 16, [128, 128], integ, 1, activation_fn=act)
+    rng = np.random.default_rng(26)
+    p = O.glorot_uniform_params(cfg, rng)
+    p = p + (p == 0) * (0.05 * rng.standard_normal(p.size)).astype(np.float32)
+    res = {}
+    try:
+        _lib.check(lib.dib_debug_set_variant(3, fwd2))
+        for B in (128 * 5 + 17, 128 * 150 + 3):
+            x = rng.standard_normal((B, 16)).astype(np.float32)
+            y = (x[:, :1] * x[:, 1:2] > 0).astype(np.float32)
+            for v in (0, 1):
+                _lib.check(lib.dib_debug_set_variant(4, v))
+                m = build_model(cfg, precision=precision)
+                m.set_flat_weights(p)
+                m.beta.assign(0.02)
+                pred = m(x, step=2)
+                g, st = m.compute_gradients(x, y, step=2)
+                g2, _ = m.compute_gradients(x, y, step=2)
+                assert torch.equal(g, g2)                                            # deterministic
+                assert torch.isfinite(g).all()
+                res[v] = (np.asarray(pred), g.cpu().numpy(), st.cpu().numpy())
+            assert rel_err(res[1][0], res[0][0]) < 1e-6
+            assert rel_err(res[1][1], res[0][1]) < 1e-6
+            np.testing.assert_allclose(res[1][2], res[0][2], rtol=1e-6)
+    finally:
+        _lib.check(lib.dib_debug_set_variant(3, 1))
+        _lib.check(lib.dib_debug_set_variant(4, 0))
