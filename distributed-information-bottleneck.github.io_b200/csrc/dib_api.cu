@@ -524,6 +524,7 @@ int dib_debug_set_variant(int32_t key, int32_t value) {
   if (key == 2) { dib_int16_head1_set(value); return 0; }
   if (key == 3) { dib_int16_fwd2_set(value); return 0; }
   if (key == 4) { dib_int16_2sm_set(value); return 0; }
+  if (key == 5) { dib_int16_dbg_set(value); return 0; }     // measurement only: wrong results
   return fail("dib_debug_set_variant: unknown key");
 }
 

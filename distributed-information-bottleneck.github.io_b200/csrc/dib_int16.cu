@@ -38,6 +38,7 @@ struct Int16Args {
   int M, T, C, R, act;
   float alpha, out_scale;
   int nsplit, rows_per_split; long long split_stride;
+  int dbg;                                    // measurement only (dib_debug_set_variant key 5): 1 = skip the epilogue's global stores
 };
 
 template <bool BF16>
@@ -186,7 +187,7 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        if (r < R && c0 + cc < C) {          // C is a multiple of 64: a 32-column chunk is entirely inside or outside
+        if (r < R && c0 + cc < C && !(a.dbg & 1)) {          // C is a multiple of 64: a 32-column chunk is entirely inside or outside
           const int c = c0 + cc;
           if constexpr (MODE == DIB_GEMM_WGRAD) {
             float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
@@ -633,7 +634,7 @@ dib_int16_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        if (live) {
+        if (live && !(a.dbg & 1)) {
           const int c = c0 + cc;
           if constexpr (MODE == DIB_GEMM_WGRAD) {
             float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
@@ -1426,6 +1427,8 @@ static int g_int16_head1 = 1;           // single-output head: 8-rows-per-pass k
 int dib_int16_head1_enabled() { return g_int16_head1; }
 void dib_int16_head1_set(int on) { g_int16_head1 = on ? 1 : 0; }
 
+int g_int16_dbg = 0;
+void dib_int16_dbg_set(int v) { g_int16_dbg = v; }
 static int g_int16_2sm = -1;             // CTA-pair (cta_group::2) GEMMs for output widths that are multiples of 256
 int dib_int16_2sm_enabled() {
   if (g_int16_2sm < 0) { const char* e = getenv("DIB_INT16_2SM"); g_int16_2sm = (e && e[0] == '1') ? 1 : 0; }
@@ -1459,6 +1462,7 @@ cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const fl
   if (!map_k(&mA, g_in, K, M, ld_in, kBM) || !map_mn(&mB, w16, N, K, N, kBN / 64))
     return cudaErrorInvalidValue;
   Int16Args a{};
+  a.dbg = g_int16_dbg;
   a.out16 = static_cast<uint16_t*>(g_out); a.ldc = ld_out; a.bias = bias; a.M = M; a.T = K; a.C = N; a.act = act; a.alpha = alpha;
   a.out_scale = 1.f; a.nsplit = 1;
   if (const int bn = rb_pick_bn(K, N)) {          // weights resident in shared memory, activations streamed
@@ -1480,6 +1484,7 @@ cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const vo
   if (!map_k(&mA, dz, N, M, ld_dz, kBM) || !map_k(&mB, w16, N, K, N, kBN))
     return cudaErrorInvalidValue;
   Int16Args a{};
+  a.dbg = g_int16_dbg;
   a.out16 = static_cast<uint16_t*>(dz_in); a.ldc = ld_out; a.X = static_cast<const uint16_t*>(g_in); a.ldx = ld_g;
   a.M = M; a.T = N; a.C = K; a.act = act; a.alpha = alpha; a.out_scale = 1.f; a.nsplit = 1; a.dbias = colsum_part;
   if (const int bn = rb_pick_bn(N, K)) {          // W^T slice resident, dz streamed
@@ -1501,6 +1506,7 @@ cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_d
   if (!map_mn(&mA, g_in, K, M, ld_g, kBM / 64) || !map_mn(&mB, dz, N, M, ld_dz, kBN / 64))
     return cudaErrorInvalidValue;
   Int16Args a{};
+  a.dbg = g_int16_dbg;
   a.out32 = dW_part; a.ldc = N; a.dbias = nullptr; a.M = M; a.T = 0; a.C = N; a.R = K; a.out_scale = out_scale;
   a.nsplit = nsplit; a.rows_per_split = rows_per_split; a.split_stride = split_stride;
   (void)db_part;   // bias gradients come from the kernel that PRODUCES dz (dgrad epilogue / output head), not from here

@@ -166,6 +166,7 @@ cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int 
 cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
                             int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, int bf16, cudaStream_t st);
 int dib_int16_head_blocks(int num_sms);
+void dib_int16_dbg_set(int v);
 int dib_int16_2sm_enabled();
 void dib_int16_2sm_set(int on);
 int dib_int16_fwd2_enabled();

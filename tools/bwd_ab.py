@@ -14,7 +14,7 @@ rb = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 lib = _lib.load()
 _lib.check(lib.dib_debug_set_variant(0, variant))
 _lib.check(lib.dib_debug_set_variant(1, rb))
-for _k, _a in ((3, 3), (4, 4)):          # optional: fused tail on/off, CTA-pair GEMMs on/off
+for _k, _a in ((3, 3), (4, 4), (5, 5)):  # optional: fused tail on/off, CTA-pair GEMMs on/off, measurement-only epilogue switch
     if len(sys.argv) > _a:
         _lib.check(lib.dib_debug_set_variant(_k, int(sys.argv[_a])))
 out = {"variant": variant, "int16_resident_b": rb}
