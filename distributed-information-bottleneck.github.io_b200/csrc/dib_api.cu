@@ -80,6 +80,7 @@ struct dib_model {
   bool int16_ok = false;
   long long emb16_off = 0, demb16_off = 0, headpart_off = 0, dbpart_off = 0, eps16_off = 0, a0g_off = 0;
   int head_stride = 0, dbpart_stride = 0;
+  long long dbpart_layer = 0;       // floats per layer of the dgrad column-sum partials
   std::vector<long long> g16_off, dg16_off, w16_off;   // [1..Li], [1..Li], [0..Li-1]
   int head_blocks = 0, lossacc_cap = 0;
   int head_used = 0;                // rows of the head partials the last forward wrote (fused tail kernel: its CTA count)
@@ -170,7 +171,8 @@ void plan(dib_model* h) {
     int wmax = 1;
     for (int j = 0; j < h->Li; ++j) if (h->int_arch[j] > wmax) wmax = h->int_arch[j];
     h->dbpart_stride = wmax;                             // dgrad-epilogue column sums: [row tile][width]
-    h->dbpart_off = take(c, (long long)DIB_CEIL_DIV(B, 128ll) * wmax);
+    h->dbpart_layer = DIB_ROUND_UP((long long)DIB_CEIL_DIV(B, 128ll) * wmax, 64);
+    h->dbpart_off = take(c, h->dbpart_layer * (h->Li > 0 ? h->Li : 1));    // one region per layer: all reduced in one launch
   }
   h->beta_eff_off = take(c, 64);
   h->wshadow_off = take(c, h->Pp);      // TF32-rounded copy of the parameters (tensor-core mode B operands)
@@ -384,8 +386,14 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
       const int bf = h->precision == DIB_PREC_BF16 ? 1 : 0;
       // ---------------- integration network on 16-bit activations + fused output head
       prof_begin(c, "int16_pack_weights");
-      for (int j = 0; j < h->Li; ++j)
-        DIB_CUDA_OK(dib_int16_convert(c.params + h->intW[j], c.ws + h->w16_off[j], (long long)int_fan_in(h, j) * int_fan_out(h, j), bf, c.st));
+      {
+        std::vector<const float*> wsrc; std::vector<void*> wdst; std::vector<long long> wn;
+        for (int j = 0; j < h->Li; ++j) {
+          wsrc.push_back(c.params + h->intW[j]); wdst.push_back(c.ws + h->w16_off[j]);
+          wn.push_back((long long)int_fan_in(h, j) * int_fan_out(h, j));
+        }
+        DIB_CUDA_OK(dib_int16_convert_many(wsrc.data(), wdst.data(), wn.data(), h->Li, bf, c.st));
+      }
       prof_end(c);
       const int Kh = h->int_arch[h->Li - 1];
       const float gscale = training ? exp2f(ceilf(log2f(1.f / inv_batch))) : 1.f;
@@ -866,9 +874,12 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     const int Kh = h->int_arch[h->Li - 1];
     const int row_tiles = (int)DIB_CEIL_DIV((long long)n, 128ll);
     const long long p_head = h->intW[h->Li];
+    // every fixed-order reduction of this phase runs as ONE launch at its end (bias gradients from the head / dgrad column sums,
+    // batch-split weight-gradient partials, the output layer's per-CTA partials)
+    std::vector<DibReduceSeg> segs;
     // bias gradient of the last hidden layer: column sums of dg accumulated by the output head
-    DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off + (long long)Kh * h->out + h->out, h->head_stride, h->head_used, Kh,
-                                       1.f / gscale, grads_flat + h->intB[h->Li - 1], c.st));
+    segs.push_back({c.ws + h->headpart_off + (long long)Kh * h->out + h->out, h->head_stride, h->head_used, Kh, 1.f / gscale,
+                    grads_flat + h->intB[h->Li - 1]});
     for (int j = h->Li - 1; j >= 0; --j) {
       const void* in_j = j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]);
       const int K = int_fan_in(h, j), N = int_fan_out(h, j);
@@ -879,16 +890,16 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
       prof_begin(c, "int16_dgrad_l", j);
       DIB_CUDA_OK(dib_int16_dgrad(c.ws + h->dg16_off[j + 1], N, c.ws + h->w16_off[j], j > 0 ? (const void*)(c.ws + h->g16_off[j]) : nullptr,
                                   K, j > 0 ? (void*)(c.ws + h->dg16_off[j]) : (void*)(c.ws + h->demb16_off), K, (int)n, K, N, h->act,
-                                  h->alpha, j > 0 ? c.ws + h->dbpart_off : nullptr, bf, c.st));
+                                  h->alpha, j > 0 ? c.ws + h->dbpart_off + (long long)j * h->dbpart_layer : nullptr, bf, c.st));
       if (j > 0)   // bias gradient of layer j-1 = column sums of the gradient this dgrad just produced
-        DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->dbpart_off, K, row_tiles, K, 1.f / gscale, grads_flat + h->intB[j - 1], c.st));
+        segs.push_back({c.ws + h->dbpart_off + (long long)j * h->dbpart_layer, K, row_tiles, K, 1.f / gscale, grads_flat + h->intB[j - 1]});
       prof_end(c);
     }
     prof_begin(c, "int_split_reduce");
-    for (int j = 0; j < h->Li; ++j)     // hidden-layer kernels: batch-split partials (their biases were reduced above)
-      DIB_CUDA_OK(dib_launch_reduce_partials(part + h->intW[j], h->Pp, nsplit, (long long)int_fan_in(h, j) * int_fan_out(h, j),
-                                             grads_flat + h->intW[j], c.st));
-    DIB_CUDA_OK(dib_launch_reduce_tall(c.ws + h->headpart_off, h->head_stride, h->head_used, h->P - p_head, 1.f, grads_flat + p_head, c.st));
+    for (int j = 0; j < h->Li; ++j)     // hidden-layer kernels: batch-split partials
+      segs.push_back({part + h->intW[j], h->Pp, nsplit, (long long)int_fan_in(h, j) * int_fan_out(h, j), 1.f, grads_flat + h->intW[j]});
+    segs.push_back({c.ws + h->headpart_off, h->head_stride, h->head_used, h->P - p_head, 1.f, grads_flat + p_head});
+    DIB_CUDA_OK(dib_launch_reduce_segments(segs.data(), (int)segs.size(), c.st));
     prof_end(c);
   } else if (phA) {
     // integration network backward (GradientTape through models.py:122)

@@ -528,6 +528,58 @@ cudaError_t dib_launch_round_copy(const float* src, float* dst, int64_t count, c
   return cudaGetLastError();
 }
 
+namespace {
+struct ReduceSegsArg { DibReduceSeg seg[kDibMaxReduceSegs]; int first_block[kDibMaxReduceSegs + 1]; int nseg; };
+// the dib_reduce_tall_kernel mapping (32 outputs x 8 row lanes per block, fixed order) over a list of independent reductions
+__global__ void __launch_bounds__(256)
+dib_reduce_segments_kernel(const ReduceSegsArg A) {
+  __shared__ float red[8][32];
+  int sidx = 0;
+#pragma unroll
+  for (int k = 1; k < kDibMaxReduceSegs; ++k) if (k < A.nseg && (int)blockIdx.x >= A.first_block[k]) sidx = k;
+  const DibReduceSeg S = A.seg[sidx];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i = (long long)((int)blockIdx.x - A.first_block[sidx]) * 32 + tx;
+  float s = 0.f;
+  if (i < S.count) {
+    int r = ty;
+    for (; r + 56 < S.nrows; r += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = S.src[(long long)(r + 8 * u) * S.row_stride + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; r < S.nrows; r += 8) s += S.src[(long long)r * S.row_stride + i];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < S.count) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k][tx];
+    S.dst[i] = t * S.scale;
+  }
+}
+}  // namespace
+
+cudaError_t dib_launch_reduce_segments(const DibReduceSeg* segs, int nseg, cudaStream_t st) {
+  for (int base = 0; base < nseg; base += kDibMaxReduceSegs) {
+    ReduceSegsArg A{};
+    int nb = 0, n = 0;
+    for (int k = base; k < nseg && n < kDibMaxReduceSegs; ++k) {
+      if (segs[k].count <= 0) continue;
+      A.seg[n] = segs[k]; A.first_block[n] = nb;
+      nb += (int)((segs[k].count + 31) / 32);
+      ++n;
+    }
+    A.first_block[n] = nb; A.nseg = n;
+    if (n == 0) continue;
+    dib_reduce_segments_kernel<<<nb, 256, 0, st>>>(A);
+    dib_note_launch();
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int nrows, int64_t count, float scale, float* out,
                                    cudaStream_t st) {
   if (count <= 0) return cudaSuccess;

@@ -353,16 +353,14 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
           DIB_EPI_SIGNAL(bar_a0);
         }
         noise8(ep, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, hsel * 16, valid, nrmA);   // while layer 1 runs
-        if (P.eps16 && valid)        // hand the noise to the backward kernel of this step (16-bit, like its gradient operands)
-          *reinterpret_cast<uint4*>(P.eps16 + (grow * F + f) * 32 + hsel * 16) =
-              make_uint4(pack2<BF16>(nrmA[0], nrmA[1]), pack2<BF16>(nrmA[2], nrmA[3]), pack2<BF16>(nrmA[4], nrmA[5]), pack2<BF16>(nrmA[6], nrmA[7]));
         mbar_wait(bar_d1, ph); tc_fence_after_sync();
         epilogue_to_tile<BF16, RELU>(tR0 + lane_addr, hbuf, r, hsel * 64, P.act, P.alpha);
         DIB_EPI_SIGNAL(bar_h2);
         noise8(ep ? ep + 8 : nullptr, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, hsel * 16 + 8, valid, nrmB);   // while layer 2 runs
-        if (P.eps16 && valid)
-          *reinterpret_cast<uint4*>(P.eps16 + (grow * F + f) * 32 + hsel * 16 + 8) =
-              make_uint4(pack2<BF16>(nrmB[0], nrmB[1]), pack2<BF16>(nrmB[2], nrmB[3]), pack2<BF16>(nrmB[4], nrmB[5]), pack2<BF16>(nrmB[6], nrmB[7]));
+        if (P.eps16 && valid)        // hand the noise to the backward kernel of this step (16-bit, like its gradient operands): one 32-byte store
+          dib_st_global_v8(P.eps16 + (grow * F + f) * 32 + hsel * 16,
+                           pack2<BF16>(nrmA[0], nrmA[1]), pack2<BF16>(nrmA[2], nrmA[3]), pack2<BF16>(nrmA[4], nrmA[5]), pack2<BF16>(nrmA[6], nrmA[7]),
+                           pack2<BF16>(nrmB[0], nrmB[1]), pack2<BF16>(nrmB[2], nrmB[3]), pack2<BF16>(nrmB[4], nrmB[5]), pack2<BF16>(nrmB[6], nrmB[7]));
         // ---- (mu, logvar) -> reparameterise, KL, emb   (16 embedding dims per thread)
         mbar_wait(bar_d2, ph); tc_fence_after_sync();
         {
@@ -375,6 +373,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
             float* dst = P.emb ? P.emb + grow * P.ldemb + f * 32 + hsel * 16 : nullptr;
             uint16_t* dst16 = P.emb16 ? P.emb16 + grow * P.ldemb16 + f * 32 + hsel * 16 : nullptr;
             float* udst = P.user_emb ? P.user_emb + grow * ((long long)F * 32) + f * 32 + hsel * 16 : nullptr;
+            uint32_t ew[8];
 #pragma unroll
             for (int e0 = 0; e0 < 16; e0 += 4) {
               float u[4];
@@ -386,7 +385,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
                 kl_acc += 0.5f * (mu * mu + s * s - lv - 1.f);
               }
               if (udst) *reinterpret_cast<float4*>(udst + e0) = make_float4(u[0], u[1], u[2], u[3]);
-              if (dst16) *reinterpret_cast<uint2*>(dst16 + e0) = make_uint2(pack2<BF16>(u[0], u[1]), pack2<BF16>(u[2], u[3]));
+              ew[e0 >> 1] = pack2<BF16>(u[0], u[1]); ew[(e0 >> 1) + 1] = pack2<BF16>(u[2], u[3]);
               if (dst) {
                 if (P.round_emb) {
 #pragma unroll
@@ -395,6 +394,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
                 *reinterpret_cast<float4*>(dst + e0) = make_float4(u[0], u[1], u[2], u[3]);
               }
             }
+            if (dst16) dib_st_global_v8(dst16, ew);      // this thread's 16 embedding dims: one full 32-byte sector
           }
         }
       }
@@ -1033,7 +1033,9 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
         uint4 dpre[2];
         if (Q.d_emb16) {
           const uint16_t* src = Q.d_emb16 + (valid ? grow : 0) * Q.ldd16 + f * 32 + csel * 16;
-          dpre[0] = *reinterpret_cast<const uint4*>(src); dpre[1] = *reinterpret_cast<const uint4*>(src + 8);
+          uint32_t dw[8];
+          dib_ld_global_v8(src, dw);
+          dpre[0] = make_uint4(dw[0], dw[1], dw[2], dw[3]); dpre[1] = make_uint4(dw[4], dw[5], dw[6], dw[7]);
         }
         if constexpr (!EPS16) { if (has_next) load_x(grow_n < P.n ? P.x + grow_n * P.ldx + xo : nullptr, d, xv); }
         const float* ep = (P.eps && valid) ? P.eps + (grow * F + f) * 32 + csel * 16 : P.eps;
@@ -1041,8 +1043,7 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
         constexpr bool have_eps16 = EPS16;
         if constexpr (have_eps16) {            // written by this step's forward kernel: 32 B per thread instead of 4 Philox calls
           const uint16_t* e16 = P.eps16 + ((valid ? grow : 0) * F + f) * 32 + csel * 16;
-          const uint4 q0 = *reinterpret_cast<const uint4*>(e16), q1 = *reinterpret_cast<const uint4*>(e16 + 8);
-          nz16[0] = q0.x; nz16[1] = q0.y; nz16[2] = q0.z; nz16[3] = q0.w; nz16[4] = q1.x; nz16[5] = q1.y; nz16[6] = q1.z; nz16[7] = q1.w;
+          dib_ld_global_v8(e16, nz16);
         }
         // buffer set (i & 1) was last used by tile i - 2: all of its MMAs (chain B commits last) have retired
         if (i >= 2) { mbar_wait(bar_wg0 + 8 * (i & 1), ((i >> 1) - 1) & 1); }

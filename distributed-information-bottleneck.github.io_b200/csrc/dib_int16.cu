@@ -168,7 +168,7 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         // samples, profiles/r02_int16_ncu_full.txt)
         const bool live = r < R && c0 + cc < C;
         float4 bpre[8];
-        uint4 xpre[4];
+        uint32_t xpre[16];
         if constexpr (MODE == DIB_GEMM_FWD) {
           if (live) {
 #pragma unroll
@@ -177,8 +177,11 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         }
         if constexpr (MODE == DIB_GEMM_DGRAD) {
           if (live && a.X) {
+            uint32_t xa[8], xb[8];
+            dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc, xa);
+            dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc + 16, xb);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) xpre[j] = *reinterpret_cast<const uint4*>(a.X + (long long)r * a.ldx + c0 + cc + 8 * j);
+            for (int j = 0; j < 8; ++j) { xpre[j] = xa[j]; xpre[8 + j] = xb[j]; }
           }
         }
         uint32_t v[32];
@@ -192,11 +195,14 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           if constexpr (MODE == DIB_GEMM_WGRAD) {
             float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * a.out_scale, __uint_as_float(v[j + 1]) * a.out_scale,
-                                                                __uint_as_float(v[j + 2]) * a.out_scale, __uint_as_float(v[j + 3]) * a.out_scale);
+            for (int j = 0; j < 32; j += 8)
+              dib_st_global_v8(dst + j, __float_as_uint(__uint_as_float(v[j]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 1]) * a.out_scale),
+                               __float_as_uint(__uint_as_float(v[j + 2]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 3]) * a.out_scale),
+                               __float_as_uint(__uint_as_float(v[j + 4]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 5]) * a.out_scale),
+                               __float_as_uint(__uint_as_float(v[j + 6]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 7]) * a.out_scale));
           } else {
             uint16_t* dst = a.out16 + (long long)r * a.ldc + c;
+            uint32_t ow[16];
             const uint16_t* xs = (MODE == DIB_GEMM_DGRAD && a.X) ? a.X + (long long)r * a.ldx + c : nullptr;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -209,8 +215,7 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = dib_act16(a.act, f[k] + bb[k], a.alpha);
               } else if (xs) {
-                const uint4 xv = xpre[j >> 3];
-                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                const uint32_t xw[4] = {xpre[j >> 1], xpre[(j >> 1) + 1], xpre[(j >> 1) + 2], xpre[(j >> 1) + 3]};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   float h0, h1;
@@ -219,7 +224,9 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                   f[2 * k + 1] *= dib_act_grad(a.act, h1, a.alpha);
                 }
               }
-              *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2<BF16>(f[0], f[1]), pack_h2<BF16>(f[2], f[3]), pack_h2<BF16>(f[4], f[5]), pack_h2<BF16>(f[6], f[7]));
+              ow[(j >> 1)] = pack_h2<BF16>(f[0], f[1]); ow[(j >> 1) + 1] = pack_h2<BF16>(f[2], f[3]);
+              ow[(j >> 1) + 2] = pack_h2<BF16>(f[4], f[5]); ow[(j >> 1) + 3] = pack_h2<BF16>(f[6], f[7]);
+              if (j & 8) dib_st_global_v8(dst + j - 8, ow[(j >> 1) - 4], ow[(j >> 1) - 3], ow[(j >> 1) - 2], ow[(j >> 1) - 1], ow[(j >> 1)], ow[(j >> 1) + 1], ow[(j >> 1) + 2], ow[(j >> 1) + 3]);
               if constexpr (MODE == DIB_GEMM_DGRAD) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[j + k] = __float_as_uint(f[k]);     // keep the gated fp32 values for the column sums
@@ -384,7 +391,7 @@ dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       for (int cc = 0; cc < BN; cc += 32) {
         const bool live = r < R && c0 + cc < C;     // global operands of the epilogue first: their latency hides under the TMEM load
         float4 bpre[8];
-        uint4 xpre[4];
+        uint32_t xpre[16];
         if constexpr (MODE == DIB_GEMM_FWD) {
           if (live) {
 #pragma unroll
@@ -393,8 +400,11 @@ dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         if constexpr (MODE == DIB_GEMM_DGRAD) {
           if (live && a.X) {
+            uint32_t xa[8], xb[8];
+            dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc, xa);
+            dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc + 16, xb);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) xpre[j] = *reinterpret_cast<const uint4*>(a.X + (long long)r * a.ldx + c0 + cc + 8 * j);
+            for (int j = 0; j < 8; ++j) { xpre[j] = xa[j]; xpre[8 + j] = xb[j]; }
           }
         }
         uint32_t v[32];
@@ -403,6 +413,7 @@ dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (r < R && c0 + cc < C) {          // C is a multiple of 64: a 32-column chunk is entirely inside or outside
           const int c = c0 + cc;
           uint16_t* dst = a.out16 + (long long)r * a.ldc + c;
+          uint32_t ow[16];
           const uint16_t* xs = (MODE == DIB_GEMM_DGRAD && a.X) ? a.X + (long long)r * a.ldx + c : nullptr;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -415,8 +426,7 @@ dib_int16_rb_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
               for (int k = 0; k < 8; ++k) f[k] = dib_act16(a.act, f[k] + bb[k], a.alpha);
             } else if (xs) {
-              const uint4 xv = xpre[j >> 3];
-              const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+              const uint32_t xw[4] = {xpre[j >> 1], xpre[(j >> 1) + 1], xpre[(j >> 1) + 2], xpre[(j >> 1) + 3]};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 float h0, h1;
@@ -615,7 +625,7 @@ dib_int16_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       for (int cc = wcol; cc < wcol + 128; cc += 32) {
         const bool live = r < R && c0 + cc < C;
         float4 bpre[8];
-        uint4 xpre[4];
+        uint32_t xpre[16];
         if constexpr (MODE == DIB_GEMM_FWD) {
           if (live) {
 #pragma unroll
@@ -624,8 +634,11 @@ dib_int16_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         }
         if constexpr (MODE == DIB_GEMM_DGRAD) {
           if (live && a.X) {
+            uint32_t xa[8], xb[8];
+            dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc, xa);
+            dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc + 16, xb);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) xpre[j] = *reinterpret_cast<const uint4*>(a.X + (long long)r * a.ldx + c0 + cc + 8 * j);
+            for (int j = 0; j < 8; ++j) { xpre[j] = xa[j]; xpre[8 + j] = xb[j]; }
           }
         }
         uint32_t v[32];
@@ -639,11 +652,14 @@ dib_int16_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           if constexpr (MODE == DIB_GEMM_WGRAD) {
             float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]) * a.out_scale, __uint_as_float(v[j + 1]) * a.out_scale,
-                                                                __uint_as_float(v[j + 2]) * a.out_scale, __uint_as_float(v[j + 3]) * a.out_scale);
+            for (int j = 0; j < 32; j += 8)
+              dib_st_global_v8(dst + j, __float_as_uint(__uint_as_float(v[j]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 1]) * a.out_scale),
+                               __float_as_uint(__uint_as_float(v[j + 2]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 3]) * a.out_scale),
+                               __float_as_uint(__uint_as_float(v[j + 4]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 5]) * a.out_scale),
+                               __float_as_uint(__uint_as_float(v[j + 6]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 7]) * a.out_scale));
           } else {
             uint16_t* dst = a.out16 + (long long)r * a.ldc + c;
+            uint32_t ow[16];
             const bool gate = (MODE == DIB_GEMM_DGRAD) && a.X != nullptr;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -656,8 +672,7 @@ dib_int16_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = dib_act16(a.act, f[k] + bb[k], a.alpha);
               } else if (gate) {
-                const uint4 xv = xpre[j >> 3];
-                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                const uint32_t xw[4] = {xpre[j >> 1], xpre[(j >> 1) + 1], xpre[(j >> 1) + 2], xpre[(j >> 1) + 3]};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   float h0, h1;
@@ -666,7 +681,9 @@ dib_int16_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
                   f[2 * k + 1] *= dib_act_grad(a.act, h1, a.alpha);
                 }
               }
-              *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_h2<BF16>(f[0], f[1]), pack_h2<BF16>(f[2], f[3]), pack_h2<BF16>(f[4], f[5]), pack_h2<BF16>(f[6], f[7]));
+              ow[(j >> 1)] = pack_h2<BF16>(f[0], f[1]); ow[(j >> 1) + 1] = pack_h2<BF16>(f[2], f[3]);
+              ow[(j >> 1) + 2] = pack_h2<BF16>(f[4], f[5]); ow[(j >> 1) + 3] = pack_h2<BF16>(f[6], f[7]);
+              if (j & 8) dib_st_global_v8(dst + j - 8, ow[(j >> 1) - 4], ow[(j >> 1) - 3], ow[(j >> 1) - 2], ow[(j >> 1) - 1], ow[(j >> 1)], ow[(j >> 1) + 1], ow[(j >> 1) + 2], ow[(j >> 1) + 3]);
               if constexpr (MODE == DIB_GEMM_DGRAD) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[j + k] = __float_as_uint(f[k]);
@@ -1183,6 +1200,7 @@ dib_int16_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + lane_off + (uint32_t)cc, v);
         tmem_ld_wait();
+        uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
 #pragma unroll
         for (int g = 0; g < 32; g += 8) {
           const float4 ba = *reinterpret_cast<const float4*>(&s_b0[cc + g]), bb = *reinterpret_cast<const float4*>(&s_b0[cc + g + 4]);
@@ -1193,7 +1211,8 @@ dib_int16_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           const uint32_t p0 = pack_h2<BF16>(f[0], f[1]), p1 = pack_h2<BF16>(f[2], f[3]), p2 = pack_h2<BF16>(f[4], f[5]), p3 = pack_h2<BF16>(f[6], f[7]);
           const int c = cc + g;
           st_shared_v4u(g1s + (c >> 6) * kF2AB + rt * 128 + ((((c & 63) >> 3) ^ (rt & 7)) << 4), p0, p1, p2, p3);
-          if (live) *reinterpret_cast<uint4*>(a.g1 + row * a.ldg1 + c) = make_uint4(p0, p1, p2, p3);
+          if (g & 8) { if (live) dib_st_global_v8(a.g1 + row * a.ldg1 + c - 8, q0, q1, q2, q3, p0, p1, p2, p3); }
+          else { q0 = p0; q1 = p1; q2 = p2; q3 = p3; }
         }
         if (j & 1) {                       // a 64-column chunk of g1 (one k-block of L1) is complete for this warp's rows
           fence_proxy_async_smem();
@@ -1255,6 +1274,7 @@ dib_int16_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         for (int j = 0; j < 4; ++j) {
           const int cc = colbase + 32 * j;
           float wa[32], wb[32];
+          uint32_t dq[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
           for (int g = 0; g < 32; g += 8) {
             const float4 w0 = *reinterpret_cast<const float4*>(&s_w[cc + g]), w1 = *reinterpret_cast<const float4*>(&s_w[cc + g + 4]);
@@ -1269,9 +1289,9 @@ dib_int16_fwd2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
               d[k + 1] = ds * wv[k + 1] * dib_act_grad(ACT, h1, a.alpha);
               wb[g + k] = d[k]; wb[g + k + 1] = d[k + 1];
             }
-            if (live)
-              *reinterpret_cast<uint4*>(a.dg2 + row * a.lddg + cc + g) =
-                  make_uint4(pack_h2<BF16>(d[0], d[1]), pack_h2<BF16>(d[2], d[3]), pack_h2<BF16>(d[4], d[5]), pack_h2<BF16>(d[6], d[7]));
+            const uint32_t e0 = pack_h2<BF16>(d[0], d[1]), e1 = pack_h2<BF16>(d[2], d[3]), e2 = pack_h2<BF16>(d[4], d[5]), e3 = pack_h2<BF16>(d[6], d[7]);
+            if (g & 8) { if (live) dib_st_global_v8(a.dg2 + row * a.lddg + cc + g - 8, dq[0], dq[1], dq[2], dq[3], e0, e1, e2, e3); }
+            else { dq[0] = e0; dq[1] = e1; dq[2] = e2; dq[3] = e3; }
           }
           const float ca = warp_colsum32(wa, lane), cb = warp_colsum32(wb, lane);
           s_col[wg][0][wq][32 * j + lane] = ca;
@@ -1445,6 +1465,42 @@ int dib_int16_rb_enabled() {
   return g_int16_rb;
 }
 void dib_int16_rb_set(int on) { g_int16_rb = on ? 1 : 0; }
+
+namespace {
+struct ConvSegs { const float* src[8]; uint16_t* dst[8]; long long first[9]; int nseg; };
+template <bool BF16>
+__global__ void dib_f32_to_16_segs_kernel(const ConvSegs A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.first[A.nseg]) return;
+  int k = 0;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) if (q < A.nseg && i >= A.first[q]) k = q;
+  const float v = A.src[k][i - A.first[k]];
+  uint16_t o;
+  if constexpr (BF16) { const __nv_bfloat16 b = __float2bfloat16_rn(v); o = *reinterpret_cast<const uint16_t*>(&b); }
+  else { const __half b = __float2half_rn(v); o = *reinterpret_cast<const uint16_t*>(&b); }
+  A.dst[k][i - A.first[k]] = o;
+}
+}  // namespace
+
+// several fp32 -> 16-bit conversions (the integration network's weight matrices) in one launch
+cudaError_t dib_int16_convert_many(const float* const* src, void* const* dst16, const long long* n, int count, int bf16, cudaStream_t st) {
+  for (int base = 0; base < count; base += 8) {
+    ConvSegs A{};
+    long long tot = 0; int m = 0;
+    for (int k = base; k < count && m < 8; ++k) {
+      if (n[k] <= 0) continue;
+      A.src[m] = src[k]; A.dst[m] = static_cast<uint16_t*>(dst16[k]); A.first[m] = tot; tot += n[k]; ++m;
+    }
+    A.first[m] = tot; A.nseg = m;
+    for (int q = m + 1; q < 9; ++q) A.first[q] = tot;
+    if (m == 0) continue;
+    if (bf16) dib_f32_to_16_segs_kernel<true><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A);
+    else dib_f32_to_16_segs_kernel<false><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A);
+    dib_note_launch();
+  }
+  return cudaGetLastError();
+}
 
 cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, int bf16, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;

@@ -156,11 +156,16 @@ cudaError_t dib_enc_fused_backward(const DibEncFusedDesc& d, const DibEncFusedIO
 
 // ---- 16-bit integration network path (dib_int16.cu) ----
 cudaError_t dib_int16_convert(const float* src, void* dst16, long long n, int bf16, cudaStream_t st);
+cudaError_t dib_int16_convert_many(const float* const* src, void* const* dst16, const long long* n, int count, int bf16, cudaStream_t st);
 cudaError_t dib_int16_fwd(const void* g_in, int ld_in, const void* w16, const float* bias, void* g_out, int ld_out, int M,
                           int K, int N, int act, float alpha, int bf16, cudaStream_t st);
 // colsum_part (nullable): [ceil(M/128)][K] per-row-tile column sums of dz_in = bias-gradient partials of the layer below
 cudaError_t dib_int16_dgrad(const void* dz, int ld_dz, const void* w16, const void* g_in, int ld_g, void* dz_in, int ld_out,
                             int M, int K, int N, int act, float alpha, float* colsum_part, int bf16, cudaStream_t st);
+// several column-sum reductions in ONE launch: dst[i] = scale * sum_{r < nrows} src[r * row_stride + i], i < count (fixed order)
+struct DibReduceSeg { const float* src; long long row_stride; int nrows; long long count; float scale; float* dst; };
+constexpr int kDibMaxReduceSegs = 8;
+cudaError_t dib_launch_reduce_segments(const DibReduceSeg* segs, int nseg, cudaStream_t st);
 cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int nrows, int64_t count, float scale, float* out,
                                    cudaStream_t st);
 cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
