@@ -159,31 +159,34 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       int r0, c0, split, t_begin, nk;
       decode(tile, r0, c0, split, t_begin, nk);
       const int acc = lt & 1;
-      if (nk > 0) { mbar_wait(tfull_bar(acc), (lt >> 1) & 1); tc_fence_after_sync(); }
       const int r = r0 + q * 32 + lane;
+      // the activation row that gates the gradient (DGRAD) is fetched one 32-column chunk ahead -- the first chunk before the wait
+      // for the accumulator -- so that its L2 / HBM latency never sits on the per-chunk critical path
+      uint32_t xpre[16], xnext[16];
+      auto load_x = [&](int cc, uint32_t (&dst)[16]) {
+        if (r < R && c0 + cc < C && a.X) {
+          uint32_t xa[8], xb[8];
+          dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc, xa);
+          dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc + 16, xb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { dst[j] = xa[j]; dst[8 + j] = xb[j]; }
+        }
+      };
+      if constexpr (MODE == DIB_GEMM_DGRAD) load_x(0, xpre);
+      if (nk > 0) { mbar_wait(tfull_bar(acc), (lt >> 1) & 1); tc_fence_after_sync(); }
 #pragma unroll 1
       for (int cc = 0; cc < kBN; cc += 32) {
-        // the epilogue's own global operands (bias slice / the activation row that gates the gradient) are fetched BEFORE the
-        // TMEM load so that their latency hides under it (they sat behind tcgen05.wait::ld: 41 % of the FWD kernel's stall
-        // samples, profiles/r02_int16_ncu_full.txt)
+        // the bias slice (FWD) is fetched BEFORE the TMEM load so that its latency hides under it (it sat behind
+        // tcgen05.wait::ld: 41 % of the FWD kernel's stall samples, profiles/r02_int16_ncu_full.txt)
         const bool live = r < R && c0 + cc < C;
         float4 bpre[8];
-        uint32_t xpre[16];
         if constexpr (MODE == DIB_GEMM_FWD) {
           if (live) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) bpre[j] = *reinterpret_cast<const float4*>(a.bias + c0 + cc + 4 * j);
           }
         }
-        if constexpr (MODE == DIB_GEMM_DGRAD) {
-          if (live && a.X) {
-            uint32_t xa[8], xb[8];
-            dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc, xa);
-            dib_ld_global_v8(a.X + (long long)r * a.ldx + c0 + cc + 16, xb);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { xpre[j] = xa[j]; xpre[8 + j] = xb[j]; }
-          }
-        }
+        if constexpr (MODE == DIB_GEMM_DGRAD) { if (cc + 32 < kBN) load_x(cc + 32, xnext); }
         uint32_t v[32];
         if (nk > 0) { tmem_ld_32x32b_x32(tmem_base + acc * kBN + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v); tmem_ld_wait(); }
         else {
@@ -255,6 +258,8 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
             }
             colsum_s[q][cc + lane] = w[0];
           }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xpre[j] = xnext[j];
         }
       }
       if constexpr (MODE == DIB_GEMM_DGRAD) {
