@@ -108,6 +108,8 @@ def algorithmic_macs(batch, cfg=None):
         macs[f"int16_fwd_l{j}"] = macs[f"int_fwd_l{j}"]
         macs[f"int16_wgrad_l{j}"] = macs[f"int_wgrad_l{j}"]
         macs[f"int16_dgrad_l{j}"] = macs[f"int_dgrad_l{j}"]
+    for j in range(nl - 2):               # two layers' weight gradients per launch (dib_int16_wgrad_pair)
+        macs[f"int16_wgrad_pair_l{j}"] = macs[f"int_wgrad_l{j}"] + macs[f"int_wgrad_l{j + 1}"]
     if nl >= 3:                           # single-output models: last two hidden layers + head in one kernel (dib_int16_fwd2_kernel)
         macs["int16_fwd2_head"] = macs[f"int_fwd_l{nl - 3}"] + macs[f"int_fwd_l{nl - 2}"] + macs[f"int_fwd_l{nl - 1}"]
     return macs, fwd, train

@@ -860,7 +860,7 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
   // deterministic split of the batch for the weight gradients
   long long rps = DIB_CEIL_DIV((long long)n, (long long)kMaxSplits);
   if (rps < 256) rps = 256;
-  rps = DIB_ROUND_UP(rps, 32);
+  rps = DIB_ROUND_UP(rps, 64);      // whole k-blocks of every WGRAD kernel (32 rows for the TF32 ones, 64 for the 16-bit ones)
   const int nsplit = (int)DIB_CEIL_DIV((long long)n, rps);
   float* part = c.ws + h->part_off;
 
@@ -880,13 +880,10 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     // bias gradient of the last hidden layer: column sums of dg accumulated by the output head
     segs.push_back({c.ws + h->headpart_off + (long long)Kh * h->out + h->out, h->head_stride, h->head_used, Kh, 1.f / gscale,
                     grads_flat + h->intB[h->Li - 1]});
+    // the dgrad chain first (layer j's dgrad produces the gradient layer j-1's wgrad consumes), then the weight gradients in PAIRS of
+    // layers per launch: one layer's [K/128 x N/128 x splits] tiles do not fill the 2 x SMs CTA slots, two layers' tiles do
     for (int j = h->Li - 1; j >= 0; --j) {
-      const void* in_j = j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]);
       const int K = int_fan_in(h, j), N = int_fan_out(h, j);
-      prof_begin(c, "int16_wgrad_l", j);
-      DIB_CUDA_OK(dib_int16_wgrad(in_j, K, c.ws + h->dg16_off[j + 1], N, part + h->intW[j], nullptr, (int)n, K, N, nsplit,
-                                  (int)rps, h->Pp, 1.f / gscale, bf, c.st));
-      prof_end(c);
       prof_begin(c, "int16_dgrad_l", j);
       DIB_CUDA_OK(dib_int16_dgrad(c.ws + h->dg16_off[j + 1], N, c.ws + h->w16_off[j], j > 0 ? (const void*)(c.ws + h->g16_off[j]) : nullptr,
                                   K, j > 0 ? (void*)(c.ws + h->dg16_off[j]) : (void*)(c.ws + h->demb16_off), K, (int)n, K, N, h->act,
@@ -895,9 +892,33 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
         segs.push_back({c.ws + h->dbpart_off + (long long)j * h->dbpart_layer, K, row_tiles, K, 1.f / gscale, grads_flat + h->intB[j - 1]});
       prof_end(c);
     }
+    std::vector<int> nsplit_of(h->Li, nsplit);
+    auto in_of = [&](int j) { return j == 0 ? (const void*)(c.ws + h->emb16_off) : (const void*)(c.ws + h->g16_off[j]); };
+    auto tiles_of = [&](int j) { return DIB_CEIL_DIV(int_fan_in(h, j), 128) * DIB_CEIL_DIV(int_fan_out(h, j), 128); };
+    int j = h->Li - 1;
+    for (; j >= 1; j -= 2) {          // layers (j, j-1) together
+      long long ns = (2ll * h->num_sms) / (tiles_of(j) + tiles_of(j - 1));
+      if (ns > h->part_rows) ns = h->part_rows;
+      if (ns > (long long)n / 256) ns = (long long)n / 256;
+      if (ns < 1) ns = 1;
+      const long long rps2 = DIB_ROUND_UP(DIB_CEIL_DIV((long long)n, ns), 64);
+      const int ns2 = (int)DIB_CEIL_DIV((long long)n, rps2);
+      nsplit_of[j] = nsplit_of[j - 1] = ns2;
+      prof_begin(c, "int16_wgrad_pair_l", j - 1);
+      DIB_CUDA_OK(dib_int16_wgrad_pair(in_of(j), int_fan_in(h, j), c.ws + h->dg16_off[j + 1], int_fan_out(h, j), part + h->intW[j], ns2, (int)rps2,
+                                       in_of(j - 1), int_fan_in(h, j - 1), c.ws + h->dg16_off[j], int_fan_out(h, j - 1), part + h->intW[j - 1], ns2,
+                                       (int)rps2, (int)n, h->Pp, 1.f / gscale, bf, c.st));
+      prof_end(c);
+    }
+    if (j == 0) {
+      prof_begin(c, "int16_wgrad_l", 0);
+      DIB_CUDA_OK(dib_int16_wgrad(in_of(0), int_fan_in(h, 0), c.ws + h->dg16_off[1], int_fan_out(h, 0), part + h->intW[0], nullptr, (int)n,
+                                  int_fan_in(h, 0), int_fan_out(h, 0), nsplit, (int)rps, h->Pp, 1.f / gscale, bf, c.st));
+      prof_end(c);
+    }
     prof_begin(c, "int_split_reduce");
-    for (int j = 0; j < h->Li; ++j)     // hidden-layer kernels: batch-split partials
-      segs.push_back({part + h->intW[j], h->Pp, nsplit, (long long)int_fan_in(h, j) * int_fan_out(h, j), 1.f, grads_flat + h->intW[j]});
+    for (int q = 0; q < h->Li; ++q)     // hidden-layer kernels: batch-split partials
+      segs.push_back({part + h->intW[q], h->Pp, nsplit_of[q], (long long)int_fan_in(h, q) * int_fan_out(h, q), 1.f, grads_flat + h->intW[q]});
     segs.push_back({c.ws + h->headpart_off, h->head_stride, h->head_used, h->P - p_head, 1.f, grads_flat + p_head});
     DIB_CUDA_OK(dib_launch_reduce_segments(segs.data(), (int)segs.size(), c.st));
     prof_end(c);
@@ -1072,7 +1093,7 @@ int dib_encoders_backward(dib_model* h, const float* params, const float* x, con
   if (ib_weight(c, beta_dev, out_stats, inv_global_batch, &bw)) return 1;
   long long rps = DIB_CEIL_DIV((long long)n, (long long)kMaxSplits);
   if (rps < 256) rps = 256;
-  rps = DIB_ROUND_UP(rps, 32);
+  rps = DIB_ROUND_UP(rps, 64);      // whole k-blocks of every WGRAD kernel (32 rows for the TF32 ones, 64 for the 16-bit ones)
   const int nsplit = (int)DIB_CEIL_DIV((long long)n, rps);
   const long long p_enc = h->intW[0];
   const int FE = h->F * h->E;

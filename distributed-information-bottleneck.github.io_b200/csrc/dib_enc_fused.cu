@@ -73,7 +73,7 @@ struct EncFusedParams {
   const unsigned int* step_dev;            // optional device addend of `step` (CUDA-Graph replay)
   float* emb; int ldemb; float* user_emb;  // outputs (forward); emb may be null when emb16 is given
   uint16_t* emb16; int ldemb16;            // 16-bit (fp16 / bf16) copy of emb for the 16-bit integration path (or null)
-  uint16_t* a0g;                           // [n, F, 16] 16-bit copy of the [pe|1] first-layer operand rows: written by the training
+  uint16_t* a0g;                           // [2 F, n, 8] 16-bit copy of the [pe|1] first-layer operand rows (k-halves): written by the training
                                            // forward, TMA-loaded by the two-chain backward instead of recomputing the encoding
   uint16_t* eps16;                         // [n, F*32] 16-bit copy of the Philox noise: written by the training forward, read by the
                                            // two-chain backward instead of regenerating it (the gradient operands are 16-bit anyway)
@@ -331,7 +331,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         const long long grow = (long long)slot * TM + ar;
         load_x(grow < P.n ? P.x + grow * P.ldx + xo : nullptr, d, xv);
         write_a0_row<BF16>(sb + ((it & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow < P.n, xv, d, P.nfreq,
-                           (P.a0g && grow < P.n) ? P.a0g + (grow * F + f) * 16 + khalf * 8 : nullptr);
+                           (P.a0g && grow < P.n) ? P.a0g + ((long long)(2 * f + khalf) * P.n + grow) * 8 : nullptr);
         DIB_EPI_SIGNAL(bar_a0);
       }
       for (int t = slot; t < ntiles; t += nslots, ++it) {
@@ -349,7 +349,7 @@ dib_enc_fused_fwd_kernel(const __grid_constant__ WeightMaps maps, const EncFused
         DIB_EPI_SIGNAL(bar_h1);
         if (has_next) {      // stage the next tile's operand in the other A0 buffer: its layer-0 MMA then runs early
           write_a0_row<BF16>(sb + (((it + 1) & 1) ? kOffFwdA0b : kOffA0), ar, khalf, grow_n < P.n, xv, d, P.nfreq,
-                             (P.a0g && grow_n < P.n) ? P.a0g + (grow_n * F + f) * 16 + khalf * 8 : nullptr);
+                             (P.a0g && grow_n < P.n) ? P.a0g + ((long long)(2 * f + khalf) * P.n + grow_n) * 8 : nullptr);
           DIB_EPI_SIGNAL(bar_a0);
         }
         noise8(ep, P.seed, nstep, P.sample_offset + (unsigned long long)grow, f, hsel * 16, valid, nrmA);   // while layer 1 runs
@@ -916,8 +916,8 @@ dib_enc_fused_bwd2_kernel(const __grid_constant__ WeightMaps maps, const EncFuse
           if (lane == 0) {
             const int row0 = (slot + k * nslots) * TM;
             mbar_expect_tx(bar_a0t, 2 * TM * 16);
-            tma_load_3d(a0_of(i), &maps.a0lo, bar_a0t, 0, f, row0);
-            tma_load_3d(a0_of(i) + TM * 16, &maps.a0hi, bar_a0t, 0, f, row0);
+            tma_load_3d(a0_of(i), &maps.a0lo, bar_a0t, 0, row0, 2 * f);
+            tma_load_3d(a0_of(i) + TM * 16, &maps.a0lo, bar_a0t, 0, row0, 2 * f + 1);
           }
           __syncwarp();
         };
@@ -1299,20 +1299,19 @@ bool make_all_maps(WeightMaps* m, const void* packed, int F, bool bf16) {
          make_wmap(&m->b2, pk + kW0Elems + kW1Elems + kW2Elems + kB1Elems, EO, K0, F, bf16);
 }
 
-// [n, F, 16] 16-bit hand-off buffer -> per k-half a 3D map (8 elements, feature, row), box 8 x 1 x 128 rows: lands as the
-// unswizzled [128 rows][16 B] half of the first-layer operand; rows past n are zero-filled (their ones column included)
+// [2 F (feature, k-half), n, 8] 16-bit hand-off buffer -- consecutive rows of one (feature, k-half) are consecutive 16-byte pieces,
+// so the forward kernel's row-per-lane stores are fully coalesced -- as a 3D map (8 elements, row, plane), box 8 x 128 rows x 1:
+// one box lands as the unswizzled [128 rows][16 B] half of the first-layer operand; rows past n are zero-filled (their ones column too)
 bool make_a0_maps(WeightMaps* m, const void* a0g, long long n, int F, bool bf16) {
-  const uint16_t* base = static_cast<const uint16_t*>(a0g);
-  cuuint64_t dims[3] = {8, (cuuint64_t)F, (cuuint64_t)n};
-  cuuint64_t strides[2] = {32, (cuuint64_t)F * 32};
-  cuuint32_t box[3] = {8, 1, (cuuint32_t)TM};
+  cuuint64_t dims[3] = {8, (cuuint64_t)n, (cuuint64_t)(2 * F)};
+  cuuint64_t strides[2] = {16, (cuuint64_t)n * 16};
+  cuuint32_t box[3] = {8, (cuuint32_t)TM, 1};
   cuuint32_t es[3] = {1, 1, 1};
   const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  for (int half = 0; half < 2; ++half)
-    if (encode_fn2()(half ? &m->a0hi : &m->a0lo, dt, 3, const_cast<uint16_t*>(base + half * 8), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return false;
+  if (encode_fn2()(&m->a0lo, dt, 3, const_cast<void*>(a0g), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  m->a0hi = m->a0lo;
   return true;
 }
 

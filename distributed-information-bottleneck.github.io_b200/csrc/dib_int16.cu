@@ -59,7 +59,10 @@ __device__ __forceinline__ void unpack_h2(uint32_t u, float& a, float& b) {
 // tile i+1.  Warp roles: 0 TMA producer | 1 MMA issuer (+ TMEM owner) | 2..5 epilogue.
 template <int MODE, bool BF16>
 __global__ void __launch_bounds__(192, 2)
-dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Int16Args a) {
+dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Int16Args a,
+                      const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const Int16Args a2) {
+  // (a2, mapA2, mapB2): an optional SECOND weight-gradient problem walked by the same launch (a2.nsplit > 0, WGRAD only): the two
+  // layers' tiles together fill one wave of CTAs, which neither fills alone
   constexpr bool A_MN = (MODE == DIB_GEMM_WGRAD), B_MN = (MODE != DIB_GEMM_DGRAD);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -74,13 +77,17 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
   __shared__ float colsum_s[4][kBN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = (MODE == DIB_GEMM_WGRAD) ? a.R : a.M, C = a.C;
-  const int tiles_r = DIB_CEIL_DIV(R, kBM), tiles_c = DIB_CEIL_DIV(C, kBN);
+  const int R0 = (MODE == DIB_GEMM_WGRAD) ? a.R : a.M, C0 = a.C;
+  const int tiles_r = DIB_CEIL_DIV(R0, kBM), tiles_c = DIB_CEIL_DIV(C0, kBN);
   const int nsp = (MODE == DIB_GEMM_WGRAD) ? a.nsplit : 1;
-  const int ntile = tiles_r * tiles_c * nsp;
+  const int ntile0 = tiles_r * tiles_c * nsp;
+  const bool two = (MODE == DIB_GEMM_WGRAD) && a2.nsplit > 0;
+  const int tiles_r2 = two ? DIB_CEIL_DIV(a2.R, kBM) : 0, tiles_c2 = two ? DIB_CEIL_DIV(a2.C, kBN) : 0;
+  const int ntile = ntile0 + tiles_r2 * tiles_c2 * (two ? a2.nsplit : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
+    if (two) { tma_prefetch_desc(&mapA2); tma_prefetch_desc(&mapB2); }
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int acc = 0; acc < 2; ++acc) { mbar_init(tfull_bar(acc), 1); mbar_init(tempty_bar(acc), 4); }
     fence_barrier_init();
@@ -91,14 +98,20 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_g;
 
+  int prob = 0;                                     // which problem the tile last decoded belongs to (per thread)
   auto decode = [&](int tile, int& r0, int& c0, int& split, int& t_begin, int& nk) {
-    const int per = tiles_r * tiles_c;
+    prob = (two && tile >= ntile0) ? 1 : 0;
+    if (prob) tile -= ntile0;
+    const int tr = prob ? tiles_r2 : tiles_r, tcn = prob ? tiles_c2 : tiles_c;
+    const int per = tr * tcn;
     split = tile / per;
     const int rem = tile - split * per;
-    r0 = (rem / tiles_c) * kBM; c0 = (rem % tiles_c) * kBN;
+    r0 = (rem / tcn) * kBM; c0 = (rem % tcn) * kBN;
     int t_end;
-    if (MODE == DIB_GEMM_WGRAD) { t_begin = split * a.rows_per_split; t_end = min(a.M, t_begin + a.rows_per_split); }
-    else { t_begin = 0; t_end = a.T; }
+    if (MODE == DIB_GEMM_WGRAD) {
+      const int rps = prob ? a2.rows_per_split : a.rows_per_split;
+      t_begin = split * rps; t_end = min(a.M, t_begin + rps);
+    } else { t_begin = 0; t_end = a.T; }
     nk = t_end > t_begin ? DIB_CEIL_DIV(t_end - t_begin, kBK) : 0;
   };
 
@@ -113,10 +126,12 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           mbar_expect_tx(full_bar(s), kStageBytes);
           const uint32_t a_dst = sb + s * kStageBytes, b_dst = a_dst + kABytes;
           const int t0 = t_begin + k * kBK;
-          if constexpr (A_MN) tma_load_3d(a_dst, &mapA, full_bar(s), 0, t0, r0 / 64);
-          else                tma_load_2d(a_dst, &mapA, full_bar(s), t0, r0);
-          if constexpr (B_MN) tma_load_3d(b_dst, &mapB, full_bar(s), 0, t0, c0 / 64);
-          else                tma_load_2d(b_dst, &mapB, full_bar(s), t0, c0);
+          const CUtensorMap* mA = prob ? &mapA2 : &mapA;
+          const CUtensorMap* mB = prob ? &mapB2 : &mapB;
+          if constexpr (A_MN) tma_load_3d(a_dst, mA, full_bar(s), 0, t0, r0 / 64);
+          else                tma_load_2d(a_dst, mA, full_bar(s), t0, r0);
+          if constexpr (B_MN) tma_load_3d(b_dst, mB, full_bar(s), 0, t0, c0 / 64);
+          else                tma_load_2d(b_dst, mB, full_bar(s), t0, c0);
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
@@ -160,6 +175,7 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       decode(tile, r0, c0, split, t_begin, nk);
       const int acc = lt & 1;
       const int r = r0 + q * 32 + lane;
+      const int R = prob ? a2.R : R0, C = prob ? a2.C : C0;
       // the activation row that gates the gradient (DGRAD) is fetched one 32-column chunk ahead -- the first chunk before the wait
       // for the accumulator -- so that its L2 / HBM latency never sits on the per-chunk critical path
       uint32_t xpre[16], xnext[16];
@@ -196,7 +212,7 @@ dib_int16_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         if (r < R && c0 + cc < C && !(a.dbg & 1)) {          // C is a multiple of 64: a 32-column chunk is entirely inside or outside
           const int c = c0 + cc;
           if constexpr (MODE == DIB_GEMM_WGRAD) {
-            float* dst = a.out32 + (long long)split * a.split_stride + (long long)r * a.ldc + c;
+            float* dst = (prob ? a2.out32 : a.out32) + (long long)split * a.split_stride + (long long)r * (prob ? a2.ldc : a.ldc) + c;
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
               dib_st_global_v8(dst + j, __float_as_uint(__uint_as_float(v[j]) * a.out_scale), __float_as_uint(__uint_as_float(v[j + 1]) * a.out_scale),
@@ -1386,7 +1402,28 @@ cudaError_t launch16(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Ar
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dib_int16_gemm_kernel<MODE, BF16><<<grid, 192, kSmemTotal, st>>>(mA, mB, a);
+  Int16Args none{};
+  dib_int16_gemm_kernel<MODE, BF16><<<grid, 192, kSmemTotal, st>>>(mA, mB, a, mA, mB, none);
+  dib_note_launch();
+  return cudaGetLastError();
+}
+
+// two weight-gradient problems (same batch, same split stride) in one launch
+template <bool BF16>
+cudaError_t launch16_wgrad2(const CUtensorMap& mA, const CUtensorMap& mB, const Int16Args& a, const CUtensorMap& mA2, const CUtensorMap& mB2,
+                            const Int16Args& a2, cudaStream_t st) {
+  if (!g_num_sms16) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms16, cudaDevAttrMultiProcessorCount, dev); }
+  const long long nt = (long long)DIB_CEIL_DIV(a.R, kBM) * DIB_CEIL_DIV(a.C, kBN) * a.nsplit +
+                       (long long)DIB_CEIL_DIV(a2.R, kBM) * DIB_CEIL_DIV(a2.C, kBN) * a2.nsplit;
+  if (nt <= 0) return cudaSuccess;
+  dim3 grid((unsigned)(nt < 2ll * g_num_sms16 ? nt : 2ll * g_num_sms16));
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dib_int16_gemm_kernel<DIB_GEMM_WGRAD, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dib_int16_gemm_kernel<DIB_GEMM_WGRAD, BF16><<<grid, 192, kSmemTotal, st>>>(mA, mB, a, mA2, mB2, a2);
   dib_note_launch();
   return cudaGetLastError();
 }
@@ -1631,6 +1668,22 @@ cudaError_t dib_int16_fwd2_head(const void* g_in, int ld_in, int K0, const void*
 #undef DIB_F2_LAUNCH
   dib_note_launch();
   return cudaGetLastError();
+}
+
+// the weight gradients of TWO layers in one launch (same batch M, same partial stride): dW_j = g_in_j^T dz_j over batch slices
+cudaError_t dib_int16_wgrad_pair(const void* g_in0, int K0, const void* dz0, int N0, float* dW_part0, int nsplit0, int rps0,
+                                 const void* g_in1, int K1, const void* dz1, int N1, float* dW_part1, int nsplit1, int rps1,
+                                 int M, long long split_stride, float out_scale, int bf16, cudaStream_t st) {
+  if (!encode_fn3()) return cudaErrorNotSupported;
+  CUtensorMap mA, mB, mA2, mB2;
+  if (!map_mn(&mA, g_in0, K0, M, K0, kBM / 64) || !map_mn(&mB, dz0, N0, M, N0, kBN / 64) ||
+      !map_mn(&mA2, g_in1, K1, M, K1, kBM / 64) || !map_mn(&mB2, dz1, N1, M, N1, kBN / 64))
+    return cudaErrorInvalidValue;
+  Int16Args a{}, b{};
+  a.dbg = b.dbg = g_int16_dbg;
+  a.out32 = dW_part0; a.ldc = N0; a.M = M; a.C = N0; a.R = K0; a.out_scale = out_scale; a.nsplit = nsplit0; a.rows_per_split = rps0; a.split_stride = split_stride;
+  b.out32 = dW_part1; b.ldc = N1; b.M = M; b.C = N1; b.R = K1; b.out_scale = out_scale; b.nsplit = nsplit1; b.rows_per_split = rps1; b.split_stride = split_stride;
+  return bf16 ? launch16_wgrad2<true>(mA, mB, a, mA2, mB2, b, st) : launch16_wgrad2<false>(mA, mB, a, mA2, mB2, b, st);
 }
 
 int dib_int16_head_blocks(int num_sms) { return num_sms * 2; }

@@ -136,7 +136,7 @@ struct DibEncFusedIO {
   float* kl_part; int kl_stride;
   void* emb16 = nullptr; int ldemb16 = 0;   // optional fp16 copy of emb (16-bit integration path)
   void* eps16 = nullptr;                    // optional [n, F*32] 16-bit noise hand-off: forward writes, two-chain backward reads
-  void* a0g = nullptr;                      // optional [n, F, 16] 16-bit [pe|1] operand hand-off (same direction)
+  void* a0g = nullptr;                      // optional [2 F, n, 8] 16-bit [pe|1] operand hand-off, k-halves as planes (same direction)
 };
 int dib_enc_bwd_version();
 void dib_enc_bwd_set_version(int v);
@@ -170,6 +170,9 @@ cudaError_t dib_launch_reduce_tall(const float* part, long long row_stride, int 
                                    cudaStream_t st);
 cudaError_t dib_int16_wgrad(const void* g_in, int ld_g, const void* dz, int ld_dz, float* dW_part, float* db_part, int M, int K,
                             int N, int nsplit, int rows_per_split, long long split_stride, float out_scale, int bf16, cudaStream_t st);
+cudaError_t dib_int16_wgrad_pair(const void* g_in0, int K0, const void* dz0, int N0, float* dW_part0, int nsplit0, int rps0,
+                                 const void* g_in1, int K1, const void* dz1, int N1, float* dW_part1, int nsplit1, int rps1,
+                                 int M, long long split_stride, float out_scale, int bf16, cudaStream_t st);
 int dib_int16_head_blocks(int num_sms);
 void dib_int16_dbg_set(int v);
 int dib_int16_2sm_enabled();
