@@ -529,8 +529,10 @@ cudaError_t dib_launch_round_copy(const float* src, float* dst, int64_t count, c
 }
 
 namespace {
-struct ReduceSegsArg { DibReduceSeg seg[kDibMaxReduceSegs]; int first_block[kDibMaxReduceSegs + 1]; int nseg; };
-// the dib_reduce_tall_kernel mapping (32 outputs x 8 row lanes per block, fixed order) over a list of independent reductions
+struct ReduceSegsArg { DibReduceSeg seg[kDibMaxReduceSegs]; int first_block[kDibMaxReduceSegs + 1]; int flat[kDibMaxReduceSegs]; int nseg; };
+// A list of independent fixed-order reductions in one launch.  Two mappings per segment: FLAT (few rows, many outputs -- the
+// batch-split weight-gradient partials): one output per thread, rows summed in order, loads batched 8 deep, coalesced across the
+// block; TALL (many rows, few outputs -- per-tile / per-CTA column sums): 32 outputs x 8 row lanes per block.
 __global__ void __launch_bounds__(256)
 dib_reduce_segments_kernel(const ReduceSegsArg A) {
   __shared__ float red[8][32];
@@ -538,8 +540,25 @@ dib_reduce_segments_kernel(const ReduceSegsArg A) {
 #pragma unroll
   for (int k = 1; k < kDibMaxReduceSegs; ++k) if (k < A.nseg && (int)blockIdx.x >= A.first_block[k]) sidx = k;
   const DibReduceSeg S = A.seg[sidx];
+  const int blk = (int)blockIdx.x - A.first_block[sidx];
+  if (A.flat[sidx]) {
+    const long long i = (long long)blk * 256 + threadIdx.x;
+    if (i >= S.count) return;
+    float s = 0.f;
+    int k = 0;
+    for (; k + 8 <= S.nrows; k += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = S.src[(long long)(k + u) * S.row_stride + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; k < S.nrows; ++k) s += S.src[(long long)k * S.row_stride + i];
+    S.dst[i] = s * S.scale;
+    return;
+  }
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long i = (long long)((int)blockIdx.x - A.first_block[sidx]) * 32 + tx;
+  const long long i = (long long)blk * 32 + tx;
   float s = 0.f;
   if (i < S.count) {
     int r = ty;
@@ -569,7 +588,8 @@ cudaError_t dib_launch_reduce_segments(const DibReduceSeg* segs, int nseg, cudaS
     for (int k = base; k < nseg && n < kDibMaxReduceSegs; ++k) {
       if (segs[k].count <= 0) continue;
       A.seg[n] = segs[k]; A.first_block[n] = nb;
-      nb += (int)((segs[k].count + 31) / 32);
+      A.flat[n] = (segs[k].nrows <= 64 && segs[k].count >= 4096) ? 1 : 0;
+      nb += (int)((segs[k].count + (A.flat[n] ? 255 : 31)) / (A.flat[n] ? 256 : 32));
       ++n;
     }
     A.first_block[n] = nb; A.nseg = n;
