@@ -26,11 +26,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint (ns): the wake-up stays event-driven, but
-  // a waiting warp re-polls every ~10 ms instead of every ~100 ns -- in the issue-bound encoder forward kernel the poll loops
-  // (SYNCS + BRA + YIELD) were 17 % of all issued instructions (profiles/r02_enc_fwd_source_summary.txt)
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  // (no suspend-time hint: a 10 ms hint removes the poll loops' instructions -- 17 % of the forward kernel's issue slots,
+  //  profiles/r02_enc_fwd_source_summary.txt -- but measured no gain there and +30 us in the latency-bound backward kernel:
+  //  warps parked with a long limit wake up later)
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
