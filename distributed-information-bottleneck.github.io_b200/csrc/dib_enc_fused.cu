@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#define DIB_MBAR_SPIN 1      // experiment: non-blocking mbarrier probes in the hand-shake chains
 #include "dib_common.cuh"
 #include "dib_kernels.h"
 #include "dib_sm100.cuh"

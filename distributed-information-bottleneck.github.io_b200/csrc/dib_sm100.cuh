@@ -34,11 +34,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   //  warps parked with a long limit wake up later)
   return ok != 0;
 }
+// non-blocking probe: a loop around it never parks the warp (fastest wake-up, costs issue slots while waiting)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef DIB_MBAR_SPIN
+  while (!mbar_test_wait(bar, parity)) {}
+#else
   while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 // for a lone control thread that shares its scheduler with working warps: back off between polls
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+#ifdef DIB_MBAR_SPIN
+  while (!mbar_test_wait(bar, parity)) {}
+  return;
+#endif
   while (!mbar_try_wait(bar, parity)) {}   // try_wait itself suspends for a bounded time; an extra nanosleep only adds hop latency
 }
 
