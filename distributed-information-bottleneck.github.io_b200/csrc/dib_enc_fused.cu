@@ -19,7 +19,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
-#define DIB_MBAR_SPIN 1      // experiment: non-blocking mbarrier probes in the hand-shake chains
+// (DIB_MBAR_SPIN: non-blocking mbarrier.test_wait probes instead of try_wait in the hand-shake chains -- measured 0.253 vs 0.244 ms
+//  for the backward kernel, 0.136 vs 0.133 ms for the forward: the spinning warps take issue slots from the working ones; not defined)
 #include "dib_common.cuh"
 #include "dib_kernels.h"
 #include "dib_sm100.cuh"
