@@ -246,6 +246,7 @@ class DistributedIBNet:
         # (0.475 vs 0.444 ms/step strong, 0.758 vs 0.744 weak -- the second NCCL launch and the stream hand-offs cost more than
         # the 0.8 MB bucket hides), so it is opt-in (DIB_OVERLAP_ALLREDUCE=1)
         self.overlap_allreduce = os.environ.get("DIB_OVERLAP_ALLREDUCE", "0") in ("1", "on", "true", "yes")
+        self.graph_nccl = os.environ.get("DIB_GRAPH_NCCL", "0") in ("1", "on", "true", "yes")
         self._inference_calls = 0          # fresh noise per un-seeded inference call (tf.random.normal, models.py:108)
         self.optimizer = None
         self.compiled_metrics_names = []
@@ -550,8 +551,8 @@ class DistributedIBNet:
     # ------------------------------------------------------------------ CUDA-graph replay of the step
     def _capture_step(self, key):
         """Capture the step for one (n, global_batch, sample_offset, world) into CUDA graphs.  Single GPU: ONE graph
-        (forward + backward + Adam + noise-step increment).  Data parallel: three graphs (phase 1 | phase 2 | Adam) with the
-        NCCL all-reduces issued eagerly between them.  Inputs are copied into static buffers before each replay; beta,
+        (forward + backward + Adam + noise-step increment).  Data parallel: two graphs (backward | Adam) with the NCCL all-reduce
+        issued eagerly between them (three -- phase 1 | phase 2 | Adam -- for the opt-in two-bucket overlap).  Inputs are copied into static buffers before each replay; beta,
         learning rate, the Adam step and the Philox step are device scalars, so nothing by-value changes between replays."""
         n, global_batch, sample_offset, world = key
         D = sum(self.feature_dimensionalities)
@@ -579,9 +580,15 @@ class DistributedIBNet:
 
                 if world == 1:
                     cap(lambda: (self._backward(gx, gy, global_batch, None, sample_offset, device_step=True), tail()))
-                else:
+                elif self.overlap_allreduce:
                     cap(lambda: self._backward(gx, gy, global_batch, None, sample_offset, phases=1, device_step=True))
                     cap(lambda: self._backward(gx, gy, global_batch, None, sample_offset, phases=2, device_step=True))
+                    cap(tail)
+                elif self.graph_nccl:       # opt-in (DIB_GRAPH_NCCL=1): the NCCL all-reduce captured inside ONE graph
+                    cap(lambda: (self._backward(gx, gy, global_batch, None, sample_offset, device_step=True),
+                                 parallel.allreduce_sum_(self._gradstats, self.process_group), tail()))
+                else:        # one all-reduce between backward and optimizer: two graphs
+                    cap(lambda: self._backward(gx, gy, global_batch, None, sample_offset, device_step=True))
                     cap(tail)
                 torch.cuda.synchronize(self.device)
                 # capture does not execute, but be safe against any eager side effect: restore the optimizer state
@@ -609,10 +616,12 @@ class DistributedIBNet:
         elif self.overlap_allreduce:
             self._reduce_overlapped(world, g["graphs"][0].replay, g["graphs"][1].replay)
             g["graphs"][2].replay()
+        elif len(g["graphs"]) == 1:          # all-reduce captured in the graph
+            g["graphs"][0].replay()
         else:
-            g["graphs"][0].replay(); g["graphs"][1].replay()
+            g["graphs"][0].replay()
             parallel.allreduce_sum_(self._gradstats, self.process_group)
-            g["graphs"][2].replay()
+            g["graphs"][1].replay()
         self._train_step_count += 1
         return self._gradstats[P:]
 
