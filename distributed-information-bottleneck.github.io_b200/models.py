@@ -246,7 +246,8 @@ class DistributedIBNet:
         # (0.475 vs 0.444 ms/step strong, 0.758 vs 0.744 weak -- the second NCCL launch and the stream hand-offs cost more than
         # the 0.8 MB bucket hides), so it is opt-in (DIB_OVERLAP_ALLREDUCE=1)
         self.overlap_allreduce = os.environ.get("DIB_OVERLAP_ALLREDUCE", "0") in ("1", "on", "true", "yes")
-        self.graph_nccl = os.environ.get("DIB_GRAPH_NCCL", "0") in ("1", "on", "true", "yes")
+        # (capturing the NCCL all-reduce inside the step's graph was tried on 2 B200s: no gain -- 0.611 vs 0.605 ms/step weak -- and
+        #  the processes hung at teardown; the all-reduce stays an eager call between the backward graph and the optimizer graph)
         self._inference_calls = 0          # fresh noise per un-seeded inference call (tf.random.normal, models.py:108)
         self.optimizer = None
         self.compiled_metrics_names = []
@@ -584,9 +585,6 @@ class DistributedIBNet:
                     cap(lambda: self._backward(gx, gy, global_batch, None, sample_offset, phases=1, device_step=True))
                     cap(lambda: self._backward(gx, gy, global_batch, None, sample_offset, phases=2, device_step=True))
                     cap(tail)
-                elif self.graph_nccl:       # opt-in (DIB_GRAPH_NCCL=1): the NCCL all-reduce captured inside ONE graph
-                    cap(lambda: (self._backward(gx, gy, global_batch, None, sample_offset, device_step=True),
-                                 parallel.allreduce_sum_(self._gradstats, self.process_group), tail()))
                 else:        # one all-reduce between backward and optimizer: two graphs
                     cap(lambda: self._backward(gx, gy, global_batch, None, sample_offset, device_step=True))
                     cap(tail)
@@ -616,8 +614,6 @@ class DistributedIBNet:
         elif self.overlap_allreduce:
             self._reduce_overlapped(world, g["graphs"][0].replay, g["graphs"][1].replay)
             g["graphs"][2].replay()
-        elif len(g["graphs"]) == 1:          # all-reduce captured in the graph
-            g["graphs"][0].replay()
         else:
             g["graphs"][0].replay()
             parallel.allreduce_sum_(self._gradstats, self.process_group)
