@@ -362,8 +362,15 @@ int run_forward(const Ctx& c, const float* x, const float* y, const float* eps, 
     d.grid = (int)(want < cap ? want : cap);
     nblk_kl = DIB_CEIL_DIV(d.grid, h->F);
     prof_begin(c, "enc_pack_weights");
-    DIB_CUDA_OK(dib_enc_fused_pack(d, c.params, c.ws + h->pack_off, c.st));
-    DIB_CUDA_OK(cudaMemsetAsync(c.ws + h->kl_part_off, 0, sizeof(float) * (size_t)h->F * h->kl_stride, c.st));
+    {
+      const long long zn = (long long)h->F * h->kl_stride, zcap = dib_enc_fused_pack_zero_capacity(h->F);
+      // the pack kernel also clears the KL partial table when it fits its grid
+      if (zn <= zcap) DIB_CUDA_OK(dib_enc_fused_pack(d, c.params, c.ws + h->pack_off, c.ws + h->kl_part_off, zn, c.st));
+      else {
+        DIB_CUDA_OK(dib_enc_fused_pack(d, c.params, c.ws + h->pack_off, nullptr, 0, c.st));
+        DIB_CUDA_OK(cudaMemsetAsync(c.ws + h->kl_part_off, 0, sizeof(float) * (size_t)zn, c.st));
+      }
+    }
     prof_end(c);
     DibEncFusedIO io;
     io.params = c.params; io.packed = c.ws + h->pack_off; io.x = x; io.ldx = h->D; io.n = c.n;
@@ -868,6 +875,7 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
   const bool i16 = fused_enc && h->int16_ok && !h->force_int32;
   const float gscale = exp2f(ceilf(log2f(1.f / inv_global_batch)));
 
+  std::vector<DibReduceSeg> segs;          // fixed-order reductions of the step; whole steps (phases == 3) run them as ONE launch at the end
   // ---------------------------------------------------------------- phase 1: integration network backward
   if (phA && i16) {
     const int bf = h->precision == DIB_PREC_BF16 ? 1 : 0;
@@ -876,7 +884,6 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     const long long p_head = h->intW[h->Li];
     // every fixed-order reduction of this phase runs as ONE launch at its end (bias gradients from the head / dgrad column sums,
     // batch-split weight-gradient partials, the output layer's per-CTA partials)
-    std::vector<DibReduceSeg> segs;
     // bias gradient of the last hidden layer: column sums of dg accumulated by the output head
     segs.push_back({c.ws + h->headpart_off + (long long)Kh * h->out + h->out, h->head_stride, h->head_used, Kh, 1.f / gscale,
                     grads_flat + h->intB[h->Li - 1]});
@@ -920,7 +927,10 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     for (int q = 0; q < h->Li; ++q)     // hidden-layer kernels: batch-split partials
       segs.push_back({part + h->intW[q], h->Pp, nsplit_of[q], (long long)int_fan_in(h, q) * int_fan_out(h, q), 1.f, grads_flat + h->intW[q]});
     segs.push_back({c.ws + h->headpart_off, h->head_stride, h->head_used, h->P - p_head, 1.f, grads_flat + p_head});
-    DIB_CUDA_OK(dib_launch_reduce_segments(segs.data(), (int)segs.size(), c.st));
+    if (!(phB && fused_enc)) {               // phase-1-only call (or unfused encoders): reduce now
+      DIB_CUDA_OK(dib_launch_reduce_segments(segs.data(), (int)segs.size(), c.st));
+      segs.clear();
+    }
     prof_end(c);
   } else if (phA) {
     // integration network backward (GradientTape through models.py:122)
@@ -962,7 +972,8 @@ int dib_train_step_phased(dib_model* h, const float* params, const float* x, con
     DIB_CUDA_OK(dib_enc_fused_backward(d, io, b, c.st));
     prof_end(c);
     prof_begin(c, "enc_split_reduce");
-    DIB_CUDA_OK(dib_launch_reduce_partials(part, h->Pp, slots_max, p_enc, grads_flat, c.st));
+    segs.push_back({part, h->Pp, slots_max, p_enc, 1.f, grads_flat});
+    DIB_CUDA_OK(dib_launch_reduce_segments(segs.data(), (int)segs.size(), c.st));
     prof_end(c);
     return 0;
   }

@@ -1239,9 +1239,13 @@ __global__ void dib_enc_pack_weights_kernel(const float* __restrict__ params, co
                                             const long long* __restrict__ b0_off, const long long* __restrict__ w1_off,
                                             const long long* __restrict__ b1_off, const long long* __restrict__ w2_off,
                                             const long long* __restrict__ b2_off, const int* __restrict__ fdim, int nfreq,
-                                            float logvar_offset, uint16_t* __restrict__ out) {
+                                            float logvar_offset, uint16_t* __restrict__ out, float* __restrict__ zero, long long zero_n) {
   const int f = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  {   // the KL partial-sum table of the forward kernel that follows is cleared here (one launch instead of a memset node)
+    const long long z = ((long long)f * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    if (z < zero_n) zero[z] = 0.f;
+  }
   if (i >= kPackElems) return;
   const int idx = i, w_in = fdim[f] * nfreq;
   float v;
@@ -1346,16 +1350,18 @@ int dib_enc_bwd_version() {
 void dib_enc_bwd_set_version(int v) { g_enc_bwd_version = v == 1 ? 1 : 2; }
 
 size_t dib_enc_fused_pack_bytes(int F) { return (size_t)F * kPackElems * 2; }
+long long dib_enc_fused_pack_zero_capacity(int F) { return (long long)DIB_CEIL_DIV(kPackElems, 256) * 256 * F; }   // floats the pack kernel can also clear
 int dib_enc_fused_fwd_ctas_per_sm() { return 2; }
 
-cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, cudaStream_t st) {
+cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, float* zero, long long zero_n, cudaStream_t st) {
   dim3 grid(DIB_CEIL_DIV(kPackElems, 256), d.F);
+  if (zero_n > (long long)grid.x * grid.y * 256) return cudaErrorInvalidValue;
   if (d.bf16)
     dib_enc_pack_weights_kernel<true><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.b1_off, d.w2_off,
-                                                           d.b2_off, d.fdim, d.nfreq, d.logvar_offset, static_cast<uint16_t*>(packed));
+                                                           d.b2_off, d.fdim, d.nfreq, d.logvar_offset, static_cast<uint16_t*>(packed), zero, zero_n);
   else
     dib_enc_pack_weights_kernel<false><<<grid, 256, 0, st>>>(params, d.w0_off, d.b0_off, d.w1_off, d.b1_off, d.w2_off,
-                                                            d.b2_off, d.fdim, d.nfreq, d.logvar_offset, static_cast<uint16_t*>(packed));
+                                                            d.b2_off, d.fdim, d.nfreq, d.logvar_offset, static_cast<uint16_t*>(packed), zero, zero_n);
   dib_note_launch();
   return cudaGetLastError();
 }

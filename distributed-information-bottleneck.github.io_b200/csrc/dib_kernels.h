@@ -141,8 +141,9 @@ struct DibEncFusedIO {
 int dib_enc_bwd_version();
 void dib_enc_bwd_set_version(int v);
 size_t dib_enc_fused_pack_bytes(int F);
+long long dib_enc_fused_pack_zero_capacity(int F);
 int dib_enc_fused_fwd_ctas_per_sm();
-cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, cudaStream_t st);
+cudaError_t dib_enc_fused_pack(const DibEncFusedDesc& d, const float* params, void* packed, float* zero, long long zero_n, cudaStream_t st);
 cudaError_t dib_enc_fused_forward(const DibEncFusedDesc& d, const DibEncFusedIO& io, cudaStream_t st);
 
 struct DibEncFusedBwdIO {
