@@ -298,7 +298,10 @@ int dib_debug_force_unfused(dib_model* h, int32_t on);
  * key 2: fused output head for output_dimensionality == 1, 1 = eight rows per pass with a lane-parallel loss (default), 0 = the
  * generic kernel.
  * key 3: single-output models whose last two hidden integration layers are 256 wide, 1 = those layers + the head + the loss as one
- * kernel (default; also DIB_INT16_FWD2=0|1), 0 = one kernel per layer and the head kernel of key 2. */
+ * kernel (default; also DIB_INT16_FWD2=0|1), 0 = one kernel per layer and the head kernel of key 2.
+ * key 4: 16-bit integration GEMMs whose output width is a multiple of 256, 1 = CTA-pair kernels (tcgen05 cta_group::2, 256 x 256 tile
+ * per pair; also DIB_INT16_2SM=1), 0 = single-CTA 128 x 128 kernels (default: measured the same or faster).
+ * key 5: MEASUREMENT ONLY, wrong results: 1 = the 16-bit GEMM epilogues skip their global stores (cost of the store path). */
 int dib_debug_set_variant(int32_t key, int32_t value);
 
 /* text of the last error raised on this thread ("" if none). */
