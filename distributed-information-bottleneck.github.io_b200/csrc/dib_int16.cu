@@ -746,30 +746,6 @@ dib_int16_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   if (warp == 1) { tc_fence_after_sync(); tmem2_dealloc(tmem_base, 2 * k2BN); }
 }
 
-// bias gradient of a hidden layer: column sums of the fp16 gradient over one batch slice -> fp32 split partial.
-// grid (C / 64, nsplit), 256 threads: lane pairs of columns (half2), 8 row lanes, fixed-order combine.
-__global__ void __launch_bounds__(256)
-dib_int16_colsum_kernel(const __half* __restrict__ dz, int ld, int M, int C, int rows_per_split, float scale,
-                        float* __restrict__ out, long long split_stride) {
-  __shared__ float red[8][64];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 64 + tx * 2, split = blockIdx.y;
-  const int t0 = split * rows_per_split, t1 = min(M, t0 + rows_per_split);
-  float s0 = 0.f, s1 = 0.f;
-  if (c < C)
-    for (int row = t0 + ty; row < t1; row += 8) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(dz + (long long)row * ld + c));
-      s0 += f.x; s1 += f.y;
-    }
-  red[ty][tx * 2] = s0; red[ty][tx * 2 + 1] = s1;
-  __syncthreads();
-  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < C) {
-    float s = 0.f;
-    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
-    out[(long long)split * split_stride + blockIdx.x * 64 + threadIdx.x] = s * scale;
-  }
-}
-
 // ----------------------------------------------------------------------------------------------------
 // output head: one warp per row; lanes own 8 hidden units each (K = 256) or loop (K = multiple of 256)
 // ----------------------------------------------------------------------------------------------------
