@@ -118,7 +118,8 @@ int64_t dib_param_count(const dib_model* h);
  * bias), cols[v].  Pass NULLs to query the number of variables (return value, negative on error). */
 int dib_param_layout(const dib_model* h, int64_t* offsets, int32_t* rows, int32_t* cols, int32_t capacity);
 
-/* bytes of scratch the caller must provide to forward / train_step / encode calls. */
+/* bytes of scratch the caller must provide to forward / train_step / encode calls.  The workspace pointer must be 256-byte
+ * aligned and `params` 16-byte aligned (checked; cudaMalloc / torch allocations are). */
 size_t dib_workspace_bytes(const dib_model* h);
 
 /* number of floats in the statistics vector: [ sum_b KL_i (F) | sum_b task loss | sum_b accuracy | n ] */
