@@ -735,10 +735,16 @@ class DistributedIBNet:
             if m not in ("accuracy", "acc"):
                 raise ValueError(f"only metrics=['accuracy'] is implemented (reference data.py:67), got {m!r}")
             self.compiled_metrics_names.append("accuracy")
-        self._lr_dev.fill_(float(self.optimizer.learning_rate))
+        self._lr_host = None
+        self._sync_lr()
 
     def _sync_lr(self):
-        self._lr_dev.fill_(float(self.optimizer.learning_rate))
+        """Device copy of optimizer.learning_rate (the step kernels read it from memory so that a schedule needs no re-capture);
+        refreshed only when the host value changed -- one fill kernel per step otherwise."""
+        lr = float(self.optimizer.learning_rate)
+        if lr != getattr(self, "_lr_host", None):
+            self._lr_dev.fill_(lr)
+            self._lr_host = lr
 
     def train_on_batch(self, x, y, return_dict=True, sync=True):
         """One optimizer step on a (host or device) batch.
